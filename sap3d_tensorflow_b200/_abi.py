@@ -1,0 +1,100 @@
+"""ctypes binding of libsap3d_b200.so (the C ABI declared in include/sap3d.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``python -m sap3d_tensorflow_b200.build``.
+There is no fallback: if the shared object is missing, import of this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsap3d_b200.so")
+
+BF16, F32 = 0, 1
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+
+
+class Sap3dError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build the CUDA extension first (python -m sap3d_tensorflow_b200.build). "
+        "This framework has no CPU / PyTorch fallback path."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("impl", C.c_int32),
+        ("N", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("nseg", C.c_int32), ("cin", C.c_int32 * 2), ("cout", C.c_int32),
+        ("kd", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+        ("sd", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
+        ("transposed", C.c_int32), ("has_bias", C.c_int32), ("out_f32", C.c_int32),
+    ]
+
+
+_vp = C.c_void_p
+_i32 = C.c_int32
+_i64 = C.c_int64
+_f32 = C.c_float
+
+lib.sap3d_last_error.restype = C.c_char_p
+lib.sap3d_abi_version.restype = C.c_int
+lib.sap3d_device_ok.restype = C.c_int
+
+
+def _sig(name, argtypes, restype=C.c_int):
+    fn = getattr(lib, name)
+    fn.argtypes = argtypes
+    fn.restype = restype
+    return fn
+
+
+_P = C.POINTER
+_sig("sap3d_conv_out_dims", [_P(ConvDesc), _P(C.c_int32)])
+_sig("sap3d_conv_stats_rows", [_P(ConvDesc)])
+_sig("sap3d_conv_packed_elems", [_P(ConvDesc), _i32], C.c_size_t)
+_sig("sap3d_conv_pack_weights", [_P(ConvDesc), _vp, _vp, _vp, _vp])
+_sig("sap3d_conv_fwd", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp])
+_sig("sap3d_conv_dgrad", [_P(ConvDesc), _i32, _vp, _vp, _vp, _vp, _i32, _vp])
+_sig("sap3d_conv_wgrad", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp])
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise Sap3dError(f"{what}: {lib.sap3d_last_error().decode()}")
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else t.data_ptr()
+
+
+def make_conv_desc(dtype, N, D, H, W, cin, cout, kernel, strides, transposed=False, has_bias=False, out_f32=False,
+                   impl=IMPL_AUTO) -> ConvDesc:
+    d = ConvDesc()
+    d.dtype, d.impl = dtype, impl
+    d.N, d.D, d.H, d.W = N, D, H, W
+    cin = list(cin)
+    d.nseg = len(cin)
+    d.cin[0] = cin[0]
+    d.cin[1] = cin[1] if len(cin) > 1 else 0
+    d.cout = cout
+    d.kd, d.kh, d.kw = kernel
+    d.sd, d.sh, d.sw = strides
+    d.transposed = int(transposed)
+    d.has_bias = int(has_bias)
+    d.out_f32 = int(out_f32)
+    return d
+
+
+def conv_out_dims(d: ConvDesc):
+    out = (C.c_int32 * 3)()
+    check(lib.sap3d_conv_out_dims(C.byref(d), out), "conv_out_dims")
+    return tuple(out)

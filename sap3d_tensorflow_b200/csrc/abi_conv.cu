@@ -1,0 +1,526 @@
+// C-ABI entry points of the convolution family (see include/sap3d.h).  Lowers a TF-semantics conv /
+// transposed-conv descriptor to (a) the tcgen05 implicit-GEMM "form F" problem of conv_tc.cu or
+// (b) the CUDA-core gather kernels of conv_simt.cu.
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <vector>
+
+#include "../../include/sap3d.h"
+#include "abi_util.cuh"
+#include "conv_simt.cuh"
+#include "conv_tc.cuh"
+
+using namespace sap3d;
+
+namespace {
+
+struct DimGeom {
+  int I, O, k, s, pb;
+};
+
+struct ConvGeom {
+  DimGeom d[3];  // D,H,W
+  int taps, cin_total, cout;
+  int seg_off[2];
+};
+
+void make_geom(const sap3d_conv_desc* c, ConvGeom& g) {
+  const int I[3] = {c->D, c->H, c->W};
+  const int k[3] = {c->kd, c->kh, c->kw};
+  const int s[3] = {c->sd, c->sh, c->sw};
+  for (int i = 0; i < 3; ++i) {
+    DimGeom& d = g.d[i];
+    d.I = I[i];
+    d.k = k[i];
+    d.s = s[i];
+    if (!c->transposed) {
+      d.O = (I[i] + s[i] - 1) / s[i];
+      int pt = (d.O - 1) * s[i] + k[i] - I[i];
+      if (pt < 0) pt = 0;
+      d.pb = pt / 2;
+    } else {
+      d.O = I[i] * s[i];
+      int pt = k[i] - s[i];
+      if (pt < 0) pt = 0;
+      d.pb = pt / 2;
+    }
+  }
+  g.taps = c->kd * c->kh * c->kw;
+  g.cin_total = c->cin[0] + (c->nseg > 1 ? c->cin[1] : 0);
+  g.cout = c->cout;
+  g.seg_off[0] = 0;
+  g.seg_off[1] = c->cin[0];
+}
+
+int check_desc(const sap3d_conv_desc* c) {
+  if (!c) return set_error("conv desc is NULL");
+  if (c->nseg < 1 || c->nseg > 2) return set_error("conv desc: nseg must be 1 or 2");
+  if (c->N < 1 || c->D < 1 || c->H < 1 || c->W < 1 || c->cout < 1 || c->cin[0] < 1) return set_error("conv desc: bad extent");
+  if (c->kd < 1 || c->kh < 1 || c->kw < 1 || c->sd < 1 || c->sh < 1 || c->sw < 1) return set_error("conv desc: bad kernel/stride");
+  if (c->dtype != SAP3D_BF16 && c->dtype != SAP3D_F32) return set_error("conv desc: bad dtype");
+  return 0;
+}
+
+// may the tensor-core path serve this descriptor (all of fwd and dgrad)?
+bool tc_eligible(const sap3d_conv_desc* c) {
+  if (c->impl == SAP3D_IMPL_SIMT) return false;
+  if (c->dtype != SAP3D_BF16) return false;
+  for (int s = 0; s < c->nseg; ++s)
+    if (c->cin[s] % 64 != 0) return false;
+  if (c->cout % 8 != 0) return false;
+  const int k[3] = {c->kd, c->kh, c->kw};
+  const int st[3] = {c->sd, c->sh, c->sw};
+  if (!c->transposed) {
+    for (int i = 0; i < 3; ++i)
+      if (st[i] != 1 && k[i] != 1) return false;  // strided taps (stem) -> SIMT
+  } else {
+    long long ncls = (long long)c->sd * c->sh * c->sw;
+    if (ncls > 64) return false;
+  }
+  return true;
+}
+// dgrad on the tensor-core path additionally needs cout % 64 == 0 (cout is the K dimension there)
+bool tc_dgrad_eligible(const sap3d_conv_desc* c) {
+  if (!tc_eligible(c)) return false;
+  if (c->cout % 64 != 0) return false;
+  if (c->transposed) {
+    // parity views of dy: at most 10 tensor maps
+    ConvGeom g;
+    make_geom(c, g);
+    int nv = 1;
+    for (int i = 0; i < 3; ++i) {
+      std::map<int, int> rs;
+      for (int k = 0; k < g.d[i].k; ++k) rs[((k - g.d[i].pb) % g.d[i].s + g.d[i].s) % g.d[i].s] = 1;
+      nv *= (int)rs.size();
+    }
+    if (nv > 10) return false;
+  }
+  return true;
+}
+
+void out_strides(const ConvGeom& g, int C, long long so[4]) {
+  so[0] = C;
+  so[1] = (long long)g.d[2].O * C;
+  so[2] = (long long)g.d[1].O * g.d[2].O * C;
+  so[3] = (long long)g.d[0].O * g.d[1].O * g.d[2].O * C;
+}
+void in_strides(const ConvGeom& g, int C, long long si[4]) {
+  si[0] = C;
+  si[1] = (long long)g.d[2].I * C;
+  si[2] = (long long)g.d[1].I * g.d[2].I * C;
+  si[3] = (long long)g.d[0].I * g.d[1].I * g.d[2].I * C;
+}
+
+int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// ---- forward -> TcProblem ---------------------------------------------------------------------
+void build_fwd_problem(const sap3d_conv_desc* c, const ConvGeom& g, const void* x0, const void* x1, TcProblem& pb) {
+  const void* xs[2] = {x0, x1};
+  pb.views.clear();
+  pb.classes.clear();
+  if (!c->transposed) {
+    // views sample the input with the conv stride (only k == 1 dims may be strided)
+    for (int s = 0; s < c->nseg; ++s) {
+      TcView v;
+      v.base = xs[s];
+      v.C = c->cin[s];
+      long long si[4];
+      in_strides(g, c->cin[s], si);
+      for (int i = 0; i < 3; ++i) {
+        const DimGeom& d = g.d[2 - i];  // i=0 -> W
+        v.dim[i] = (d.s == 1) ? d.I : d.O;
+        v.stride[i] = si[i] * d.s;
+      }
+      v.dim[3] = c->N;
+      v.stride[3] = si[3];
+      pb.views.push_back(v);
+    }
+    TcClassH cls;
+    cls.out_ofs = 0;
+    for (int kd = 0; kd < c->kd; ++kd)
+      for (int kh = 0; kh < c->kh; ++kh)
+        for (int kw = 0; kw < c->kw; ++kw) {
+          const int tap = (kd * c->kh + kh) * c->kw + kw;
+          for (int s = 0; s < c->nseg; ++s) {
+            TcTapH t;
+            t.view = s;
+            t.off[0] = (g.d[2].s == 1) ? kw - g.d[2].pb : 0;
+            t.off[1] = (g.d[1].s == 1) ? kh - g.d[1].pb : 0;
+            t.off[2] = (g.d[0].s == 1) ? kd - g.d[0].pb : 0;
+            t.off[3] = 0;
+            t.kofs = tap * g.cin_total + g.seg_off[s];
+            t.c_begin = 0;
+            t.nch = c->cin[s];
+            cls.taps.push_back(t);
+          }
+        }
+    pb.classes.push_back(cls);
+    pb.ext[0] = g.d[2].O; pb.ext[1] = g.d[1].O; pb.ext[2] = g.d[0].O; pb.ext[3] = c->N;
+    out_strides(g, c->cout, pb.so);
+  } else {
+    for (int s = 0; s < c->nseg; ++s) {
+      TcView v;
+      v.base = xs[s];
+      v.C = c->cin[s];
+      long long si[4];
+      in_strides(g, c->cin[s], si);
+      for (int i = 0; i < 3; ++i) {
+        v.dim[i] = g.d[2 - i].I;
+        v.stride[i] = si[i];
+      }
+      v.dim[3] = c->N;
+      v.stride[3] = si[3];
+      pb.views.push_back(v);
+    }
+    long long so[4];
+    out_strides(g, c->cout, so);
+    for (int rd = 0; rd < c->sd; ++rd)
+      for (int rh = 0; rh < c->sh; ++rh)
+        for (int rw = 0; rw < c->sw; ++rw) {
+          TcClassH cls;
+          cls.out_ofs = rd * so[2] + rh * so[1] + rw * so[0];
+          for (int kd = 0; kd < c->kd; ++kd) {
+            if ((rd + g.d[0].pb - kd) % c->sd != 0) continue;
+            for (int kh = 0; kh < c->kh; ++kh) {
+              if ((rh + g.d[1].pb - kh) % c->sh != 0) continue;
+              for (int kw = 0; kw < c->kw; ++kw) {
+                if ((rw + g.d[2].pb - kw) % c->sw != 0) continue;
+                const int tap = (kd * c->kh + kh) * c->kw + kw;
+                for (int s = 0; s < c->nseg; ++s) {
+                  TcTapH t;
+                  t.view = s;
+                  t.off[0] = (rw + g.d[2].pb - kw) / c->sw;
+                  t.off[1] = (rh + g.d[1].pb - kh) / c->sh;
+                  t.off[2] = (rd + g.d[0].pb - kd) / c->sd;
+                  t.off[3] = 0;
+                  t.kofs = tap * g.cin_total + g.seg_off[s];
+                  t.c_begin = 0;
+                  t.nch = c->cin[s];
+                  cls.taps.push_back(t);
+                }
+              }
+            }
+          }
+          pb.classes.push_back(cls);
+        }
+    pb.ext[0] = g.d[2].I; pb.ext[1] = g.d[1].I; pb.ext[2] = g.d[0].I; pb.ext[3] = c->N;
+    pb.so[0] = so[0] * c->sw; pb.so[1] = so[1] * c->sh; pb.so[2] = so[2] * c->sd; pb.so[3] = so[3];
+  }
+  pb.Ktot = g.taps * g.cin_total;
+  pb.rowsB = (c->cout + 63) / 64 * 64;
+  pb.cout = c->cout;
+}
+
+int simt_stats_rows(const sap3d_conv_desc* c, const ConvGeom& g) {
+  long long P = (long long)c->N * g.d[0].O * g.d[1].O * g.d[2].O;
+  long long rows = (P + 127) / 128;
+  if (rows > 592) rows = 592;
+  if (rows < 1) rows = 1;
+  return (int)rows;
+}
+
+void fill_simt_common(SimtGeom& sg, const ConvGeom& g, bool gather_is_conv_like) {
+  for (int i = 0; i < 3; ++i) {
+    if (gather_is_conv_like) {
+      sg.mul[i] = g.d[i].s; sg.off0[i] = -g.d[i].pb; sg.offk[i] = 1; sg.div[i] = 1;
+    } else {
+      sg.mul[i] = 1; sg.off0[i] = g.d[i].pb; sg.offk[i] = -1; sg.div[i] = g.d[i].s;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sap3d_conv_out_dims(const sap3d_conv_desc* d, int32_t* out_dhw) {
+  if (check_desc(d)) return 1;
+  ConvGeom g;
+  make_geom(d, g);
+  out_dhw[0] = g.d[0].O;
+  out_dhw[1] = g.d[1].O;
+  out_dhw[2] = g.d[2].O;
+  return 0;
+}
+
+int sap3d_conv_stats_rows(const sap3d_conv_desc* d) {
+  if (check_desc(d)) return -1;
+  ConvGeom g;
+  make_geom(d, g);
+  if (tc_eligible(d)) {
+    TcProblem pb;
+    build_fwd_problem(d, g, nullptr, nullptr, pb);
+    return (int)pb.classes.size() * tc_plan_tiles(pb);
+  }
+  return simt_stats_rows(d, g);
+}
+
+size_t sap3d_conv_packed_elems(const sap3d_conv_desc* d, int32_t which) {
+  if (check_desc(d)) return 0;
+  ConvGeom g;
+  make_geom(d, g);
+  const size_t co_pad = (size_t)(d->cout + 63) / 64 * 64, ci_pad = (size_t)(g.cin_total + 63) / 64 * 64;
+  if (which == 0) return co_pad * (size_t)g.taps * (size_t)g.cin_total;
+  return ci_pad * (size_t)g.taps * (size_t)d->cout;
+}
+
+int sap3d_conv_pack_weights(const sap3d_conv_desc* d, const float* w_tf, void* w_fwd, void* w_dgrad, void* stream) {
+  if (check_desc(d)) return 1;
+  ConvGeom g;
+  make_geom(d, g);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int ci = g.cin_total, co = d->cout, taps = g.taps;
+  const int co_pad = (co + 63) / 64 * 64, ci_pad = (ci + 63) / 64 * 64;
+  int rc = 0;
+  if (!d->transposed) {
+    // TF DHWIO: w[tap][ci][co]
+    if (w_fwd) rc |= pack_weights_launch(w_tf, w_fwd, taps, co, co_pad, ci, (long long)ci * co, 1, co, st);
+    if (w_dgrad) rc |= pack_weights_launch(w_tf, w_dgrad, taps, ci, ci_pad, co, (long long)ci * co, co, 1, st);
+  } else {
+    // tf.layers.conv3d_transpose kernel: w[tap][co][ci]
+    if (w_fwd) rc |= pack_weights_launch(w_tf, w_fwd, taps, co, co_pad, ci, (long long)ci * co, ci, 1, st);
+    if (w_dgrad) rc |= pack_weights_launch(w_tf, w_dgrad, taps, ci, ci_pad, co, (long long)ci * co, 1, ci, st);
+  }
+  if (rc) return set_error("pack_weights launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
+int sap3d_conv_fwd(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf, const void* w_fwd_packed,
+                   const float* bias, void* y, float* stats, void* stream) {
+  if (check_desc(d)) return 1;
+  if (!x0 || !y || (d->nseg > 1 && !x1)) return set_error("conv_fwd: NULL tensor pointer");
+  if (require_device()) return 1;
+  ConvGeom g;
+  make_geom(d, g);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char err[512];
+  if (tc_eligible(d)) {
+    if (!w_fwd_packed) return set_error("conv_fwd: tensor-core path needs packed weights");
+    TcProblem pb;
+    build_fwd_problem(d, g, x0, x1, pb);
+    pb.B = w_fwd_packed;
+    pb.out = y;
+    pb.bias = d->has_bias ? bias : nullptr;
+    pb.stats = stats;
+    pb.scale = pb.shift = nullptr;
+    pb.relu = 0;
+    pb.accumulate = 0;
+    pb.out_f32 = d->out_f32;
+    pb.force_block_n = 0;
+    if (tc_launch(pb, st, err, sizeof(err))) return set_error("%s", err);
+    return 0;
+  }
+  if (d->impl == SAP3D_IMPL_TC) return set_error("conv_fwd: descriptor not eligible for the tensor-core path");
+  if (!w_tf) return set_error("conv_fwd: CUDA-core path needs the fp32 TF-layout weights");
+  SimtGeom sg;
+  memset(&sg, 0, sizeof(sg));
+  sg.x[0] = x0; sg.x[1] = x1 ? x1 : x0;
+  sg.cseg[0] = d->cin[0]; sg.cseg[1] = d->nseg > 1 ? d->cin[1] : 0;
+  sg.cin_total = g.cin_total;
+  sg.N = d->N; sg.iD = d->D; sg.iH = d->H; sg.iW = d->W;
+  sg.oD = g.d[0].O; sg.oH = g.d[1].O; sg.oW = g.d[2].O;
+  sg.kd = d->kd; sg.kh = d->kh; sg.kw = d->kw;
+  fill_simt_common(sg, g, !d->transposed);
+  sg.w = w_tf;
+  sg.ws_tap = (long long)g.cin_total * d->cout;
+  if (!d->transposed) { sg.ws_ci = d->cout; sg.ws_co = 1; }
+  else { sg.ws_ci = 1; sg.ws_co = g.cin_total; }
+  sg.co_off = 0;
+  sg.bias = d->has_bias ? bias : nullptr;
+  sg.cout = d->cout;
+  sg.y = y;
+  out_strides(g, d->cout, sg.yo);
+  sg.accumulate = 0;
+  if (simt_conv_launch(sg, d->dtype, d->out_f32, st, err, sizeof(err))) return set_error("%s", err);
+  if (stats) {
+    long long P = (long long)d->N * sg.oD * sg.oH * sg.oW;
+    if (col_stats_launch(y, d->out_f32 ? SAP3D_F32 : d->dtype, P, d->cout, simt_stats_rows(d, g), stats, st))
+      return set_error("col_stats launch failed");
+  }
+  return 0;
+}
+
+int sap3d_conv_dgrad(const sap3d_conv_desc* d, int32_t seg, const void* dy, const float* w_tf, const void* w_dgrad_packed,
+                     void* dx, int32_t accumulate, void* stream) {
+  if (check_desc(d)) return 1;
+  if (seg < 0 || seg >= d->nseg) return set_error("conv_dgrad: bad segment");
+  if (!dy || !dx) return set_error("conv_dgrad: NULL tensor pointer");
+  if (require_device()) return 1;
+  ConvGeom g;
+  make_geom(d, g);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char err[512];
+  const int cseg = d->cin[seg];
+  const size_t esize = d->dtype == SAP3D_BF16 ? 2 : 4;
+  long long si[4];
+  in_strides(g, cseg, si);
+  bool strided_scatter = false;  // conv with stride > 1: only a sub-lattice of dx is written
+  if (!d->transposed)
+    for (int i = 0; i < 3; ++i)
+      if (g.d[i].s != 1) strided_scatter = true;
+
+  if (tc_dgrad_eligible(d)) {
+    if (!w_dgrad_packed) return set_error("conv_dgrad: tensor-core path needs packed weights");
+    TcProblem pb;
+    const int Ktot = g.taps * d->cout;
+    if (!d->transposed) {
+      if (strided_scatter && !accumulate) {
+        if (cudaMemsetAsync(dx, 0, (size_t)si[3] * d->N * esize, st) != cudaSuccess) return set_error("conv_dgrad: memset failed");
+      }
+      TcView v;
+      v.base = dy;
+      v.C = d->cout;
+      long long so[4];
+      out_strides(g, d->cout, so);
+      for (int i = 0; i < 3; ++i) {
+        v.dim[i] = g.d[2 - i].O;
+        v.stride[i] = so[i];
+      }
+      v.dim[3] = d->N;
+      v.stride[3] = so[3];
+      pb.views.push_back(v);
+      TcClassH cls;
+      cls.out_ofs = 0;
+      for (int kd = 0; kd < d->kd; ++kd)
+        for (int kh = 0; kh < d->kh; ++kh)
+          for (int kw = 0; kw < d->kw; ++kw) {
+            TcTapH t;
+            t.view = 0;
+            // stride-1 dims: o = i + pb - k ; strided dims have k == 1, pb == 0: o = i / s handled by the output view
+            t.off[0] = (g.d[2].s == 1) ? g.d[2].pb - kw : 0;
+            t.off[1] = (g.d[1].s == 1) ? g.d[1].pb - kh : 0;
+            t.off[2] = (g.d[0].s == 1) ? g.d[0].pb - kd : 0;
+            t.off[3] = 0;
+            t.kofs = ((kd * d->kh + kh) * d->kw + kw) * d->cout;
+            t.c_begin = 0;
+            t.nch = d->cout;
+            cls.taps.push_back(t);
+          }
+      pb.classes.push_back(cls);
+      // class-local coordinates = dy coordinates; dx written at i = o*s
+      pb.ext[0] = g.d[2].O; pb.ext[1] = g.d[1].O; pb.ext[2] = g.d[0].O; pb.ext[3] = d->N;
+      pb.so[0] = si[0] * g.d[2].s; pb.so[1] = si[1] * g.d[1].s; pb.so[2] = si[2] * g.d[0].s; pb.so[3] = si[3];
+    } else {
+      // dx[i] = sum_k dy[s*i + k - pb] * W[k]: parity views of dy
+      long long so[4];
+      out_strides(g, d->cout, so);
+      std::map<int, int> view_of;  // key = (rd*16+rh)*16+rw
+      TcClassH cls;
+      cls.out_ofs = 0;
+      for (int kd = 0; kd < d->kd; ++kd)
+        for (int kh = 0; kh < d->kh; ++kh)
+          for (int kw = 0; kw < d->kw; ++kw) {
+            const int kk[3] = {kd, kh, kw};
+            int r[3], q[3];
+            for (int i = 0; i < 3; ++i) {
+              const int e = kk[i] - g.d[i].pb;
+              q[i] = floordiv(e, g.d[i].s);
+              r[i] = e - q[i] * g.d[i].s;
+            }
+            const int key = (r[0] * 16 + r[1]) * 16 + r[2];
+            if (view_of.find(key) == view_of.end()) {
+              TcView v;
+              v.base = reinterpret_cast<const char*>(dy) + (size_t)(r[0] * so[2] + r[1] * so[1] + r[2] * so[0]) * 2;
+              v.C = d->cout;
+              for (int i = 0; i < 3; ++i) {
+                const DimGeom& dg = g.d[2 - i];
+                v.dim[i] = (dg.O - r[2 - i] + dg.s - 1) / dg.s;
+                v.stride[i] = so[i] * dg.s;
+              }
+              v.dim[3] = d->N;
+              v.stride[3] = so[3];
+              view_of[key] = (int)pb.views.size();
+              pb.views.push_back(v);
+            }
+            TcTapH t;
+            t.view = view_of[key];
+            t.off[0] = q[2]; t.off[1] = q[1]; t.off[2] = q[0]; t.off[3] = 0;
+            t.kofs = ((kd * d->kh + kh) * d->kw + kw) * d->cout;
+            t.c_begin = 0;
+            t.nch = d->cout;
+            cls.taps.push_back(t);
+          }
+      pb.classes.push_back(cls);
+      pb.ext[0] = g.d[2].I; pb.ext[1] = g.d[1].I; pb.ext[2] = g.d[0].I; pb.ext[3] = d->N;
+      for (int i = 0; i < 4; ++i) pb.so[i] = si[i];
+    }
+    pb.Ktot = Ktot;
+    pb.B = reinterpret_cast<const char*>(w_dgrad_packed) + (size_t)g.seg_off[seg] * Ktot * 2;
+    pb.rowsB = (cseg + 63) / 64 * 64;
+    pb.cout = cseg;
+    pb.out = dx;
+    pb.bias = nullptr;
+    pb.stats = nullptr;
+    pb.scale = pb.shift = nullptr;
+    pb.relu = 0;
+    pb.accumulate = accumulate;
+    pb.out_f32 = 0;
+    pb.force_block_n = 0;
+    if (tc_launch(pb, st, err, sizeof(err))) return set_error("%s", err);
+    return 0;
+  }
+  if (d->impl == SAP3D_IMPL_TC) return set_error("conv_dgrad: descriptor not eligible for the tensor-core path");
+  if (!w_tf) return set_error("conv_dgrad: CUDA-core path needs the fp32 TF-layout weights");
+  SimtGeom sg;
+  memset(&sg, 0, sizeof(sg));
+  sg.x[0] = dy; sg.x[1] = dy;
+  sg.cseg[0] = d->cout; sg.cseg[1] = 0;
+  sg.cin_total = d->cout;
+  sg.N = d->N;
+  sg.iD = g.d[0].O; sg.iH = g.d[1].O; sg.iW = g.d[2].O;  // gathered tensor = dy
+  sg.oD = d->D; sg.oH = d->H; sg.oW = d->W;              // produced tensor = dx
+  sg.kd = d->kd; sg.kh = d->kh; sg.kw = d->kw;
+  fill_simt_common(sg, g, d->transposed != 0);
+  sg.w = w_tf;
+  sg.ws_tap = (long long)g.cin_total * d->cout;
+  if (!d->transposed) { sg.ws_ci = 1; sg.ws_co = d->cout; }       // w[k][ci][co]: K index = co, out = ci
+  else { sg.ws_ci = g.cin_total; sg.ws_co = 1; }                   // w[k][co][ci]
+  sg.co_off = g.seg_off[seg];
+  sg.bias = nullptr;
+  sg.cout = cseg;
+  sg.y = dx;
+  for (int i = 0; i < 4; ++i) sg.yo[i] = si[i];
+  sg.accumulate = accumulate;
+  if (simt_conv_launch(sg, d->dtype, 0, st, err, sizeof(err))) return set_error("%s", err);
+  return 0;
+}
+
+int sap3d_conv_wgrad(const sap3d_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw, float* db,
+                     void* stream) {
+  if (check_desc(d)) return 1;
+  if (!x0 || !dy || !dw) return set_error("conv_wgrad: NULL pointer");
+  if (require_device()) return 1;
+  ConvGeom g;
+  make_geom(d, g);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char err[512];
+  const void* xs[2] = {x0, x1};
+  for (int s = 0; s < d->nseg; ++s) {
+    SimtWgradGeom wg;
+    memset(&wg, 0, sizeof(wg));
+    wg.N = d->N;
+    wg.kd = d->kd; wg.kh = d->kh; wg.kw = d->kw;
+    for (int i = 0; i < 3; ++i) { wg.mul[i] = g.d[i].s; wg.off0[i] = -g.d[i].pb; wg.offk[i] = 1; wg.div[i] = 1; }
+    wg.dw = dw;
+    wg.ws_tap = (long long)g.cin_total * d->cout;
+    if (!d->transposed) {
+      wg.g = xs[s]; wg.cg = d->cin[s]; wg.gD = d->D; wg.gH = d->H; wg.gW = d->W;
+      wg.q = dy; wg.cq = d->cout; wg.qD = g.d[0].O; wg.qH = g.d[1].O; wg.qW = g.d[2].O;
+      wg.ws_g = d->cout; wg.g_c0 = g.seg_off[s]; wg.q_c0 = 0;
+    } else {
+      wg.g = dy; wg.cg = d->cout; wg.gD = g.d[0].O; wg.gH = g.d[1].O; wg.gW = g.d[2].O;
+      wg.q = xs[s]; wg.cq = d->cin[s]; wg.qD = d->D; wg.qH = d->H; wg.qW = d->W;
+      wg.ws_g = g.cin_total; wg.g_c0 = 0; wg.q_c0 = g.seg_off[s];
+    }
+    if (simt_wgrad_launch(wg, d->dtype, st, err, sizeof(err))) return set_error("%s", err);
+  }
+  if (db) {
+    long long P = (long long)d->N * g.d[0].O * g.d[1].O * g.d[2].O;
+    if (col_sum_accum_launch(dy, d->dtype, P, d->cout, db, st)) return set_error("bias-grad launch failed");
+  }
+  return 0;
+}
+
+}  // extern "C"

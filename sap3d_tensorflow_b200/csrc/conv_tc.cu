@@ -1,0 +1,570 @@
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a, operands fed by TMA.
+//
+// One CTA computes a [128 output positions] x [BLOCK_N output channels] tile.  The 128 positions
+// are a (bn x bd x bh x bw) box of the NDHWC output; for every filter tap the matching input box
+// (shifted by the tap offset; out-of-bounds = TF 'SAME' zero padding, filled by the TMA unit) is
+// fetched with ONE 5-D cp.async.bulk.tensor into a 128-byte-swizzled K-major tile, so no im2col
+// buffer ever exists.  Concatenated inputs are extra K segments (extra tensor maps), transposed
+// convolutions are output-parity classes (each a stride-1 problem with a strided output view).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + tcgen05.mma issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias / affine / ReLU -> per-channel sum & sum-of-squares for
+// BatchNorm/GroupNorm -> bf16 128-bit stores).
+//
+// Replaces the cuDNN conv3d fprop/dgrad kernels TensorFlow dispatches for tf.nn.conv3d /
+// tf.layers.conv3d / tf.layers.conv3d_transpose (reference p3d.py:18-27,86,112,125,375-393;
+// utils/network.py:100-110).
+#include "conv_tc.cuh"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sap3d {
+
+constexpr int TC_MAX_MAPS = 10;
+constexpr int TC_MAX_TAPS = 128;
+constexpr int TC_MAX_CLS = 64;
+constexpr int TC_THREADS = 192;
+
+struct TcTap {
+  int8_t map, dw, dh, dd;
+  int16_t nchunk, c0;  // channel chunks of 64; first chunk
+  int32_t kofs;
+};
+struct TcClass {
+  int16_t tap_begin, tap_count;
+  int32_t nkb;  // total k-blocks of the class
+  long long out_ofs;
+};
+
+struct alignas(64) TcConvParams {
+  CUtensorMap amap[TC_MAX_MAPS];
+  CUtensorMap bmap;
+  TcTap taps[TC_MAX_TAPS];
+  TcClass cls[TC_MAX_CLS];
+  int ncls, m_tiles, n_tiles;
+  int tiles[4];  // W,H,D,N
+  int box[4];
+  int ext[4];
+  long long so[4];
+  int cout, box_rows;
+  void* out;
+  const float* bias;
+  float* stats;
+  const float* scale;
+  const float* shift;
+  int relu, accumulate, out_f32;
+};
+
+// column sums of a 32(lanes) x 32(values) block: on return lane l holds the sum over all lanes of
+// the caller's v[l].  31 shuffles instead of 160.
+SAP3D_DEVINL float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      float send = upper ? v[i] : v[i + o];
+      float keep = upper ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8);
+  float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16);  // [4][2][BLOCK_N]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile decode -------------------------------------------------------------------------
+  int tile = blockIdx.x;
+  const int nt = tile % p.n_tiles;
+  tile /= p.n_tiles;
+  const int cls_id = tile / p.m_tiles;
+  const int mt = tile - cls_id * p.m_tiles;
+  int t = mt;
+  const int tw = t % p.tiles[0];
+  t /= p.tiles[0];
+  const int th = t % p.tiles[1];
+  t /= p.tiles[1];
+  const int td = t % p.tiles[2];
+  const int tn = t / p.tiles[2];
+  const int w0 = tw * p.box[0], h0 = th * p.box[1], d0 = td * p.box[2], n0 = tn * p.box[3];
+  const TcClass cls = p.cls[cls_id];
+  const int nkb = cls.nkb;
+
+  // ---- one-time setup ----------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_base + s * 8, 1);
+      mbar_init(bar_base + (STAGES + s) * 8, 1);
+    }
+    mbar_init(bar_base + 2 * STAGES * 8, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.bmap);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = p.box_rows * 128 + B_BYTES;
+      for (int ti = 0; ti < cls.tap_count; ++ti) {
+        const TcTap tap = p.taps[cls.tap_begin + ti];
+        const void* amap = &p.amap[tap.map];
+        for (int ch = 0; ch < tap.nchunk; ++ch) {
+          mbar_wait(bar_base + (STAGES + stage) * 8, phase ^ 1u);
+          const uint32_t full = bar_base + stage * 8;
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          mbar_expect_tx(full, tx_bytes);
+          tma_load_5d(sa, amap, full, (tap.c0 + ch) * 64, w0 + tap.dw, h0 + tap.dh, d0 + tap.dd, n0);
+          tma_load_2d(sa + A_BYTES, &p.bmap, full, tap.kofs + ch * 64, nt * BLOCK_N);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(bar_base + stage * 8, phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * STAGE_BYTES;
+        const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+        const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // advance 16 K-elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr>>4) field
+          tc_mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(bar_base + (STAGES + stage) * 8);  // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (nkb > 0) tc_commit(bar_base + 2 * STAGES * 8);  // accumulator ready
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    int r = row;
+    const int iw = r % p.box[0];
+    r /= p.box[0];
+    const int ih = r % p.box[1];
+    r /= p.box[1];
+    const int id = r % p.box[2];
+    const int in = r / p.box[2];
+    const int ow = w0 + iw, oh = h0 + ih, od = d0 + id, on = n0 + in;
+    const bool valid = row < p.box_rows && ow < p.ext[0] && oh < p.ext[1] && od < p.ext[2] && on < p.ext[3];
+    const long long row_off = cls.out_ofs + ow * p.so[0] + oh * p.so[1] + od * p.so[2] + on * p.so[3];
+    const bool want_stats = p.stats != nullptr;
+
+    if (nkb > 0) {
+      mbar_wait(bar_base + 2 * STAGES * 8, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      const int col0 = nt * BLOCK_N + c * 32;
+      if (col0 >= p.cout) break;  // warp-uniform
+      uint32_t rr[32];
+      if (nkb > 0) {
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rr[j] = 0u;
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.cout) v[j] += __ldg(p.bias + col0 + j);
+      }
+      if (want_stats) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float m = valid ? v[j] : 0.f;
+          s1[j] = m;
+          s2[j] = m * m;
+        }
+        const float c1 = warp_transpose_sum32(s1, lane);
+        const float c2 = warp_transpose_sum32(s2, lane);
+        s_stats[(q * 2 + 0) * BLOCK_N + c * 32 + lane] = c1;
+        s_stats[(q * 2 + 1) * BLOCK_N + c * 32 + lane] = c2;
+      }
+      if (p.scale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.cout) v[j] = fmaf(v[j], __ldg(p.scale + col0 + j), __ldg(p.shift + col0 + j));
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (valid) {
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (col0 + g * 4 < p.cout) {
+              float4 f = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              if (p.accumulate) {
+                const float4 e = *reinterpret_cast<const float4*>(o + g * 4);
+                f.x += e.x; f.y += e.y; f.z += e.z; f.w += e.w;
+              }
+              *reinterpret_cast<float4*>(o + g * 4) = f;
+            }
+          }
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + row_off + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (col0 + g * 8 < p.cout) {
+              float w8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w8[j] = v[g * 8 + j];
+              if (p.accumulate) {
+                float e[8];
+                Vec8<bf16>::load(o + g * 8, e);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w8[j] += e[j];
+              }
+              Vec8<bf16>::store(o + g * 8, w8);
+            }
+          }
+        }
+      }
+    }
+    if (want_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = threadIdx.x - 64;  // 0..127
+      const long long srow = static_cast<long long>(cls_id) * p.m_tiles + mt;
+      for (int cc = et; cc < BLOCK_N; cc += 128) {
+        const int col = nt * BLOCK_N + cc;
+        if (col < p.cout) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            a += s_stats[(qq * 2 + 0) * BLOCK_N + cc];
+            b += s_stats[(qq * 2 + 1) * BLOCK_N + cc];
+          }
+          p.stats[(srow * 2 + 0) * p.cout + col] = a;
+          p.stats[(srow * 2 + 1) * p.cout + col] = b;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BLOCK_N);
+  }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// bf16 view with channels innermost -> rank-5 map {C, d0, d1, d2, d3}, 128B swizzle, zero OOB fill
+static int encode_view(CUtensorMap* m, const void* base, int C, const int dim[4], const long long stride[4],
+                       const int box[4], char* err, size_t errlen) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)dim[0], (cuuint64_t)dim[1], (cuuint64_t)dim[2], (cuuint64_t)dim[3]};
+  cuuint64_t gstr[4] = {(cuuint64_t)stride[0] * 2, (cuuint64_t)stride[1] * 2, (cuuint64_t)stride[2] * 2,
+                        (cuuint64_t)stride[3] * 2};
+  // the driver wants strides of size-1 dims to still be valid multiples of 16
+  for (int i = 0; i < 4; ++i)
+    if (gstr[i] == 0) gstr[i] = 16;
+  cuuint32_t bdim[5] = {64u, (cuuint32_t)box[0], (cuuint32_t)box[1], (cuuint32_t)box[2], (cuuint32_t)box[3]};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen,
+             "cuTensorMapEncodeTiled(view) failed: %d (C=%d dims=%d,%d,%d,%d strides=%lld,%lld,%lld,%lld box=%d,%d,%d,%d "
+             "base=%p)",
+             (int)r, C, dim[0], dim[1], dim[2], dim[3], stride[0], stride[1], stride[2], stride[3], box[0], box[1],
+             box[2], box[3], base);
+    return 1;
+  }
+  return 0;
+}
+
+static int encode_b(CUtensorMap* m, const void* base, int Ktot, int rows, int block_n, char* err, size_t errlen) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t bdim[2] = {64u, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled(B) failed: %d (K=%d rows=%d box_n=%d)", (int)r, Ktot, rows, block_n);
+    return 1;
+  }
+  return 0;
+}
+
+// --- dimension merging + box search ---------------------------------------------------------------
+struct Merged {
+  int ext[4];
+  long long so[4];
+  std::vector<TcView> views;
+  std::vector<TcClassH> classes;
+};
+
+static void merge_dims(const TcProblem& pb, Merged& m) {
+  for (int i = 0; i < 4; ++i) {
+    m.ext[i] = pb.ext[i];
+    m.so[i] = pb.so[i];
+  }
+  m.views = pb.views;
+  m.classes = pb.classes;
+  // try to fold dim i+1 into dim i (W<-H, then <-D, then <-N) while geometry allows
+  int i = 0;
+  int live = 4;
+  while (i + 1 < live) {
+    bool ok = m.so[i + 1] == m.so[i] * m.ext[i];
+    for (const TcView& v : m.views)
+      ok = ok && v.dim[i] == m.ext[i] && v.dim[i + 1] == m.ext[i + 1] && v.stride[i + 1] == v.stride[i] * v.dim[i];
+    for (const TcClassH& c : m.classes)
+      for (const TcTapH& tp : c.taps) ok = ok && tp.off[i] == 0 && tp.off[i + 1] == 0;
+    if (ok && (long long)m.ext[i] * m.ext[i + 1] < (1ll << 31)) {
+      m.ext[i] *= m.ext[i + 1];
+      for (TcView& v : m.views) v.dim[i] *= v.dim[i + 1];
+      for (int j = i + 1; j + 1 < 4; ++j) {
+        m.ext[j] = m.ext[j + 1];
+        m.so[j] = m.so[j + 1];
+        for (TcView& v : m.views) {
+          v.dim[j] = v.dim[j + 1];
+          v.stride[j] = v.stride[j + 1];
+        }
+        for (TcClassH& c : m.classes)
+          for (TcTapH& tp : c.taps) tp.off[j] = tp.off[j + 1];
+      }
+      m.ext[3] = 1;
+      m.so[3] = 0;
+      for (TcView& v : m.views) {
+        v.dim[3] = 1;
+        v.stride[3] = 0;
+      }
+      for (TcClassH& c : m.classes)
+        for (TcTapH& tp : c.taps) tp.off[3] = 0;
+      --live;
+    } else {
+      ++i;
+    }
+  }
+}
+
+static long long choose_box(const int ext[4], int box[4]) {
+  long long best = -1;
+  int bb[4] = {1, 1, 1, 1};
+  for (int bw = 1; bw <= std::min(ext[0], 128); ++bw) {
+    for (int bh = 1; bh <= std::min(ext[1], 128 / bw); ++bh) {
+      for (int bd = 1; bd <= std::min(ext[2], 128 / (bw * bh)); ++bd) {
+        int bn = std::min(ext[3], 128 / (bw * bh * bd));
+        if (bn < 1) continue;
+        long long tiles = (long long)((ext[0] + bw - 1) / bw) * ((ext[1] + bh - 1) / bh) * ((ext[2] + bd - 1) / bd) *
+                          ((ext[3] + bn - 1) / bn);
+        bool better = best < 0 || tiles < best || (tiles == best && bw > bb[0]);
+        if (better) {
+          best = tiles;
+          bb[0] = bw; bb[1] = bh; bb[2] = bd; bb[3] = bn;
+        }
+      }
+    }
+  }
+  for (int i = 0; i < 4; ++i) box[i] = bb[i];
+  return best;
+}
+
+int tc_plan_tiles(const TcProblem& pb) {
+  Merged m;
+  merge_dims(pb, m);
+  int box[4];
+  return (int)choose_box(m.ext, box);
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_t(const TcConvParams& prm, int grid, cudaStream_t stream, char* err, size_t errlen) {
+  constexpr int SMEM = STAGES * (128 * 128 + BLOCK_N * 128) + (2 * STAGES + 1) * 8 + 16 + 4 * 2 * BLOCK_N * 4 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "cudaFuncSetAttribute(conv_tc) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    attr_done = true;
+  }
+  conv_tc_kernel<BLOCK_N, STAGES><<<grid, TC_THREADS, SMEM, stream>>>(prm);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "conv_tc launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen) {
+  Merged m;
+  merge_dims(pb, m);
+  if ((int)m.views.size() > TC_MAX_MAPS) {
+    snprintf(err, errlen, "tc_launch: too many views (%d)", (int)m.views.size());
+    return 1;
+  }
+  if ((int)m.classes.size() > TC_MAX_CLS) {
+    snprintf(err, errlen, "tc_launch: too many classes (%d)", (int)m.classes.size());
+    return 1;
+  }
+  if (pb.cout % 8 != 0 || pb.Ktot % 64 != 0) {
+    snprintf(err, errlen, "tc_launch: cout %% 8 / Ktot %% 64 violated (cout=%d Ktot=%d)", pb.cout, pb.Ktot);
+    return 1;
+  }
+  static thread_local TcConvParams prm;  // ~4 KB, filled per call
+  memset(&prm, 0, sizeof(prm));
+  int box[4];
+  long long m_tiles = choose_box(m.ext, box);
+  int block_n = pb.force_block_n;
+  if (block_n == 0) {
+    if (pb.cout <= 64) block_n = 64;
+    else if (pb.cout % 256 == 0 && m_tiles * (long long)m.classes.size() * (pb.cout / 256) >= 2 * 148) block_n = 256;
+    else block_n = 128;
+  }
+  if (block_n > 64 && pb.rowsB % block_n != 0 && pb.rowsB < block_n) block_n = 64;
+  for (size_t v = 0; v < m.views.size(); ++v)
+    if (encode_view(&prm.amap[v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, box, err, errlen))
+      return 1;
+  if (encode_b(&prm.bmap, pb.B, pb.Ktot, pb.rowsB, block_n, err, errlen)) return 1;
+  int ntap = 0;
+  for (size_t c = 0; c < m.classes.size(); ++c) {
+    TcClass& dc = prm.cls[c];
+    dc.tap_begin = (int16_t)ntap;
+    dc.tap_count = (int16_t)m.classes[c].taps.size();
+    dc.out_ofs = m.classes[c].out_ofs;
+    int nkb = 0;
+    for (const TcTapH& tp : m.classes[c].taps) {
+      if (ntap >= TC_MAX_TAPS) {
+        snprintf(err, errlen, "tc_launch: too many taps");
+        return 1;
+      }
+      if (tp.nch % 64 != 0 || tp.c_begin % 64 != 0) {
+        snprintf(err, errlen, "tc_launch: tap channels must be multiples of 64 (nch=%d c_begin=%d)", tp.nch, tp.c_begin);
+        return 1;
+      }
+      TcTap& dt = prm.taps[ntap++];
+      dt.map = (int8_t)tp.view;
+      dt.dw = (int8_t)tp.off[0];
+      dt.dh = (int8_t)tp.off[1];
+      dt.dd = (int8_t)tp.off[2];
+      if (tp.off[3] != 0) {
+        snprintf(err, errlen, "tc_launch: batch offset unsupported");
+        return 1;
+      }
+      dt.nchunk = (int16_t)(tp.nch / 64);
+      dt.c0 = (int16_t)(tp.c_begin / 64);
+      dt.kofs = tp.kofs;
+      nkb += tp.nch / 64;
+    }
+    dc.nkb = nkb;
+  }
+  prm.ncls = (int)m.classes.size();
+  prm.m_tiles = (int)m_tiles;
+  prm.n_tiles = (pb.cout + block_n - 1) / block_n;
+  for (int i = 0; i < 4; ++i) {
+    prm.box[i] = box[i];
+    prm.ext[i] = m.ext[i];
+    prm.so[i] = m.so[i];
+    prm.tiles[i] = (m.ext[i] + box[i] - 1) / box[i];
+  }
+  prm.cout = pb.cout;
+  prm.box_rows = box[0] * box[1] * box[2] * box[3];
+  prm.out = pb.out;
+  prm.bias = pb.bias;
+  prm.stats = pb.stats;
+  prm.scale = pb.scale;
+  prm.shift = pb.shift;
+  prm.relu = pb.relu;
+  prm.accumulate = pb.accumulate;
+  prm.out_f32 = pb.out_f32;
+  long long grid = (long long)prm.ncls * prm.m_tiles * prm.n_tiles;
+  if (grid <= 0 || grid > 0x7fffffffll) {
+    snprintf(err, errlen, "tc_launch: bad grid %lld", grid);
+    return 1;
+  }
+  switch (block_n) {
+    case 64: return launch_t<64, 6>(prm, (int)grid, stream, err, errlen);
+    case 128: return launch_t<128, 4>(prm, (int)grid, stream, err, errlen);
+    case 256: return launch_t<256, 4>(prm, (int)grid, stream, err, errlen);
+  }
+  snprintf(err, errlen, "tc_launch: unsupported block_n %d", block_n);
+  return 1;
+}
+
+}  // namespace sap3d

@@ -1,0 +1,70 @@
+// Host-side description of a tensor-core implicit-GEMM problem ("form F"):
+//   out[cls-local position o, col] = sum over taps t of class, channels c:
+//        view[t.view](o + t.offset, t.c_begin + c) * B[col][t.kofs + c]
+// Every conv / transposed conv / data-gradient of the P3D graph is lowered to this form by abi.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+namespace sap3d {
+
+struct TcView {
+  const void* base;   // bf16, channels contiguous
+  int C;              // channels addressable through this view
+  int dim[4];         // extents along W,H,D,N of the view
+  long long stride[4];// element strides along W,H,D,N
+};
+struct TcTapH {
+  int view;
+  int off[4];         // coordinate offset added to the class-local output position (W,H,D,N)
+  int kofs;           // first K index of this tap in B
+  int c_begin, nch;   // channel range of the view consumed by the tap (nch % 64 == 0)
+};
+struct TcClassH {
+  std::vector<TcTapH> taps;
+  long long out_ofs;  // element offset of the class inside the output tensor
+};
+struct TcProblem {
+  std::vector<TcView> views;
+  std::vector<TcClassH> classes;
+  int ext[4];         // class-local output extents W,H,D,N
+  long long so[4];    // output element strides for class-local coordinates
+  const void* B;      // bf16 [rowsB][Ktot], K contiguous
+  int Ktot, rowsB;
+  int cout;           // valid output columns (multiple of 8)
+  void* out;          // bf16 (or f32 when out_f32)
+  const float* bias;  // nullable, [cout]
+  float* stats;       // nullable, [ncls*m_tiles][2][cout]
+  const float* scale; // nullable epilogue affine (inference-folded norm)
+  const float* shift;
+  int relu, accumulate, out_f32;
+  int force_block_n;  // 0 = auto
+};
+
+// number of M tiles (per class) the launcher will use for these extents (after dim merging)
+int tc_plan_tiles(const TcProblem& pb);
+// returns 0 on success; on failure writes a message into err
+int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen);
+
+// wgrad: D[m][n] (+)= sum_pos P(pos + off)[m] * Q(pos)[n], fp32 atomics into dw
+struct TcWgradTap {
+  int view;           // P view
+  int off[4];
+  long long dw_ofs;   // element offset of this tap's [M][N] block in dw
+};
+struct TcWgradProblem {
+  std::vector<TcView> pviews;
+  TcView q;
+  std::vector<TcWgradTap> taps;
+  int ext[4];         // positions iterated (W,H,D,N), Q coordinates
+  int M, N;           // channels of P consumed (rows of dw block), channels of Q (cols)
+  int p_c_begin;      // channel offset inside the P views
+  long long ldw;      // row stride of the dw block (elements)
+  float* dw;
+};
+int tc_wgrad_launch(const TcWgradProblem& pb, cudaStream_t stream, char* err, size_t errlen);
+
+}  // namespace sap3d
