@@ -91,6 +91,77 @@ int sap3d_conv_dgrad(const sap3d_conv_desc* d, int32_t seg, const void* dy, cons
 int sap3d_conv_wgrad(const sap3d_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw,
                      float* db, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Normalisation.  Replaces tf.layers.batch_normalization (p3d.py:58-127,344; utils/network.py:91),
+ * GroupNorm (utils/network.py:65-87 == gn/p3d_gn.py:24-46), tf.nn.relu and the residual adds
+ * (p3d.py:72,81,133-134).
+ * ---------------------------------------------------------------------------------------------- */
+/* stats [rows][2][C] (from conv_fwd) -> scale/shift so that y = x*scale+shift is the normalised
+ * tensor.  training != 0: biased batch variance over `count` positions, moving averages updated in
+ * place with `momentum` (TF: 0.99); training == 0: the moving statistics are used (stats ignored).
+ * save_mean/save_rstd (nullable) are kept for the backward pass. */
+int sap3d_bn_finalize(const float* stats, int32_t rows, int32_t C, double count, const float* gamma, const float* beta,
+                      float* moving_mean, float* moving_var, int32_t training, float momentum, float eps, float* scale,
+                      float* shift, float* save_mean, float* save_rstd, void* stream);
+/* GroupNorm statistics of x [N][S][C] (G groups): per-(sample,channel) scale/shift [N][C] and
+ * per-(sample,group) mean/rstd [N][G]. */
+int sap3d_gn_stats(int32_t dtype, const void* x, int32_t N, int64_t S, int32_t C, int32_t G, const float* gamma,
+                   const float* beta, float eps, float* scale, float* shift, float* save_mean, float* save_rstd, void* stream);
+/* y = relu_out?( relu1?(a*s1+t1) + relu2?(b*s2+t2) ); b, s1, s2 nullable (identity).  scale index is
+ * c (positions_per_sample == 0) or n*C + c. */
+int sap3d_affine_act(int32_t dtype, const void* a, const float* s1, const float* t1, int32_t relu1, const void* b,
+                     const float* s2, const float* t2, int32_t relu2, int32_t relu_out, void* y, int64_t P, int32_t C,
+                     int64_t positions_per_sample, void* stream);
+size_t sap3d_affine_act_bwd_workspace(int32_t C);
+/* backward of sap3d_affine_act for per-channel statistics.  mean/rstd non-NULL => that branch is a
+ * batch-statistics BatchNorm (full BN backward); NULL => frozen scale.  da/db nullable; d{gamma,beta}
+ * (nullable) are accumulated (+=). */
+int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
+                         const float* rstd1, int32_t relu1, const void* b, const float* s2, const float* t2,
+                         const float* mean2, const float* rstd2, int32_t relu2, int32_t relu_out, int64_t P, int32_t C,
+                         void* da, int32_t acc_a, void* db, int32_t acc_b, float* dgamma1, float* dbeta1, float* dgamma2,
+                         float* dbeta2, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pooling.  Replaces tf.nn.max_pool3d (p3d.py:347-348,354,360,366) and tf.layers.max_pooling3d
+ * (utils/network.py:6-7).  same != 0: TF 'SAME' (padding never wins), else 'VALID'.
+ * ---------------------------------------------------------------------------------------------- */
+int sap3d_maxpool3d_out_dims(int32_t D, int32_t H, int32_t W, const int32_t* ksize, const int32_t* strides, int32_t same,
+                             int32_t* out_dhw);
+int sap3d_maxpool3d_fwd(int32_t dtype, const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,
+                        const int32_t* ksize, const int32_t* strides, int32_t same, void* y, void* stream);
+int sap3d_maxpool3d_bwd(int32_t dtype, const void* x, const void* dy, int32_t N, int32_t D, int32_t H, int32_t W,
+                        int32_t C, const int32_t* ksize, const int32_t* strides, int32_t same, void* dx,
+                        int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder head, loss, dropout, attention gate, optimizer.
+ * ---------------------------------------------------------------------------------------------- */
+/* logits = conv3d_transpose(x, w[kd,kh,kw,1,C], stride, 'same') + bias; pred = sigmoid(logits) (nullable).
+ * Replaces p3d.py:393,397 (tf.layers.conv3d_transpose -> 1 channel, tf.sigmoid). */
+int sap3d_head_fwd(int32_t dtype, const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, const int32_t* ksize,
+                   int32_t stride, const float* w, const float* bias, float* logits, float* pred, void* stream);
+int sap3d_head_bwd(int32_t dtype, const float* dlogits, const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,
+                   const int32_t* ksize, int32_t stride, const float* w, void* dx, int32_t accumulate, float* dw, void* stream);
+/* smooth_l1_loss(sigma=1, weights 1) summed over all elements (utils/network.py:49-62, train.py:159):
+ * loss_sum[0] += loss; dlogits = dLoss/dlogits; dbias[0] += sum(dlogits); pred = sigmoid(logits). */
+int sap3d_loss_smooth_l1(const float* logits, const float* target, int64_t n, int32_t apply_sigmoid, float* pred,
+                         float* dlogits, double* loss_sum, float* dbias, void* stream);
+/* tf.layers.dropout (p3d.py:392): y = x*keep/(1-rate), keep = splitmix64(base_seed + *step, index) >= rate.
+ * The backward pass is the same call on dy. */
+int sap3d_dropout(int32_t dtype, const void* x, void* y, int64_t n, float rate, uint64_t base_seed, const int32_t* step,
+                  int32_t accumulate, void* stream);
+/* x = o*gamma + x  (utils/network.py:191-192) */
+int sap3d_gate_fwd(int32_t dtype, const void* o, const void* x, const float* gamma, void* y, int64_t n, void* stream);
+int sap3d_gate_bwd(int32_t dtype, const void* dy, const void* o, const float* gamma, void* d_o, void* dx, int32_t acc_x,
+                   float* dgamma, int64_t n, void* stream);
+/* tf.train.AdamOptimizer (train.py:168) over flat fp32 arrays; *step (device) is the 1-based iteration. */
+int sap3d_adam_step(float* w, const float* g, float* m, float* v, int64_t n, const int32_t* step, float lr, float b1, float b2,
+                    float eps, float grad_scale, void* stream);
+int sap3d_step_increment(int32_t* step, void* stream);
+/* f32 -> bf16 (src_dtype == SAP3D_F32) or bf16 -> f32 */
+int sap3d_cast(int32_t src_dtype, const void* src, void* dst, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

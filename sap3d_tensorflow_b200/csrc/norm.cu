@@ -1,0 +1,465 @@
+// BatchNorm / GroupNorm statistics finalisation, the fused affine + ReLU + residual "apply" pass and
+// its backward, for NDHWC activations (bf16 or f32 storage, fp32/fp64 statistics).
+//
+// Replaces, per reference layer, the chain TensorFlow runs for tf.layers.batch_normalization on 5-D
+// input (moments + ~5 Eigen elementwise kernels), tf.nn.relu and the residual adds
+// (p3d.py:56-81,88,97,114,127,133-134; utils/network.py:65-94).  Bandwidth-bound: 128-bit accesses,
+// one read per operand and one write.
+#include <stdio.h>
+
+#include "../../include/sap3d.h"
+#include "abi_util.cuh"
+#include "common.cuh"
+
+using namespace sap3d;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// finalize: partial [rows][2][C] -> mean/var -> scale/shift (+ moving-average update)
+// block = 32 channels x 32 row lanes, deterministic fp64 reduction
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* moving_mean, float* moving_var, int training,
+                                                            float momentum, float eps, float* scale, float* shift,
+                                                            float* save_mean, float* save_rstd) {
+  const int cx = threadIdx.x, ry = threadIdx.y;
+  const int c = blockIdx.x * 32 + cx;
+  __shared__ double s1[32][33], s2[32][33];
+  double a = 0.0, b = 0.0;
+  if (training && c < C) {
+    for (int r = ry; r < rows; r += 32) {
+      a += (double)stats[((long long)r * 2 + 0) * C + c];
+      b += (double)stats[((long long)r * 2 + 1) * C + c];
+    }
+  }
+  s1[ry][cx] = a;
+  s2[ry][cx] = b;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float mean, var;
+    if (training) {
+      double ta = 0.0, tb = 0.0;
+      for (int i = 0; i < 32; ++i) {
+        ta += s1[i][cx];
+        tb += s2[i][cx];
+      }
+      const double m = ta / count;
+      double v = tb / count - m * m;
+      if (v < 0.0) v = 0.0;
+      mean = (float)m;
+      var = (float)v;
+      if (moving_mean) {
+        moving_mean[c] = moving_mean[c] * momentum + mean * (1.f - momentum);
+        moving_var[c] = moving_var[c] * momentum + var * (1.f - momentum);
+      }
+    } else {
+      mean = moving_mean[c];
+      var = moving_var[c];
+    }
+    const float rstd = rsqrtf(var + eps);
+    const float g = gamma ? gamma[c] : 1.f;
+    const float bt = beta ? beta[c] : 0.f;
+    scale[c] = g * rstd;
+    shift[c] = bt - mean * g * rstd;
+    if (save_mean) save_mean[c] = mean;
+    if (save_rstd) save_rstd[c] = rstd;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics: x [N][S][C] -> per (n, group) mean / rstd -> per (n, c) scale / shift
+// one block per (n, group)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, long long S, int C, int G,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, float* scale, float* shift, float* save_mean,
+                                                        float* save_rstd) {
+  const int n = blockIdx.x / G, g = blockIdx.x % G;
+  const int cpg = C / G;
+  const T* xb = x + (long long)n * S * C + g * cpg;
+  double a = 0.0, b = 0.0;
+  const long long total = S * cpg;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const long long s = i / cpg;
+    const int c = (int)(i - s * cpg);
+    const float v = to_f32<T>(xb[s * C + c]);
+    a += v;
+    b += (double)v * v;
+  }
+  __shared__ double sa[8], sb[8];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) {
+    sa[threadIdx.x >> 5] = a;
+    sb[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double ta = 0.0, tb = 0.0;
+    for (int i = 0; i < 8; ++i) {
+      ta += sa[i];
+      tb += sb[i];
+    }
+    const double m = ta / (double)total;
+    double v = tb / (double)total - m * m;
+    if (v < 0.0) v = 0.0;
+    const float rstd = (float)(1.0 / sqrt(v + (double)eps));
+    if (threadIdx.x == 0) {
+      save_mean[n * G + g] = (float)m;
+      save_rstd[n * G + g] = rstd;
+    }
+    for (int c = threadIdx.x; c < cpg; c += 32) {
+      const int ch = g * cpg + c;
+      const float gm = gamma[ch];
+      scale[n * C + ch] = gm * rstd;
+      shift[n * C + ch] = beta[ch] - (float)m * gm * rstd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply:  z1 = a*s1+t1 ; r1 = relu1 ? max(z1,0) : z1
+//         z2 = b ? (s2 ? b*s2+t2 : b) : 0 ; r2 = relu2 ? max(z2,0) : z2
+//         y  = relu_out ? max(r1+r2,0) : r1+r2
+// scale index = (per-sample ? n*C : 0) + c
+// ------------------------------------------------------------------------------------------------
+struct ApplyArgs {
+  const void* a; const float* s1; const float* t1;
+  const void* b; const float* s2; const float* t2;
+  void* y;
+  long long P;       // positions
+  long long psp;     // positions per sample (0 = per-channel scale)
+  int C;
+  int relu1, relu2, relu_out;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) apply_kernel(const ApplyArgs p) {
+  const long long nvec = p.P * p.C / 8;
+  const T* a = reinterpret_cast<const T*>(p.a);
+  const T* b = reinterpret_cast<const T*>(p.b);
+  T* y = reinterpret_cast<T*>(p.y);
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    const long long e = v * 8;
+    const long long pos = e / p.C;
+    const int c = (int)(e - pos * p.C);
+    const long long sidx = (p.psp ? (pos / p.psp) * p.C : 0) + c;
+    float av[8], r[8];
+    Vec8<T>::load(a + e, av);
+    if (p.s1) {
+      const float4 sa = *reinterpret_cast<const float4*>(p.s1 + sidx), sb = *reinterpret_cast<const float4*>(p.s1 + sidx + 4);
+      const float4 ta = *reinterpret_cast<const float4*>(p.t1 + sidx), tb = *reinterpret_cast<const float4*>(p.t1 + sidx + 4);
+      const float s[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+      const float t[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaf(av[j], s[j], t[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = av[j];
+    }
+    if (p.relu1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaxf(r[j], 0.f);
+    }
+    if (p.b) {
+      float bv[8];
+      Vec8<T>::load(b + e, bv);
+      if (p.s2) {
+        const float4 sa = *reinterpret_cast<const float4*>(p.s2 + sidx), sb = *reinterpret_cast<const float4*>(p.s2 + sidx + 4);
+        const float4 ta = *reinterpret_cast<const float4*>(p.t2 + sidx), tb = *reinterpret_cast<const float4*>(p.t2 + sidx + 4);
+        const float s[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+        const float t[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bv[j] = fmaf(bv[j], s[j], t[j]);
+      }
+      if (p.relu2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bv[j] = fmaxf(bv[j], 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] += bv[j];
+    }
+    if (p.relu_out) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaxf(r[j], 0.f);
+    }
+    Vec8<T>::store(y + e, r);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of apply.  Pass 1: per-channel (or per sample-group for GN) reductions
+//     S1a = sum g1, S1b = sum g1*xhat1, S2a = sum g2, S2b = sum g2*xhat2
+// with g = dy * mask(relu_out) * mask(relu branch), xhat = (raw - mean) * rstd.
+// Pass 2: d raw = (gamma*rstd) * (g - S_a/M - xhat * S_b/M)   (batch-statistics norm)
+//         d raw = g * scale                                      (frozen statistics)
+//         d b   = g2 (plain tensor), optionally accumulated.
+// ------------------------------------------------------------------------------------------------
+struct ApplyBwdArgs {
+  const void* dy;
+  const void* a; const float* s1; const float* t1; const float* mean1; const float* rstd1;
+  const void* b; const float* s2; const float* t2; const float* mean2; const float* rstd2;
+  long long P, psp;
+  int C, G;           // G > 0: GroupNorm (statistics per sample and group of C/G channels)
+  int relu1, relu2, relu_out;
+  // pass 1
+  float* partial;     // [rows][4][C]
+  int rows;
+  // pass 2
+  const float* coef;  // [4][C] (BN) or [4][N*C] (GN): S1a/M, S1b/M, S2a/M, S2b/M
+  void* da; void* db;
+  int batch_stats1, batch_stats2, acc_a, acc_b;
+};
+
+template <typename T>
+SAP3D_DEVINL void bwd_common(const ApplyBwdArgs& p, long long e, long long sidx, long long midx, float (&g1)[8], float (&g2)[8],
+                             float (&xh1)[8], float (&xh2)[8]) {
+  const T* dy = reinterpret_cast<const T*>(p.dy);
+  const T* a = reinterpret_cast<const T*>(p.a);
+  const T* b = reinterpret_cast<const T*>(p.b);
+  float d[8], av[8], z1[8], z2[8];
+  Vec8<T>::load(dy + e, d);
+  Vec8<T>::load(a + e, av);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float s = p.s1 ? p.s1[sidx + j] : 1.f, t = p.t1 ? p.t1[sidx + j] : 0.f;
+    z1[j] = fmaf(av[j], s, t);
+    xh1[j] = p.mean1 ? (av[j] - p.mean1[midx + (p.G ? 0 : j)]) * p.rstd1[midx + (p.G ? 0 : j)] : 0.f;
+  }
+  if (p.b) {
+    float bv[8];
+    Vec8<T>::load(b + e, bv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = p.s2 ? p.s2[sidx + j] : 1.f, t = p.s2 ? p.t2[sidx + j] : 0.f;
+      z2[j] = fmaf(bv[j], s, t);
+      xh2[j] = p.mean2 ? (bv[j] - p.mean2[midx + (p.G ? 0 : j)]) * p.rstd2[midx + (p.G ? 0 : j)] : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { z2[j] = 0.f; xh2[j] = 0.f; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float r1 = p.relu1 ? fmaxf(z1[j], 0.f) : z1[j];
+    const float r2 = p.relu2 ? fmaxf(z2[j], 0.f) : z2[j];
+    float u = d[j];
+    if (p.relu_out && !(r1 + r2 > 0.f)) u = 0.f;
+    g1[j] = (p.relu1 && !(z1[j] > 0.f)) ? 0.f : u;
+    g2[j] = (p.relu2 && !(z2[j] > 0.f)) ? 0.f : u;
+  }
+}
+
+// grid.x = rows (slabs of positions); block = 256 threads = (C/8) vec lanes x pos lanes
+template <typename T>
+__global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArgs p) {
+  extern __shared__ float red[];  // [pos lanes][4][C]
+  const int vl = p.C / 8;
+  const int lanes = blockDim.x / vl;  // position lanes (>= 1)
+  const int cv = threadIdx.x % vl, pl = threadIdx.x / vl;
+  const long long per = (p.P + p.rows - 1) / p.rows;
+  const long long pbeg = blockIdx.x * per, pend = pbeg + per < p.P ? pbeg + per : p.P;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  if (pl < lanes) {
+    const int c = cv * 8;
+    for (long long pos = pbeg + pl; pos < pend; pos += lanes) {
+      float g1[8], g2[8], xh1[8], xh2[8];
+      bwd_common<T>(p, pos * p.C + c, c, c, g1, g2, xh1, xh2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += g1[j];
+        acc[1][j] += g1[j] * xh1[j];
+        acc[2][j] += g2[j];
+        acc[3][j] += g2[j] * xh2[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[(pl * 4 + i) * p.C + c + j] = acc[i][j];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 4 * p.C; idx += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * 4 * p.C + idx];
+    p.partial[(long long)blockIdx.x * 4 * p.C + idx] = s;
+  }
+}
+
+// partial [rows][4][C] -> coef [4][C] (divided by M) ; dgamma/dbeta accumulation (fp32, +=)
+__global__ void apply_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double M, float* coef,
+                                          float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s[4] = {0, 0, 0, 0};
+  for (int r = 0; r < rows; ++r)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] += (double)partial[((long long)r * 4 + i) * C + c];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) coef[i * C + c] = (float)(s[i] / M);
+  if (dbeta1) dbeta1[c] += (float)s[0];
+  if (dgamma1) dgamma1[c] += (float)s[1];
+  if (dbeta2) dbeta2[c] += (float)s[2];
+  if (dgamma2) dgamma2[c] += (float)s[3];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs p) {
+  const long long nvec = p.P * p.C / 8;
+  T* da = reinterpret_cast<T*>(p.da);
+  T* db = reinterpret_cast<T*>(p.db);
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    const long long e = v * 8;
+    const long long pos = e / p.C;
+    const int c = (int)(e - pos * p.C);
+    float g1[8], g2[8], xh1[8], xh2[8];
+    bwd_common<T>(p, e, c, c, g1, g2, xh1, xh2);
+    if (da) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float s = p.s1 ? p.s1[c + j] : 1.f;
+        o[j] = p.batch_stats1 ? s * (g1[j] - p.coef[0 * p.C + c + j] - xh1[j] * p.coef[1 * p.C + c + j]) : s * g1[j];
+      }
+      if (p.acc_a) {
+        float old[8];
+        Vec8<T>::load(da + e, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += old[j];
+      }
+      Vec8<T>::store(da + e, o);
+    }
+    if (db) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float s = p.s2 ? p.s2[c + j] : 1.f;
+        o[j] = p.batch_stats2 ? s * (g2[j] - p.coef[2 * p.C + c + j] - xh2[j] * p.coef[3 * p.C + c + j]) : s * g2[j];
+      }
+      if (p.acc_b) {
+        float old[8];
+        Vec8<T>::load(db + e, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += old[j];
+      }
+      Vec8<T>::store(db + e, o);
+    }
+  }
+}
+
+int ew_grid(long long nvec) {
+  long long b = (nvec + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sap3d_bn_finalize(const float* stats, int32_t rows, int32_t C, double count, const float* gamma, const float* beta,
+                      float* moving_mean, float* moving_var, int32_t training, float momentum, float eps, float* scale,
+                      float* shift, float* save_mean, float* save_rstd, void* stream) {
+  if (require_device()) return 1;
+  if (!scale || !shift) return set_error("bn_finalize: NULL output");
+  if (training && !stats) return set_error("bn_finalize: training mode needs statistics");
+  if (!training && (!moving_mean || !moving_var)) return set_error("bn_finalize: inference mode needs moving statistics");
+  dim3 block(32, 32);
+  bn_finalize_kernel<<<(C + 31) / 32, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      stats, rows, C, count, gamma, beta, moving_mean, moving_var, training, momentum, eps, scale, shift, save_mean, save_rstd);
+  return check_launch("bn_finalize");
+}
+
+int sap3d_gn_stats(int32_t dtype, const void* x, int32_t N, int64_t S, int32_t C, int32_t G, const float* gamma,
+                   const float* beta, float eps, float* scale, float* shift, float* save_mean, float* save_rstd, void* stream) {
+  if (require_device()) return 1;
+  if (C % G != 0) return set_error("gn_stats: C %% G != 0");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == SAP3D_BF16)
+    gn_stats_kernel<bf16><<<N * G, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), S, C, G, gamma, beta, eps, scale, shift, save_mean, save_rstd);
+  else
+    gn_stats_kernel<float><<<N * G, 256, 0, st>>>(reinterpret_cast<const float*>(x), S, C, G, gamma, beta, eps, scale, shift, save_mean, save_rstd);
+  return check_launch("gn_stats");
+}
+
+int sap3d_affine_act(int32_t dtype, const void* a, const float* s1, const float* t1, int32_t relu1, const void* b,
+                     const float* s2, const float* t2, int32_t relu2, int32_t relu_out, void* y, int64_t P, int32_t C,
+                     int64_t positions_per_sample, void* stream) {
+  if (require_device()) return 1;
+  if (C % 8 != 0) return set_error("affine_act: C must be a multiple of 8 (got %d)", C);
+  ApplyArgs p;
+  p.a = a; p.s1 = s1; p.t1 = t1; p.b = b; p.s2 = s2; p.t2 = t2; p.y = y;
+  p.P = P; p.psp = positions_per_sample; p.C = C;
+  p.relu1 = relu1; p.relu2 = relu2; p.relu_out = relu_out;
+  const long long nvec = P * C / 8;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == SAP3D_BF16) apply_kernel<bf16><<<ew_grid(nvec), 256, 0, st>>>(p);
+  else apply_kernel<float><<<ew_grid(nvec), 256, 0, st>>>(p);
+  return check_launch("affine_act");
+}
+
+size_t sap3d_affine_act_bwd_workspace(int32_t C) { return (size_t)(296 * 4 + 4) * (size_t)C * sizeof(float); }
+
+int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
+                         const float* rstd1, int32_t relu1, const void* b, const float* s2, const float* t2,
+                         const float* mean2, const float* rstd2, int32_t relu2, int32_t relu_out, int64_t P, int32_t C,
+                         void* da, int32_t acc_a, void* db, int32_t acc_b, float* dgamma1, float* dbeta1, float* dgamma2,
+                         float* dbeta2, void* workspace, void* stream) {
+  if (require_device()) return 1;
+  if (C % 8 != 0 || C > 2048) return set_error("affine_act_bwd: C must be a multiple of 8 and <= 2048 (got %d)", C);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ApplyBwdArgs p;
+  memset(&p, 0, sizeof(p));
+  p.dy = dy; p.a = a; p.s1 = s1; p.t1 = t1; p.mean1 = mean1; p.rstd1 = rstd1;
+  p.b = b; p.s2 = s2; p.t2 = t2; p.mean2 = mean2; p.rstd2 = rstd2;
+  p.P = P; p.psp = 0; p.C = C; p.G = 0;
+  p.relu1 = relu1; p.relu2 = relu2; p.relu_out = relu_out;
+  p.batch_stats1 = mean1 != nullptr; p.batch_stats2 = mean2 != nullptr;
+  p.da = da; p.db = db; p.acc_a = acc_a; p.acc_b = acc_b;
+  float* ws = reinterpret_cast<float*>(workspace);
+  const bool need_reduce = p.batch_stats1 || p.batch_stats2 || dgamma1 || dbeta1 || dgamma2 || dbeta2;
+  if (need_reduce) {
+    if (!workspace) return set_error("affine_act_bwd: workspace required");
+    int rows = (int)((P + 63) / 64);
+    if (rows > 296) rows = 296;
+    if (rows < 1) rows = 1;
+    p.rows = rows;
+    p.partial = ws + 4 * C;
+    const int vl = C / 8;
+    int threads = 256;
+    if (vl > 256) threads = vl;  // C = 2048 -> 256 lanes exactly; larger C rejected above
+    int lanes = threads / vl;
+    if (lanes < 1) lanes = 1;
+    const size_t smem = (size_t)lanes * 4 * C * sizeof(float);
+    if (smem > 48 * 1024) {
+      // shrink the number of position lanes to fit default shared memory
+      lanes = (int)(48 * 1024 / (4 * C * sizeof(float)));
+      if (lanes < 1) return set_error("affine_act_bwd: C too large for the reduce kernel");
+      threads = lanes * vl;
+    }
+    const size_t smem2 = (size_t)lanes * 4 * C * sizeof(float);
+    if (dtype == SAP3D_BF16) apply_bwd_reduce_kernel<bf16><<<rows, threads, smem2, st>>>(p);
+    else apply_bwd_reduce_kernel<float><<<rows, threads, smem2, st>>>(p);
+    if (check_launch("affine_act_bwd reduce")) return 1;
+    apply_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(p.partial, rows, C, (double)P, ws, dgamma1, dbeta1, dgamma2, dbeta2);
+    if (check_launch("affine_act_bwd finalize")) return 1;
+    p.coef = ws;
+  }
+  if (da || db) {
+    const long long nvec = P * C / 8;
+    if (dtype == SAP3D_BF16) apply_bwd_kernel<bf16><<<ew_grid(nvec), 256, 0, st>>>(p);
+    else apply_bwd_kernel<float><<<ew_grid(nvec), 256, 0, st>>>(p);
+    if (check_launch("affine_act_bwd apply")) return 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

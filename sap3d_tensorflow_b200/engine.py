@@ -1,0 +1,521 @@
+"""Static-schedule execution engine for the P3D saliency hot path.
+
+The graph builders (p3d.py, gn/p3d_gn.py, network.py of this package — same public names as the
+reference's) describe a model once against this engine; the engine owns the activation / gradient /
+parameter buffers (torch tensors used purely as a device allocator) and a tape of launches into
+libsap3d_b200.so.  forward()/backward()/adam run the tape on the current CUDA stream, so a whole
+training step can be captured into ONE CUDA graph (no tracing compiler involved).
+
+Replaces the TF-1.x graph executor walking the ~450 op kernels of one sess.run (train.py:217,
+gen_pred.py:151).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _abi as A
+
+BN_EPS = 1e-3        # tf.layers.batch_normalization defaults (TF-1.x)
+BN_MOMENTUM = 0.99
+
+
+def _dt(dtype: str):
+    return (A.BF16, torch.bfloat16) if dtype == "bf16" else (A.F32, torch.float32)
+
+
+class T:
+    """activation tensor handle (NDHWC)"""
+
+    __slots__ = ("shape", "buf", "grad", "name", "needs_grad", "gflag", "eng")
+
+    def __init__(self, eng, shape, name="", needs_grad=None, torch_dtype=None):
+        self.eng = eng
+        self.shape = tuple(int(s) for s in shape)
+        self.name = name
+        self.buf = torch.empty(self.shape, device=eng.device, dtype=torch_dtype or eng.tdt)
+        self.needs_grad = eng.training_graph if needs_grad is None else needs_grad
+        self.grad = None
+        self.gflag = False
+
+    def ensure_grad(self):
+        if self.grad is None:
+            self.grad = torch.empty_like(self.buf)
+        return self.grad
+
+    @property
+    def positions(self):
+        return int(np.prod(self.shape[:-1]))
+
+    @property
+    def C(self):
+        return self.shape[-1]
+
+    def take_acc(self) -> int:
+        """returns 1 if a previous consumer already wrote this tensor's gradient (then accumulate)"""
+        acc = 1 if self.gflag else 0
+        self.gflag = True
+        return acc
+
+
+class Param:
+    __slots__ = ("name", "shape", "kind", "trainable", "numel", "offset", "w", "g", "fan")
+
+    def __init__(self, name, shape, kind, trainable):
+        self.name = name
+        self.shape = tuple(int(s) for s in shape)
+        self.kind = kind
+        self.trainable = trainable
+        self.numel = int(np.prod(self.shape))
+        self.offset = -1
+        self.w = None
+        self.g = None
+
+
+class NameScope:
+    """TF-1.x default-name uniquification: conv3d, conv3d_1, ... per enclosing variable scope."""
+
+    def __init__(self):
+        self.counters: Dict[str, int] = {}
+
+    def unique(self, scope: str, base: str) -> str:
+        key = scope + "/" + base
+        n = self.counters.get(key, 0)
+        self.counters[key] = n + 1
+        name = base if n == 0 else f"{base}_{n}"
+        return (scope + "/" + name) if scope else name
+
+
+class ConvOut:
+    """raw (pre-normalisation) conv output plus the per-tile statistics its epilogue produced"""
+
+    def __init__(self, raw: T, stats: Optional[torch.Tensor], rows: int):
+        self.raw = raw
+        self.stats = stats
+        self.rows = rows
+
+
+class NormState:
+    def __init__(self, eng, C, gamma: Optional[Param], beta: Optional[Param], mm: Optional[Param], mv: Optional[Param]):
+        self.gamma, self.beta, self.mm, self.mv = gamma, beta, mm, mv
+        f = lambda: torch.empty(C, device=eng.device, dtype=torch.float32)  # noqa: E731
+        self.scale, self.shift, self.mean, self.rstd = f(), f(), f(), f()
+
+
+class Engine:
+    def __init__(self, dtype: str = "bf16", training_graph: bool = False, device: str = "cuda:0", conv_impl: int = A.IMPL_AUTO,
+                 dropout_seed: int = 1234):
+        if not torch.cuda.is_available():
+            raise A.Sap3dError("sap3d_tensorflow_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self.device = torch.device(device)
+        self.dtype_name = dtype
+        self.dt, self.tdt = _dt(dtype)
+        self.training_graph = training_graph
+        self.conv_impl = conv_impl
+        self.names = NameScope()
+        self.params: "OrderedDict[str, Param]" = OrderedDict()
+        self.fwd_ops: List = []
+        self.bwd_ops: List = []
+        self.tensors: List[T] = []
+        self.convs: List = []
+        self.taps: Dict[str, T] = {}
+        self.finalized = False
+        self.dropout_seed = dropout_seed
+        self.step = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.loss_buf = torch.zeros(1, device=self.device, dtype=torch.float64)
+        self.bwd_ws: Optional[torch.Tensor] = None
+        self._max_c = 8
+        self.launches_fwd = 0
+        self.launches_bwd = 0
+        self._counting = None
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def tensor(self, shape, name="", needs_grad=None, torch_dtype=None) -> T:
+        t = T(self, shape, name, needs_grad, torch_dtype)
+        self.tensors.append(t)
+        return t
+
+    def tap(self, name: str, t: T) -> T:
+        self.taps[name] = t
+        return t
+
+    def param(self, name, shape, kind, trainable=True) -> Param:
+        if name in self.params:
+            p = self.params[name]
+            assert p.shape == tuple(shape), (name, p.shape, shape)
+            return p
+        assert not self.finalized
+        p = Param(name, shape, kind, trainable)
+        self.params[name] = p
+        return p
+
+    def _count(self, n=1):
+        if self._counting == "fwd":
+            self.launches_fwd += n
+        elif self._counting == "bwd":
+            self.launches_bwd += n
+
+    # ------------------------------------------------------------------------------------------
+    # parameter storage: ONE flat fp32 buffer each for weights / grads / adam m / adam v
+    # ------------------------------------------------------------------------------------------
+    def finalize(self):
+        assert not self.finalized
+        off = 0
+        ordered = [p for p in self.params.values() if p.trainable] + [p for p in self.params.values() if not p.trainable]
+        n_train = 0
+        for p in ordered:
+            p.offset = off
+            off += (p.numel + 63) // 64 * 64
+            if p.trainable:
+                n_train = off
+        self.n_train = n_train
+        self.flat_w = torch.zeros(off, device=self.device, dtype=torch.float32)
+        self.flat_g = torch.zeros(max(n_train, 1), device=self.device, dtype=torch.float32) if self.training_graph else None
+        self.flat_m = torch.zeros(max(n_train, 1), device=self.device, dtype=torch.float32) if self.training_graph else None
+        self.flat_v = torch.zeros(max(n_train, 1), device=self.device, dtype=torch.float32) if self.training_graph else None
+        for p in ordered:
+            p.w = self.flat_w[p.offset:p.offset + p.numel].view(p.shape)
+            if p.trainable and self.training_graph:
+                p.g = self.flat_g[p.offset:p.offset + p.numel].view(p.shape)
+        if self.training_graph:
+            nbytes = A.lib.sap3d_affine_act_bwd_workspace(self._max_c)
+            self.bwd_ws = torch.zeros(nbytes // 4 + 16, device=self.device, dtype=torch.float32)
+        self.finalized = True
+        self.init_params_tf(0)
+
+    def init_params_tf(self, seed: int = 0):
+        """TensorFlow's default initialisers for every variable kind (p3d.py:12; tf.layers defaults)."""
+        rng = np.random.RandomState(seed)
+        for p in self.params.values():
+            shp = p.shape
+            if p.kind in ("glorot", "glorot_t"):
+                rf = int(np.prod(shp[:-2])) if len(shp) > 2 else 1
+                lim = math.sqrt(6.0 / ((shp[-1] + shp[-2]) * rf))
+                v = rng.uniform(-lim, lim, size=shp)
+            elif p.kind == "xavier1d":  # get_conv_weight(name+'_bias',[C],0): xavier on a rank-1 shape
+                lim = math.sqrt(6.0 / (2 * shp[0]))
+                v = rng.uniform(-lim, lim, size=shp)
+            elif p.kind == "vscale":  # variance_scaling_initializer(): truncated normal, factor 2, FAN_IN
+                rf = int(np.prod(shp[:-2])) if len(shp) > 2 else 1
+                std = math.sqrt(2.0 / (shp[-2] * rf)) / 0.8796
+                v = np.clip(rng.normal(0, std, size=shp), -2 * std, 2 * std)
+            elif p.kind in ("ones", "var"):
+                v = np.ones(shp)
+            elif p.kind in ("zeros", "mean", "bias", "sa_gamma"):
+                v = np.zeros(shp)
+            else:
+                raise ValueError(p.kind)
+            p.w.copy_(torch.tensor(v, dtype=torch.float32))
+        self.pack_weights()
+
+    def load_params(self, values: Dict[str, "np.ndarray | torch.Tensor"], strict: bool = True):
+        for name, p in self.params.items():
+            if name not in values:
+                if strict:
+                    raise KeyError(f"missing variable {name}")
+                continue
+            v = values[name]
+            v = v if isinstance(v, torch.Tensor) else torch.tensor(np.asarray(v))
+            p.w.copy_(v.to(torch.float32).reshape(p.shape))
+        extra = set(values) - set(self.params)
+        if strict and extra:
+            raise KeyError(f"unknown variables {sorted(extra)[:5]} ...")
+        self.pack_weights()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {n: p.w.detach().cpu().clone() for n, p in self.params.items()}
+
+    def pack_weights(self):
+        for c in self.convs:
+            c.pack()
+
+    # ------------------------------------------------------------------------------------------
+    # ops
+    # ------------------------------------------------------------------------------------------
+    def conv(self, xs: Sequence[T], cout: int, kernel, strides, w: Param, b: Optional[Param] = None, transposed=False,
+             want_stats=True, name="", out_f32=False) -> ConvOut:
+        op = _ConvOp(self, list(xs), cout, tuple(kernel), tuple(strides), w, b, transposed, want_stats, name, out_f32)
+        self.convs.append(op)
+        self.fwd_ops.append(op.fwd)
+        self.bwd_ops.append(op.bwd)
+        return op.out
+
+    def norm_state(self, C, gamma=None, beta=None, mm=None, mv=None) -> NormState:
+        self._max_c = max(self._max_c, C)
+        return NormState(self, C, gamma, beta, mm, mv)
+
+    def norm_act(self, a: ConvOut, n1: Optional[NormState], train1: bool, relu1: bool, b=None, n2: Optional[NormState] = None,
+                 train2: bool = False, relu2: bool = False, relu_out: bool = False, name="") -> T:
+        op = _NormActOp(self, a, n1, train1, relu1, b, n2, train2, relu2, relu_out, name)
+        self.fwd_ops.append(op.fwd)
+        self.bwd_ops.append(op.bwd)
+        return op.y
+
+    def maxpool(self, x: T, ksize, strides, same=True, name="") -> T:
+        op = _PoolOp(self, x, ksize, strides, same, name)
+        self.fwd_ops.append(op.fwd)
+        self.bwd_ops.append(op.bwd)
+        return op.y
+
+    def dropout(self, x: T, rate: float, name="") -> T:
+        if rate <= 0.0:
+            return x
+        op = _DropoutOp(self, x, rate, name)
+        self.fwd_ops.append(op.fwd)
+        self.bwd_ops.append(op.bwd)
+        return op.y
+
+    def head(self, x: T, w: Param, b: Param, ksize, stride, sigmoid=True, name="") -> "_HeadOp":
+        op = _HeadOp(self, x, w, b, ksize, stride, sigmoid, name)
+        self.fwd_ops.append(op.fwd)
+        self.bwd_ops.append(op.bwd)
+        return op
+
+    # ------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------
+    def forward(self):
+        self._counting = "fwd"
+        self.launches_fwd = 0
+        for f in self.fwd_ops:
+            f()
+        self._counting = None
+
+    def backward(self):
+        assert self.training_graph
+        self._counting = "bwd"
+        self.launches_bwd = 0
+        for t in self.tensors:
+            t.gflag = False
+        self.flat_g.zero_()
+        self._count()
+        for f in reversed(self.bwd_ops):
+            f()
+        self._counting = None
+
+    def adam(self, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
+        A.check(A.lib.sap3d_adam_step(A.ptr(self.flat_w), A.ptr(self.flat_g), A.ptr(self.flat_m), A.ptr(self.flat_v),
+                                      self.n_train, A.ptr(self.step), lr, b1, b2, eps, grad_scale, self.stream), "adam")
+        self.pack_weights()
+
+    def begin_step(self):
+        A.check(A.lib.sap3d_step_increment(A.ptr(self.step), self.stream), "step_increment")
+        self.loss_buf.zero_()
+
+
+# ==================================================================================================
+class _ConvOp:
+    def __init__(self, eng: Engine, xs, cout, kernel, strides, w: Param, b, transposed, want_stats, name, out_f32):
+        self.eng = eng
+        self.xs = xs
+        self.w, self.b = w, b
+        self.name = name
+        N, D, H, W, _ = xs[0].shape
+        cin = [x.C for x in xs]
+        self.desc = A.make_conv_desc(eng.dt, N, D, H, W, cin, cout, kernel, strides, transposed, b is not None, out_f32,
+                                     eng.conv_impl)
+        Do, Ho, Wo = A.conv_out_dims(self.desc)
+        raw = eng.tensor((N, Do, Ho, Wo, cout), name + "/raw", torch_dtype=torch.float32 if out_f32 else None)
+        rows = A.lib.sap3d_conv_stats_rows(C.byref(self.desc)) if want_stats else 0
+        stats = torch.zeros(rows, 2, cout, device=eng.device, dtype=torch.float32) if want_stats else None
+        self.out = ConvOut(raw, stats, rows)
+        self.use_tc = eng.dt == A.BF16
+        nf = A.lib.sap3d_conv_packed_elems(C.byref(self.desc), 0)
+        nd = A.lib.sap3d_conv_packed_elems(C.byref(self.desc), 1)
+        self.wf = torch.zeros(nf, device=eng.device, dtype=torch.bfloat16) if self.use_tc else None
+        self.wd = torch.zeros(nd, device=eng.device, dtype=torch.bfloat16) if (self.use_tc and eng.training_graph) else None
+
+    def pack(self):
+        if self.use_tc:
+            A.check(A.lib.sap3d_conv_pack_weights(C.byref(self.desc), A.ptr(self.w.w), A.ptr(self.wf), A.ptr(self.wd),
+                                                  self.eng.stream), "pack " + self.name)
+
+    def fwd(self):
+        e = self.eng
+        x1 = self.xs[1].buf if len(self.xs) > 1 else None
+        A.check(A.lib.sap3d_conv_fwd(C.byref(self.desc), A.ptr(self.xs[0].buf), A.ptr(x1), A.ptr(self.w.w), A.ptr(self.wf),
+                                     A.ptr(self.b.w) if self.b is not None else None, A.ptr(self.out.raw.buf),
+                                     A.ptr(self.out.stats), e.stream), "conv_fwd " + self.name)
+        e._count()
+
+    def bwd(self):
+        e = self.eng
+        raw = self.out.raw
+        if not raw.gflag:
+            return
+        dy = raw.grad
+        for si, x in enumerate(self.xs):
+            if not x.needs_grad:
+                continue
+            acc = x.take_acc()
+            A.check(A.lib.sap3d_conv_dgrad(C.byref(self.desc), si, A.ptr(dy), A.ptr(self.w.w), A.ptr(self.wd),
+                                           A.ptr(x.ensure_grad()), acc, e.stream), "conv_dgrad " + self.name)
+            e._count()
+        x1 = self.xs[1].buf if len(self.xs) > 1 else None
+        A.check(A.lib.sap3d_conv_wgrad(C.byref(self.desc), A.ptr(self.xs[0].buf), A.ptr(x1), A.ptr(dy), A.ptr(self.w.g),
+                                       A.ptr(self.b.g) if self.b is not None else None, e.stream), "conv_wgrad " + self.name)
+        e._count(len(self.xs) + (1 if self.b is not None else 0))
+
+
+class _NormActOp:
+    """y = relu_out?( relu1?(norm1(a)) + relu2?(norm2(b) | b) )"""
+
+    def __init__(self, eng, a: ConvOut, n1, train1, relu1, b, n2, train2, relu2, relu_out, name):
+        self.eng = eng
+        self.a, self.n1, self.train1, self.relu1 = a, n1, train1, relu1
+        self.b, self.n2, self.train2, self.relu2 = b, n2, train2, relu2
+        self.relu_out = relu_out
+        self.name = name
+        self.b_t: Optional[T] = None if b is None else (b.raw if isinstance(b, ConvOut) else b)
+        self.y = eng.tensor(a.raw.shape, name)
+        if eng.training_graph:
+            a.raw.ensure_grad()
+
+    def _finalize(self, co: ConvOut, ns: NormState, training: bool):
+        e = self.eng
+        cnt = float(co.raw.positions)
+        A.check(A.lib.sap3d_bn_finalize(A.ptr(co.stats), co.rows, co.raw.C, cnt, A.ptr(ns.gamma.w), A.ptr(ns.beta.w),
+                                        A.ptr(ns.mm.w), A.ptr(ns.mv.w), int(training), BN_MOMENTUM, BN_EPS, A.ptr(ns.scale),
+                                        A.ptr(ns.shift), A.ptr(ns.mean), A.ptr(ns.rstd), e.stream), "bn_finalize " + self.name)
+        e._count()
+
+    def fwd(self):
+        e = self.eng
+        if self.n1 is not None:
+            self._finalize(self.a, self.n1, self.train1)
+        if self.n2 is not None:
+            self._finalize(self.b, self.n2, self.train2)
+        n1, n2 = self.n1, self.n2
+        A.check(A.lib.sap3d_affine_act(e.dt, A.ptr(self.a.raw.buf), A.ptr(n1.scale) if n1 else None,
+                                       A.ptr(n1.shift) if n1 else None, int(self.relu1),
+                                       A.ptr(self.b_t.buf) if self.b_t is not None else None,
+                                       A.ptr(n2.scale) if n2 else None, A.ptr(n2.shift) if n2 else None, int(self.relu2),
+                                       int(self.relu_out), A.ptr(self.y.buf), self.y.positions, self.y.C, 0, e.stream),
+                "affine_act " + self.name)
+        e._count()
+
+    def bwd(self):
+        e = self.eng
+        if not self.y.gflag:
+            return
+        n1, n2 = self.n1, self.n2
+        a_raw = self.a.raw
+        acc_a = a_raw.take_acc()
+        db_ptr, acc_b = None, 0
+        if self.b_t is not None and self.b_t.needs_grad:
+            acc_b = self.b_t.take_acc()
+            db_ptr = A.ptr(self.b_t.ensure_grad())
+        bs1 = n1 is not None and self.train1
+        bs2 = n2 is not None and self.train2
+        A.check(A.lib.sap3d_affine_act_bwd(
+            e.dt, A.ptr(self.y.grad), A.ptr(a_raw.buf),
+            A.ptr(n1.scale) if n1 else None, A.ptr(n1.shift) if n1 else None,
+            A.ptr(n1.mean) if bs1 else None, A.ptr(n1.rstd) if bs1 else None, int(self.relu1),
+            A.ptr(self.b_t.buf) if self.b_t is not None else None,
+            A.ptr(n2.scale) if n2 else None, A.ptr(n2.shift) if n2 else None,
+            A.ptr(n2.mean) if bs2 else None, A.ptr(n2.rstd) if bs2 else None, int(self.relu2),
+            int(self.relu_out), self.y.positions, self.y.C,
+            A.ptr(a_raw.ensure_grad()), acc_a, db_ptr, acc_b,
+            A.ptr(n1.gamma.g) if n1 else None, A.ptr(n1.beta.g) if n1 else None,
+            A.ptr(n2.gamma.g) if n2 else None, A.ptr(n2.beta.g) if n2 else None,
+            A.ptr(e.bwd_ws), e.stream), "affine_act_bwd " + self.name)
+        e._count(3)
+
+
+class _PoolOp:
+    def __init__(self, eng, x: T, ksize, strides, same, name):
+        self.eng, self.x = eng, x
+        self.k, self.s, self.same = A.i3(ksize), A.i3(strides), int(same)
+        N, D, H, W, Cc = x.shape
+        out = (C.c_int32 * 3)()
+        A.check(A.lib.sap3d_maxpool3d_out_dims(D, H, W, self.k, self.s, self.same, out), "maxpool dims")
+        self.y = eng.tensor((N, out[0], out[1], out[2], Cc), name, needs_grad=x.needs_grad)
+        self.name = name
+
+    def fwd(self):
+        e, x = self.eng, self.x
+        N, D, H, W, Cc = x.shape
+        A.check(A.lib.sap3d_maxpool3d_fwd(e.dt, A.ptr(x.buf), N, D, H, W, Cc, self.k, self.s, self.same, A.ptr(self.y.buf),
+                                          e.stream), "maxpool_fwd " + self.name)
+        e._count()
+
+    def bwd(self):
+        e, x = self.eng, self.x
+        if not self.y.gflag or not x.needs_grad:
+            return
+        N, D, H, W, Cc = x.shape
+        acc = x.take_acc()
+        A.check(A.lib.sap3d_maxpool3d_bwd(e.dt, A.ptr(x.buf), A.ptr(self.y.grad), N, D, H, W, Cc, self.k, self.s, self.same,
+                                          A.ptr(x.ensure_grad()), acc, e.stream), "maxpool_bwd " + self.name)
+        e._count()
+
+
+class _DropoutOp:
+    _next_salt = 0
+
+    def __init__(self, eng, x: T, rate, name):
+        self.eng, self.x, self.rate, self.name = eng, x, float(rate), name
+        self.y = eng.tensor(x.shape, name)
+        self.seed = eng.dropout_seed * 1000003 + _DropoutOp._next_salt
+        _DropoutOp._next_salt += 1
+
+    def fwd(self):
+        e = self.eng
+        A.check(A.lib.sap3d_dropout(e.dt, A.ptr(self.x.buf), A.ptr(self.y.buf), self.x.buf.numel(), self.rate, self.seed,
+                                    A.ptr(e.step), 0, e.stream), "dropout " + self.name)
+        e._count()
+
+    def bwd(self):
+        e = self.eng
+        if not self.y.gflag or not self.x.needs_grad:
+            return
+        acc = self.x.take_acc()
+        A.check(A.lib.sap3d_dropout(e.dt, A.ptr(self.y.grad), A.ptr(self.x.ensure_grad()), self.x.buf.numel(), self.rate,
+                                    self.seed, A.ptr(e.step), acc, e.stream), "dropout_bwd " + self.name)
+        e._count()
+
+
+class _HeadOp:
+    """final 1-channel transposed conv (+ sigmoid) and, in training graphs, the smooth-L1 loss"""
+
+    def __init__(self, eng, x: T, w: Param, b: Param, ksize, stride, sigmoid, name):
+        self.eng, self.x, self.w, self.b = eng, x, w, b
+        self.k, self.stride, self.sigmoid, self.name = A.i3(ksize), int(stride), sigmoid, name
+        N, D, H, W, _ = x.shape
+        shp = (N, D * stride, H * stride, W * stride, 1)
+        self.logits = torch.empty(shp, device=eng.device, dtype=torch.float32)
+        self.pred = torch.empty(shp, device=eng.device, dtype=torch.float32)
+        self.target = torch.zeros(shp[:-1], device=eng.device, dtype=torch.float32) if eng.training_graph else None
+        self.dlogits = torch.empty(shp, device=eng.device, dtype=torch.float32) if eng.training_graph else None
+
+    def fwd(self):
+        e, x = self.eng, self.x
+        N, D, H, W, Cc = x.shape
+        A.check(A.lib.sap3d_head_fwd(e.dt, A.ptr(x.buf), N, D, H, W, Cc, self.k, self.stride, A.ptr(self.w.w), A.ptr(self.b.w),
+                                     A.ptr(self.logits), A.ptr(self.pred) if self.sigmoid else None, e.stream),
+                "head_fwd " + self.name)
+        e._count()
+
+    def bwd(self):
+        e, x = self.eng, self.x
+        N, D, H, W, Cc = x.shape
+        A.check(A.lib.sap3d_loss_smooth_l1(A.ptr(self.logits), A.ptr(self.target), self.logits.numel(), int(self.sigmoid), None,
+                                           A.ptr(self.dlogits), A.ptr(e.loss_buf), A.ptr(self.b.g), e.stream), "loss")
+        acc = x.take_acc()
+        A.check(A.lib.sap3d_head_bwd(e.dt, A.ptr(self.dlogits), A.ptr(x.buf), N, D, H, W, Cc, self.k, self.stride,
+                                     A.ptr(self.w.w), A.ptr(x.ensure_grad()), acc, A.ptr(self.w.g), e.stream),
+                "head_bwd " + self.name)
+        e._count(3)
+
+    @property
+    def output(self):
+        return self.pred if self.sigmoid else self.logits

@@ -1,0 +1,111 @@
+"""Layer helpers with the public names of the reference's utils/network.py, lowered onto the engine's
+fused primitives (conv + statistics epilogue -> finalize -> fused affine/ReLU/residual pass).
+
+Reference surface mirrored (utils/network.py): pool3d :6, smooth_l1_loss :49, GroupNorm :65,
+normalize :89, concat :97, conv3d :100, transpose_conv3d :106, attention :157, cbam_block :198.
+Handles are engine tensors (`engine.T`); `concat` returns a lazy channel concatenation that the
+convolution kernels consume as K-segments (it is never materialised).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Union
+
+from . import _abi as A
+from .engine import ConvOut, Engine, T
+
+DEFAULT_PADDING = "SAME"
+
+
+class Cat:
+    """lazy tf.concat(xs, axis=-1)"""
+
+    def __init__(self, parts: Sequence[T]):
+        self.parts: List[T] = list(parts)
+        self.eng: Engine = parts[0].eng
+
+    @property
+    def shape(self):
+        s = list(self.parts[0].shape)
+        s[-1] = sum(p.C for p in self.parts)
+        return tuple(s)
+
+
+Handle = Union[T, Cat]
+
+
+def _parts(x: Handle) -> List[T]:
+    return x.parts if isinstance(x, Cat) else [x]
+
+
+def _k3(k):
+    return (k, k, k) if isinstance(k, int) else tuple(k)
+
+
+def concat(x: Sequence[T]) -> Cat:  # utils/network.py:97
+    return Cat(x)
+
+
+def pool3d(value: T, sub_size: int) -> T:  # utils/network.py:6 (tf.layers.max_pooling3d, 'valid')
+    if sub_size == 1:
+        return value
+    return value.eng.maxpool(value, _k3(sub_size), _k3(sub_size), same=False, name="pool3d")
+
+
+# ---- normalisation -------------------------------------------------------------------------------
+def _bn_state(eng: Engine, C: int, name=None, scope=""):
+    """variables of one tf.layers.batch_normalization call (auto-named unless `name`)"""
+    nm = name if name is not None else eng.names.unique(scope, "batch_normalization")
+    return eng.norm_state(C, eng.param(nm + "/gamma", [C], "ones"), eng.param(nm + "/beta", [C], "zeros"),
+                          eng.param(nm + "/moving_mean", [C], "mean", trainable=False),
+                          eng.param(nm + "/moving_variance", [C], "var", trainable=False))
+
+
+def bn_relu(co: ConvOut, training: bool, name=None, relu=True, tap: str = "") -> T:
+    eng = co.raw.eng
+    ns = _bn_state(eng, co.raw.C, name)
+    return eng.norm_act(co, ns, training, relu, name=tap or (name or "bn"))
+
+
+def normalize(x: ConvOut, training, mode="bn"):  # utils/network.py:89 (without the ReLU)
+    if mode != "bn":
+        raise NotImplementedError("GroupNorm graphs are built by gn/p3d_gn.py")
+    return bn_relu(x, training, relu=False)
+
+
+# ---- conv / deconv + norm + relu -----------------------------------------------------------------
+def layers_conv3d(x: Handle, channel: int, kernel, strides, name=None, scope="", use_bias=True, want_stats=True) -> ConvOut:
+    """tf.layers.conv3d(x, channel, kernel, strides, 'same', name=name): '<name>/kernel' DHWIO, '<name>/bias'"""
+    parts = _parts(x)
+    eng = parts[0].eng
+    k, s = _k3(kernel), _k3(strides)
+    nm = ((scope + "/" + name) if scope else name) if name is not None else eng.names.unique(scope, "conv3d")
+    cin = sum(p.C for p in parts)
+    w = eng.param(nm + "/kernel", [*k, cin, channel], "glorot")
+    b = eng.param(nm + "/bias", [channel], "zeros") if use_bias else None
+    return eng.conv(parts, channel, k, s, w, b, transposed=False, want_stats=want_stats, name=nm)
+
+
+def layers_conv3d_transpose(x: Handle, channel: int, kernel, strides, name=None, scope="", want_stats=True) -> ConvOut:
+    """tf.layers.conv3d_transpose(x, channel, kernel, strides, 'same', name=name): kernel [k..., Cout, Cin]"""
+    parts = _parts(x)
+    eng = parts[0].eng
+    k, s = _k3(kernel), _k3(strides)
+    nm = ((scope + "/" + name) if scope else name) if name is not None else eng.names.unique(scope, "conv3d_transpose")
+    cin = sum(p.C for p in parts)
+    w = eng.param(nm + "/kernel", [*k, channel, cin], "glorot_t")
+    b = eng.param(nm + "/bias", [channel], "zeros")
+    return eng.conv(parts, channel, k, s, w, b, transposed=True, want_stats=want_stats, name=nm)
+
+
+def conv3d(x: Handle, channel, kernel, strides, training, name, mode="bn") -> T:  # utils/network.py:100
+    co = layers_conv3d(x, channel, kernel, strides, name)
+    return co.raw.eng.tap(name, bn_relu(co, training, tap=name))
+
+
+def transpose_conv3d(x: Handle, channel, kernel, strides, training, name, mode="bn") -> T:  # utils/network.py:106
+    co = layers_conv3d_transpose(x, channel, kernel, strides, name)
+    return co.raw.eng.tap(name, bn_relu(co, training, tap=name))
+
+
+def smooth_l1_loss(*_args, **_kw):  # utils/network.py:49 — fused into the head's backward (engine._HeadOp)
+    raise NotImplementedError("the smooth-L1 loss is fused into Session.train_step (sap3d_loss_smooth_l1)")

@@ -1,0 +1,191 @@
+"""P3D-199 (minus layer4) backbone + saliency decoders on the B200 engine.
+
+Public surface = the reference's p3d.py: get_conv_weight :10, convS :18, convT :23, Bottleneck :30,
+make_block :139, p3d_unet :169, p3d_concat :224, p3d_unetplusplus_ds :340, p3d_unetplusplus_nonsa :401
+(same argument lists; `_X` is a `placeholder`, the result is an engine handle consumed by `Session`).
+Variable names are the reference's (firstconv1, conv3_{id}_{1,3}, ST{A,B,C}_{id}_2_{S,T}[_bias],
+dw3d_{id}, auto-numbered batch_normalization_N, named decoder layers) so checkpoints line up.
+
+The wiring is table-driven; every conv -> BN -> ReLU (-> add) chain is lowered to
+  tcgen05 implicit-GEMM (statistics in the epilogue) -> bn_finalize -> one fused apply pass.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+from . import network as nw
+from .engine import ConvOut, Engine, T
+
+CROP_SIZE = 112
+NUM_FRAMES_PER_CLIP = 16
+RGB_CHANNEL = 3
+BLOCK_EXPANSION = 4
+
+# (planes, number of bottlenecks, inplanes, spatial stride of the first bottleneck)  p3d.py:350-363
+STAGES = ((64, 3, 64, 1), (128, 8, 256, 2), (256, 36, 512, 2))
+TEMPORAL_POOL = ((2, 1, 1), (2, 1, 1))
+
+
+def get_conv_weight(eng: Engine, name, kshape, wd=0.001):
+    """p3d.py:10-16.  Xavier-uniform variable; the weight-decay collection is never added to the loss
+    in the reference (train.py:161-162), so `wd` is accepted and ignored."""
+    return eng.param(name, kshape, "glorot" if len(kshape) > 1 else "xavier1d")
+
+
+def convS(name, l_input: T, in_channels, out_channels) -> ConvOut:  # p3d.py:18-22: 1x3x3 + bias
+    eng = l_input.eng
+    return eng.conv([l_input], out_channels, (1, 3, 3), (1, 1, 1), get_conv_weight(eng, name, [1, 3, 3, in_channels, out_channels]),
+                    get_conv_weight(eng, name + "_bias", [out_channels], 0), name=name)
+
+
+def convT(name, l_input: T, in_channels, out_channels) -> ConvOut:  # p3d.py:23-27: 3x1x1 + bias
+    eng = l_input.eng
+    return eng.conv([l_input], out_channels, (3, 1, 1), (1, 1, 1), get_conv_weight(eng, name, [3, 1, 1, in_channels, out_channels]),
+                    get_conv_weight(eng, name + "_bias", [out_channels], 0), name=name)
+
+
+class Bottleneck:
+    """p3d.py:30-136 for the 3-D branch (n_s < depth_3d; the 2-D branches are unreachable with 47 blocks)."""
+
+    def __init__(self, l_input: T, inplanes, planes, stride=1, downsample="", training=True, n_s=0, depth_3d=47):
+        if n_s >= depth_3d:
+            raise NotImplementedError("2-D bottlenecks (n_s >= depth_3d) are dead code in the reference graphs")
+        self.x, self.inplanes, self.planes = l_input, inplanes, planes
+        self.id = n_s
+        self.training = training
+        self.first = downsample != ""
+        self.hw_stride = 2 if (self.first and n_s != 0) else 1  # p3d.py:45-49
+        self.ST = "ABC"[n_s % 3]
+
+    def infer(self) -> T:
+        x, eng, tr, pl, i = self.x, self.x.eng, self.training, self.planes, self.id
+        s = (1, self.hw_stride, self.hw_stride)
+        one = (1, 1, 1)
+        c1 = eng.conv([x], pl, one, s, get_conv_weight(eng, f"conv3_{i}_1", [1, 1, 1, self.inplanes, pl]), name=f"conv3_{i}_1")
+        o = nw.bn_relu(c1, tr, tap=f"b{i}/1")
+        nm = f"ST{self.ST}_{i}_2"
+        if self.ST == "A":      # S -> T in series
+            o = nw.bn_relu(convS(nm + "_S", o, pl, pl), tr, tap=nm + "_S")
+            o = nw.bn_relu(convT(nm + "_T", o, pl, pl), tr, tap=nm + "_T")
+        elif self.ST == "B":    # relu(bn(T(o))) + relu(bn(S(o))) in one fused pass
+            s_raw = convS(nm + "_S", o, pl, pl)
+            ns_s = nw._bn_state(eng, pl)
+            t_raw = convT(nm + "_T", o, pl, pl)
+            ns_t = nw._bn_state(eng, pl)
+            o = eng.norm_act(t_raw, ns_t, tr, True, b=s_raw, n2=ns_s, train2=tr, relu2=True, name=nm)
+        else:                   # C: s = relu(bn(S(o))); s + relu(bn(T(s)))
+            s_act = nw.bn_relu(convS(nm + "_S", o, pl, pl), tr, tap=nm + "_S")
+            t_raw = convT(nm + "_T", s_act, pl, pl)
+            o = eng.norm_act(t_raw, nw._bn_state(eng, pl), tr, True, b=s_act, name=nm)
+        c3 = eng.conv([o], pl * BLOCK_EXPANSION, one, one,
+                      get_conv_weight(eng, f"conv3_{i}_3", [1, 1, 1, pl, pl * BLOCK_EXPANSION]), name=f"conv3_{i}_3")
+        ns3 = nw._bn_state(eng, pl * BLOCK_EXPANSION)
+        if self.first:          # projection shortcut dw3d_{id} (p3d.py:124-127)
+            r = eng.conv([x], pl * BLOCK_EXPANSION, one, s,
+                         get_conv_weight(eng, f"dw3d_{i}", [1, 1, 1, self.inplanes, pl * BLOCK_EXPANSION]), name=f"dw3d_{i}")
+            nsr = nw._bn_state(eng, pl * BLOCK_EXPANSION)
+            y = eng.norm_act(c3, ns3, tr, False, b=r, n2=nsr, train2=tr, relu2=False, relu_out=True, name=f"b{i}")
+        else:
+            y = eng.norm_act(c3, ns3, tr, False, b=x, relu_out=True, name=f"b{i}")
+        return eng.tap(f"b{i}", y)
+
+
+class make_block:
+    """p3d.py:139-166.  NB: no caller passes `training`, so backbone BatchNorm always uses batch statistics."""
+
+    def __init__(self, _X: T, planes, num, inplanes, cnt, training=True, depth_3d=47, stride=1):
+        self.input, self.planes, self.num, self.inplanes, self.cnt = _X, planes, num, inplanes, cnt
+        self.training, self.depth_3d, self.stride = training, depth_3d, stride
+
+    def infer(self) -> T:
+        x = self.input
+        for j in range(self.num):
+            x = Bottleneck(x, self.inplanes if j == 0 else BLOCK_EXPANSION * self.planes, self.planes, self.stride,
+                           downsample="3d" if j == 0 else "", training=self.training, n_s=self.cnt, depth_3d=self.depth_3d).infer()
+            self.cnt += 1
+        self.inplanes = BLOCK_EXPANSION * self.planes
+        return x
+
+
+def _stem(_X: T, training: bool) -> T:
+    """conv 1x7x7 s(1,2,2) 3->64 (no bias) -> BN(training) -> ReLU   (p3d.py:343-345)"""
+    eng = _X.eng
+    c = eng.conv([_X], 64, (1, 7, 7), (1, 2, 2), get_conv_weight(eng, "firstconv1", [1, 7, 7, 3, 64]), name="firstconv1")
+    eng.tap("firstconv1", c.raw)
+    return eng.tap("stem", nw.bn_relu(c, training, tap="stem"))
+
+
+def _backbone(_X: T, training: bool, skip_1_0: bool = True):
+    eng = _X.eng
+    stem = _stem(_X, training)
+    t = {}
+    if skip_1_0:
+        t["x_1_0"] = eng.tap("x_1_0", eng.maxpool(stem, *TEMPORAL_POOL, name="x_1_0"))
+    x = eng.tap("pool1", eng.maxpool(stem, (2, 3, 3), (2, 2, 2), name="pool1"))
+    cnt = 0
+    for si, (planes, num, inplanes, stride) in enumerate(STAGES):
+        blk = make_block(x, planes, num, inplanes, cnt, stride=stride)
+        res = blk.infer()
+        cnt = blk.cnt
+        x = eng.tap(f"x_{si + 2}_0", eng.maxpool(res, *TEMPORAL_POOL, name=f"x_{si + 2}_0"))
+        t[f"x_{si + 2}_0"] = x
+    return t
+
+
+def _unetpp(_X: T, _dropout: float, training: bool, sa: bool):
+    eng = _X.eng
+    t = _backbone(_X, training)
+    x10, x20, x30, x40 = t["x_1_0"], t["x_2_0"], t["x_3_0"], t["x_4_0"]
+    att = (lambda h, name, **kw: eng.tap(name, nw.attention(h, name, training=training, **kw))) if sa else (lambda h, name, **kw: h)
+    x40 = att(x40, "x_4_0_sa")
+    up40 = nw.transpose_conv3d(x40, 512, [1, 3, 3], [2, 2, 2], training, "upx_4_0")
+    x31 = nw.conv3d(nw.concat([x30, up40]), 512, [2, 3, 3], [1, 1, 1], training, "x_3_1")
+    x31 = att(x31, "x_3_1_sa")
+    up30 = nw.transpose_conv3d(x30, 256, [2, 3, 3], [2, 2, 2], training, "upx_3_0")
+    x21 = nw.conv3d(nw.concat([x20, up30]), 256, [3, 3, 3], [1, 1, 1], training, "x_2_1")
+    up31 = nw.transpose_conv3d(x31, 256, [2, 3, 3], [2, 2, 2], training, "upx_3_1")
+    x22 = nw.conv3d(nw.concat([x21, up31]), 256, [3, 3, 3], [1, 1, 1], training, "x_2_2")
+    x22 = att(x22, "x_2_2_sa")
+    up20 = nw.transpose_conv3d(x20, 128, [3, 3, 3], [2, 2, 2], training, "upx_2_0")
+    x11 = nw.conv3d(nw.concat([x10, up20]), 128, [3, 3, 3], [1, 1, 1], training, "x_1_1")
+    up21 = nw.transpose_conv3d(x21, 128, [3, 3, 3], [2, 2, 2], training, "upx_2_1")
+    x12 = nw.conv3d(nw.concat([x11, up21]), 128, [3, 3, 3], [1, 1, 1], training, "x_1_2")
+    up22 = nw.transpose_conv3d(x22, 128, [3, 3, 3], [2, 2, 2], training, "upx_2_2")
+    x13 = nw.conv3d(nw.concat([x12, up22]), 128, [3, 3, 3], [1, 1, 1], training, "x_1_3")
+    x13 = att(x13, "x_1_3_sa", subsample=True)
+    if training:
+        x13 = eng.dropout(x13, _dropout, name="x_1_3_drop")
+    w = eng.param("x_0_1/kernel", [3, 3, 3, 1, x13.C], "glorot_t")
+    b = eng.param("x_0_1/bias", [1], "zeros")
+    return eng.head(x13, w, b, (3, 3, 3), 2, sigmoid=True, name="x_0_1")
+
+
+def p3d_unetplusplus_ds(_X, _dropout, batch_size=2, training=True, SA=False):
+    """p3d.py:340-399 — UNet++ decoder with self-attention at x_4_0, x_3_1, x_2_2, x_1_3 (what gen_pred.py:46 builds)."""
+    return _unetpp(_X, _dropout, training, True)
+
+
+def p3d_unetplusplus_nonsa(_X, _dropout, batch_size=2, training=True, SA=False):
+    """p3d.py:401-459 — the same decoder without the attention blocks."""
+    return _unetpp(_X, _dropout, training, False)
+
+
+def p3d_unetplusplus(_X, _dropout, batch_size=2, training=True, SA=False):
+    """p3d.py:280-338 is not buildable in the reference (shape error at p3d.py:334)."""
+    raise NotImplementedError("p3d_unetplusplus has a shape mismatch at p3d.py:334; use p3d_unetplusplus_ds")
+
+
+def p3d_unet(_X, _dropout, batch_size=2, training=True):
+    """p3d.py:169-221"""
+    eng = _X.eng
+    t = _backbone(_X, training, skip_1_0=False)
+    d1 = nw.bn_relu(nw.layers_conv3d_transpose(t["x_4_0"], 512, [1, 3, 3], [2, 2, 2]), training, name="deconv1_bn")
+    d2 = nw.bn_relu(nw.layers_conv3d_transpose(nw.concat([d1, t["x_3_0"]]), 256, [2, 3, 3], [2, 2, 2]), training, name="deconv2_bn")
+    d3 = nw.bn_relu(nw.layers_conv3d_transpose(nw.concat([d2, t["x_2_0"]]), 128, 3, [2, 2, 2]), training, name="deconv3_bn")
+    if training:
+        d3 = eng.dropout(d3, _dropout, name="deconv3_drop")
+    eng.tap("deconv3", d3)
+    c = nw.layers_conv3d(d3, 32, 1, 1, want_stats=False)
+    w = eng.param(eng.names.unique("", "conv3d_transpose") + "/kernel", [3, 3, 3, 1, 32], "glorot_t")
+    b = eng.param(w.name.rsplit("/", 1)[0] + "/bias", [1], "zeros")
+    return eng.head(c.raw, w, b, (3, 3, 3), 2, sigmoid=True, name="results")

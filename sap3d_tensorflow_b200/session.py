@@ -1,0 +1,142 @@
+"""placeholder / Session: the TF-1.x-shaped front door used by the drivers (train.py:141-217,
+gen_pred.py:45-46,151, test.py:157-160), backed by the static engine and CUDA graphs.
+
+    x = placeholder([B, 16, 112, 112, 3], dtype="bf16", training_graph=True)
+    pred = p3d.p3d_unetplusplus_ds(x, 0.5, B, True)
+    sess = Session(pred)
+    loss = sess.train_step(clips, targets)          # fwd + smooth-L1 + bwd + Adam (train.py:217)
+    sal  = sess.run(clips)                           # forward only (gen_pred.py:151)
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _abi as A
+from .engine import Engine, T
+
+
+def placeholder(shape, dtype: str = "bf16", training_graph: bool = False, conv_impl: int = A.IMPL_AUTO, device="cuda:0",
+                dropout_seed: int = 1234) -> T:
+    """tf.placeholder(tf.float32, [B, 16, H, W, 3]) (train.py:143): creates the engine and its input tensor."""
+    eng = Engine(dtype, training_graph, device, conv_impl, dropout_seed)
+    x = eng.tensor(shape, "input", needs_grad=False)
+    eng.input = x
+    eng.input_f32 = torch.zeros(tuple(shape), device=eng.device, dtype=torch.float32)
+    return x
+
+
+class Session:
+    def __init__(self, head, lr: float = 1e-4):
+        self.head = head
+        self.eng: Engine = head.eng
+        self.lr = lr
+        if not self.eng.finalized:
+            self.eng.finalize()
+        self.graph_fwd: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_train: Optional[torch.cuda.CUDAGraph] = None
+        self.grad_hook = None  # called between backward and adam (data-parallel all-reduce)
+
+    # ---- input staging ---------------------------------------------------------------------------
+    def _feed(self, x: torch.Tensor):
+        e = self.eng
+        if x.device.type != "cuda":
+            e.input_f32.copy_(x, non_blocking=True)
+        elif x.data_ptr() != e.input_f32.data_ptr():
+            e.input_f32.copy_(x)
+        self._stage_input()
+
+    def _stage_input(self):
+        e = self.eng
+        if e.dt == A.F32:
+            e.input.buf.copy_(e.input_f32)
+        else:
+            A.check(A.lib.sap3d_cast(A.F32, A.ptr(e.input_f32), A.ptr(e.input.buf), e.input_f32.numel(), e.stream), "cast input")
+
+    # ---- eager execution -------------------------------------------------------------------------
+    def forward_eager(self):
+        self._stage_input()
+        self.eng.forward()
+
+    def train_eager(self):
+        e = self.eng
+        self._stage_input()
+        e.begin_step()
+        e.forward()
+        e.backward()
+        if self.grad_hook is not None:
+            self.grad_hook(e)
+        e.adam(self.lr)
+
+    # ---- CUDA-graph capture ----------------------------------------------------------------------
+    def capture(self, train: bool):
+        """captures one forward (or one full training step) into a CUDA graph; run it once eagerly first so
+        lazily-allocated gradient buffers exist."""
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            if train:
+                if self.grad_hook is not None:
+                    raise A.Sap3dError("graph capture with a gradient hook is not supported; use train_step(graph=False)")
+                # warm-up step must not disturb the optimiser state: snapshot and restore
+                e = self.eng
+                snap = (e.flat_w.clone(), e.flat_m.clone(), e.flat_v.clone(), e.step.clone())
+                self.train_eager()
+                torch.cuda.synchronize()
+                e.flat_w.copy_(snap[0]); e.flat_m.copy_(snap[1]); e.flat_v.copy_(snap[2]); e.step.copy_(snap[3])
+                e.pack_weights()
+            else:
+                self.forward_eager()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            if train:
+                self.train_eager()
+            else:
+                self.forward_eager()
+        if train:
+            self.graph_train = g
+        else:
+            self.graph_fwd = g
+        torch.cuda.synchronize()
+
+    # ---- public API ------------------------------------------------------------------------------
+    def run(self, x: torch.Tensor, graph: bool = False) -> torch.Tensor:
+        """forward pass; returns the [B,16,H,W,1] fp32 saliency tensor (device)."""
+        self._feed(x)
+        if graph:
+            if self.graph_fwd is None:
+                self.capture(train=False)
+            self.graph_fwd.replay()
+        else:
+            self.eng.forward()
+        return self.head.output
+
+    def train_step(self, x: torch.Tensor, y: torch.Tensor, graph: bool = False) -> torch.Tensor:
+        """one iteration of train.py:217: returns the (device, fp64) loss scalar tensor."""
+        e = self.eng
+        if x.device.type != "cuda":
+            e.input_f32.copy_(x, non_blocking=True)
+        elif x.data_ptr() != e.input_f32.data_ptr():
+            e.input_f32.copy_(x)
+        self.head.target.copy_(y.reshape(self.head.target.shape), non_blocking=True)
+        if graph:
+            if self.graph_train is None:
+                self.capture(train=True)
+            self.graph_train.replay()
+        else:
+            self.train_eager()
+        return e.loss_buf
+
+    def tap(self, name: str) -> torch.Tensor:
+        return self.eng.taps[name].buf
+
+    def variables(self) -> Dict[str, torch.Tensor]:
+        return {n: p.w for n, p in self.eng.params.items()}
+
+    def gradients(self) -> Dict[str, torch.Tensor]:
+        return {n: p.g for n, p in self.eng.params.items() if p.trainable}
