@@ -74,6 +74,8 @@ class VarStore:
             v = self.rng.normal(0, 0.05, size=shape)
         elif kind == "gamma":
             v = self.rng.uniform(0.5, 1.5, size=shape)
+        elif kind == "gamma_res":  # last BN of a residual branch: small, as in trained / zero-init-residual ResNets,
+            v = self.rng.uniform(0.1, 0.3, size=shape)  # keeps the 47-block chain well conditioned
         elif kind == "beta":
             v = self.rng.normal(0, 0.1, size=shape)
         elif kind == "mean":
@@ -110,11 +112,11 @@ class Ctx:
 # ------------------------------------------------------------------------------------------------
 # layer helpers
 # ------------------------------------------------------------------------------------------------
-def bn(ctx: Ctx, x, training: bool, name: Optional[str] = None, scope: str = ""):
+def bn(ctx: Ctx, x, training: bool, name: Optional[str] = None, scope: str = "", gamma_kind: str = "gamma"):
     """tf.layers.batch_normalization (auto-named batch_normalization[_N] unless `name`)."""
     nm = name if name is not None else ctx.vs.unique(scope, "batch_normalization")
     c = x.shape[-1]
-    g = ctx.vs.get(nm + "/gamma", [c], "gamma")
+    g = ctx.vs.get(nm + "/gamma", [c], gamma_kind)
     b = ctx.vs.get(nm + "/beta", [c], "beta")
     mm = ctx.vs.get(nm + "/moving_mean", [c], "mean", trainable=False)
     mv = ctx.vs.get(nm + "/moving_variance", [c], "var", trainable=False)
@@ -125,12 +127,12 @@ def bn(ctx: Ctx, x, training: bool, name: Optional[str] = None, scope: str = "")
     return y
 
 
-def gn_layer(ctx: Ctx, x, scope: str = ""):
+def gn_layer(ctx: Ctx, x, scope: str = "", gamma_kind: str = "gamma"):
     """GroupNorm (network.py:65-87): tf.Variable gamma/beta inside variable_scope('group_norm') —
     tf.Variable names are uniquified per graph: group_norm/gamma, group_norm_1/gamma, ..."""
     nm = ctx.vs.unique(scope, "group_norm")
     c = x.shape[-1]
-    g = ctx.vs.get(nm + "/gamma", [c], "gamma")
+    g = ctx.vs.get(nm + "/gamma", [c], gamma_kind)
     b = ctx.vs.get(nm + "/beta", [c], "beta")
     return tfs.group_norm(x, g, b)
 
@@ -243,7 +245,7 @@ def bottleneck(ctx: Ctx, x, inplanes, planes, idx, first_of_stage, mode):
     """Bottleneck.infer for n_s < depth_3d (the 2-D branches are dead code: 47 blocks == depth_3d)."""
     tr = ctx.backbone_training
     stride_hw = 2 if (first_of_stage and idx != 0) else 1  # p3d.py:45-49
-    nrm = (lambda t: bn(ctx, t, tr)) if mode == "bn" else (lambda t: gn_layer(ctx, t))
+    nrm = (lambda t, gk="gamma": bn(ctx, t, tr, gamma_kind=gk)) if mode == "bn" else (lambda t, gk="gamma": gn_layer(ctx, t, gamma_kind=gk))
     residual = x
     out = tfs.conv3d_same(x, conv_w(ctx, f"conv3_{idx}_1", [1, 1, 1, inplanes, planes]), (1, stride_hw, stride_hw))
     out = torch.relu(nrm(out))
@@ -260,7 +262,7 @@ def bottleneck(ctx: Ctx, x, inplanes, planes, idx, first_of_stage, mode):
         s_br = torch.relu(nrm(convS(ctx, nm + "_S", out, planes, planes)))
         t_br = torch.relu(nrm(convT(ctx, nm + "_T", s_br, planes, planes)))
         out = s_br + t_br
-    out = nrm(tfs.conv3d_same(out, conv_w(ctx, f"conv3_{idx}_3", [1, 1, 1, planes, planes * BLOCK_EXPANSION])))
+    out = nrm(tfs.conv3d_same(out, conv_w(ctx, f"conv3_{idx}_3", [1, 1, 1, planes, planes * BLOCK_EXPANSION])), "gamma_res")
     if first_of_stage:  # downsample=['3d', stride_p] (p3d.py:149-155,124-127)
         residual = tfs.conv3d_same(residual, conv_w(ctx, f"dw3d_{idx}", [1, 1, 1, inplanes, planes * BLOCK_EXPANSION]),
                                    (1, stride_hw, stride_hw))

@@ -38,6 +38,7 @@ class Session:
         self.graph_fwd: Optional[torch.cuda.CUDAGraph] = None
         self.graph_train: Optional[torch.cuda.CUDAGraph] = None
         self.grad_hook = None  # called between backward and adam (data-parallel all-reduce)
+        self.grad_scale = 1.0
 
     # ---- input staging ---------------------------------------------------------------------------
     def _feed(self, x: torch.Tensor):
@@ -60,31 +61,36 @@ class Session:
         self._stage_input()
         self.eng.forward()
 
-    def train_eager(self):
+    def _train_front(self):
         e = self.eng
         self._stage_input()
         e.begin_step()
         e.forward()
         e.backward()
+
+    def _train_back(self):
+        self.eng.adam(self.lr, grad_scale=self.grad_scale)
+
+    def train_eager(self):
+        self._train_front()
         if self.grad_hook is not None:
-            self.grad_hook(e)
-        e.adam(self.lr)
+            self.grad_hook(self.eng)
+        self._train_back()
 
     # ---- CUDA-graph capture ----------------------------------------------------------------------
     def capture(self, train: bool):
-        """captures one forward (or one full training step) into a CUDA graph; run it once eagerly first so
-        lazily-allocated gradient buffers exist."""
+        """captures one forward, or one training step as two graphs (fwd+bwd | optimizer) so that the
+        data-parallel gradient exchange can run between them.  One eager run first so lazily-allocated
+        gradient buffers exist; the optimiser state is snapshotted around it."""
         torch.cuda.synchronize()
+        e = self.eng
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             if train:
-                if self.grad_hook is not None:
-                    raise A.Sap3dError("graph capture with a gradient hook is not supported; use train_step(graph=False)")
-                # warm-up step must not disturb the optimiser state: snapshot and restore
-                e = self.eng
                 snap = (e.flat_w.clone(), e.flat_m.clone(), e.flat_v.clone(), e.step.clone())
-                self.train_eager()
+                self._train_front()
+                self._train_back()
                 torch.cuda.synchronize()
                 e.flat_w.copy_(snap[0]); e.flat_m.copy_(snap[1]); e.flat_v.copy_(snap[2]); e.step.copy_(snap[3])
                 e.pack_weights()
@@ -92,15 +98,17 @@ class Session:
                 self.forward_eager()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            if train:
-                self.train_eager()
-            else:
-                self.forward_eager()
         if train:
-            self.graph_train = g
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._train_front()
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                self._train_back()
+            self.graph_train = (ga, gb)
         else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.forward_eager()
             self.graph_fwd = g
         torch.cuda.synchronize()
 
@@ -127,7 +135,10 @@ class Session:
         if graph:
             if self.graph_train is None:
                 self.capture(train=True)
-            self.graph_train.replay()
+            self.graph_train[0].replay()
+            if self.grad_hook is not None:
+                self.grad_hook(e)
+            self.graph_train[1].replay()
         else:
             self.train_eager()
         return e.loss_buf

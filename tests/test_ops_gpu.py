@@ -1,0 +1,182 @@
+"""Op-level parity of the CUDA kernels (through the C ABI) against the torch oracle primitives."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tf_semantics as tfs  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def A(lib_built):
+    from sap3d_tensorflow_b200 import _abi
+
+    assert _abi.lib.sap3d_device_ok() == 1, _abi.lib.sap3d_last_error()
+    return _abi
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+DT = [("f32", torch.float32, 2e-5), ("bf16", torch.bfloat16, 1.5e-2)]
+
+
+def _stats(x):
+    xf = x.float().reshape(-1, x.shape[-1])
+    return torch.stack([xf.sum(0), (xf * xf).sum(0)], 0).reshape(1, 2, -1).contiguous()
+
+
+@pytest.mark.parametrize("dtn,tdt,tol", DT)
+@pytest.mark.parametrize("pattern", ["relu_bn", "bn_plus_relu_bn", "act_plus_relu_bn", "relu_bn_plus_t", "relu_bn_plus_bn"])
+def test_affine_act_fwd_bwd(A, dtn, tdt, tol, pattern):
+    torch.manual_seed(0)
+    dev = "cuda"
+    dt = A.BF16 if dtn == "bf16" else A.F32
+    N, D, H, W, Cc = 2, 3, 5, 6, 64
+    P = N * D * H * W
+    a = (torch.randn(N, D, H, W, Cc, device=dev) * 1.5 + 0.7).to(tdt)
+    b = (torch.randn(N, D, H, W, Cc, device=dev) * 0.8 - 0.2).to(tdt)
+    g1, b1 = torch.rand(Cc, device=dev) + 0.5, torch.randn(Cc, device=dev) * 0.1
+    g2, b2 = torch.rand(Cc, device=dev) + 0.5, torch.randn(Cc, device=dev) * 0.1
+    dy = torch.randn(N, D, H, W, Cc, device=dev).to(tdt)
+    relu1, relu2, relu_out, use_b, bn2 = {
+        "relu_bn": (1, 0, 0, False, False),
+        "bn_plus_relu_bn": (1, 1, 0, True, True),       # ST_B
+        "act_plus_relu_bn": (1, 0, 0, True, False),     # ST_C
+        "relu_bn_plus_t": (0, 0, 1, True, False),       # identity shortcut
+        "relu_bn_plus_bn": (0, 0, 1, True, True),       # projection shortcut
+    }[pattern]
+    f = lambda: torch.empty(Cc, device=dev)  # noqa: E731
+    s1, t1, m1, r1, s2, t2, m2, r2 = f(), f(), f(), f(), f(), f(), f(), f()
+    mm, mv = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    sa = _stats(a)
+    A.check(A.lib.sap3d_bn_finalize(A.ptr(sa), 1, Cc, float(P), A.ptr(g1), A.ptr(b1), A.ptr(mm), A.ptr(mv), 1, 0.99, 1e-3,
+                                    A.ptr(s1), A.ptr(t1), A.ptr(m1), A.ptr(r1), stream()), "fin1")
+    if bn2:
+        sb = _stats(b)
+        A.check(A.lib.sap3d_bn_finalize(A.ptr(sb), 1, Cc, float(P), A.ptr(g2), A.ptr(b2), A.ptr(mm), A.ptr(mv), 1, 0.99, 1e-3,
+                                        A.ptr(s2), A.ptr(t2), A.ptr(m2), A.ptr(r2), stream()), "fin2")
+    y = torch.empty_like(a)
+    A.check(A.lib.sap3d_affine_act(dt, A.ptr(a), A.ptr(s1), A.ptr(t1), relu1, A.ptr(b) if use_b else None,
+                                   A.ptr(s2) if bn2 else None, A.ptr(t2) if bn2 else None, relu2, relu_out, A.ptr(y), P, Cc, 0,
+                                   stream()), "apply")
+    # oracle
+    af, bf = a.float().requires_grad_(True), b.float().requires_grad_(True)
+    g1r, b1r, g2r, b2r = [t.clone().requires_grad_(True) for t in (g1, b1, g2, b2)]
+    z1, _, _ = tfs.batch_norm(af, g1r, b1r, mm, mv, True)
+    z1 = torch.relu(z1) if relu1 else z1
+    if use_b:
+        z2 = tfs.batch_norm(bf, g2r, b2r, mm, mv, True)[0] if bn2 else bf
+        z2 = torch.relu(z2) if relu2 else z2
+        z1 = z1 + z2
+    ref = torch.relu(z1) if relu_out else z1
+    assert rel(y, ref) < tol
+    ref.backward(dy.float())
+    da, db = torch.empty_like(a), torch.empty_like(b)
+    dg1, db1, dg2, db2 = [torch.zeros(Cc, device=dev) for _ in range(4)]
+    ws = torch.zeros(A.lib.sap3d_affine_act_bwd_workspace(Cc) // 4 + 16, device=dev)
+    A.check(A.lib.sap3d_affine_act_bwd(dt, A.ptr(dy), A.ptr(a), A.ptr(s1), A.ptr(t1), A.ptr(m1), A.ptr(r1), relu1,
+                                       A.ptr(b) if use_b else None, A.ptr(s2) if bn2 else None, A.ptr(t2) if bn2 else None,
+                                       A.ptr(m2) if bn2 else None, A.ptr(r2) if bn2 else None, relu2, relu_out, P, Cc,
+                                       A.ptr(da), 0, A.ptr(db) if use_b else None, 0, A.ptr(dg1), A.ptr(db1),
+                                       A.ptr(dg2) if bn2 else None, A.ptr(db2) if bn2 else None, A.ptr(ws), stream()), "bwd")
+    torch.cuda.synchronize()
+    assert rel(da, af.grad) < 3 * tol
+    assert rel(dg1, g1r.grad) < 3 * tol and rel(db1, b1r.grad) < 3 * tol
+    if use_b:
+        assert rel(db, bf.grad) < 3 * tol
+    if bn2:
+        assert rel(dg2, g2r.grad) < 3 * tol and rel(db2, b2r.grad) < 3 * tol
+
+
+@pytest.mark.parametrize("dtn,tdt,tol", DT)
+@pytest.mark.parametrize("k,s,same", [((2, 1, 1), (2, 1, 1), 1), ((2, 3, 3), (2, 2, 2), 1), ((2, 2, 2), (2, 2, 2), 0)])
+def test_maxpool(A, dtn, tdt, tol, k, s, same):
+    torch.manual_seed(1)
+    dt = A.BF16 if dtn == "bf16" else A.F32
+    N, D, H, W, Cc = 2, 4, 9, 10, 16
+    x = torch.randn(N, D, H, W, Cc, device="cuda").to(tdt)
+    xr = x.float().requires_grad_(True)
+    ref = tfs.max_pool3d_same(xr, k, s) if same else tfs.max_pool3d_valid(xr, 2)
+    y = torch.empty(ref.shape, device="cuda", dtype=tdt)
+    A.check(A.lib.sap3d_maxpool3d_fwd(dt, A.ptr(x), N, D, H, W, Cc, A.i3(k), A.i3(s), same, A.ptr(y), stream()), "pool")
+    assert rel(y, ref) == 0.0
+    dy = torch.randn_like(ref).to(tdt)
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    A.check(A.lib.sap3d_maxpool3d_bwd(dt, A.ptr(x), A.ptr(dy), N, D, H, W, Cc, A.i3(k), A.i3(s), same, A.ptr(dx), 0, stream()), "poolb")
+    torch.cuda.synchronize()
+    assert rel(dx, xr.grad) < tol
+
+
+@pytest.mark.parametrize("dtn,tdt,tol", DT)
+def test_head_loss(A, dtn, tdt, tol):
+    torch.manual_seed(2)
+    dt = A.BF16 if dtn == "bf16" else A.F32
+    N, D, H, W, Cc = 2, 3, 5, 6, 128
+    x = torch.randn(N, D, H, W, Cc, device="cuda").to(tdt)
+    w = torch.randn(3, 3, 3, 1, Cc, device="cuda") * 0.05
+    b = torch.randn(1, device="cuda")
+    tgt = torch.rand(N, 2 * D, 2 * H, 2 * W, device="cuda")
+    logits = torch.empty(N, 2 * D, 2 * H, 2 * W, 1, device="cuda")
+    pred = torch.empty_like(logits)
+    A.check(A.lib.sap3d_head_fwd(dt, A.ptr(x), N, D, H, W, Cc, A.i3((3, 3, 3)), 2, A.ptr(w), A.ptr(b), A.ptr(logits), A.ptr(pred),
+                                 stream()), "head")
+    xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    lref = tfs.conv3d_transpose_same(xr, wr, (2, 2, 2), br)
+    pref = torch.sigmoid(lref)
+    assert rel(logits, lref) < tol and rel(pred, pref) < tol
+    loss_ref = tfs.smooth_l1_loss(pref.reshape(tgt.shape), tgt)
+    loss_ref.backward()
+    dlog = torch.empty_like(logits)
+    loss = torch.zeros(1, device="cuda", dtype=torch.float64)
+    dbias = torch.zeros(1, device="cuda")
+    A.check(A.lib.sap3d_loss_smooth_l1(A.ptr(logits), A.ptr(tgt), logits.numel(), 1, None, A.ptr(dlog), A.ptr(loss), A.ptr(dbias),
+                                       stream()), "loss")
+    dx = torch.empty_like(x)
+    dw = torch.zeros_like(w)
+    A.check(A.lib.sap3d_head_bwd(dt, A.ptr(dlog), A.ptr(x), N, D, H, W, Cc, A.i3((3, 3, 3)), 2, A.ptr(w), A.ptr(dx), 0, A.ptr(dw),
+                                 stream()), "headb")
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 1e-4 if dtn == "f32" else 5e-3
+    assert rel(dx, xr.grad) < 3 * tol
+    assert rel(dw, wr.grad) < 3 * tol
+    assert rel(dbias, br.grad) < 3 * tol
+
+
+def test_adam_tf_formula(A):
+    torch.manual_seed(3)
+    n = 1000
+    w, g = torch.randn(n, device="cuda"), torch.randn(n, device="cuda")
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.zeros(1, device="cuda", dtype=torch.int32)
+    wr, mr, vr = w.clone(), m.clone(), v.clone()
+    for t in (1, 2, 3):
+        A.check(A.lib.sap3d_step_increment(A.ptr(step), stream()), "inc")
+        A.check(A.lib.sap3d_adam_step(A.ptr(w), A.ptr(g), A.ptr(m), A.ptr(v), n, A.ptr(step), 1e-4, 0.9, 0.999, 1e-8, 1.0, stream()), "adam")
+        wr, mr, vr = tfs.adam_step_tf(wr, g, mr, vr, t)
+    torch.cuda.synchronize()
+    assert rel(w, wr) < 1e-6 and rel(m, mr) < 1e-6 and rel(v, vr) < 1e-6
+
+
+def test_dropout_matches_numpy_hash(A):
+    import numpy as np
+
+    n = 4096
+    x = torch.ones(n, device="cuda")
+    y = torch.empty_like(x)
+    step = torch.full((1,), 5, device="cuda", dtype=torch.int32)
+    A.check(A.lib.sap3d_dropout(A.F32, A.ptr(x), A.ptr(y), n, 0.5, 1234, A.ptr(step), 0, stream()), "dropout")
+    torch.cuda.synchronize()
+    from oracle.dropout_hash import keep_mask
+
+    ref = keep_mask(1234 + 5, n, 0.5).astype(np.float32) * 2.0
+    assert np.array_equal(y.cpu().numpy(), ref)

@@ -77,6 +77,22 @@ def main():
                 sess.eng.load_params(vs.params, strict=False)
                 loss = sess.train_step(x.cuda(), y.cuda())
                 torch.cuda.synchronize()
+                if dtype == "f32":
+                    # activation-gradient comparison (localises backward bugs)
+                    vs3 = O.VarStore(seed=0, params={k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in vs.params.items()})
+                    taps3 = {}
+                    pr3 = O.forward(graph, x, vs3, True, taps=taps3)
+                    for t in taps3.values():
+                        if t.requires_grad:
+                            t.retain_grad()
+                    O.tfs.smooth_l1_loss(pr3.reshape(y.shape), y).backward()
+                    for name in reversed(list(taps3.keys())):
+                        t = taps3[name]
+                        et = sess.eng.taps.get(name)
+                        if t.grad is None or et is None or et.grad is None:
+                            continue
+                        r, m = relerr(et.grad, t.grad)
+                        print(f"    dtap {name:12s} rel={r:.2e} max={m:.2e} gflag={et.gflag}", flush=True)
                 lv = float(loss.item())
                 print(f"  [{mode}/{dtype}] loss={lv:.4f} ref={loss_ref:.4f} rel={(lv - loss_ref) / loss_ref:.2e} bwd launches={sess.eng.launches_bwd}", flush=True)
                 gtol = 5e-3 if dtype == "f32" else 1e-1
