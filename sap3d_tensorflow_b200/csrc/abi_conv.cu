@@ -497,7 +497,100 @@ int sap3d_conv_wgrad(const sap3d_conv_desc* d, const void* x0, const void* x1, c
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   char err[512];
   const void* xs[2] = {x0, x1};
+  const bool use_tc = tc_dgrad_eligible(d);  // same constraints: bf16, channels % 64, <= 10 parity views
   for (int s = 0; s < d->nseg; ++s) {
+    if (use_tc) {
+      TcWgradProblem pb;
+      long long so[4], si[4];
+      out_strides(g, d->cout, so);
+      in_strides(g, d->cin[s], si);
+      if (!d->transposed) {
+        TcView pv;
+        pv.base = xs[s];
+        pv.C = d->cin[s];
+        for (int i = 0; i < 3; ++i) {
+          const DimGeom& dg = g.d[2 - i];
+          pv.dim[i] = (dg.s == 1) ? dg.I : dg.O;
+          pv.stride[i] = si[i] * dg.s;
+        }
+        pv.dim[3] = d->N;
+        pv.stride[3] = si[3];
+        pb.pviews.push_back(pv);
+        pb.q.base = dy;
+        pb.q.C = d->cout;
+        for (int i = 0; i < 3; ++i) {
+          pb.q.dim[i] = g.d[2 - i].O;
+          pb.q.stride[i] = so[i];
+        }
+        pb.q.dim[3] = d->N;
+        pb.q.stride[3] = so[3];
+        pb.ext[0] = g.d[2].O; pb.ext[1] = g.d[1].O; pb.ext[2] = g.d[0].O; pb.ext[3] = d->N;
+        for (int kd = 0; kd < d->kd; ++kd)
+          for (int kh = 0; kh < d->kh; ++kh)
+            for (int kw = 0; kw < d->kw; ++kw) {
+              TcWgradTap t;
+              t.view = 0;
+              t.off[0] = (g.d[2].s == 1) ? kw - g.d[2].pb : 0;
+              t.off[1] = (g.d[1].s == 1) ? kh - g.d[1].pb : 0;
+              t.off[2] = (g.d[0].s == 1) ? kd - g.d[0].pb : 0;
+              t.off[3] = 0;
+              t.dw_ofs = (long long)((kd * d->kh + kh) * d->kw + kw) * g.cin_total * d->cout + (long long)g.seg_off[s] * d->cout;
+              pb.taps.push_back(t);
+            }
+        pb.M = d->cin[s];
+        pb.N = d->cout;
+        pb.ldw = d->cout;
+      } else {
+        std::map<int, int> view_of;
+        for (int kd = 0; kd < d->kd; ++kd)
+          for (int kh = 0; kh < d->kh; ++kh)
+            for (int kw = 0; kw < d->kw; ++kw) {
+              const int kk[3] = {kd, kh, kw};
+              int r[3], q[3];
+              for (int i = 0; i < 3; ++i) {
+                const int e = kk[i] - g.d[i].pb;
+                q[i] = floordiv(e, g.d[i].s);
+                r[i] = e - q[i] * g.d[i].s;
+              }
+              const int key = (r[0] * 16 + r[1]) * 16 + r[2];
+              if (view_of.find(key) == view_of.end()) {
+                TcView v;
+                v.base = reinterpret_cast<const char*>(dy) + (size_t)(r[0] * so[2] + r[1] * so[1] + r[2] * so[0]) * 2;
+                v.C = d->cout;
+                for (int i = 0; i < 3; ++i) {
+                  const DimGeom& dg = g.d[2 - i];
+                  v.dim[i] = (dg.O - r[2 - i] + dg.s - 1) / dg.s;
+                  v.stride[i] = so[i] * dg.s;
+                }
+                v.dim[3] = d->N;
+                v.stride[3] = so[3];
+                view_of[key] = (int)pb.pviews.size();
+                pb.pviews.push_back(v);
+              }
+              TcWgradTap t;
+              t.view = view_of[key];
+              t.off[0] = q[2]; t.off[1] = q[1]; t.off[2] = q[0]; t.off[3] = 0;
+              t.dw_ofs = (long long)((kd * d->kh + kh) * d->kw + kw) * g.cin_total * d->cout + g.seg_off[s];
+              pb.taps.push_back(t);
+            }
+        pb.q.base = xs[s];
+        pb.q.C = d->cin[s];
+        for (int i = 0; i < 3; ++i) {
+          pb.q.dim[i] = g.d[2 - i].I;
+          pb.q.stride[i] = si[i];
+        }
+        pb.q.dim[3] = d->N;
+        pb.q.stride[3] = si[3];
+        pb.ext[0] = g.d[2].I; pb.ext[1] = g.d[1].I; pb.ext[2] = g.d[0].I; pb.ext[3] = d->N;
+        pb.M = d->cout;
+        pb.N = d->cin[s];
+        pb.ldw = g.cin_total;
+      }
+      pb.p_c_begin = 0;
+      pb.dw = dw;
+      if (tc_wgrad_launch(pb, st, err, sizeof(err))) return set_error("%s", err);
+      continue;
+    }
     SimtWgradGeom wg;
     memset(&wg, 0, sizeof(wg));
     wg.N = d->N;

@@ -106,6 +106,25 @@ def run_case(name, N, D, H, W, cin, cout, k, s, transposed=False, bias=True, imp
         pos = N * D * H * W if transposed else N * Do * Ho * Wo
         fl = 2.0 * pos * taps * cin_t * cout
         line += f" | {ms:.3f} ms {fl / ms / 1e9:.1f} TFLOP/s"
+        dy = torch.randn_like(y)
+        dw = torch.zeros_like(w)
+        dxs = [torch.empty_like(t) for t in xs]
+        for what in ("dgrad", "wgrad"):
+            def run():
+                if what == "dgrad":
+                    for si in range(len(cin)):
+                        A.lib.sap3d_conv_dgrad(C.byref(d), si, A.ptr(dy), A.ptr(w), A.ptr(wd), A.ptr(dxs[si]), 0, stream)
+                else:
+                    A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(x1), A.ptr(dy), A.ptr(dw), None, stream)
+            for _ in range(2):
+                run()
+            e0.record()
+            for _ in range(5):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            line += f" | {what} {ms:.3f} ms {fl / ms / 1e9:.1f} TF/s"
     print(("PASS " if ok else "FAIL ") + line, flush=True)
     return ok
 
