@@ -155,6 +155,33 @@ int sap3d_dropout(int32_t dtype, const void* x, void* y, int64_t n, float rate, 
 int sap3d_gate_fwd(int32_t dtype, const void* o, const void* x, const float* gamma, void* y, int64_t n, void* stream);
 int sap3d_gate_bwd(int32_t dtype, const void* dy, const void* o, const float* gamma, void* d_o, void* dx, int32_t acc_x,
                    float* dgamma, int64_t n, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Self-attention core (utils/network.py:184-186: tf.matmul, tf.nn.softmax, tf.matmul) and the GEMM /
+ * softmax / transpose pieces used to run it on the tensor cores.
+ * ---------------------------------------------------------------------------------------------- */
+/* generic CUDA-core path: beta[b] = softmax(g[b] f[b]^T) ([B][Nq][ldb], zero padded), o[b] = beta[b] h[b] */
+int sap3d_attention_fwd(int32_t dtype, const void* g, const void* f, const void* h, void* beta, void* o, int32_t B, int32_t Nq,
+                        int32_t Nk, int32_t dk, int32_t dv, int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldb, int32_t ldo,
+                        void* stream);
+int sap3d_attention_bwd(int32_t dtype, const void* g, const void* f, const void* h, const void* beta, const void* d_o, void* ds,
+                        void* dg, void* df, void* dh, int32_t B, int32_t Nq, int32_t Nk, int32_t dk, int32_t dv, int32_t ldq,
+                        int32_t ldk, int32_t ldv, int32_t ldb, int32_t ldo, void* stream);
+/* bf16 tensor-core GEMMs: C[M][N] (+)= A[M][K] B[N][K]^T  (K % 64 == 0, ldb == K, N % 64 == 0) */
+int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t M, int32_t N,
+                  int32_t K, int32_t out_f32, int32_t accumulate, void* stream);
+/* D[M][N] (fp32) += sum_pos P[pos][m] Q[pos][n]  (M, N % 64 == 0); the caller zeroes D */
+int sap3d_gemm_tn(const void* P, int64_t ldp, const void* Q, int64_t ldq, float* D, int64_t ldd, int32_t M, int32_t N,
+                  int32_t Kpos, void* stream);
+int sap3d_softmax_rows(int32_t in_dtype, const void* logits, void* probs_bf16, int64_t rows, int32_t cols, int32_t ld_in,
+                       int32_t ld_out, void* stream);
+/* dbeta <- beta * (dbeta - rowsum(dbeta * beta)), bf16 in place */
+int sap3d_softmax_bwd_rows(const void* beta_bf16, void* dbeta_bf16, int64_t rows, int32_t cols, int32_t ld, void* stream);
+int sap3d_transpose(int32_t dtype, const void* in, void* out, int32_t batch, int32_t R, int32_t C, int32_t ld_in, int32_t ld_out,
+                    int64_t bs_in, int64_t bs_out, void* stream);
+/* [P][c] -> [P][c_pad] zero padded (unpad == 0) or back (unpad != 0, optionally accumulating) */
+int sap3d_pad_channels(int32_t dtype, const void* in, void* out, int64_t P, int32_t c, int32_t c_pad, int32_t unpad,
+                       int32_t accumulate, void* stream);
+
 /* tf.train.AdamOptimizer (train.py:168) over flat fp32 arrays; *step (device) is the 1-based iteration. */
 int sap3d_adam_step(float* w, const float* g, float* m, float* v, int64_t n, const int32_t* step, float lr, float b1, float b2,
                     float eps, float grad_scale, void* stream);

@@ -121,6 +121,15 @@ _sig("sap3d_gate_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp])
 _sig("sap3d_adam_step", [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp])
 _sig("sap3d_step_increment", [_vp, _vp])
 _sig("sap3d_cast", [_i32, _vp, _vp, _i64, _vp])
+_i32x = _i32
+_sig("sap3d_attention_fwd", [_i32, _vp, _vp, _vp, _vp, _vp] + [_i32] * 10 + [_vp])
+_sig("sap3d_attention_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 10 + [_vp])
+_sig("sap3d_gemm_nt", [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp])
+_sig("sap3d_gemm_tn", [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp])
+_sig("sap3d_softmax_rows", [_i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp])
+_sig("sap3d_softmax_bwd_rows", [_vp, _vp, _i64, _i32, _i32, _vp])
+_sig("sap3d_transpose", [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp])
+_sig("sap3d_pad_channels", [_i32, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp])
 
 
 def i3(v):

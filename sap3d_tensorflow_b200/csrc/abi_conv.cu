@@ -617,3 +617,78 @@ int sap3d_conv_wgrad(const sap3d_conv_desc* d, const void* x0, const void* x1, c
 }
 
 }  // extern "C"
+
+// ---- plain GEMMs on the same tensor-core kernels (attention matmuls, utils/network.py:184,186) ----
+extern "C" {
+
+int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* Cout, int64_t ldc, int32_t M, int32_t N,
+                  int32_t K, int32_t out_f32, int32_t accumulate, void* stream) {
+  if (require_device()) return 1;
+  if (!A || !B || !Cout) return set_error("gemm_nt: NULL pointer");
+  if (K % 64 != 0 || ldb != K || N % 64 != 0 || lda % 8 != 0 || ldc % 8 != 0)
+    return set_error("gemm_nt: need K %% 64 == 0, ldb == K, N %% 64 == 0, lda/ldc %% 8 == 0 (M=%d N=%d K=%d lda=%lld ldb=%lld)", M, N, K,
+                     (long long)lda, (long long)ldb);
+  TcProblem pb;
+  TcView v;
+  v.base = A;
+  v.C = K;
+  v.dim[0] = M; v.dim[1] = 1; v.dim[2] = 1; v.dim[3] = 1;
+  v.stride[0] = lda; v.stride[1] = 0; v.stride[2] = 0; v.stride[3] = 0;
+  pb.views.push_back(v);
+  TcClassH cls;
+  cls.out_ofs = 0;
+  TcTapH t;
+  t.view = 0;
+  t.off[0] = t.off[1] = t.off[2] = t.off[3] = 0;
+  t.kofs = 0;
+  t.c_begin = 0;
+  t.nch = K;
+  cls.taps.push_back(t);
+  pb.classes.push_back(cls);
+  pb.ext[0] = M; pb.ext[1] = 1; pb.ext[2] = 1; pb.ext[3] = 1;
+  pb.so[0] = ldc; pb.so[1] = 0; pb.so[2] = 0; pb.so[3] = 0;
+  pb.B = B;
+  pb.Ktot = K;
+  pb.rowsB = N;
+  pb.cout = N;
+  pb.out = Cout;
+  pb.bias = nullptr; pb.stats = nullptr; pb.scale = nullptr; pb.shift = nullptr;
+  pb.relu = 0; pb.accumulate = accumulate; pb.out_f32 = out_f32; pb.force_block_n = 0;
+  char err[512];
+  if (tc_launch(pb, reinterpret_cast<cudaStream_t>(stream), err, sizeof(err))) return set_error("%s", err);
+  return 0;
+}
+
+int sap3d_gemm_tn(const void* P, int64_t ldp, const void* Q, int64_t ldq, float* D, int64_t ldd, int32_t M, int32_t N,
+                  int32_t Kpos, void* stream) {
+  if (require_device()) return 1;
+  if (!P || !Q || !D) return set_error("gemm_tn: NULL pointer");
+  if (M % 64 != 0 || N % 64 != 0 || ldp % 8 != 0 || ldq % 8 != 0) return set_error("gemm_tn: M, N %% 64 and ldp, ldq %% 8 required");
+  TcWgradProblem pb;
+  TcView pv;
+  pv.base = P;
+  pv.C = M;
+  pv.dim[0] = Kpos; pv.dim[1] = 1; pv.dim[2] = 1; pv.dim[3] = 1;
+  pv.stride[0] = ldp; pv.stride[1] = 0; pv.stride[2] = 0; pv.stride[3] = 0;
+  pb.pviews.push_back(pv);
+  pb.q = pv;
+  pb.q.base = Q;
+  pb.q.C = N;
+  pb.q.stride[0] = ldq;
+  TcWgradTap t;
+  t.view = 0;
+  t.off[0] = t.off[1] = t.off[2] = t.off[3] = 0;
+  t.dw_ofs = 0;
+  pb.taps.push_back(t);
+  pb.ext[0] = Kpos; pb.ext[1] = 1; pb.ext[2] = 1; pb.ext[3] = 1;
+  pb.M = M;
+  pb.N = N;
+  pb.p_c_begin = 0;
+  pb.ldw = ldd;
+  pb.dw = D;
+  char err[512];
+  if (tc_wgrad_launch(pb, reinterpret_cast<cudaStream_t>(stream), err, sizeof(err))) return set_error("%s", err);
+  return 0;
+}
+
+}  // extern "C"

@@ -511,3 +511,38 @@ int sap3d_cast(int32_t src_dtype, const void* src, void* dst, int64_t n, void* s
 }
 
 }  // extern "C"
+
+// ---- channel pad / unpad: [P][c] <-> [P][c_pad] (zero padded), used to give the attention f/g
+// projections (C/8 = 16 or 32 channels) the 64-channel rows the tensor-core GEMM needs -------------
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) pad_channels_kernel(const T* __restrict__ in, T* __restrict__ out, long long P, int c, int cp,
+                                                            int unpad, int accumulate) {
+  const long long total = P * (unpad ? c : cp);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (!unpad) {
+      const long long pos = i / cp;
+      const int ch = (int)(i - pos * cp);
+      out[i] = ch < c ? in[pos * c + ch] : from_f32<T>(0.f);
+    } else {
+      const long long pos = i / c;
+      const int ch = (int)(i - pos * c);
+      float v = to_f32<T>(in[pos * cp + ch]);
+      if (accumulate) v += to_f32<T>(out[i]);
+      out[i] = from_f32<T>(v);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int sap3d_pad_channels(int32_t dtype, const void* in, void* out, int64_t P, int32_t c, int32_t c_pad, int32_t unpad,
+                                  int32_t accumulate, void* stream) {
+  if (require_device()) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = P * (unpad ? c : c_pad);
+  if (dtype == SAP3D_BF16)
+    pad_channels_kernel<bf16><<<egrid(total), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), P, c, c_pad, unpad, accumulate);
+  else
+    pad_channels_kernel<float><<<egrid(total), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), P, c, c_pad, unpad, accumulate);
+  return check_launch("pad_channels");
+}

@@ -274,6 +274,18 @@ class Engine:
         self.bwd_ops.append(op.bwd)
         return op.y
 
+    def attn_core(self, g: T, f: T, h: T, name="") -> T:
+        op = _AttnCoreOp(self, g, f, h, name)
+        self.fwd_ops.append(op.fwd)
+        self.bwd_ops.append(op.bwd)
+        return op.o
+
+    def gate(self, o: T, x: T, gamma: Param, name="") -> T:
+        op = _GateOp(self, o, x, gamma, name)
+        self.fwd_ops.append(op.fwd)
+        self.bwd_ops.append(op.bwd)
+        return op.y
+
     def head(self, x: T, w: Param, b: Param, ksize, stride, sigmoid=True, name="") -> "_HeadOp":
         op = _HeadOp(self, x, w, b, ksize, stride, sigmoid, name)
         self.fwd_ops.append(op.fwd)
@@ -519,3 +531,138 @@ class _HeadOp:
     @property
     def output(self):
         return self.pred if self.sigmoid else self.logits
+
+
+class _GateOp:
+    """y = o * gamma + x  (utils/network.py:191-192)"""
+
+    def __init__(self, eng, o: T, x: T, gamma: Param, name):
+        self.eng, self.o, self.x, self.gamma, self.name = eng, o, x, gamma, name
+        self.y = eng.tensor(x.shape, name)
+
+    def fwd(self):
+        e = self.eng
+        A.check(A.lib.sap3d_gate_fwd(e.dt, A.ptr(self.o.buf), A.ptr(self.x.buf), A.ptr(self.gamma.w), A.ptr(self.y.buf),
+                                     self.y.buf.numel(), e.stream), "gate_fwd " + self.name)
+        e._count()
+
+    def bwd(self):
+        e = self.eng
+        if not self.y.gflag:
+            return
+        self.o.take_acc()
+        dx_ptr, acc = None, 0
+        if self.x.needs_grad:
+            acc = self.x.take_acc()
+            dx_ptr = A.ptr(self.x.ensure_grad())
+        A.check(A.lib.sap3d_gate_bwd(e.dt, A.ptr(self.y.grad), A.ptr(self.o.buf), A.ptr(self.gamma.w), A.ptr(self.o.ensure_grad()),
+                                     dx_ptr, acc, A.ptr(self.gamma.g), self.y.buf.numel(), e.stream), "gate_bwd " + self.name)
+        e._count()
+
+
+class _AttnCoreOp:
+    """o[b] = softmax(g[b] f[b]^T) h[b]  (utils/network.py:184-186).  Large aligned problems run on the
+    tcgen05 GEMMs (logits -> row softmax -> P.V), everything else on the generic CUDA-core kernels."""
+
+    def __init__(self, eng, g: T, f: T, h: T, name):
+        self.eng, self.g, self.f, self.h, self.name = eng, g, f, h, name
+        B = g.shape[0]
+        self.B = B
+        self.Nq = int(np.prod(g.shape[1:4]))
+        self.Nk = int(np.prod(f.shape[1:4]))
+        self.dk, self.dv = g.C, h.C
+        self.o = eng.tensor((*g.shape[:4], self.dv), name + "/o")
+        dev = eng.device
+        self.use_tc = (eng.dt == A.BF16 and self.Nk % 64 == 0 and self.Nq >= 128 and self.dv % 64 == 0 and self.dk % 8 == 0)
+        self.ldb = self.Nk
+        self.beta = torch.zeros(B, self.Nq, self.ldb, device=dev, dtype=eng.tdt)
+        tr = eng.training_graph
+        if self.use_tc:
+            self.dkp = (self.dk + 63) // 64 * 64
+            self.pad = self.dkp != self.dk
+            bf = torch.bfloat16
+            self.gp = torch.zeros(B, self.Nq, self.dkp, device=dev, dtype=bf) if self.pad else None
+            self.fp = torch.zeros(B, self.Nk, self.dkp, device=dev, dtype=bf) if self.pad else None
+            self.logits = torch.empty(self.Nq, self.Nk, device=dev, dtype=torch.float32)
+            self.vt = torch.empty(B, self.dv, self.Nk, device=dev, dtype=bf)
+            if tr:
+                self.ds = torch.empty(self.Nq, self.Nk, device=dev, dtype=bf)
+                self.ft = torch.empty(self.dkp, self.Nk, device=dev, dtype=bf)
+                self.dv32 = torch.empty(self.Nk, self.dv, device=dev, dtype=torch.float32)
+                self.dk32 = torch.empty(self.Nk, self.dkp, device=dev, dtype=torch.float32)
+                self.dgp = torch.empty(B, self.Nq, self.dkp, device=dev, dtype=bf) if self.pad else None
+                self.dfp = torch.empty(B, self.Nk, self.dkp, device=dev, dtype=bf) if self.pad else None
+        elif tr:
+            self.ds = torch.empty_like(self.beta)
+
+    # -- tensor-core path -------------------------------------------------------------------------
+    def _fwd_tc(self):
+        e, st = self.eng, self.eng.stream
+        B, Nq, Nk, dkp, dv = self.B, self.Nq, self.Nk, self.dkp, self.dv
+        if self.pad:
+            A.check(A.lib.sap3d_pad_channels(e.dt, A.ptr(self.g.buf), A.ptr(self.gp), B * Nq, self.dk, dkp, 0, 0, st), "pad g")
+            A.check(A.lib.sap3d_pad_channels(e.dt, A.ptr(self.f.buf), A.ptr(self.fp), B * Nk, self.dk, dkp, 0, 0, st), "pad f")
+            e._count(2)
+        gq = self.gp if self.pad else self.g.buf.view(B, Nq, dkp)
+        fk = self.fp if self.pad else self.f.buf.view(B, Nk, dkp)
+        hv = self.h.buf.view(B, Nk, dv)
+        ob = self.o.buf.view(B, Nq, dv)
+        A.check(A.lib.sap3d_transpose(e.dt, A.ptr(hv), A.ptr(self.vt), B, Nk, dv, dv, Nk, Nk * dv, dv * Nk, st), "transpose h")
+        e._count()
+        for b in range(B):
+            A.check(A.lib.sap3d_gemm_nt(A.ptr(gq[b]), dkp, A.ptr(fk[b]), dkp, A.ptr(self.logits), Nk, Nq, Nk, dkp, 1, 0, st), "QK^T")
+            A.check(A.lib.sap3d_softmax_rows(A.F32, A.ptr(self.logits), A.ptr(self.beta[b]), Nq, Nk, Nk, Nk, st), "softmax")
+            A.check(A.lib.sap3d_gemm_nt(A.ptr(self.beta[b]), Nk, A.ptr(self.vt[b]), Nk, A.ptr(ob[b]), dv, Nq, dv, Nk, 0, 0, st), "PV")
+        e._count(3 * B)
+
+    def _bwd_tc(self):
+        e, st = self.eng, self.eng.stream
+        B, Nq, Nk, dkp, dv, dk = self.B, self.Nq, self.Nk, self.dkp, self.dv, self.dk
+        gq = self.gp if self.pad else self.g.buf.view(B, Nq, dkp)
+        fk = self.fp if self.pad else self.f.buf.view(B, Nk, dkp)
+        hv = self.h.buf.view(B, Nk, dv)
+        do = self.o.grad.view(B, Nq, dv)
+        dh = self.h.ensure_grad().view(B, Nk, dv)
+        dg = self.dgp if self.pad else self.g.ensure_grad().view(B, Nq, dkp)
+        df = self.dfp if self.pad else self.f.ensure_grad().view(B, Nk, dkp)
+        for b in range(B):
+            self.dv32.zero_()
+            A.check(A.lib.sap3d_gemm_tn(A.ptr(self.beta[b]), Nk, A.ptr(do[b]), dv, A.ptr(self.dv32), dv, Nk, dv, Nq, st), "dV")
+            A.check(A.lib.sap3d_cast(A.F32, A.ptr(self.dv32), A.ptr(dh[b]), Nk * dv, st), "cast dV")
+            A.check(A.lib.sap3d_gemm_nt(A.ptr(do[b]), dv, A.ptr(hv[b]), dv, A.ptr(self.ds), Nk, Nq, Nk, dv, 0, 0, st), "dP")
+            A.check(A.lib.sap3d_softmax_bwd_rows(A.ptr(self.beta[b]), A.ptr(self.ds), Nq, Nk, Nk, st), "softmax bwd")
+            A.check(A.lib.sap3d_transpose(e.dt, A.ptr(fk[b]), A.ptr(self.ft), 1, Nk, dkp, dkp, Nk, 0, 0, st), "transpose f")
+            A.check(A.lib.sap3d_gemm_nt(A.ptr(self.ds), Nk, A.ptr(self.ft), Nk, A.ptr(dg[b]), dkp, Nq, dkp, Nk, 0, 0, st), "dQ")
+            self.dk32.zero_()
+            A.check(A.lib.sap3d_gemm_tn(A.ptr(self.ds), Nk, A.ptr(gq[b]), dkp, A.ptr(self.dk32), dkp, Nk, dkp, Nq, st), "dK")
+            A.check(A.lib.sap3d_cast(A.F32, A.ptr(self.dk32), A.ptr(df[b]), Nk * dkp, st), "cast dK")
+        e._count(10 * B)
+        if self.pad:
+            A.check(A.lib.sap3d_pad_channels(e.dt, A.ptr(self.dgp), A.ptr(self.g.ensure_grad()), B * Nq, dk, dkp, 1, 0, st), "unpad dg")
+            A.check(A.lib.sap3d_pad_channels(e.dt, A.ptr(self.dfp), A.ptr(self.f.ensure_grad()), B * Nk, dk, dkp, 1, 0, st), "unpad df")
+            e._count(2)
+
+    # -- dispatch ---------------------------------------------------------------------------------
+    def fwd(self):
+        e = self.eng
+        if self.use_tc:
+            return self._fwd_tc()
+        A.check(A.lib.sap3d_attention_fwd(e.dt, A.ptr(self.g.buf), A.ptr(self.f.buf), A.ptr(self.h.buf), A.ptr(self.beta),
+                                          A.ptr(self.o.buf), self.B, self.Nq, self.Nk, self.dk, self.dv, self.dk, self.dk, self.dv,
+                                          self.ldb, self.dv, e.stream), "attention_fwd " + self.name)
+        e._count(2)
+
+    def bwd(self):
+        e = self.eng
+        if not self.o.gflag:
+            return
+        for t in (self.g, self.f, self.h):
+            if t.take_acc():
+                raise A.Sap3dError("attention operands must have a single consumer")
+        if self.use_tc:
+            return self._bwd_tc()
+        A.check(A.lib.sap3d_attention_bwd(e.dt, A.ptr(self.g.buf), A.ptr(self.f.buf), A.ptr(self.h.buf), A.ptr(self.beta),
+                                          A.ptr(self.o.grad), A.ptr(self.ds), A.ptr(self.g.ensure_grad()), A.ptr(self.f.ensure_grad()),
+                                          A.ptr(self.h.ensure_grad()), self.B, self.Nq, self.Nk, self.dk, self.dv, self.dk, self.dk,
+                                          self.dv, self.ldb, self.dv, e.stream), "attention_bwd " + self.name)
+        e._count(3)

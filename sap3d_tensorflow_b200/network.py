@@ -107,5 +107,27 @@ def transpose_conv3d(x: Handle, channel, kernel, strides, training, name, mode="
     return co.raw.eng.tap(name, bn_relu(co, training, tap=name))
 
 
+def attention(x: T, name, training, mode="bn", subsample=False, sub_size=2) -> T:
+    """utils/network.py:157-193 (SAGAN-style self-attention; Python-2 integer division at :182,187,188).
+    f, g: 1x1x1 conv -> max(1, C/8) channels, h: 1x1x1 conv -> C (inside variable_scope(name));
+    optional max-pool of f/h (sub_size) and g (sub_size/2); o = softmax(g f^T) h -> 1x1x1 conv
+    (stride sub_size/2) -> BN -> ReLU; result = o * gamma + x with the scalar variable 'gamma'+name."""
+    eng = x.eng
+    ch = x.C
+    inter = max(1, ch // 8)
+    f = layers_conv3d(x, inter, 1, 1, scope=name, want_stats=False).raw
+    g = layers_conv3d(x, inter, 1, 1, scope=name, want_stats=False).raw
+    h = layers_conv3d(x, ch, 1, 1, scope=name, want_stats=False).raw
+    if subsample:
+        f = pool3d(f, sub_size)
+        g = pool3d(g, sub_size // 2)
+        h = pool3d(h, sub_size)
+    o = eng.attn_core(g, f, h, name=name)
+    oc = layers_conv3d(o, ch, 1, sub_size // 2)
+    o = bn_relu(oc, training, tap=name + "/o")
+    gamma = eng.param("gamma" + name, [1], "sa_gamma")
+    return eng.gate(o, x, gamma, name=name)
+
+
 def smooth_l1_loss(*_args, **_kw):  # utils/network.py:49 — fused into the head's backward (engine._HeadOp)
     raise NotImplementedError("the smooth-L1 loss is fused into Session.train_step (sap3d_loss_smooth_l1)")
