@@ -1,0 +1,150 @@
+"""Parity of the convolution family (tcgen05 implicit-GEMM, tcgen05 wgrad, CUDA-core kernels) through the
+C ABI against the CPU oracle (oracle/tf_semantics.py) on the same seeded inputs.
+
+Tolerances: bf16 storage -> 1e-2 relative (Frobenius) on activations / data gradients (the stated bf16
+tolerance of BASELINE.json); fp32 path -> 1e-4; statistics and filter gradients accumulate in fp32 -> 1e-3."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tf_semantics as tfs  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def A(lib_built):
+    from sap3d_tensorflow_b200 import _abi
+
+    assert _abi.lib.sap3d_device_ok() == 1, _abi.lib.sap3d_last_error()
+    return _abi
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def run_case(A, N, D, H, W, cin, cout, k, s, transposed, dtype, impl):
+    dev = "cuda"
+    st = torch.cuda.current_stream().cuda_stream
+    tdt = torch.bfloat16 if dtype == A.BF16 else torch.float32
+    torch.manual_seed(hash((N, D, H, W, tuple(cin), cout, k, s, transposed)) % 2**31)
+    cin_t = sum(cin)
+    xs = [torch.randn(N, D, H, W, c, device=dev).to(tdt) for c in cin]
+    shape = (*k, cout, cin_t) if transposed else (*k, cin_t, cout)
+    w = (torch.randn(*shape, device=dev) / (cin_t * k[0] * k[1] * k[2]) ** 0.5)
+    if dtype == A.BF16:
+        w = w.to(torch.bfloat16).float()  # the tensor-core path rounds weights to bf16: compare on equal inputs
+    b = torch.randn(cout, device=dev)
+    d = A.make_conv_desc(dtype, N, D, H, W, cin, cout, k, s, transposed, True, False, impl)
+    Do, Ho, Wo = A.conv_out_dims(d)
+    y = torch.full((N, Do, Ho, Wo, cout), float("nan"), device=dev, dtype=tdt)
+    rows = A.lib.sap3d_conv_stats_rows(C.byref(d))
+    stats = torch.zeros(rows, 2, cout, device=dev)
+    wf = torch.zeros(A.lib.sap3d_conv_packed_elems(C.byref(d), 0), device=dev, dtype=torch.bfloat16)
+    wd = torch.zeros(A.lib.sap3d_conv_packed_elems(C.byref(d), 1), device=dev, dtype=torch.bfloat16)
+    A.check(A.lib.sap3d_conv_pack_weights(C.byref(d), A.ptr(w), A.ptr(wf), A.ptr(wd), st), "pack")
+    x1 = xs[1] if len(xs) > 1 else None
+    A.check(A.lib.sap3d_conv_fwd(C.byref(d), A.ptr(xs[0]), A.ptr(x1), A.ptr(w), A.ptr(wf), A.ptr(b), A.ptr(y), A.ptr(stats), st), "fwd")
+    # CPU oracle (exact fp32, no TF32)
+    xcat = torch.cat([t.float().cpu() for t in xs], dim=-1).requires_grad_(True)
+    wr = w.cpu().clone().requires_grad_(True)
+    ref = (tfs.conv3d_transpose_same if transposed else tfs.conv3d_same)(xcat, wr, s, b.cpu())
+    tol = 1e-2 if dtype == A.BF16 else 1e-4
+    torch.cuda.synchronize()
+    assert not torch.isnan(y.float()).any()
+    assert rel(y, ref) < tol
+    s1 = stats[:, 0].double().sum(0).float().cpu()
+    s2 = stats[:, 1].double().sum(0).float().cpu()
+    assert ((s2 - (ref * ref).sum(dim=(0, 1, 2, 3))).norm() / (ref * ref).sum(dim=(0, 1, 2, 3)).norm()).item() < 2e-3 if dtype == A.BF16 else 1e-4
+    assert ((s1 - ref.sum(dim=(0, 1, 2, 3))).abs().max() / ref.abs().sum(dim=(0, 1, 2, 3)).max()).item() < 2e-3
+    dy = torch.randn(ref.shape).to(tdt)
+    ref.backward(dy.float())
+    dyd = dy.to(dev)
+    off = 0
+    for si, c in enumerate(cin):
+        dx = torch.full_like(xs[si], float("nan"))
+        A.check(A.lib.sap3d_conv_dgrad(C.byref(d), si, A.ptr(dyd), A.ptr(w), A.ptr(wd), A.ptr(dx), 0, st), "dgrad")
+        torch.cuda.synchronize()
+        assert rel(dx, xcat.grad[..., off:off + c]) < tol
+        A.check(A.lib.sap3d_conv_dgrad(C.byref(d), si, A.ptr(dyd), A.ptr(w), A.ptr(wd), A.ptr(dx), 1, st), "dgrad accumulate")
+        torch.cuda.synchronize()
+        assert rel(dx, 2 * xcat.grad[..., off:off + c]) < 2 * tol
+        off += c
+    dw, db = torch.zeros_like(w), torch.zeros(cout, device=dev)
+    A.check(A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(x1), A.ptr(dyd), A.ptr(dw), A.ptr(db), st), "wgrad")
+    torch.cuda.synchronize()
+    assert rel(dw, wr.grad) < 1e-3
+    assert rel(db, dy.float().sum(dim=(0, 1, 2, 3))) < 1e-3
+
+
+# every distinct implicit-GEMM geometry of the P3D graphs, at reduced extents
+TC_CASES = [
+    ("1x1x1 reduce", 2, 8, 28, 28, [256], 64, (1, 1, 1), (1, 1, 1), False),
+    ("1x1x1 expand", 2, 8, 14, 14, [64], 256, (1, 1, 1), (1, 1, 1), False),
+    ("1x1x1 s(1,2,2) reduce id 3", 2, 4, 28, 28, [256], 128, (1, 1, 1), (1, 2, 2), False),
+    ("1x1x1 s(1,2,2) dw3d_11", 1, 2, 14, 14, [512], 1024, (1, 1, 1), (1, 2, 2), False),
+    ("convS stage 1", 2, 8, 28, 28, [64], 64, (1, 3, 3), (1, 1, 1), False),
+    ("convT stage 1", 2, 8, 28, 28, [64], 64, (3, 1, 1), (1, 1, 1), False),
+    ("convS stage 3", 2, 2, 7, 7, [256], 256, (1, 3, 3), (1, 1, 1), False),
+    ("convT stage 3 (D=2)", 2, 2, 7, 7, [256], 256, (3, 1, 1), (1, 1, 1), False),
+    ("x_1_1 concat 64+128", 1, 8, 28, 28, [64, 128], 128, (3, 3, 3), (1, 1, 1), False),
+    ("x_2_x concat 256+256", 1, 4, 14, 14, [256, 256], 256, (3, 3, 3), (1, 1, 1), False),
+    ("x_3_1 k(2,3,3) concat 512+512", 1, 2, 14, 14, [512, 512], 512, (2, 3, 3), (1, 1, 1), False),
+    ("upx_2_x deconv k3 s2", 1, 4, 14, 14, [256], 128, (3, 3, 3), (2, 2, 2), True),
+    ("upx_3_x deconv k(2,3,3) s2", 1, 2, 14, 14, [512], 256, (2, 3, 3), (2, 2, 2), True),
+    ("upx_4_0 deconv k(1,3,3) s2", 2, 1, 7, 7, [1024], 512, (1, 3, 3), (2, 2, 2), True),
+    ("ragged extents", 1, 3, 9, 11, [64], 72, (3, 3, 3), (1, 1, 1), False),
+    ("deconv k3 s1 (p3d_concat)", 1, 2, 6, 6, [64], 64, (3, 3, 3), (1, 1, 1), True),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_tensor_core_conv(A, case):
+    run_case(A, *case[1:], dtype=A.BF16, impl=A.IMPL_TC)
+
+
+SIMT_CASES = [
+    ("stem 1x7x7 s(1,2,2) 3->64", 1, 4, 32, 32, [3], 64, (1, 7, 7), (1, 2, 2), False),
+    ("concat 8+16", 1, 3, 9, 10, [8, 16], 24, (3, 3, 3), (1, 1, 1), False),
+    ("deconv -> 1 channel", 1, 4, 10, 10, [16], 1, (3, 3, 3), (2, 2, 2), True),
+    ("deconv k3 s4 (holes)", 1, 1, 5, 5, [16], 8, (3, 3, 3), (4, 4, 4), True),
+    ("deconv k3 s1", 1, 3, 6, 6, [16], 8, (3, 3, 3), (1, 1, 1), True),
+    ("k(2,3,3)", 2, 2, 7, 7, [8], 8, (2, 3, 3), (1, 1, 1), False),
+    ("attention f: 128->16", 1, 4, 8, 8, [128], 16, (1, 1, 1), (1, 1, 1), False),
+]
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("case", SIMT_CASES, ids=[c[0] for c in SIMT_CASES])
+def test_cuda_core_conv(A, case, dtype):
+    run_case(A, *case[1:], dtype=A.F32 if dtype == "f32" else A.BF16, impl=A.IMPL_SIMT)
+
+
+def test_linearity_at_full_decoder_size(A):
+    """size-independent property at the BASELINE size (8 x 56 x 56, 128+128 -> 128): conv(a*x) == a*conv(x)
+    (bias off) and per-channel statistics consistent with the stored output."""
+    dev = "cuda"
+    st = torch.cuda.current_stream().cuda_stream
+    N, D, H, W = 2, 8, 56, 56
+    torch.manual_seed(0)
+    xs = [torch.randn(N, D, H, W, 128, device=dev).to(torch.bfloat16) for _ in range(2)]
+    w = torch.randn(3, 3, 3, 256, 128, device=dev) * 0.02
+    d = A.make_conv_desc(A.BF16, N, D, H, W, [128, 128], 128, (3, 3, 3), (1, 1, 1), False, False, False, A.IMPL_TC)
+    wf = torch.zeros(A.lib.sap3d_conv_packed_elems(C.byref(d), 0), device=dev, dtype=torch.bfloat16)
+    A.check(A.lib.sap3d_conv_pack_weights(C.byref(d), A.ptr(w), A.ptr(wf), None, st), "pack")
+    rows = A.lib.sap3d_conv_stats_rows(C.byref(d))
+    outs = []
+    for scale in (1.0, 2.0):
+        xa = [(t.float() * scale).to(torch.bfloat16) for t in xs]
+        y = torch.empty(N, D, H, W, 128, device=dev, dtype=torch.bfloat16)
+        stats = torch.zeros(rows, 2, 128, device=dev)
+        A.check(A.lib.sap3d_conv_fwd(C.byref(d), A.ptr(xa[0]), A.ptr(xa[1]), A.ptr(w), A.ptr(wf), None, A.ptr(y), A.ptr(stats), st), "fwd")
+        torch.cuda.synchronize()
+        outs.append((y.float(), stats))
+    assert torch.equal(outs[1][0], 2 * outs[0][0])  # power-of-two scaling is exact in bf16
+    y, stats = outs[0]
+    assert rel(stats[:, 0].sum(0), y.sum(dim=(0, 1, 2, 3))) < 5e-3
+    assert rel(stats[:, 1].sum(0), (y * y).sum(dim=(0, 1, 2, 3))) < 5e-3
