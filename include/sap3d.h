@@ -166,9 +166,10 @@ int sap3d_attention_fwd(int32_t dtype, const void* g, const void* f, const void*
 int sap3d_attention_bwd(int32_t dtype, const void* g, const void* f, const void* h, const void* beta, const void* d_o, void* ds,
                         void* dg, void* df, void* dh, int32_t B, int32_t Nq, int32_t Nk, int32_t dk, int32_t dv, int32_t ldq,
                         int32_t ldk, int32_t ldv, int32_t ldb, int32_t ldo, void* stream);
-/* bf16 tensor-core GEMMs: C[M][N] (+)= A[M][K] B[N][K]^T  (K % 64 == 0, ldb == K, N % 64 == 0) */
-int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t M, int32_t N,
-                  int32_t K, int32_t out_f32, int32_t accumulate, void* stream);
+/* bf16 tensor-core GEMMs: C[M][N] (+)= A[M][K] B[N][K]^T  (K % 64 == 0, ldb == K, N % 8 == 0); B has rows_b <= N
+ * rows, the remaining output columns are computed against zeros */
+int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t rows_b, void* C, int64_t ldc, int32_t M,
+                  int32_t N, int32_t K, int32_t out_f32, int32_t accumulate, void* stream);
 /* D[M][N] (fp32) += sum_pos P[pos][m] Q[pos][n]  (M, N % 64 == 0); the caller zeroes D */
 int sap3d_gemm_tn(const void* P, int64_t ldp, const void* Q, int64_t ldq, float* D, int64_t ldd, int32_t M, int32_t N,
                   int32_t Kpos, void* stream);
@@ -181,6 +182,18 @@ int sap3d_transpose(int32_t dtype, const void* in, void* out, int32_t batch, int
 /* [P][c] -> [P][c_pad] zero padded (unpad == 0) or back (unpad != 0, optionally accumulating) */
 int sap3d_pad_channels(int32_t dtype, const void* in, void* out, int64_t P, int32_t c, int32_t c_pad, int32_t unpad,
                        int32_t accumulate, void* stream);
+
+/* one-launch re-packing of all filters after an optimizer step (table built with sap3d_conv_pack_entries) */
+typedef struct sap3d_pack_entry {
+  const float* src;   /* fp32 TF-layout filter */
+  void* dst;          /* bf16 [rows_pad][taps*cols] */
+  int32_t taps, rows, rows_pad, cols;
+  int64_t s_tap, s_r, s_c;
+  int64_t start;      /* first element of this entry in the concatenated index space (filled by the caller) */
+} sap3d_pack_entry;
+/* fills up to two entries (forward / data-gradient operand; NULL destination skips one); returns the count */
+int sap3d_conv_pack_entries(const sap3d_conv_desc* d, const float* w_tf, void* w_fwd, void* w_dgrad, sap3d_pack_entry* out2);
+int sap3d_pack_multi(const sap3d_pack_entry* entries_dev, int32_t n, int64_t total, void* stream);
 
 /* tf.train.AdamOptimizer (train.py:168) over flat fp32 arrays; *step (device) is the 1-based iteration. */
 int sap3d_adam_step(float* w, const float* g, float* m, float* v, int64_t n, const int32_t* step, float lr, float b1, float b2,

@@ -1,6 +1,7 @@
-"""Builds libsap3d_b200.so in-tree with nvcc for sm_100a (no torch dependency in the library).
+"""Builds sap3d_tensorflow_b200/lib/libsap3d_b200.so in-tree with nvcc for sm_100a (no torch dependency
+in the library).  Stand-alone on purpose: it must run before the package (whose import loads the library).
 
-    python -m sap3d_tensorflow_b200.build [--force]
+    python sap3d_build.py [--force] [--verbose]
 """
 from __future__ import annotations
 
@@ -9,7 +10,8 @@ import os
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.join(ROOT, "sap3d_tensorflow_b200")
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libsap3d_b200.so")
 

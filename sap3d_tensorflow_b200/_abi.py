@@ -1,6 +1,6 @@
 """ctypes binding of libsap3d_b200.so (the C ABI declared in include/sap3d.h).
 
-The library is built in-tree by ``__graft_entry__.build()`` / ``python -m sap3d_tensorflow_b200.build``.
+The library is built in-tree by ``__graft_entry__.build()`` / ``python sap3d_build.py``.
 There is no fallback: if the shared object is missing, import of this module raises.
 """
 from __future__ import annotations
@@ -21,7 +21,7 @@ class Sap3dError(RuntimeError):
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        f"{LIB_PATH} not found: build the CUDA extension first (python -m sap3d_tensorflow_b200.build). "
+        f"{LIB_PATH} not found: build the CUDA extension first (python sap3d_build.py). "
         "This framework has no CPU / PyTorch fallback path."
     )
 
@@ -124,12 +124,21 @@ _sig("sap3d_cast", [_i32, _vp, _vp, _i64, _vp])
 _i32x = _i32
 _sig("sap3d_attention_fwd", [_i32, _vp, _vp, _vp, _vp, _vp] + [_i32] * 10 + [_vp])
 _sig("sap3d_attention_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 10 + [_vp])
-_sig("sap3d_gemm_nt", [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp])
+_sig("sap3d_gemm_nt", [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp])
 _sig("sap3d_gemm_tn", [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp])
 _sig("sap3d_softmax_rows", [_i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp])
 _sig("sap3d_softmax_bwd_rows", [_vp, _vp, _i64, _i32, _i32, _vp])
 _sig("sap3d_transpose", [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _vp])
 _sig("sap3d_pad_channels", [_i32, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp])
+
+
+class PackEntry(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("taps", C.c_int32), ("rows", C.c_int32), ("rows_pad", C.c_int32),
+                ("cols", C.c_int32), ("s_tap", C.c_int64), ("s_r", C.c_int64), ("s_c", C.c_int64), ("start", C.c_int64)]
+
+
+_sig("sap3d_conv_pack_entries", [_P(ConvDesc), _vp, _vp, _vp, _P(PackEntry)])
+_sig("sap3d_pack_multi", [_vp, _i32, _i64, _vp])
 
 
 def i3(v):

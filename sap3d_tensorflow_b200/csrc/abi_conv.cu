@@ -621,13 +621,13 @@ int sap3d_conv_wgrad(const sap3d_conv_desc* d, const void* x0, const void* x1, c
 // ---- plain GEMMs on the same tensor-core kernels (attention matmuls, utils/network.py:184,186) ----
 extern "C" {
 
-int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* Cout, int64_t ldc, int32_t M, int32_t N,
-                  int32_t K, int32_t out_f32, int32_t accumulate, void* stream) {
+int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t rows_b, void* Cout, int64_t ldc, int32_t M,
+                  int32_t N, int32_t K, int32_t out_f32, int32_t accumulate, void* stream) {
   if (require_device()) return 1;
   if (!A || !B || !Cout) return set_error("gemm_nt: NULL pointer");
-  if (K % 64 != 0 || ldb != K || N % 64 != 0 || lda % 8 != 0 || ldc % 8 != 0)
-    return set_error("gemm_nt: need K %% 64 == 0, ldb == K, N %% 64 == 0, lda/ldc %% 8 == 0 (M=%d N=%d K=%d lda=%lld ldb=%lld)", M, N, K,
-                     (long long)lda, (long long)ldb);
+  if (K % 64 != 0 || ldb != K || N % 8 != 0 || lda % 8 != 0 || ldc % 8 != 0 || rows_b < 1 || rows_b > N)
+    return set_error("gemm_nt: need K %% 64 == 0, ldb == K, N %% 8 == 0, lda/ldc %% 8 == 0, rows_b <= N (M=%d N=%d K=%d lda=%lld ldb=%lld)",
+                     M, N, K, (long long)lda, (long long)ldb);
   TcProblem pb;
   TcView v;
   v.base = A;
@@ -649,7 +649,7 @@ int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, void* 
   pb.so[0] = ldc; pb.so[1] = 0; pb.so[2] = 0; pb.so[3] = 0;
   pb.B = B;
   pb.Ktot = K;
-  pb.rowsB = N;
+  pb.rowsB = rows_b;  // rows beyond rows_b are zero-filled by the TMA unit
   pb.cout = N;
   pb.out = Cout;
   pb.bias = nullptr; pb.stats = nullptr; pb.scale = nullptr; pb.shift = nullptr;
@@ -692,3 +692,25 @@ int sap3d_gemm_tn(const void* P, int64_t ldp, const void* Q, int64_t ldq, float*
 }
 
 }  // extern "C"
+
+extern "C" int sap3d_conv_pack_entries(const sap3d_conv_desc* d, const float* w_tf, void* w_fwd, void* w_dgrad, sap3d_pack_entry* out2) {
+  if (check_desc(d)) return -1;
+  ConvGeom g;
+  make_geom(d, g);
+  const int ci = g.cin_total, co = d->cout, taps = g.taps;
+  const int co_pad = (co + 63) / 64 * 64, ci_pad = (ci + 63) / 64 * 64;
+  int n = 0;
+  auto add = [&](void* dst, int rows, int rows_pad, int cols, long long s_r, long long s_c) {
+    sap3d_pack_entry& e = out2[n++];
+    e.src = w_tf; e.dst = dst; e.taps = taps; e.rows = rows; e.rows_pad = rows_pad; e.cols = cols;
+    e.s_tap = (long long)ci * co; e.s_r = s_r; e.s_c = s_c; e.start = 0;
+  };
+  if (!d->transposed) {
+    if (w_fwd) add(w_fwd, co, co_pad, ci, 1, co);
+    if (w_dgrad) add(w_dgrad, ci, ci_pad, co, co, 1);
+  } else {
+    if (w_fwd) add(w_fwd, co, co_pad, ci, ci, 1);
+    if (w_dgrad) add(w_dgrad, ci, ci_pad, co, 1, ci);
+  }
+  return n;
+}

@@ -84,6 +84,92 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs p) {
   }
 }
 
+// k = 3, s = 2 specialisation: one warp per INPUT anchor voxel j produces the 2x2x2 output cube p = 2j + r.
+// Output parity r = 0 uses taps k = 0 (input j) and k = 2 (input j-1), r = 1 uses k = 1 (input j): the cube
+// needs the 8 inputs j - {0,1}^3, each loaded ONCE per lane (3.4x fewer loads than the gather form).
+template <typename T>
+__global__ void __launch_bounds__(256) head_fwd_k3s2_kernel(const HeadArgs p) {
+  extern __shared__ float sw[];  // [27][C]
+  for (int i = threadIdx.x; i < 27 * p.C; i += blockDim.x) sw[i] = p.w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int Do = p.D * 2, Ho = p.H * 2, Wo = p.W * 2;
+  const long long total = (long long)p.N * p.D * p.H * p.W;
+  const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const T* x = reinterpret_cast<const T*>(p.x);
+  const float b0 = p.bias ? p.bias[0] : 0.f;
+  for (long long a = warp_id; a < total; a += nwarps) {
+    long long r = a;
+    const int jw = (int)(r % p.W); r /= p.W;
+    const int jh = (int)(r % p.H); r /= p.H;
+    const int jd = (int)(r % p.D);
+    const int n = (int)(r / p.D);
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    for (int c = lane * 4; c < p.C; c += 128) {
+#pragma unroll
+      for (int dd = 0; dd < 2; ++dd) {
+        if (jd - dd < 0) continue;
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh) {
+          if (jh - dh < 0) continue;
+#pragma unroll
+          for (int dw = 0; dw < 2; ++dw) {
+            if (jw - dw < 0) continue;
+            const T* xp = x + ((((long long)n * p.D + jd - dd) * p.H + jh - dh) * p.W + jw - dw) * p.C + c;
+            float v0, v1, v2, v3;
+            if (sizeof(T) == 2) {
+              const uint2 u = *reinterpret_cast<const uint2*>(xp);
+              const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
+              v0 = f0.x; v1 = f0.y; v2 = f1.x; v3 = f1.y;
+            } else {
+              const float4 f = *reinterpret_cast<const float4*>(xp);
+              v0 = f.x; v1 = f.y; v2 = f.z; v3 = f.w;
+            }
+            // input offset 0 feeds parity 0 (tap 0) and parity 1 (tap 1); offset 1 feeds parity 0 only (tap 2)
+#pragma unroll
+            for (int rd = 0; rd < 2; ++rd) {
+              if (dd == 1 && rd == 1) continue;
+              const int kd = dd == 1 ? 2 : rd;
+#pragma unroll
+              for (int rh = 0; rh < 2; ++rh) {
+                if (dh == 1 && rh == 1) continue;
+                const int kh = dh == 1 ? 2 : rh;
+#pragma unroll
+                for (int rw = 0; rw < 2; ++rw) {
+                  if (dw == 1 && rw == 1) continue;
+                  const int kw = dw == 1 ? 2 : rw;
+                  const float* wp = sw + ((kd * 3 + kh) * 3 + kw) * p.C + c;
+                  float t = acc[(rd * 2 + rh) * 2 + rw];
+                  t = fmaf(v0, wp[0], t);
+                  t = fmaf(v1, wp[1], t);
+                  t = fmaf(v2, wp[2], t);
+                  t = fmaf(v3, wp[3], t);
+                  acc[(rd * 2 + rh) * 2 + rw] = t;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = warp_sum(acc[o]);
+    if (lane < 8) {
+      float z = acc[0];
+#pragma unroll
+      for (int o = 1; o < 8; ++o) z = lane == o ? acc[o] : z;
+      z += b0;
+      const int rd = lane >> 2, rh = (lane >> 1) & 1, rw = lane & 1;
+      const long long o = (((long long)n * Do + 2 * jd + rd) * Ho + 2 * jh + rh) * Wo + 2 * jw + rw;
+      p.logits[o] = z;
+      if (p.pred) p.pred[o] = 1.f / (1.f + __expf(-z));
+    }
+  }
+}
+
 // dx[n,i,c] (+)= sum_k dlog[n, s*i + k - pb] * w[k][c] ; thread = (voxel, 8 channels)
 struct HeadBwdArgs {
   const float* dlog; const void* x; const float* w; void* dx; float* dw;
@@ -401,7 +487,10 @@ int sap3d_head_fwd(int32_t dtype, const void* x, int32_t N, int32_t D, int32_t H
   if (smem > 48 * 1024) return set_error("head_fwd: filter too large for shared memory");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int blocks = 148 * 8;
-  if (dtype == SAP3D_BF16) head_fwd_kernel<bf16><<<blocks, 256, smem, st>>>(p);
+  if (p.kd == 3 && p.kh == 3 && p.kw == 3 && stride == 2) {
+    if (dtype == SAP3D_BF16) head_fwd_k3s2_kernel<bf16><<<blocks, 256, smem, st>>>(p);
+    else head_fwd_k3s2_kernel<float><<<blocks, 256, smem, st>>>(p);
+  } else if (dtype == SAP3D_BF16) head_fwd_kernel<bf16><<<blocks, 256, smem, st>>>(p);
   else head_fwd_kernel<float><<<blocks, 256, smem, st>>>(p);
   return check_launch("head_fwd");
 }

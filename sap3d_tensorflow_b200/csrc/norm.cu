@@ -253,13 +253,13 @@ SAP3D_DEVINL void bwd_common(const ApplyBwdArgs& p, long long e, long long sidx,
   }
 }
 
-// grid.x = rows (slabs of positions); block = 256 threads = (C/8) vec lanes x pos lanes
+// grid = (rows, C/64): each block reduces a slab of positions for one 64-channel chunk.
+// 256 threads = 8 channel-vector lanes (64 channels, one 128-byte line per position) x 32 position lanes.
 template <typename T>
 __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArgs p) {
-  extern __shared__ float red[];  // [pos lanes][4][C]
-  const int vl = p.C / 8;
-  const int lanes = blockDim.x / vl;  // position lanes (>= 1)
-  const int cv = threadIdx.x % vl, pl = threadIdx.x / vl;
+  __shared__ float red[8][4][64];  // [warp][sum][channel]
+  const int cv = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = blockIdx.y * 64 + cv * 8;
   const long long per = (p.P + p.rows - 1) / p.rows;
   const long long pbeg = blockIdx.x * per, pend = pbeg + per < p.P ? pbeg + per : p.P;
   float acc[4][8];
@@ -267,9 +267,8 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  if (pl < lanes) {
-    const int c = cv * 8;
-    for (long long pos = pbeg + pl; pos < pend; pos += lanes) {
+  if (c < p.C) {
+    for (long long pos = pbeg + pl; pos < pend; pos += 32) {
       float g1[8], g2[8], xh1[8], xh2[8];
       bwd_common<T>(p, pos * p.C + c, c, c, g1, g2, xh1, xh2);
 #pragma unroll
@@ -280,34 +279,58 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
         acc[3][j] += g2[j] * xh2[j];
       }
     }
+  }
+  // lanes with equal (lane & 7) hold the same channels: fold the 4 positions of a warp
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[i][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      acc[i][j] = v;
+    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[(pl * 4 + i) * p.C + c + j] = acc[i][j];
+      for (int j = 0; j < 8; ++j) red[warp][i][lane * 8 + j] = acc[i][j];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 4 * p.C; idx += blockDim.x) {
-    float s = 0.f;
-    for (int l = 0; l < lanes; ++l) s += red[l * 4 * p.C + idx];
-    p.partial[(long long)blockIdx.x * 4 * p.C + idx] = s;
+  {
+    const int i = threadIdx.x >> 6, ch = threadIdx.x & 63;  // 4 sums x 64 channels = 256 threads
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][i][ch];
+    const int cc = blockIdx.y * 64 + ch;
+    if (cc < p.C) p.partial[((long long)blockIdx.x * 4 + i) * p.C + cc] = v;
   }
 }
 
 // partial [rows][4][C] -> coef [4][C] (divided by M) ; dgamma/dbeta accumulation (fp32, +=)
-__global__ void apply_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double M, float* coef,
-                                          float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// block = 32 channels x 32 row lanes, deterministic fp64 reduction
+__global__ void __launch_bounds__(1024) apply_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double M,
+                                                                   float* coef, float* dgamma1, float* dbeta1, float* dgamma2,
+                                                                   float* dbeta2) {
+  __shared__ double sh[4][32][33];
+  const int cx = threadIdx.x, ry = threadIdx.y;
+  const int c = blockIdx.x * 32 + cx;
   double s[4] = {0, 0, 0, 0};
-  for (int r = 0; r < rows; ++r)
+  if (c < C)
+    for (int r = ry; r < rows; r += 32)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s[i] += (double)partial[((long long)r * 4 + i) * C + c];
+      for (int i = 0; i < 4; ++i) s[i] += (double)partial[((long long)r * 4 + i) * C + c];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) coef[i * C + c] = (float)(s[i] / M);
-  if (dbeta1) dbeta1[c] += (float)s[0];
-  if (dgamma1) dgamma1[c] += (float)s[1];
-  if (dbeta2) dbeta2[c] += (float)s[2];
-  if (dgamma2) dgamma2[c] += (float)s[3];
+  for (int i = 0; i < 4; ++i) sh[i][ry][cx] = s[i];
+  __syncthreads();
+  if (ry < 4 && c < C) {
+    double t = 0.0;
+    for (int r = 0; r < 32; ++r) t += sh[ry][r][cx];
+    coef[ry * C + c] = (float)(t / M);
+    float* dst = ry == 0 ? dbeta1 : (ry == 1 ? dgamma1 : (ry == 2 ? dbeta2 : dgamma2));
+    if (dst) dst[c] += (float)t;
+  }
 }
 
 template <typename T>
@@ -428,28 +451,19 @@ int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const flo
   const bool need_reduce = p.batch_stats1 || p.batch_stats2 || dgamma1 || dbeta1 || dgamma2 || dbeta2;
   if (need_reduce) {
     if (!workspace) return set_error("affine_act_bwd: workspace required");
-    int rows = (int)((P + 63) / 64);
+    const int chunks = (C + 63) / 64;
+    long long rows = (2 * 148 + chunks - 1) / chunks;
+    const long long max_rows = (P + 31) / 32;
+    if (rows > max_rows) rows = max_rows;
     if (rows > 296) rows = 296;
     if (rows < 1) rows = 1;
-    p.rows = rows;
+    p.rows = (int)rows;
     p.partial = ws + 4 * C;
-    const int vl = C / 8;
-    int threads = 256;
-    if (vl > 256) threads = vl;  // C = 2048 -> 256 lanes exactly; larger C rejected above
-    int lanes = threads / vl;
-    if (lanes < 1) lanes = 1;
-    const size_t smem = (size_t)lanes * 4 * C * sizeof(float);
-    if (smem > 48 * 1024) {
-      // shrink the number of position lanes to fit default shared memory
-      lanes = (int)(48 * 1024 / (4 * C * sizeof(float)));
-      if (lanes < 1) return set_error("affine_act_bwd: C too large for the reduce kernel");
-      threads = lanes * vl;
-    }
-    const size_t smem2 = (size_t)lanes * 4 * C * sizeof(float);
-    if (dtype == SAP3D_BF16) apply_bwd_reduce_kernel<bf16><<<rows, threads, smem2, st>>>(p);
-    else apply_bwd_reduce_kernel<float><<<rows, threads, smem2, st>>>(p);
+    dim3 rgrid((unsigned)rows, (unsigned)chunks);
+    if (dtype == SAP3D_BF16) apply_bwd_reduce_kernel<bf16><<<rgrid, 256, 0, st>>>(p);
+    else apply_bwd_reduce_kernel<float><<<rgrid, 256, 0, st>>>(p);
     if (check_launch("affine_act_bwd reduce")) return 1;
-    apply_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(p.partial, rows, C, (double)P, ws, dgamma1, dbeta1, dgamma2, dbeta2);
+    apply_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, st>>>(p.partial, (int)rows, C, (double)P, ws, dgamma1, dbeta1, dgamma2, dbeta2);
     if (check_launch("affine_act_bwd finalize")) return 1;
     p.coef = ws;
   }

@@ -171,9 +171,14 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
       tmem_ld_wait();
       if (m < p.M) {
+        // N is a multiple of 64 on this path, so whole 4-float groups are valid: vector reductions (RED.128)
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nb * BLOCK_N + c * 32 + j < p.N) atomicAdd(out + c * 32 + j, __uint_as_float(rr[j]));
+        for (int j = 0; j < 32; j += 4) {
+          if (nb * BLOCK_N + c * 32 + j < p.N)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c * 32 + j), "f"(__uint_as_float(rr[j])),
+                         "f"(__uint_as_float(rr[j + 1])), "f"(__uint_as_float(rr[j + 2])), "f"(__uint_as_float(rr[j + 3]))
+                         : "memory");
+        }
       }
     }
     tc_fence_before();

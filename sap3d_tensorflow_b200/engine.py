@@ -133,6 +133,7 @@ class Engine:
         self.launches_fwd = 0
         self.launches_bwd = 0
         self._counting = None
+        self._pack_table = None
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -235,15 +236,34 @@ class Engine:
         return {n: p.w.detach().cpu().clone() for n, p in self.params.items()}
 
     def pack_weights(self):
-        for c in self.convs:
-            c.pack()
+        """fp32 master filters -> bf16 tensor-core operands for every conv, in ONE kernel launch"""
+        if self.dt != A.BF16 or not self.convs:
+            return
+        if self._pack_table is None:
+            ents = []
+            start = 0
+            for c in self.convs:
+                two = (A.PackEntry * 2)()
+                n = A.lib.sap3d_conv_pack_entries(C.byref(c.desc), A.ptr(c.w.w), A.ptr(c.wf), A.ptr(c.wd), two)
+                for i in range(n):
+                    e = two[i]
+                    e.start = start
+                    start += e.rows_pad * e.taps * e.cols
+                    ents.append(bytes(e))
+            raw = b"".join(ents)
+            self._pack_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+            self._pack_n, self._pack_total = len(ents), start
+        A.check(A.lib.sap3d_pack_multi(A.ptr(self._pack_table), self._pack_n, self._pack_total, self.stream), "pack_multi")
 
     # ------------------------------------------------------------------------------------------
     # ops
     # ------------------------------------------------------------------------------------------
     def conv(self, xs: Sequence[T], cout: int, kernel, strides, w: Param, b: Optional[Param] = None, transposed=False,
-             want_stats=True, name="", out_f32=False) -> ConvOut:
+             want_stats=True, name="", out_f32=False, bias_grad=True) -> ConvOut:
+        """bias_grad=False: the bias feeds a batch-statistics norm, whose mean subtraction makes dL/dbias exactly
+        zero in exact arithmetic (TF computes rounding noise there); the gradient is left at zero."""
         op = _ConvOp(self, list(xs), cout, tuple(kernel), tuple(strides), w, b, transposed, want_stats, name, out_f32)
+        op.bias_grad = bias_grad
         self.convs.append(op)
         self.fwd_ops.append(op.fwd)
         self.bwd_ops.append(op.bwd)
@@ -374,8 +394,9 @@ class _ConvOp:
             e._count()
         x1 = self.xs[1].buf if len(self.xs) > 1 else None
         A.check(A.lib.sap3d_conv_wgrad(C.byref(self.desc), A.ptr(self.xs[0].buf), A.ptr(x1), A.ptr(dy), A.ptr(self.w.g),
-                                       A.ptr(self.b.g) if self.b is not None else None, e.stream), "conv_wgrad " + self.name)
-        e._count(len(self.xs) + (1 if self.b is not None else 0))
+                                       A.ptr(self.b.g) if (self.b is not None and self.bias_grad) else None, e.stream),
+                "conv_wgrad " + self.name)
+        e._count(len(self.xs) + (1 if (self.b is not None and self.bias_grad) else 0))
 
 
 class _NormActOp:
@@ -573,8 +594,9 @@ class _AttnCoreOp:
         self.dk, self.dv = g.C, h.C
         self.o = eng.tensor((*g.shape[:4], self.dv), name + "/o")
         dev = eng.device
-        self.use_tc = (eng.dt == A.BF16 and self.Nk % 64 == 0 and self.Nq >= 128 and self.dv % 64 == 0 and self.dk % 8 == 0)
-        self.ldb = self.Nk
+        self.use_tc = eng.dt == A.BF16 and self.dv % 64 == 0 and self.dk % 8 == 0
+        self.Nkp = (self.Nk + 63) // 64 * 64 if self.use_tc else self.Nk   # keys padded (zero probabilities) for K % 64
+        self.ldb = self.Nkp
         self.beta = torch.zeros(B, self.Nq, self.ldb, device=dev, dtype=eng.tdt)
         tr = eng.training_graph
         if self.use_tc:
@@ -583,13 +605,13 @@ class _AttnCoreOp:
             bf = torch.bfloat16
             self.gp = torch.zeros(B, self.Nq, self.dkp, device=dev, dtype=bf) if self.pad else None
             self.fp = torch.zeros(B, self.Nk, self.dkp, device=dev, dtype=bf) if self.pad else None
-            self.logits = torch.empty(self.Nq, self.Nk, device=dev, dtype=torch.float32)
-            self.vt = torch.empty(B, self.dv, self.Nk, device=dev, dtype=bf)
+            self.logits = torch.empty(self.Nq, self.Nkp, device=dev, dtype=torch.float32)
+            self.vt = torch.zeros(B, self.dv, self.Nkp, device=dev, dtype=bf)
             if tr:
-                self.ds = torch.empty(self.Nq, self.Nk, device=dev, dtype=bf)
-                self.ft = torch.empty(self.dkp, self.Nk, device=dev, dtype=bf)
-                self.dv32 = torch.empty(self.Nk, self.dv, device=dev, dtype=torch.float32)
-                self.dk32 = torch.empty(self.Nk, self.dkp, device=dev, dtype=torch.float32)
+                self.ds = torch.empty(self.Nq, self.Nkp, device=dev, dtype=bf)
+                self.ft = torch.zeros(self.dkp, self.Nkp, device=dev, dtype=bf)
+                self.dv32 = torch.empty(self.Nkp, self.dv, device=dev, dtype=torch.float32)
+                self.dk32 = torch.empty(self.Nkp, self.dkp, device=dev, dtype=torch.float32)
                 self.dgp = torch.empty(B, self.Nq, self.dkp, device=dev, dtype=bf) if self.pad else None
                 self.dfp = torch.empty(B, self.Nk, self.dkp, device=dev, dtype=bf) if self.pad else None
         elif tr:
@@ -598,7 +620,7 @@ class _AttnCoreOp:
     # -- tensor-core path -------------------------------------------------------------------------
     def _fwd_tc(self):
         e, st = self.eng, self.eng.stream
-        B, Nq, Nk, dkp, dv = self.B, self.Nq, self.Nk, self.dkp, self.dv
+        B, Nq, Nk, Nkp, dkp, dv = self.B, self.Nq, self.Nk, self.Nkp, self.dkp, self.dv
         if self.pad:
             A.check(A.lib.sap3d_pad_channels(e.dt, A.ptr(self.g.buf), A.ptr(self.gp), B * Nq, self.dk, dkp, 0, 0, st), "pad g")
             A.check(A.lib.sap3d_pad_channels(e.dt, A.ptr(self.f.buf), A.ptr(self.fp), B * Nk, self.dk, dkp, 0, 0, st), "pad f")
@@ -607,17 +629,17 @@ class _AttnCoreOp:
         fk = self.fp if self.pad else self.f.buf.view(B, Nk, dkp)
         hv = self.h.buf.view(B, Nk, dv)
         ob = self.o.buf.view(B, Nq, dv)
-        A.check(A.lib.sap3d_transpose(e.dt, A.ptr(hv), A.ptr(self.vt), B, Nk, dv, dv, Nk, Nk * dv, dv * Nk, st), "transpose h")
+        A.check(A.lib.sap3d_transpose(e.dt, A.ptr(hv), A.ptr(self.vt), B, Nk, dv, dv, Nkp, Nk * dv, dv * Nkp, st), "transpose h")
         e._count()
         for b in range(B):
-            A.check(A.lib.sap3d_gemm_nt(A.ptr(gq[b]), dkp, A.ptr(fk[b]), dkp, A.ptr(self.logits), Nk, Nq, Nk, dkp, 1, 0, st), "QK^T")
-            A.check(A.lib.sap3d_softmax_rows(A.F32, A.ptr(self.logits), A.ptr(self.beta[b]), Nq, Nk, Nk, Nk, st), "softmax")
-            A.check(A.lib.sap3d_gemm_nt(A.ptr(self.beta[b]), Nk, A.ptr(self.vt[b]), Nk, A.ptr(ob[b]), dv, Nq, dv, Nk, 0, 0, st), "PV")
+            A.check(A.lib.sap3d_gemm_nt(A.ptr(gq[b]), dkp, A.ptr(fk[b]), dkp, Nk, A.ptr(self.logits), Nkp, Nq, Nkp, dkp, 1, 0, st), "QK^T")
+            A.check(A.lib.sap3d_softmax_rows(A.F32, A.ptr(self.logits), A.ptr(self.beta[b]), Nq, Nk, Nkp, Nkp, st), "softmax")
+            A.check(A.lib.sap3d_gemm_nt(A.ptr(self.beta[b]), Nkp, A.ptr(self.vt[b]), Nkp, dv, A.ptr(ob[b]), dv, Nq, dv, Nkp, 0, 0, st), "PV")
         e._count(3 * B)
 
     def _bwd_tc(self):
         e, st = self.eng, self.eng.stream
-        B, Nq, Nk, dkp, dv, dk = self.B, self.Nq, self.Nk, self.dkp, self.dv, self.dk
+        B, Nq, Nk, Nkp, dkp, dv, dk = self.B, self.Nq, self.Nk, self.Nkp, self.dkp, self.dv, self.dk
         gq = self.gp if self.pad else self.g.buf.view(B, Nq, dkp)
         fk = self.fp if self.pad else self.f.buf.view(B, Nk, dkp)
         hv = self.h.buf.view(B, Nk, dv)
@@ -627,14 +649,14 @@ class _AttnCoreOp:
         df = self.dfp if self.pad else self.f.ensure_grad().view(B, Nk, dkp)
         for b in range(B):
             self.dv32.zero_()
-            A.check(A.lib.sap3d_gemm_tn(A.ptr(self.beta[b]), Nk, A.ptr(do[b]), dv, A.ptr(self.dv32), dv, Nk, dv, Nq, st), "dV")
+            A.check(A.lib.sap3d_gemm_tn(A.ptr(self.beta[b]), Nkp, A.ptr(do[b]), dv, A.ptr(self.dv32), dv, Nkp, dv, Nq, st), "dV")
             A.check(A.lib.sap3d_cast(A.F32, A.ptr(self.dv32), A.ptr(dh[b]), Nk * dv, st), "cast dV")
-            A.check(A.lib.sap3d_gemm_nt(A.ptr(do[b]), dv, A.ptr(hv[b]), dv, A.ptr(self.ds), Nk, Nq, Nk, dv, 0, 0, st), "dP")
-            A.check(A.lib.sap3d_softmax_bwd_rows(A.ptr(self.beta[b]), A.ptr(self.ds), Nq, Nk, Nk, st), "softmax bwd")
-            A.check(A.lib.sap3d_transpose(e.dt, A.ptr(fk[b]), A.ptr(self.ft), 1, Nk, dkp, dkp, Nk, 0, 0, st), "transpose f")
-            A.check(A.lib.sap3d_gemm_nt(A.ptr(self.ds), Nk, A.ptr(self.ft), Nk, A.ptr(dg[b]), dkp, Nq, dkp, Nk, 0, 0, st), "dQ")
+            A.check(A.lib.sap3d_gemm_nt(A.ptr(do[b]), dv, A.ptr(hv[b]), dv, Nk, A.ptr(self.ds), Nkp, Nq, Nkp, dv, 0, 0, st), "dP")
+            A.check(A.lib.sap3d_softmax_bwd_rows(A.ptr(self.beta[b]), A.ptr(self.ds), Nq, Nk, Nkp, st), "softmax bwd")
+            A.check(A.lib.sap3d_transpose(e.dt, A.ptr(fk[b]), A.ptr(self.ft), 1, Nk, dkp, dkp, Nkp, 0, 0, st), "transpose f")
+            A.check(A.lib.sap3d_gemm_nt(A.ptr(self.ds), Nkp, A.ptr(self.ft), Nkp, dkp, A.ptr(dg[b]), dkp, Nq, dkp, Nkp, 0, 0, st), "dQ")
             self.dk32.zero_()
-            A.check(A.lib.sap3d_gemm_tn(A.ptr(self.ds), Nk, A.ptr(gq[b]), dkp, A.ptr(self.dk32), dkp, Nk, dkp, Nq, st), "dK")
+            A.check(A.lib.sap3d_gemm_tn(A.ptr(self.ds), Nkp, A.ptr(gq[b]), dkp, A.ptr(self.dk32), dkp, Nkp, dkp, Nq, st), "dK")
             A.check(A.lib.sap3d_cast(A.F32, A.ptr(self.dk32), A.ptr(df[b]), Nk * dkp, st), "cast dK")
         e._count(10 * B)
         if self.pad:

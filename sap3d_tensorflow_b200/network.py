@@ -73,7 +73,8 @@ def normalize(x: ConvOut, training, mode="bn"):  # utils/network.py:89 (without 
 
 
 # ---- conv / deconv + norm + relu -----------------------------------------------------------------
-def layers_conv3d(x: Handle, channel: int, kernel, strides, name=None, scope="", use_bias=True, want_stats=True) -> ConvOut:
+def layers_conv3d(x: Handle, channel: int, kernel, strides, name=None, scope="", use_bias=True, want_stats=True,
+                  bias_grad=True) -> ConvOut:
     """tf.layers.conv3d(x, channel, kernel, strides, 'same', name=name): '<name>/kernel' DHWIO, '<name>/bias'"""
     parts = _parts(x)
     eng = parts[0].eng
@@ -82,10 +83,11 @@ def layers_conv3d(x: Handle, channel: int, kernel, strides, name=None, scope="",
     cin = sum(p.C for p in parts)
     w = eng.param(nm + "/kernel", [*k, cin, channel], "glorot")
     b = eng.param(nm + "/bias", [channel], "zeros") if use_bias else None
-    return eng.conv(parts, channel, k, s, w, b, transposed=False, want_stats=want_stats, name=nm)
+    return eng.conv(parts, channel, k, s, w, b, transposed=False, want_stats=want_stats, name=nm, bias_grad=bias_grad)
 
 
-def layers_conv3d_transpose(x: Handle, channel: int, kernel, strides, name=None, scope="", want_stats=True) -> ConvOut:
+def layers_conv3d_transpose(x: Handle, channel: int, kernel, strides, name=None, scope="", want_stats=True,
+                            bias_grad=True) -> ConvOut:
     """tf.layers.conv3d_transpose(x, channel, kernel, strides, 'same', name=name): kernel [k..., Cout, Cin]"""
     parts = _parts(x)
     eng = parts[0].eng
@@ -94,16 +96,16 @@ def layers_conv3d_transpose(x: Handle, channel: int, kernel, strides, name=None,
     cin = sum(p.C for p in parts)
     w = eng.param(nm + "/kernel", [*k, channel, cin], "glorot_t")
     b = eng.param(nm + "/bias", [channel], "zeros")
-    return eng.conv(parts, channel, k, s, w, b, transposed=True, want_stats=want_stats, name=nm)
+    return eng.conv(parts, channel, k, s, w, b, transposed=True, want_stats=want_stats, name=nm, bias_grad=bias_grad)
 
 
 def conv3d(x: Handle, channel, kernel, strides, training, name, mode="bn") -> T:  # utils/network.py:100
-    co = layers_conv3d(x, channel, kernel, strides, name)
+    co = layers_conv3d(x, channel, kernel, strides, name, bias_grad=not training)  # bias in front of batch-stat BN
     return co.raw.eng.tap(name, bn_relu(co, training, tap=name))
 
 
 def transpose_conv3d(x: Handle, channel, kernel, strides, training, name, mode="bn") -> T:  # utils/network.py:106
-    co = layers_conv3d_transpose(x, channel, kernel, strides, name)
+    co = layers_conv3d_transpose(x, channel, kernel, strides, name, bias_grad=not training)
     return co.raw.eng.tap(name, bn_relu(co, training, tap=name))
 
 
@@ -123,7 +125,7 @@ def attention(x: T, name, training, mode="bn", subsample=False, sub_size=2) -> T
         g = pool3d(g, sub_size // 2)
         h = pool3d(h, sub_size)
     o = eng.attn_core(g, f, h, name=name)
-    oc = layers_conv3d(o, ch, 1, sub_size // 2)
+    oc = layers_conv3d(o, ch, 1, sub_size // 2, bias_grad=not training)
     o = bn_relu(oc, training, tap=name + "/o")
     gamma = eng.param("gamma" + name, [1], "sa_gamma")
     return eng.gate(o, x, gamma, name=name)

@@ -15,6 +15,6 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def lib_built():
     """build the C-ABI library (nvcc cross-compiles without a GPU)"""
-    from sap3d_tensorflow_b200 import build
+    import sap3d_build
 
-    return build.build()
+    return sap3d_build.build()
