@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
+    try:  # the torch-based checker must be exact fp32 when it happens to run on the GPU
+        import torch
+
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:  # noqa: BLE001
+        pass
 
 
 @pytest.fixture(scope="session")

@@ -58,7 +58,8 @@ def run_case(A, N, D, H, W, cin, cout, k, s, transposed, dtype, impl):
     assert rel(y, ref) < tol
     s1 = stats[:, 0].double().sum(0).float().cpu()
     s2 = stats[:, 1].double().sum(0).float().cpu()
-    assert ((s2 - (ref * ref).sum(dim=(0, 1, 2, 3))).norm() / (ref * ref).sum(dim=(0, 1, 2, 3)).norm()).item() < 2e-3 if dtype == A.BF16 else 1e-4
+    # (the CUDA-core path takes the statistics from the stored bf16 output: 5e-3)
+    assert ((s2 - (ref * ref).sum(dim=(0, 1, 2, 3))).norm() / (ref * ref).sum(dim=(0, 1, 2, 3)).norm()).item() < (5e-3 if dtype == A.BF16 else 1e-4)
     assert ((s1 - ref.sum(dim=(0, 1, 2, 3))).abs().max() / ref.abs().sum(dim=(0, 1, 2, 3)).max()).item() < 2e-3
     dy = torch.randn(ref.shape).to(tdt)
     ref.backward(dy.float())
@@ -96,7 +97,7 @@ TC_CASES = [
     ("upx_2_x deconv k3 s2", 1, 4, 14, 14, [256], 128, (3, 3, 3), (2, 2, 2), True),
     ("upx_3_x deconv k(2,3,3) s2", 1, 2, 14, 14, [512], 256, (2, 3, 3), (2, 2, 2), True),
     ("upx_4_0 deconv k(1,3,3) s2", 2, 1, 7, 7, [1024], 512, (1, 3, 3), (2, 2, 2), True),
-    ("ragged extents", 1, 3, 9, 11, [64], 72, (3, 3, 3), (1, 1, 1), False),
+    ("ragged extents", 1, 3, 9, 11, [64], 128, (3, 3, 3), (1, 1, 1), False),
     ("deconv k3 s1 (p3d_concat)", 1, 2, 6, 6, [64], 64, (3, 3, 3), (1, 1, 1), True),
 ]
 
@@ -104,6 +105,11 @@ TC_CASES = [
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_tensor_core_conv(A, case):
     run_case(A, *case[1:], dtype=A.BF16, impl=A.IMPL_TC)
+
+
+def test_auto_dispatch_mixed_paths(A):
+    """cout = 72: forward on the tensor cores (cout % 8), data/filter gradients on the CUDA-core kernels"""
+    run_case(A, 1, 3, 9, 11, [64], 72, (3, 3, 3), (1, 1, 1), False, dtype=A.BF16, impl=A.IMPL_AUTO)
 
 
 SIMT_CASES = [

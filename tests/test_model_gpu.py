@@ -74,9 +74,12 @@ def test_training_step_parity_fp32(lib_built):
     torch.cuda.synchronize()
     assert abs(loss - loss_ref) / loss_ref < 1e-5
     cos_min, n = 1.0, 0
+    gmax = max(float(g.norm()) for g in grads_ref.values())
     for name, g in sess.gradients().items():
         gr = grads_ref[name]
-        if gr.abs().max() < 1e-4:      # mathematically-zero gradients (bias in front of batch-statistics BN)
+        # mathematically-zero gradients (a bias in front of a batch-statistics BN, incl. the attention h bias whose
+        # effect is a per-channel constant removed by the following BN): the oracle holds rounding noise there
+        if float(gr.norm()) < 1e-5 * gmax:
             continue
         a, b = g.float().cpu().reshape(-1), gr.reshape(-1)
         cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
@@ -128,7 +131,7 @@ def test_gradcheck_engine_self_consistency(lib_built):
         pred = sess.run(x)
         return float(O.tfs.smooth_l1_loss(pred.double().cpu().reshape(y.shape), y.double()))
 
-    eps = 2e-3
+    eps = 2e-5
     num = (loss_at(eps) - loss_at(-eps)) / (2 * eps)
     ana = float(g.norm())
     assert abs(num - ana) / ana < 2e-2, (num, ana)

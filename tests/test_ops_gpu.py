@@ -164,7 +164,8 @@ def test_adam_tf_formula(A):
         A.check(A.lib.sap3d_adam_step(A.ptr(w), A.ptr(g), A.ptr(m), A.ptr(v), n, A.ptr(step), 1e-4, 0.9, 0.999, 1e-8, 1.0, stream()), "adam")
         wr, mr, vr = tfs.adam_step_tf(wr, g, mr, vr, t)
     torch.cuda.synchronize()
-    assert rel(w, wr) < 1e-6 and rel(m, mr) < 1e-6 and rel(v, vr) < 1e-6
+    # the kernel evaluates (1 - beta2) in fp32 like TF's ApplyAdam (0.0010000467 instead of 0.001): 5e-5 on v
+    assert rel(w, wr) < 1e-6 and rel(m, mr) < 1e-6 and rel(v, vr) < 1e-4
 
 
 def test_dropout_matches_numpy_hash(A):
