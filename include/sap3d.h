@@ -183,6 +183,14 @@ int sap3d_transpose(int32_t dtype, const void* in, void* out, int32_t batch, int
 int sap3d_pad_channels(int32_t dtype, const void* in, void* out, int64_t P, int32_t c, int32_t c_pad, int32_t unpad,
                        int32_t accumulate, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Saliency metrics (utils/metrics.py CC :227, SIM :258, NSS :200, KLdiv :338): out[n][4] = CC, SIM, NSS, KLdiv
+ * (fp64) for n (prediction, density, fixation) map triples; fixation may be NULL (NSS = NaN).
+ * ---------------------------------------------------------------------------------------------- */
+int sap3d_saliency_metrics(const float* pred, const float* density, const float* fixation, int32_t n_maps,
+                           int64_t elems_per_map, int64_t pred_stride, int64_t density_stride, int64_t fixation_stride,
+                           double* out, void* stream);
+
 /* one-launch re-packing of all filters after an optimizer step (table built with sap3d_conv_pack_entries) */
 typedef struct sap3d_pack_entry {
   const float* src;   /* fp32 TF-layout filter */

@@ -139,6 +139,7 @@ class PackEntry(C.Structure):
 
 _sig("sap3d_conv_pack_entries", [_P(ConvDesc), _vp, _vp, _vp, _P(PackEntry)])
 _sig("sap3d_pack_multi", [_vp, _i32, _i64, _vp])
+_sig("sap3d_saliency_metrics", [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp])
 
 
 def i3(v):

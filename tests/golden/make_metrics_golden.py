@@ -1,0 +1,64 @@
+"""Generates tests/golden/metrics_golden.npz by running the REFERENCE's utils/metrics.py (imported from
+/root/reference; build container only) on seeded synthetic maps.  skimage is absent from the image and is
+stubbed (the metrics under test never call it); scipy.misc.imresize (removed from SciPy) is provided by the
+restatement in oracle/metrics_oracle.py, so KLdiv runs the reference's own function body.
+
+    python tests/golden/make_metrics_golden.py
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import metrics_oracle as MO  # noqa: E402
+
+sk = types.ModuleType("skimage")
+sk.img_as_float = lambda x: x
+sk.exposure = types.ModuleType("skimage.exposure")
+tr = types.ModuleType("skimage.transform")
+tr.resize = None
+sys.modules.update({"skimage": sk, "skimage.exposure": sk.exposure, "skimage.transform": tr})
+import scipy  # noqa: E402
+
+misc = types.ModuleType("scipy.misc")
+misc.imresize = MO.imresize
+sys.modules["scipy.misc"] = misc
+scipy.misc = misc
+if not hasattr(np, "float_"):
+    np.float_ = np.float64  # metric_utils.py:43 uses the NumPy-1 alias
+sys.path.insert(0, "/root/reference/utils")
+import metrics as ref  # noqa: E402
+
+
+def make_case(rng, h, w, kind):
+    yy, xx = np.mgrid[0:h, 0:w]
+    if kind == "blobs":
+        pred = sum(np.exp(-((yy - rng.uniform(0, h)) ** 2 + (xx - rng.uniform(0, w)) ** 2) / (2 * rng.uniform(3, 15) ** 2)) for _ in range(3))
+        dens = sum(np.exp(-((yy - rng.uniform(0, h)) ** 2 + (xx - rng.uniform(0, w)) ** 2) / (2 * rng.uniform(3, 15) ** 2)) for _ in range(3))
+    elif kind == "uniform":
+        pred, dens = rng.uniform(0, 1, (h, w)), rng.uniform(0, 1, (h, w))
+    else:  # sigmoid-like network output vs 8-bit ground truth
+        pred = 1.0 / (1.0 + np.exp(-rng.normal(0, 2, (h, w))))
+        dens = rng.randint(0, 256, (h, w)) / 255.0
+    fix = (rng.uniform(0, 1, (h, w)) < 0.01).astype(np.float32)
+    fix[rng.randint(h), rng.randint(w)] = 1.0
+    return pred.astype(np.float32), dens.astype(np.float32), fix
+
+
+def main():
+    rng = np.random.RandomState(1234)
+    preds, denss, fixs, vals = [], [], [], []
+    for i in range(12):
+        p, d, f = make_case(rng, 112, 112, ["blobs", "uniform", "sigmoid"][i % 3])
+        vals.append([ref.CC(p, d), ref.SIM(p, d), ref.NSS(p, f), ref.KLdiv(p, d)])
+        preds.append(p); denss.append(d); fixs.append(f)
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "metrics_golden.npz")
+    np.savez_compressed(out, pred=np.stack(preds), density=np.stack(denss), fixation=np.stack(fixs), values=np.array(vals, dtype=np.float64))
+    print("wrote", out, np.array(vals)[:3])
+
+
+if __name__ == "__main__":
+    main()
