@@ -191,6 +191,28 @@ int sap3d_saliency_metrics(const float* pred, const float* density, const float*
                            int64_t elems_per_map, int64_t pred_stride, int64_t density_stride, int64_t fixation_stride,
                            double* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm + CBAM of the GN model variant (gn/p3d_gn.py:24-46,175; utils/network.py:65-87,198-274).
+ * ---------------------------------------------------------------------------------------------- */
+int sap3d_sample_stats_rows(int64_t S, int32_t C, int32_t N);
+/* part [N][rows][3][C] = per-sample per-channel (sum, sum of squares, max) partials of x [N][S][C] (optionally of
+ * x*scale[n][c]) */
+int sap3d_sample_channel_partials(int32_t dtype, const void* x, const float* scale, int32_t N, int64_t S, int32_t C, int32_t rows,
+                                  float* part, void* stream);
+/* GroupNorm: partials -> per-(sample,channel) scale/shift [N][C] (+ per-(sample,group) mean/rstd [N][G]) */
+int sap3d_gn_finalize(const float* part, int32_t rows, int32_t N, int64_t S, int32_t C, int32_t G, const float* gamma,
+                      const float* beta, float eps, float* scale, float* shift, float* save_mean, float* save_rstd, void* stream);
+/* CBAM attention maps of r: channel scale cscale [N][C] (mean & max over D,H,W -> shared MLP C->hidden->C -> sigmoid) and
+ * spatial map att [N][D*H*W] (mean & max over C of r*cscale -> 7x7x7 conv, no bias -> sigmoid); scratch: part, sp */
+int sap3d_cbam_fwd(int32_t dtype, const void* r, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t hidden,
+                   const float* w0, const float* b0, const float* w1, const float* b1, const float* w_sp, float* part,
+                   int32_t rows, float* cscale, float* sp, float* att, void* stream);
+/* y = relu((a*s1[n][c]+t1[n][c]) + r*cscale[n][c]*att[n][pos])  (out += cbam(residual); relu — gn/p3d_gn.py:175-177) */
+int sap3d_cbam_merge(int32_t dtype, const void* a, const float* s1, const float* t1, const void* r, const float* cscale,
+                     const float* att, void* y, int32_t N, int64_t S, int32_t C, void* stream);
+/* y [P][ca+cb] = concat(a [P][ca], b [P][cb]) (materialised tf.concat for three-way concatenations) */
+int sap3d_concat_channels(int32_t dtype, const void* a, const void* b, void* y, int64_t P, int32_t ca, int32_t cb, void* stream);
+
 /* one-launch re-packing of all filters after an optimizer step (table built with sap3d_conv_pack_entries) */
 typedef struct sap3d_pack_entry {
   const float* src;   /* fp32 TF-layout filter */

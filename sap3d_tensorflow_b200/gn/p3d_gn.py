@@ -1,0 +1,137 @@
+"""GroupNorm + CBAM variant of the P3D saliency model on the B200 engine — public surface of the reference's
+gn/p3d_gn.py: GroupNorm :24, GNReLU :49, conv3d_layers :14, deconv3d_layers :19, Bottleneck :74, make_block :182,
+inference_p3d :214, inference_p3d_concat :279.  Every block ends with cbam_block on the residual
+(gn/p3d_gn.py:175).  Variables: group_norm[_N]/{gamma,beta}, cbam_{id}/ch_at/mlp_{0,1}/{kernel,bias},
+cbam_{id}/sp_at/conv3d/kernel, conv names as in p3d.py.
+
+The *_sa_* builders of the reference call attention() with a stale signature (gn/p3d_gn.py:340 vs
+utils/network.py:157) and cannot be built; they are not mirrored."""
+from __future__ import annotations
+
+from .. import network as nw
+from ..engine import ConvOut, T
+from ..engine_gn import CbamBlockTailOp, ConcatOp, GNActOp, GNState
+from ..p3d import BLOCK_EXPANSION, STAGES, TEMPORAL_POOL, convS, convT, get_conv_weight
+
+
+def _gn_state(t: T) -> GNState:
+    eng = t.eng
+    nm = eng.names.unique("", "group_norm")
+    N, Cc = t.shape[0], t.C
+    return GNState(eng, N, Cc, t.positions // N, eng.param(nm + "/gamma", [Cc], "ones"), eng.param(nm + "/beta", [Cc], "zeros"))
+
+
+def GroupNorm(x: ConvOut, G=32, esp=1e-5, relu=False, name="") -> T:   # gn/p3d_gn.py:24-46
+    return GNActOp(x.raw.eng, x, _gn_state(x.raw), relu, name=name).y
+
+
+def GNReLU(x: ConvOut, name=None) -> T:                                 # gn/p3d_gn.py:49-51
+    return GroupNorm(x, relu=True, name=name or "gnrelu")
+
+
+def conv3d_layers(x, filters, kernel, strides, name) -> T:              # gn/p3d_gn.py:14-17
+    return GNReLU(nw.layers_conv3d(x, filters, kernel, strides, name, want_stats=False), name)
+
+
+def deconv3d_layers(x, filters, kernel, strides, name) -> T:            # gn/p3d_gn.py:19-22
+    return GNReLU(nw.layers_conv3d_transpose(x, filters, kernel, strides, name, want_stats=False), name)
+
+
+class Bottleneck:
+    """gn/p3d_gn.py:74-179 (3-D branch)"""
+
+    def __init__(self, l_input: T, inplanes, planes, stride=1, downsample="", training=True, n_s=0, depth_3d=47):
+        if n_s >= depth_3d:
+            raise NotImplementedError("2-D bottlenecks are dead code in the reference graphs")
+        self.x, self.inplanes, self.planes, self.id = l_input, inplanes, planes, n_s
+        self.first = downsample != ""
+        self.hw_stride = 2 if (self.first and n_s != 0) else 1
+        self.ST = "ABC"[n_s % 3]
+
+    def infer(self) -> T:
+        x, eng, pl, i = self.x, self.x.eng, self.planes, self.id
+        s = (1, self.hw_stride, self.hw_stride)
+        one = (1, 1, 1)
+        conv = lambda t, cout, st, nm: eng.conv([t], cout, one, st, get_conv_weight(eng, nm, [1, 1, 1, t.C, cout]), name=nm, want_stats=False)  # noqa: E731
+        o = GroupNorm(conv(x, pl, s, f"conv3_{i}_1"), relu=True, name=f"b{i}/1")
+        nm = f"ST{self.ST}_{i}_2"
+        if self.ST == "A":
+            o = GroupNorm(convS(nm + "_S", o, pl, pl), relu=True, name=nm + "_S")
+            o = GroupNorm(convT(nm + "_T", o, pl, pl), relu=True, name=nm + "_T")
+        elif self.ST == "B":
+            s_raw = convS(nm + "_S", o, pl, pl)
+            gs = _gn_state(s_raw.raw)
+            t_raw = convT(nm + "_T", o, pl, pl)
+            gt = _gn_state(t_raw.raw)
+            o = GNActOp(eng, t_raw, gt, True, b=s_raw, g2=gs, relu2=True, name=nm).y
+        else:
+            s_act = GroupNorm(convS(nm + "_S", o, pl, pl), relu=True, name=nm + "_S")
+            t_raw = convT(nm + "_T", s_act, pl, pl)
+            o = GNActOp(eng, t_raw, _gn_state(t_raw.raw), True, b=s_act, name=nm).y
+        c3 = conv(o, pl * BLOCK_EXPANSION, one, f"conv3_{i}_3")
+        g3 = _gn_state(c3.raw)
+        residual = x
+        if self.first:
+            residual = GroupNorm(conv(x, pl * BLOCK_EXPANSION, s, f"dw3d_{i}"), relu=False, name=f"dw3d_{i}")
+        Cc = pl * BLOCK_EXPANSION
+        sc = f"cbam_{i}"
+        tail = CbamBlockTailOp(eng, c3, g3, residual,
+                               eng.param(sc + "/ch_at/mlp_0/kernel", [Cc, Cc // 8], "vscale"), eng.param(sc + "/ch_at/mlp_0/bias", [Cc // 8], "zeros"),
+                               eng.param(sc + "/ch_at/mlp_1/kernel", [Cc // 8, Cc], "vscale"), eng.param(sc + "/ch_at/mlp_1/bias", [Cc], "zeros"),
+                               eng.param(sc + "/sp_at/conv3d/kernel", [7, 7, 7, 2, 1], "vscale"), name=f"b{i}")
+        return eng.tap(f"b{i}", tail.y)
+
+
+class make_block:
+    """gn/p3d_gn.py:182-209"""
+
+    def __init__(self, _X: T, planes, num, inplanes, cnt, training=True, depth_3d=47, stride=1):
+        self.input, self.planes, self.num, self.inplanes, self.cnt, self.stride, self.depth_3d = _X, planes, num, inplanes, cnt, stride, depth_3d
+
+    def infer(self) -> T:
+        x = self.input
+        for j in range(self.num):
+            x = Bottleneck(x, self.inplanes if j == 0 else BLOCK_EXPANSION * self.planes, self.planes, self.stride,
+                           downsample="3d" if j == 0 else "", n_s=self.cnt, depth_3d=self.depth_3d).infer()
+            self.cnt += 1
+        return x
+
+
+def _backbone(_X: T):
+    eng = _X.eng
+    c = eng.conv([_X], 64, (1, 7, 7), (1, 2, 2), get_conv_weight(eng, "firstconv1", [1, 7, 7, 3, 64]), name="firstconv1", want_stats=False)
+    x = eng.maxpool(GroupNorm(c, relu=True, name="stem"), (2, 3, 3), (2, 2, 2), name="pool1")
+    pools, cnt = [], 0
+    for planes, num, inplanes, stride in STAGES:
+        blk = make_block(x, planes, num, inplanes, cnt, stride=stride)
+        res = blk.infer()
+        cnt = blk.cnt
+        x = eng.maxpool(res, *TEMPORAL_POOL, name=f"pool{len(pools) + 2}")
+        pools.append(eng.tap(f"pool{len(pools) + 2}", x))
+    return pools  # pool2 [4,28,28,256], pool3 [2,14,14,512], pool4 [1,7,7,1024]
+
+
+def _inference(_X: T, _dropout, training, pool4_filters):
+    eng = _X.eng
+    pool2, pool3, pool4 = _backbone(_X)
+    dp3 = GNReLU(nw.layers_conv3d_transpose(pool3, 512, 3, [2, 2, 2], "deconv_pool3", want_stats=False), "deconv_pool3_gn")
+    dp4 = GNReLU(nw.layers_conv3d_transpose(pool4, pool4_filters, 3, [4, 4, 4], "deconv_pool4", want_stats=False), "deconv_pool4_gn")
+    cat = ConcatOp(eng, dp3, dp4, name="concat_dp3_dp4").y
+    cc = GNReLU(nw.layers_conv3d(nw.concat([cat, pool2]), 1024, 3, 1, "conv_concat", want_stats=False), "conv_concat")
+    eng.tap("conv_concat", cc)
+    dr = GNReLU(nw.layers_conv3d_transpose(cc, 256, 3, 2, "deconv_revise", want_stats=False), "deconv_revise")
+    if training:
+        dr = eng.dropout(dr, _dropout, name="deconv_revise_drop")
+    w = eng.param("predict_revise/kernel", [3, 3, 3, 1, 256], "glorot_t")
+    b = eng.param("predict_revise/bias", [1], "zeros")
+    return eng.head(dr, w, b, (3, 3, 3), 2, sigmoid=False, name="predict_revise")  # returns logits (gn/p3d_gn.py:257-258)
+
+
+def inference_p3d(_X, _dropout, batch_size=2, training=True):
+    """gn/p3d_gn.py:214-258"""
+    return _inference(_X, _dropout, training, 1024)
+
+
+def inference_p3d_concat(_X, _dropout, batch_size=2, training=True):
+    """gn/p3d_gn.py:279-324"""
+    return _inference(_X, _dropout, training, 512)

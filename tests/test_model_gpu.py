@@ -122,16 +122,24 @@ def test_gradcheck_engine_self_consistency(lib_built):
     e.begin_step(); e.forward(); e.backward()
     torch.cuda.synchronize()
     g = e.flat_g[:e.n_train].clone()
-    direction = g / g.norm()
+    # one direction per probed variable: sign(grad) on that variable only, so every touched weight moves by eps
+    # (a global normalised direction would move each of the 85 M weights by less than one fp32 ulp)
+    probes = ["x_1_3/kernel", "upx_2_2/kernel", "x_2_2_sa/conv3d/kernel", "gammax_2_2_sa", "conv3_20_3", "STB_4_2_T",
+              "dw3d_3", "firstconv1", "batch_normalization_100/gamma", "batch_normalization_5/beta", "x_0_1/kernel"]
 
-    def loss_at(eps):
+    def loss_at(direction, eps):
         e.flat_w.copy_(w0)
         e.flat_w[:e.n_train] += eps * direction
         e.pack_weights()
         pred = sess.run(x)
         return float(O.tfs.smooth_l1_loss(pred.double().cpu().reshape(y.shape), y.double()))
 
-    eps = 2e-5
-    num = (loss_at(eps) - loss_at(-eps)) / (2 * eps)
-    ana = float(g.norm())
-    assert abs(num - ana) / ana < 2e-2, (num, ana)
+    for name in probes:
+        par = e.params[name]
+        direction = torch.zeros_like(g)
+        sl = slice(par.offset, par.offset + par.numel)
+        direction[sl] = torch.sign(g[sl])
+        ana = float(g[sl].abs().sum())
+        eps = 1e-4
+        num = (loss_at(direction, eps) - loss_at(direction, -eps)) / (2 * eps)
+        assert abs(num - ana) / ana < 5e-2, (name, num, ana)

@@ -27,9 +27,10 @@ def main():
     torch.set_num_threads(os.cpu_count())
     x = O.synthetic_clip(batch, 16, size, seed=0)
     y = O.synthetic_target(batch, 16, size, seed=1)
-    builder = getattr(sp.p3d, graph)
+    builder = getattr(sp.p3d, graph) if hasattr(sp.p3d, graph) else getattr(sp.gn.p3d_gn, graph)
+    modes = ("eval",) if graph.startswith("inference") else ("eval", "train")
     ok = True
-    for mode in ("eval", "train"):
+    for mode in modes:
         training = mode == "train"
         vs = O.VarStore(seed=0)
         taps_ref = {}
