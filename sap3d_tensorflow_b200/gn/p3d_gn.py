@@ -97,24 +97,20 @@ class make_block:
         return x
 
 
-def _backbone(_X: T):
+def _inference(_X: T, _dropout, training, pool4_filters):
     eng = _X.eng
     c = eng.conv([_X], 64, (1, 7, 7), (1, 2, 2), get_conv_weight(eng, "firstconv1", [1, 7, 7, 3, 64]), name="firstconv1", want_stats=False)
     x = eng.maxpool(GroupNorm(c, relu=True, name="stem"), (2, 3, 3), (2, 2, 2), name="pool1")
-    pools, cnt = [], 0
-    for planes, num, inplanes, stride in STAGES:
+    pools, cnt, dp3 = [], 0, None
+    for si, (planes, num, inplanes, stride) in enumerate(STAGES):
         blk = make_block(x, planes, num, inplanes, cnt, stride=stride)
         res = blk.infer()
         cnt = blk.cnt
-        x = eng.maxpool(res, *TEMPORAL_POOL, name=f"pool{len(pools) + 2}")
-        pools.append(eng.tap(f"pool{len(pools) + 2}", x))
-    return pools  # pool2 [4,28,28,256], pool3 [2,14,14,512], pool4 [1,7,7,1024]
-
-
-def _inference(_X: T, _dropout, training, pool4_filters):
-    eng = _X.eng
-    pool2, pool3, pool4 = _backbone(_X)
-    dp3 = GNReLU(nw.layers_conv3d_transpose(pool3, 512, 3, [2, 2, 2], "deconv_pool3", want_stats=False), "deconv_pool3_gn")
+        x = eng.tap(f"pool{si + 2}", eng.maxpool(res, *TEMPORAL_POOL, name=f"pool{si + 2}"))
+        pools.append(x)
+        if si == 1:  # the reference creates deconv_pool3 (and its GroupNorm variables) BEFORE stage 3 (gn/p3d_gn.py:234-237)
+            dp3 = GNReLU(nw.layers_conv3d_transpose(x, 512, 3, [2, 2, 2], "deconv_pool3", want_stats=False), "deconv_pool3_gn")
+    pool2, pool3, pool4 = pools  # [4,28,28,256], [2,14,14,512], [1,7,7,1024]
     dp4 = GNReLU(nw.layers_conv3d_transpose(pool4, pool4_filters, 3, [4, 4, 4], "deconv_pool4", want_stats=False), "deconv_pool4_gn")
     cat = ConcatOp(eng, dp3, dp4, name="concat_dp3_dp4").y
     cc = GNReLU(nw.layers_conv3d(nw.concat([cat, pool2]), 1024, 3, 1, "conv_concat", want_stats=False), "conv_concat")
