@@ -14,21 +14,42 @@ import torch.distributed as dist
 from . import _abi as A
 
 
+def make_buckets(n: int, per: int):
+    """[lo, hi) element ranges covering [0, n), built from the END of the flat gradient buffer: parameters are laid
+    out in forward order, so backward completes them tail-first and the tail buckets can be reduced first."""
+    buckets = []
+    hi = n
+    while hi > 0:
+        lo = max(0, hi - per)
+        buckets.append((lo, hi))
+        hi = lo
+    return buckets
+
+
+def shard_clips(n_clips: int, rank: int, world: int):
+    """contiguous clip range of `rank` (inference / evaluation sharding: no communication during forward)"""
+    per = (n_clips + world - 1) // world
+    lo = min(n_clips, rank * per)
+    return lo, min(n_clips, lo + per)
+
+
+def reduce_metric_sums(sums: torch.Tensor, counts: torch.Tensor):
+    """end-of-evaluation exchange: all-reduce per-metric (sum over non-NaN clips, count) pairs, return the means
+    (NaN filtering mirrors test.py:177-181)"""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        packed = torch.stack([sums, counts]).contiguous()
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+        sums, counts = packed[0], packed[1]
+    return sums / counts
+
+
 class GradientExchange:
     def __init__(self, eng, bucket_mb: int = 32):
         self.eng = eng
         n = eng.n_train
         self.n = n
         self.buf = torch.zeros(n, device=eng.device, dtype=torch.bfloat16)
-        per = bucket_mb * 1024 * 1024 // 2
-        # buckets from the END of the flat gradient buffer: parameters are laid out in forward order, so
-        # backward completes them tail-first
-        self.buckets = []
-        hi = n
-        while hi > 0:
-            lo = max(0, hi - per)
-            self.buckets.append((lo, hi))
-            hi = lo
+        self.buckets = make_buckets(n, bucket_mb * 1024 * 1024 // 2)
         self.comm_stream = torch.cuda.Stream(device=eng.device)
 
     def __call__(self, eng):

@@ -1,0 +1,70 @@
+"""world_size-2 gloo tests (CPU) of the host-side data-parallel logic: bucket partition, clip sharding, the
+sum-semantics of the gradient exchange (the loss is a SUM over elements, so shard gradients add up to the
+global-batch gradient with no averaging) and the NaN-filtered metric reduction of the sharded evaluation."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_buckets_cover_exactly_once():
+    from sap3d_tensorflow_b200.parallel import make_buckets
+
+    for n, per in [(10, 3), (85_000_000, 16 * 1024 * 1024), (5, 100), (64, 64)]:
+        b = make_buckets(n, per)
+        assert b[0][1] == n and b[-1][0] == 0
+        assert all(b[i][0] == b[i + 1][1] for i in range(len(b) - 1))
+        assert all(0 < hi - lo <= per for lo, hi in b)
+
+
+def test_clip_sharding_partitions_the_evaluation_set():
+    from sap3d_tensorflow_b200.parallel import shard_clips
+
+    for n, world in [(1024, 8), (10, 4), (3, 8)]:
+        got = [shard_clips(n, r, world) for r in range(world)]
+        covered = [i for lo, hi in got for i in range(lo, hi)]
+        assert covered == list(range(n))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import tf_semantics as tfs
+    from sap3d_tensorflow_b200.parallel import make_buckets, reduce_metric_sums
+
+    # (1) gradient exchange semantics on a tiny model: sum-loss => grad(global batch) == sum of shard grads
+    torch.manual_seed(0)
+    w = torch.randn(6, 4, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(4, 6, dtype=torch.float64)      # global batch of 4 "clips"
+    y = torch.rand(4, 4, dtype=torch.float64)
+    tfs.smooth_l1_loss(torch.sigmoid(x @ w), y).backward()
+    g_global = w.grad.clone()
+    w.grad = None
+    lo, hi = rank * 2, rank * 2 + 2
+    tfs.smooth_l1_loss(torch.sigmoid(x[lo:hi] @ w), y[lo:hi]).backward()
+    flat = w.grad.reshape(-1).clone().float()
+    for a, b in make_buckets(flat.numel(), 7):      # bucketed all-reduce, tail first
+        dist.all_reduce(flat[a:b], op=dist.ReduceOp.SUM)
+    ok1 = torch.allclose(flat.double().reshape(6, 4), g_global, atol=1e-6)
+    # (2) sharded evaluation: NaN-filtered means
+    vals = torch.tensor([[0.5, float("nan")], [0.7, 0.2]]) if rank == 0 else torch.tensor([[0.9, 0.4], [float("nan"), 0.6]])
+    okm = ~torch.isnan(vals)
+    means = reduce_metric_sums(torch.where(okm, vals, torch.zeros_like(vals)).sum(0), okm.sum(0).float())
+    ok2 = torch.allclose(means, torch.tensor([0.7, 0.4]), atol=1e-6)
+    q.put((rank, bool(ok1), bool(ok2)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_exchange():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(a and b for _, a, b in res), res
