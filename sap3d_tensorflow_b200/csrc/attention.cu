@@ -158,19 +158,50 @@ __global__ void __launch_bounds__(128) attn_dk_kernel(const AttnArgs p, const T*
 }
 
 // ---- row softmax over f32 / bf16 logits -> bf16/f32 probabilities (TC path glue) ------------------
+// one CTA per row; the row lives in registers (<= 16 values per thread for rows up to 4096 columns), so the
+// logits are read from HBM exactly once.  Longer rows fall back to re-reading (L2-resident) data.
+constexpr int SM_MAXV = 16;
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const TI* __restrict__ s, TO* __restrict__ out, int cols, int ld_in, int ld_out) {
   __shared__ float sh[8];
   const TI* r = s + (long long)blockIdx.x * ld_in;
   TO* o = out + (long long)blockIdx.x * ld_out;
+  const bool in_regs = cols <= SM_MAXV * 256;
+  float v[SM_MAXV];
   float mx = -INFINITY;
-  for (int j = threadIdx.x; j < cols; j += blockDim.x) mx = fmaxf(mx, to_f32<TI>(r[j]));
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+      const int j = threadIdx.x + i * 256;
+      v[i] = j < cols ? to_f32<TI>(r[j]) : -INFINITY;
+      mx = fmaxf(mx, v[i]);
+    }
+  } else {
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) mx = fmaxf(mx, to_f32<TI>(r[j]));
+  }
   mx = block_reduce<TI>(mx, true, sh);
   float sum = 0.f;
-  for (int j = threadIdx.x; j < cols; j += blockDim.x) sum += __expf(to_f32<TI>(r[j]) - mx);
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+      v[i] = __expf(v[i] - mx);  // exp(-inf) = 0 for the padding
+      sum += v[i];
+    }
+  } else {
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) sum += __expf(to_f32<TI>(r[j]) - mx);
+  }
   sum = block_reduce<TI>(sum, false, sh);
   const float inv = 1.f / sum;
-  for (int j = threadIdx.x; j < ld_out; j += blockDim.x) o[j] = from_f32<TO>(j < cols ? __expf(to_f32<TI>(r[j]) - mx) * inv : 0.f);
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+      const int j = threadIdx.x + i * 256;
+      if (j < ld_out) o[j] = from_f32<TO>(j < cols ? v[i] * inv : 0.f);
+    }
+  } else {
+    for (int j = threadIdx.x; j < ld_out; j += blockDim.x) o[j] = from_f32<TO>(j < cols ? __expf(to_f32<TI>(r[j]) - mx) * inv : 0.f);
+  }
 }
 
 // dS = beta * (dbeta - sum_j dbeta_j beta_j), in place over dbeta
@@ -179,10 +210,30 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const T* __restri
   __shared__ float sh[8];
   const T* br = beta + (long long)blockIdx.x * ld;
   T* dr = dbeta + (long long)blockIdx.x * ld;
+  const bool in_regs = cols <= SM_MAXV * 256;
+  float b[SM_MAXV], d[SM_MAXV];
   float dot = 0.f;
-  for (int j = threadIdx.x; j < cols; j += blockDim.x) dot += to_f32<T>(br[j]) * to_f32<T>(dr[j]);
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+      const int j = threadIdx.x + i * 256;
+      b[i] = j < cols ? to_f32<T>(br[j]) : 0.f;
+      d[i] = j < cols ? to_f32<T>(dr[j]) : 0.f;
+      dot = fmaf(b[i], d[i], dot);
+    }
+  } else {
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) dot += to_f32<T>(br[j]) * to_f32<T>(dr[j]);
+  }
   dot = block_reduce<T>(dot, false, sh);
-  for (int j = threadIdx.x; j < ld; j += blockDim.x) dr[j] = from_f32<T>(j < cols ? to_f32<T>(br[j]) * (to_f32<T>(dr[j]) - dot) : 0.f);
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+      const int j = threadIdx.x + i * 256;
+      if (j < ld) dr[j] = from_f32<T>(j < cols ? b[i] * (d[i] - dot) : 0.f);
+    }
+  } else {
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) dr[j] = from_f32<T>(j < cols ? to_f32<T>(br[j]) * (to_f32<T>(dr[j]) - dot) : 0.f);
+  }
 }
 
 // batched transpose [R][C] (row stride ld_in) -> [C][R] (row stride ld_out, zero padded up to ld_out)

@@ -42,6 +42,7 @@ struct TcProblem {
   const float* shift;
   int relu, accumulate, out_f32;
   int force_block_n;  // 0 = auto
+  int force_mt = 0;   // 0 = auto, 1 / 2 = M sub-tiles per CTA
 };
 
 // number of M tiles (per class) the launcher will use for these extents (after dim merging)

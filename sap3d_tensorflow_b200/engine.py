@@ -134,6 +134,8 @@ class Engine:
         self.launches_bwd = 0
         self._counting = None
         self._pack_table = None
+        self.side_stream = torch.cuda.Stream(device=self.device)   # filter gradients run here, off the critical path
+        self.use_side_stream = True
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -332,6 +334,8 @@ class Engine:
         self._count()
         for f in reversed(self.bwd_ops):
             f()
+        if self.use_side_stream:
+            torch.cuda.current_stream(self.device).wait_stream(self.side_stream)   # join the filter-gradient branch
         self._counting = None
 
     def adam(self, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
@@ -393,8 +397,15 @@ class _ConvOp:
                                            A.ptr(x.ensure_grad()), acc, e.stream), "conv_dgrad " + self.name)
             e._count()
         x1 = self.xs[1].buf if len(self.xs) > 1 else None
+        main = torch.cuda.current_stream(e.device)
+        if e.use_side_stream:
+            # fork: the filter gradient only needs dy (ready on `main`) and the saved inputs; it is joined before Adam
+            e.side_stream.wait_stream(main)
+            st = e.side_stream.cuda_stream
+        else:
+            st = e.stream
         A.check(A.lib.sap3d_conv_wgrad(C.byref(self.desc), A.ptr(self.xs[0].buf), A.ptr(x1), A.ptr(dy), A.ptr(self.w.g),
-                                       A.ptr(self.b.g) if (self.b is not None and self.bias_grad) else None, e.stream),
+                                       A.ptr(self.b.g) if (self.b is not None and self.bias_grad) else None, st),
                 "conv_wgrad " + self.name)
         e._count(len(self.xs) + (1 if (self.b is not None and self.bias_grad) else 0))
 

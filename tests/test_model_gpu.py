@@ -140,6 +140,13 @@ def test_gradcheck_engine_self_consistency(lib_built):
         sl = slice(par.offset, par.offset + par.numel)
         direction[sl] = torch.sign(g[sl])
         ana = float(g[sl].abs().sum())
-        eps = 1e-4
-        num = (loss_at(direction, eps) - loss_at(direction, -eps)) / (2 * eps)
-        assert abs(num - ana) / ana < 5e-2, (name, num, ana)
+        # central differences with a decreasing step until the curvature term is below 5 % (sign(g) moves up to 9e5
+        # weights coherently, so the first steps are far from infinitesimal)
+        tried = []
+        for eps in (1e-4, 2e-5, 4e-6, 1e-6):
+            num = (loss_at(direction, eps) - loss_at(direction, -eps)) / (2 * eps)
+            tried.append((eps, num))
+            if abs(num - ana) / ana < 5e-2:
+                break
+        else:
+            raise AssertionError((name, ana, tried))
