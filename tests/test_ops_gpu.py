@@ -181,3 +181,48 @@ def test_dropout_matches_numpy_hash(A):
 
     ref = keep_mask(1234 + 5, n, 0.5).astype(np.float32) * 2.0
     assert np.array_equal(y.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("dtn,tdt,tol", DT)
+def test_attention_gate(A, dtn, tdt, tol):
+    """x = o * gamma + x (utils/network.py:191-192) and its gradients (d_o, dx accumulate, dgamma)"""
+    torch.manual_seed(5)
+    dt = A.BF16 if dtn == "bf16" else A.F32
+    n = 2 * 3 * 4 * 5 * 64
+    o, x, dy = [torch.randn(n, device="cuda").to(tdt) for _ in range(3)]
+    gamma = torch.tensor([0.37], device="cuda")
+    y = torch.empty_like(o)
+    A.check(A.lib.sap3d_gate_fwd(dt, A.ptr(o), A.ptr(x), A.ptr(gamma), A.ptr(y), n, stream()), "gate")
+    assert rel(y, o.float() * 0.37 + x.float()) < tol
+    d_o, dx, dg = torch.empty_like(o), torch.ones_like(o), torch.zeros(1, device="cuda")
+    A.check(A.lib.sap3d_gate_bwd(dt, A.ptr(dy), A.ptr(o), A.ptr(gamma), A.ptr(d_o), A.ptr(dx), 1, A.ptr(dg), n, stream()), "gateb")
+    torch.cuda.synchronize()
+    assert rel(d_o, dy.float() * 0.37) < tol and rel(dx, dy.float() + 1) < tol
+    assert rel(dg, (dy.float() * o.float()).sum().reshape(1)) < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 49, 49, 128, 1024), (1, 392, 392, 64, 512), (2, 256, 64, 16, 128)])
+@pytest.mark.parametrize("dtn,tdt,tol", DT)
+def test_attention_core(A, dtn, tdt, tol, shape):
+    """o = softmax(g f^T) h and its gradients: CUDA-core kernels (fp32 / tiny sites) against torch autograd"""
+    torch.manual_seed(6)
+    dt = A.BF16 if dtn == "bf16" else A.F32
+    B, Nq, Nk, dk, dv = shape
+    g = (torch.randn(B, Nq, dk, device="cuda") * 0.3).to(tdt)
+    f = (torch.randn(B, Nk, dk, device="cuda") * 0.3).to(tdt)
+    h = torch.randn(B, Nk, dv, device="cuda").to(tdt)
+    d_o = torch.randn(B, Nq, dv, device="cuda").to(tdt)
+    beta = torch.empty(B, Nq, Nk, device="cuda", dtype=tdt)
+    o = torch.empty(B, Nq, dv, device="cuda", dtype=tdt)
+    A.check(A.lib.sap3d_attention_fwd(dt, A.ptr(g), A.ptr(f), A.ptr(h), A.ptr(beta), A.ptr(o), B, Nq, Nk, dk, dv, dk, dk, dv, Nk, dv,
+                                      stream()), "attn")
+    gr, fr, hr = [t.float().requires_grad_(True) for t in (g, f, h)]
+    ref = torch.softmax(gr @ fr.transpose(1, 2), dim=-1) @ hr
+    assert rel(o, ref) < tol
+    ref.backward(d_o.float())
+    ds = torch.empty_like(beta)
+    dg, df, dh = torch.empty_like(g), torch.empty_like(f), torch.empty_like(h)
+    A.check(A.lib.sap3d_attention_bwd(dt, A.ptr(g), A.ptr(f), A.ptr(h), A.ptr(beta), A.ptr(d_o), A.ptr(ds), A.ptr(dg), A.ptr(df), A.ptr(dh),
+                                      B, Nq, Nk, dk, dv, dk, dk, dv, Nk, dv, stream()), "attnb")
+    torch.cuda.synchronize()
+    assert rel(dg, gr.grad) < 4 * tol and rel(df, fr.grad) < 4 * tol and rel(dh, hr.grad) < 4 * tol
