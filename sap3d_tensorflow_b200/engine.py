@@ -134,6 +134,7 @@ class Engine:
         self.launches_bwd = 0
         self._counting = None
         self._pack_table = None
+        self.pre_pack_ops: List = []
         self.side_stream = torch.cuda.Stream(device=self.device)   # filter gradients run here, off the critical path
         self.use_side_stream = True
 
@@ -239,6 +240,8 @@ class Engine:
 
     def pack_weights(self):
         """fp32 master filters -> bf16 tensor-core operands for every conv, in ONE kernel launch"""
+        for f in self.pre_pack_ops:   # derived parameters (zero-padded filters) must be current before packing
+            f()
         if self.dt != A.BF16 or not self.convs:
             return
         if self._pack_table is None:
@@ -270,6 +273,14 @@ class Engine:
         self.fwd_ops.append(op.fwd)
         self.bwd_ops.append(op.bwd)
         return op.out
+
+    def conv_padded_cout(self, xs: Sequence[T], cout_pad: int, kernel, strides, w: Param, b: Optional[Param], name="") -> ConvOut:
+        """conv whose TF variable has cout = w.shape[-1] output channels but which is EXECUTED with cout_pad channels
+        (zero filters / biases for the padding): keeps 16- and 32-channel projections on the tensor-core path in forward,
+        data-gradient and filter-gradient.  Output channels >= cout are exactly zero."""
+        op = _PaddedParams(self, w, b, cout_pad)
+        self.bwd_ops.append(op.bwd)   # registered BEFORE the conv: the bwd list is walked in reverse, so it runs right after it
+        return self.conv(xs, cout_pad, kernel, strides, op.wp, op.bp, transposed=False, want_stats=False, name=name)
 
     def norm_state(self, C, gamma=None, beta=None, mm=None, mv=None) -> NormState:
         self._max_c = max(self._max_c, C)
@@ -565,6 +576,54 @@ class _HeadOp:
         return self.pred if self.sigmoid else self.logits
 
 
+class _PaddedParams:
+    """zero-padded fp32 copies of a filter [..., cin, cout] -> [..., cin, cout_pad] and its bias, refreshed before every
+    weight packing; gradients of the padded copies are folded back into the real variables after the conv's backward"""
+
+    def __init__(self, eng: Engine, w: Param, b: Optional[Param], cout_pad: int):
+        self.eng, self.w, self.b, self.cp = eng, w, b, cout_pad
+        self.c = w.shape[-1]
+        self.rows = w.numel // self.c
+        dev = eng.device
+        mk = lambda shape, nm: _TempParam(nm, shape, dev, eng.training_graph)  # noqa: E731
+        self.wp = mk((*w.shape[:-1], cout_pad), w.name + "#pad")
+        self.bp = mk((cout_pad,), b.name + "#pad") if b is not None else None
+        eng.pre_pack_ops.append(self.refresh)
+        eng.fwd_ops.append(self.zero_grads)
+
+    def refresh(self):
+        st = self.eng.stream
+        A.check(A.lib.sap3d_pad_channels(A.F32, A.ptr(self.w.w), A.ptr(self.wp.w), self.rows, self.c, self.cp, 0, 0, st), "pad filter")
+        if self.b is not None:
+            A.check(A.lib.sap3d_pad_channels(A.F32, A.ptr(self.b.w), A.ptr(self.bp.w), 1, self.c, self.cp, 0, 0, st), "pad bias")
+
+    def zero_grads(self):
+        if self.wp.g is not None:
+            self.wp.g.zero_()
+            if self.bp is not None:
+                self.bp.g.zero_()
+
+    def bwd(self):
+        e = self.eng
+        # the filter gradient was produced on the side stream: fold it back there (stream order = dependency)
+        st = e.side_stream.cuda_stream if e.use_side_stream else e.stream
+        A.check(A.lib.sap3d_pad_channels(A.F32, A.ptr(self.wp.g), A.ptr(self.w.g), self.rows, self.c, self.cp, 1, 1, st), "unpad dW")
+        if self.b is not None:
+            A.check(A.lib.sap3d_pad_channels(A.F32, A.ptr(self.bp.g), A.ptr(self.b.g), 1, self.c, self.cp, 1, 1, st), "unpad db")
+        e._count(2)
+
+
+class _TempParam:
+    """parameter-shaped buffers that are not TF variables (not in the flat optimizer state)"""
+
+    def __init__(self, name, shape, device, with_grad):
+        self.name, self.shape = name, tuple(shape)
+        self.numel = int(np.prod(self.shape))
+        self.w = torch.zeros(self.shape, device=device, dtype=torch.float32)
+        self.g = torch.zeros(self.shape, device=device, dtype=torch.float32) if with_grad else None
+        self.trainable = False
+
+
 class _GateOp:
     """y = o * gamma + x  (utils/network.py:191-192)"""
 
@@ -612,7 +671,7 @@ class _AttnCoreOp:
         tr = eng.training_graph
         if self.use_tc:
             self.dkp = (self.dk + 63) // 64 * 64
-            self.pad = self.dkp != self.dk
+            self.pad = self.dkp != self.dk   # (network.attention hands over 64-padded projections: no pad kernels)
             bf = torch.bfloat16
             self.gp = torch.zeros(B, self.Nq, self.dkp, device=dev, dtype=bf) if self.pad else None
             self.fp = torch.zeros(B, self.Nk, self.dkp, device=dev, dtype=bf) if self.pad else None

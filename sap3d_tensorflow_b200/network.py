@@ -117,8 +117,19 @@ def attention(x: T, name, training, mode="bn", subsample=False, sub_size=2) -> T
     eng = x.eng
     ch = x.C
     inter = max(1, ch // 8)
-    f = layers_conv3d(x, inter, 1, 1, scope=name, want_stats=False).raw
-    g = layers_conv3d(x, inter, 1, 1, scope=name, want_stats=False).raw
+    def proj(cout):
+        """f / g projection (tf.layers.conv3d 1x1x1, utils/network.py:164-173).  In the bf16 path 16- and 32-channel
+        projections are executed with 64 output channels (zero-padded filters) so they stay on the tensor cores;
+        the extra channels are exactly zero and do not change g.f^T."""
+        nm = eng.names.unique(name, "conv3d")
+        w = eng.param(nm + "/kernel", [1, 1, 1, ch, cout], "glorot")
+        b = eng.param(nm + "/bias", [cout], "zeros")
+        if eng.dt == A.BF16 and cout % 64 != 0:
+            return eng.conv_padded_cout([x], (cout + 63) // 64 * 64, (1, 1, 1), (1, 1, 1), w, b, name=nm).raw
+        return eng.conv([x], cout, (1, 1, 1), (1, 1, 1), w, b, want_stats=False, name=nm).raw
+
+    f = proj(inter)
+    g = proj(inter)
     h = layers_conv3d(x, ch, 1, 1, scope=name, want_stats=False).raw
     if subsample:
         f = pool3d(f, sub_size)
