@@ -203,15 +203,40 @@ int sap3d_sample_channel_partials(int32_t dtype, const void* x, const float* sca
 int sap3d_gn_finalize(const float* part, int32_t rows, int32_t N, int64_t S, int32_t C, int32_t G, const float* gamma,
                       const float* beta, float eps, float* scale, float* shift, float* save_mean, float* save_rstd, void* stream);
 /* CBAM attention maps of r: channel scale cscale [N][C] (mean & max over D,H,W -> shared MLP C->hidden->C -> sigmoid) and
- * spatial map att [N][D*H*W] (mean & max over C of r*cscale -> 7x7x7 conv, no bias -> sigmoid); scratch: part, sp */
+ * spatial map att [N][D*H*W] (mean & max over C of r*cscale -> 7x7x7 conv, no bias -> sigmoid); scratch: part, sp;
+ * save (nullable) [N][2C + 2 hidden] keeps (avg, max, relu hidden(avg), relu hidden(max)) for sap3d_cbam_tail_bwd */
 int sap3d_cbam_fwd(int32_t dtype, const void* r, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t hidden,
                    const float* w0, const float* b0, const float* w1, const float* b1, const float* w_sp, float* part,
-                   int32_t rows, float* cscale, float* sp, float* att, void* stream);
+                   int32_t rows, float* cscale, float* sp, float* att, float* save, void* stream);
 /* y = relu((a*s1[n][c]+t1[n][c]) + r*cscale[n][c]*att[n][pos])  (out += cbam(residual); relu — gn/p3d_gn.py:175-177) */
 int sap3d_cbam_merge(int32_t dtype, const void* a, const float* s1, const float* t1, const void* r, const float* cscale,
                      const float* att, void* y, int32_t N, int64_t S, int32_t C, void* stream);
 /* y [P][ca+cb] = concat(a [P][ca], b [P][cb]) (materialised tf.concat for three-way concatenations) */
 int sap3d_concat_channels(int32_t dtype, const void* a, const void* b, void* y, int64_t P, int32_t ca, int32_t cb, void* stream);
+/* gradient of sap3d_concat_channels: dy [P][ca+cb] -> da, db (nullable; acc_* != 0 accumulates) */
+int sap3d_split_channels(int32_t dtype, const void* dy, void* da, int32_t acc_a, void* db, int32_t acc_b, int64_t P, int32_t ca,
+                         int32_t cb, void* stream);
+
+/* Backward passes of the GN variant (what tf.gradients derives for gn/p3d_gn.py:24-46 and utils/network.py:198-274;
+ * training driver gn/train_p3d_gn_dataset.py:186-199).  One workspace of sap3d_gn_bwd_workspace(N,S,C) bytes serves both. */
+size_t sap3d_gn_bwd_workspace(int32_t N, int64_t S, int32_t C);
+/* backward of y = relu_out?( relu1?(GN1(a)) + relu2?(GN2(b) | b) ) with per-sample scale/shift [N][C] and group
+ * statistics mean/rstd [N][G] from sap3d_gn_finalize.  s2 == NULL: b is a plain tensor (db = masked dy).
+ * da/db nullable; d{gamma,beta} are accumulated (+=). */
+int sap3d_gn_act_bwd(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
+                     const float* rstd1, const float* gamma1, int32_t relu1, const void* b, const float* s2, const float* t2,
+                     const float* mean2, const float* rstd2, const float* gamma2, int32_t relu2, int32_t relu_out, int32_t N,
+                     int64_t S, int32_t C, int32_t G, void* da, int32_t acc_a, void* db, int32_t acc_b, float* dgamma1,
+                     float* dbeta1, float* dgamma2, float* dbeta2, void* workspace, void* stream);
+/* backward of the block tail y = relu(GN(c3) + cbam_block(r)) (gn/p3d_gn.py:175-177): gradients w.r.t. c3, r, the GroupNorm
+ * affine, the channel-attention MLP (w0 [C][hidden], b0, w1 [hidden][C], b1) and the 7x7x7 spatial filter (all +=).
+ * cscale / sp / att / save are the tensors sap3d_cbam_fwd produced; reduce_max gradients are split evenly among ties. */
+int sap3d_cbam_tail_bwd(int32_t dtype, const void* dy, const void* y, const void* c3, const float* s3, const float* mean3,
+                        const float* rstd3, const float* gamma3, const void* r, int32_t N, int32_t D, int32_t H, int32_t W,
+                        int32_t C, int32_t G, int32_t hidden, const float* w0, const float* w1, const float* w_sp,
+                        const float* cscale, const float* sp, const float* att, const float* save, void* dc3, int32_t acc_c3,
+                        void* dr, int32_t acc_r, float* dgamma3, float* dbeta3, float* dw0, float* db0, float* dw1, float* db1,
+                        float* dw_sp, void* workspace, void* stream);
 
 /* one-launch re-packing of all filters after an optimizer step (table built with sap3d_conv_pack_entries) */
 typedef struct sap3d_pack_entry {

@@ -142,7 +142,13 @@ _sig("sap3d_pack_multi", [_vp, _i32, _i64, _vp])
 _sig("sap3d_sample_stats_rows", [_i64, _i32, _i32])
 _sig("sap3d_sample_channel_partials", [_i32, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp])
 _sig("sap3d_gn_finalize", [_vp, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp])
-_sig("sap3d_cbam_fwd", [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp])
+_sig("sap3d_cbam_fwd", [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp])
+_sig("sap3d_split_channels", [_i32, _vp, _vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp])
+_sig("sap3d_gn_bwd_workspace", [_i32, _i64, _i32], C.c_size_t)
+_sig("sap3d_gn_act_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _i32,
+                          _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp])
+_sig("sap3d_cbam_tail_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp,
+                             _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_cbam_merge", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp])
 _sig("sap3d_concat_channels", [_i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp])
 _sig("sap3d_saliency_metrics", [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp])

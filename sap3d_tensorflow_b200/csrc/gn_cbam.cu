@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
 __global__ void __launch_bounds__(256) cbam_channel_mlp_kernel(const float* __restrict__ part, int rows, int C, int hidden, long long S,
                                                                 const float* __restrict__ w0, const float* __restrict__ b0,
                                                                 const float* __restrict__ w1, const float* __restrict__ b1,
-                                                                float* __restrict__ cscale) {
+                                                                float* __restrict__ cscale, float* __restrict__ save) {
   extern __shared__ float sm[];  // avg[C], mx[C], h_avg[hidden], h_max[hidden]
   float* avg = sm;
   float* mx = sm + C;
@@ -130,6 +130,10 @@ __global__ void __launch_bounds__(256) cbam_channel_mlp_kernel(const float* __re
     for (int j = 0; j < hidden; ++j) s = fmaf(ha[j] + hm[j], w1[(long long)j * C + c], s);
     cscale[(long long)n * C + c] = 1.f / (1.f + __expf(-s));
   }
+  if (save) {  // [N][2C + 2 hidden]: avg, max, relu(hidden(avg)), relu(hidden(max)) — kept for the backward pass
+    float* sv = save + (long long)n * (2 * C + 2 * hidden);
+    for (int i = threadIdx.x; i < 2 * C + 2 * hidden; i += blockDim.x) sv[i] = sm[i];
+  }
 }
 
 // spatial pooling of the channel-scaled tensor: sp[n][pos][0] = mean_c(x*cscale), [1] = max_c  (one warp per position)
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(256) cbam_spatial_pool_kernel(const T* __restr
       Vec8<T>::load(xp + c, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float t = v[j] * cs[c + j];
+        const float t = __fmul_rn(v[j], cs[c + j]);  // rounded product: the backward pass re-derives arg-max from it
         a += t;
         m = fmaxf(m, t);
       }
@@ -286,14 +290,14 @@ int sap3d_gn_finalize(const float* part, int32_t rows, int32_t N, int64_t S, int
  * y = relu(a*s1+t1 + r*cscale*att) with per-sample affine (s1, t1) of the main branch. */
 int sap3d_cbam_fwd(int32_t dtype, const void* r, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t hidden,
                    const float* w0, const float* b0, const float* w1, const float* b1, const float* w_sp, float* part,
-                   int32_t rows, float* cscale, float* sp, float* att, void* stream) {
+                   int32_t rows, float* cscale, float* sp, float* att, float* save, void* stream) {
   if (require_device()) return 1;
   if (C % 8 != 0) return set_error("cbam_fwd: C %% 8 != 0");
   const long long S = (long long)D * H * W;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (sap3d_sample_channel_partials(dtype, r, nullptr, N, S, C, rows, part, stream)) return 1;
   const size_t sm = (size_t)(2 * C + 2 * hidden) * sizeof(float);
-  cbam_channel_mlp_kernel<<<N, 256, sm, st>>>(part, rows, C, hidden, S, w0, b0, w1, b1, cscale);
+  cbam_channel_mlp_kernel<<<N, 256, sm, st>>>(part, rows, C, hidden, S, w0, b0, w1, b1, cscale, save);
   if (check_launch("cbam_channel_mlp")) return 1;
   const long long total = (long long)N * S;
   const int blocks = (int)((total * 32 + 255) / 256 > 148 * 8 ? 148 * 8 : (total * 32 + 255) / 256);

@@ -1,6 +1,6 @@
 """Engine ops of the GroupNorm + CBAM model variant (gn/p3d_gn.py): per-sample GroupNorm statistics ->
-fused affine/ReLU/add pass, and the CBAM-on-residual block tail.  Forward path (inference / parity); the
-training backward of these two ops is the next item of the build plan."""
+fused affine/ReLU/add pass, and the CBAM-on-residual block tail, forward and backward (training driver:
+gn/train_p3d_gn_dataset.py:169-199)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -28,10 +28,17 @@ class GNState:
         self.rstd = torch.empty(N, self.G, device=dev, dtype=torch.float32)
 
 
-def _no_backward(name):
-    def f():
-        raise A.Sap3dError(f"backward of {name} (GroupNorm/CBAM graph) is not implemented in this round")
-    return f
+def _reserve_ws(eng: Engine, N: int, S: int, Cc: int):
+    """one shared backward workspace per engine (ops run in stream order), sized for the largest user"""
+    need = A.lib.sap3d_gn_bwd_workspace(N, S, Cc)
+    eng._gn_ws_bytes = max(getattr(eng, "_gn_ws_bytes", 0), need)
+
+
+def _ws(eng: Engine) -> torch.Tensor:
+    ws = getattr(eng, "_gn_ws", None)
+    if ws is None or ws.numel() * 4 < eng._gn_ws_bytes:
+        ws = eng._gn_ws = torch.zeros(eng._gn_ws_bytes // 4 + 16, device=eng.device, dtype=torch.float32)
+    return ws
 
 
 class GNActOp:
@@ -44,7 +51,10 @@ class GNActOp:
         self.b_t = None if b is None else (b.raw if isinstance(b, ConvOut) else b)
         self.y = eng.tensor(a.raw.shape, name)
         eng.fwd_ops.append(self.fwd)
-        eng.bwd_ops.append(_no_backward(name) if eng.training_graph else (lambda: None))
+        eng.bwd_ops.append(self.bwd)
+        if eng.training_graph:
+            t = a.raw
+            _reserve_ws(eng, t.shape[0], t.positions // t.shape[0], t.C)
 
     def _stats(self, t: T, gs: GNState):
         e = self.eng
@@ -69,6 +79,27 @@ class GNActOp:
         e._count()
 
 
+    def bwd(self):
+        e = self.eng
+        if not self.y.gflag:
+            return
+        g1, g2, a_raw, b_t = self.g1, self.g2, self.a.raw, self.b_t
+        acc_a = a_raw.take_acc()
+        db_ptr, acc_b = None, 0
+        if b_t is not None and b_t.needs_grad:
+            acc_b = b_t.take_acc()
+            db_ptr = A.ptr(b_t.ensure_grad())
+        N, S, Cc = a_raw.shape[0], a_raw.positions // a_raw.shape[0], a_raw.C
+        A.check(A.lib.sap3d_gn_act_bwd(
+            e.dt, A.ptr(self.y.grad), A.ptr(a_raw.buf), A.ptr(g1.scale), A.ptr(g1.shift), A.ptr(g1.mean), A.ptr(g1.rstd),
+            A.ptr(g1.gamma.w), int(self.relu1), A.ptr(b_t.buf) if b_t is not None else None,
+            A.ptr(g2.scale) if g2 else None, A.ptr(g2.shift) if g2 else None, A.ptr(g2.mean) if g2 else None,
+            A.ptr(g2.rstd) if g2 else None, A.ptr(g2.gamma.w) if g2 else None, int(self.relu2), int(self.relu_out), N, S, Cc, g1.G,
+            A.ptr(a_raw.ensure_grad()), acc_a, db_ptr, acc_b, A.ptr(g1.gamma.g), A.ptr(g1.beta.g),
+            A.ptr(g2.gamma.g) if g2 else None, A.ptr(g2.beta.g) if g2 else None, A.ptr(_ws(e)), e.stream), "gn_act_bwd " + self.name)
+        e._count(3)
+
+
 class CbamBlockTailOp:
     """out = relu(GN(c3) + cbam_block(residual))  (gn/p3d_gn.py:175-177; utils/network.py:198-274)"""
 
@@ -84,9 +115,14 @@ class CbamBlockTailOp:
         self.cscale = torch.empty(N, Cc, device=dev, dtype=torch.float32)
         self.sp = torch.empty(N, S, 2, device=dev, dtype=torch.float32)
         self.att = torch.empty(N, S, device=dev, dtype=torch.float32)
+        self.hidden = w0.shape[1]
+        self.save = torch.empty(N, 2 * Cc + 2 * self.hidden, device=dev, dtype=torch.float32) if eng.training_graph else None
         self.y = eng.tensor(residual.shape, name)
         eng.fwd_ops.append(self.fwd)
-        eng.bwd_ops.append(_no_backward(name) if eng.training_graph else (lambda: None))
+        eng.bwd_ops.append(self.bwd)
+        if eng.training_graph:
+            c3.raw.ensure_grad()
+            _reserve_ws(eng, N, S, Cc)
 
     def fwd(self):
         e = self.eng
@@ -98,10 +134,30 @@ class CbamBlockTailOp:
                                         A.ptr(g3.scale), A.ptr(g3.shift), A.ptr(g3.mean), A.ptr(g3.rstd), e.stream), "gn finalize")
         A.check(A.lib.sap3d_cbam_fwd(e.dt, A.ptr(self.r.buf), N, D, H, W, Cc, self.w0.shape[1], A.ptr(self.w0.w), A.ptr(self.b0.w),
                                      A.ptr(self.w1.w), A.ptr(self.b1.w), A.ptr(self.w_sp.w), A.ptr(self.part), self.rows,
-                                     A.ptr(self.cscale), A.ptr(self.sp), A.ptr(self.att), e.stream), "cbam_fwd " + self.name)
+                                     A.ptr(self.cscale), A.ptr(self.sp), A.ptr(self.att), A.ptr(self.save), e.stream), "cbam_fwd " + self.name)
         A.check(A.lib.sap3d_cbam_merge(e.dt, A.ptr(raw.buf), A.ptr(g3.scale), A.ptr(g3.shift), A.ptr(self.r.buf), A.ptr(self.cscale),
                                        A.ptr(self.att), A.ptr(self.y.buf), N, S, Cc, e.stream), "cbam_merge " + self.name)
         e._count(7)
+
+
+    def bwd(self):
+        e = self.eng
+        if not self.y.gflag:
+            return
+        N, D, H, W, Cc = self.r.shape
+        raw, g3, r = self.c3.raw, self.g3, self.r
+        acc_c3 = raw.take_acc()
+        dr_ptr, acc_r = None, 0
+        if r.needs_grad:
+            acc_r = r.take_acc()
+            dr_ptr = A.ptr(r.ensure_grad())
+        A.check(A.lib.sap3d_cbam_tail_bwd(
+            e.dt, A.ptr(self.y.grad), A.ptr(self.y.buf), A.ptr(raw.buf), A.ptr(g3.scale), A.ptr(g3.mean), A.ptr(g3.rstd),
+            A.ptr(g3.gamma.w), A.ptr(r.buf), N, D, H, W, Cc, g3.G, self.hidden, A.ptr(self.w0.w), A.ptr(self.w1.w), A.ptr(self.w_sp.w),
+            A.ptr(self.cscale), A.ptr(self.sp), A.ptr(self.att), A.ptr(self.save), A.ptr(raw.ensure_grad()), acc_c3, dr_ptr, acc_r,
+            A.ptr(g3.gamma.g), A.ptr(g3.beta.g), A.ptr(self.w0.g), A.ptr(self.b0.g), A.ptr(self.w1.g), A.ptr(self.b1.g),
+            A.ptr(self.w_sp.g), A.ptr(_ws(e)), e.stream), "cbam_tail_bwd " + self.name)
+        e._count(8)
 
 
 class ConcatOp:
@@ -111,7 +167,23 @@ class ConcatOp:
         self.eng, self.a, self.b = eng, a, b
         self.y = eng.tensor((*a.shape[:4], a.C + b.C), name)
         eng.fwd_ops.append(self.fwd)
-        eng.bwd_ops.append(_no_backward(name) if eng.training_graph else (lambda: None))
+        eng.bwd_ops.append(self.bwd)
+
+    def bwd(self):
+        e = self.eng
+        if not self.y.gflag:
+            return
+        da = db = None
+        acc_a = acc_b = 0
+        if self.a.needs_grad:
+            acc_a = self.a.take_acc()
+            da = A.ptr(self.a.ensure_grad())
+        if self.b.needs_grad:
+            acc_b = self.b.take_acc()
+            db = A.ptr(self.b.ensure_grad())
+        A.check(A.lib.sap3d_split_channels(e.dt, A.ptr(self.y.grad), da, acc_a, db, acc_b, self.a.positions, self.a.C, self.b.C,
+                                           e.stream), "split_channels")
+        e._count()
 
     def fwd(self):
         e = self.eng

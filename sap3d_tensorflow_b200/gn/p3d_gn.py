@@ -11,7 +11,16 @@ from __future__ import annotations
 from .. import network as nw
 from ..engine import ConvOut, T
 from ..engine_gn import CbamBlockTailOp, ConcatOp, GNActOp, GNState
-from ..p3d import BLOCK_EXPANSION, STAGES, TEMPORAL_POOL, convS, convT, get_conv_weight
+from ..p3d import BLOCK_EXPANSION, STAGES, TEMPORAL_POOL, get_conv_weight
+from ..p3d import convS as _convS_bn, convT as _convT_bn
+
+
+def convS(name, l_input, in_channels, out_channels):   # gn/p3d_gn.py:62-65 (a GroupNorm does not cancel the bias gradient)
+    return _convS_bn(name, l_input, in_channels, out_channels, bias_grad=True)
+
+
+def convT(name, l_input, in_channels, out_channels):   # gn/p3d_gn.py:67-70
+    return _convT_bn(name, l_input, in_channels, out_channels, bias_grad=True)
 
 
 def _gn_state(t: T) -> GNState:

@@ -32,16 +32,17 @@ def get_conv_weight(eng: Engine, name, kshape, wd=0.001):
     return eng.param(name, kshape, "glorot" if len(kshape) > 1 else "xavier1d")
 
 
-def convS(name, l_input: T, in_channels, out_channels) -> ConvOut:  # p3d.py:18-22: 1x3x3 + bias
+def convS(name, l_input: T, in_channels, out_channels, bias_grad=False) -> ConvOut:  # p3d.py:18-22: 1x3x3 + bias
+    """bias_grad=False: under BatchNorm the bias gradient is exactly zero (engine.conv); the GroupNorm variant passes True"""
     eng = l_input.eng
     return eng.conv([l_input], out_channels, (1, 3, 3), (1, 1, 1), get_conv_weight(eng, name, [1, 3, 3, in_channels, out_channels]),
-                    get_conv_weight(eng, name + "_bias", [out_channels], 0), name=name, bias_grad=False)
+                    get_conv_weight(eng, name + "_bias", [out_channels], 0), name=name, bias_grad=bias_grad)
 
 
-def convT(name, l_input: T, in_channels, out_channels) -> ConvOut:  # p3d.py:23-27: 3x1x1 + bias
+def convT(name, l_input: T, in_channels, out_channels, bias_grad=False) -> ConvOut:  # p3d.py:23-27: 3x1x1 + bias
     eng = l_input.eng
     return eng.conv([l_input], out_channels, (3, 1, 1), (1, 1, 1), get_conv_weight(eng, name, [3, 1, 1, in_channels, out_channels]),
-                    get_conv_weight(eng, name + "_bias", [out_channels], 0), name=name, bias_grad=False)
+                    get_conv_weight(eng, name + "_bias", [out_channels], 0), name=name, bias_grad=bias_grad)
 
 
 class Bottleneck:
