@@ -43,9 +43,11 @@ class VarStore:
         self.frozen = params is not None
         self.counters: Dict[str, int] = {}
         self.trainable: Dict[str, bool] = {}
+        self.prefix = ""  # enclosing tf.variable_scope of a whole builder (gn/p3d_gn.py:490)
 
     def reset_names(self):
         self.counters = {}
+        self.prefix = ""
 
     def unique(self, scope: str, base: str) -> str:
         key = scope + "/" + base
@@ -55,6 +57,7 @@ class VarStore:
         return (scope + "/" + name) if scope else name
 
     def get(self, name: str, shape: Sequence[int], kind: str, trainable: bool = True) -> torch.Tensor:
+        name = self.prefix + name
         if name in self.params:
             p = self.params[name]
             assert tuple(p.shape) == tuple(shape), (name, tuple(p.shape), tuple(shape))
@@ -401,6 +404,32 @@ def gn_inference_p3d_concat(ctx, x):
     return gn_inference_p3d(ctx, x, pool4_filters=512)
 
 
+def gn_inference_p3d_decoder_block(ctx, x):  # gn/p3d_gn.py:489-539 (inside tf.variable_scope('P3D'))
+    ctx.vs.prefix = "P3D/"
+    gnrelu = lambda t: torch.relu(gn_layer(ctx, t))  # noqa: E731
+    w = conv_w(ctx, "firstconv1", [1, 7, 7, 3, 64])
+    c1 = gnrelu(tfs.conv3d_same(x, w, (1, 2, 2)))
+    pool1 = tfs.max_pool3d_same(c1, (2, 3, 3), (2, 2, 2))
+    res1, cnt = make_block(ctx, pool1, 64, 3, 64, 0, "gn")
+    pool2 = ctx.tap("pool2", tfs.max_pool3d_same(res1, *TPOOL))
+    dp2 = gnrelu(layers_deconv3d(ctx, pool2, 128, 3, 1, "deconv_pool2"))
+    res2, cnt = make_block(ctx, pool2, 128, 8, 256, cnt, "gn")
+    pool3 = ctx.tap("pool3", tfs.max_pool3d_same(res2, *TPOOL))
+    dp3 = gnrelu(layers_deconv3d(ctx, pool3, 256, (2, 3, 3), 2, "deconv_pool3"))
+    res3, cnt = make_block(ctx, pool3, 256, 36, 512, cnt, "gn")
+    pool4 = ctx.tap("pool4", tfs.max_pool3d_same(res3, *TPOOL))
+    dp4 = gnrelu(layers_deconv3d(ctx, pool4, 512, (1, 3, 3), 4, "deconv_pool4"))
+    cc = ctx.tap("conv_concat", gnrelu(layers_conv3d(ctx, torch.cat([dp2, dp3, dp4], dim=-1), 1024, 3, 1, "conv_concat")))
+    d = gnrelu(layers_conv3d(ctx, cc, 256, 3, 1, "decoder1_conv1"))
+    d = gnrelu(layers_deconv3d(ctx, d, 256, 3, 2, "decoder1_deconv"))
+    d = gnrelu(layers_conv3d(ctx, d, 128, 3, 1, "decoder1_conv2"))
+    d = gnrelu(layers_conv3d(ctx, d, 32, 3, 1, "decoder2_conv1"))
+    d = gnrelu(layers_deconv3d(ctx, d, 32, 3, 2, "decoder2_deconv"))
+    d = ctx.tap("decoder2_conv2", gnrelu(layers_conv3d(ctx, d, 16, 3, 1, "decoder2_conv2")))
+    d = dropout(ctx, d, "final_drop")
+    return ctx.tap("pred", layers_conv3d(ctx, d, 1, 3, 1, "results"))
+
+
 GRAPHS = {
     "p3d_unetplusplus_ds": p3d_unetplusplus_ds,
     "p3d_unetplusplus_nonsa": p3d_unetplusplus_nonsa,
@@ -408,6 +437,7 @@ GRAPHS = {
     "p3d_concat": p3d_concat,
     "inference_p3d": gn_inference_p3d,
     "inference_p3d_concat": gn_inference_p3d_concat,
+    "inference_p3d_decoder_block": gn_inference_p3d_decoder_block,
 }
 
 

@@ -135,6 +135,7 @@ class Engine:
         self._counting = None
         self._pack_table = None
         self.pre_pack_ops: List = []
+        self.var_prefix = ""   # tf.variable_scope wrapped around a whole builder (gn/p3d_gn.py:490 'P3D')
         self.side_stream = torch.cuda.Stream(device=self.device)   # filter gradients run here, off the critical path
         self.use_side_stream = True
 
@@ -153,6 +154,7 @@ class Engine:
         return t
 
     def param(self, name, shape, kind, trainable=True) -> Param:
+        name = self.var_prefix + name
         if name in self.params:
             p = self.params[name]
             assert p.shape == tuple(shape), (name, p.shape, shape)
@@ -322,6 +324,12 @@ class Engine:
     def head(self, x: T, w: Param, b: Param, ksize, stride, sigmoid=True, name="") -> "_HeadOp":
         op = _HeadOp(self, x, w, b, ksize, stride, sigmoid, name)
         self.fwd_ops.append(op.fwd)
+        self.bwd_ops.append(op.bwd)
+        return op
+
+    def logits_loss(self, co: ConvOut, name="") -> "_LogitsLossOp":
+        """network output produced by an ordinary convolution (fp32 logits) + the smooth-L1 loss in training graphs"""
+        op = _LogitsLossOp(self, co, name)
         self.bwd_ops.append(op.bwd)
         return op
 
@@ -574,6 +582,36 @@ class _HeadOp:
     @property
     def output(self):
         return self.pred if self.sigmoid else self.logits
+
+
+class _LogitsLossOp:
+    """final tf.layers.conv3d -> 1 channel (gn/p3d_gn.py:538; the conv itself is an engine conv with fp32 output) and, in
+    training graphs, smooth_l1_loss on it (gn/train_p3d_gn_dataset.py:186)"""
+
+    def __init__(self, eng, co: ConvOut, name):
+        self.eng, self.raw, self.name = eng, co.raw, name
+        assert self.raw.buf.dtype == torch.float32, "logits_loss needs a conv built with out_f32=True"
+        shp = self.raw.shape
+        self.logits = self.raw.buf
+        self.target = torch.zeros(shp[:-1], device=eng.device, dtype=torch.float32) if eng.training_graph else None
+        self.dlogits = torch.empty(shp, device=eng.device, dtype=torch.float32) if eng.training_graph else None
+        if eng.training_graph:
+            self.raw.grad = torch.empty(shp, device=eng.device, dtype=eng.tdt)   # the conv's backward reads dy in storage dtype
+
+    def bwd(self):
+        e = self.eng
+        A.check(A.lib.sap3d_loss_smooth_l1(A.ptr(self.logits), A.ptr(self.target), self.logits.numel(), 0, None,
+                                           A.ptr(self.dlogits), A.ptr(e.loss_buf), None, e.stream), "loss " + self.name)
+        self.raw.take_acc()
+        if e.dt == A.F32:
+            self.raw.grad.copy_(self.dlogits)
+        else:
+            A.check(A.lib.sap3d_cast(A.F32, A.ptr(self.dlogits), A.ptr(self.raw.grad), self.dlogits.numel(), e.stream), "cast dlogits")
+        e._count(2)
+
+    @property
+    def output(self):
+        return self.logits
 
 
 class _PaddedParams:

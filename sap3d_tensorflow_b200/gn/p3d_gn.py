@@ -1,6 +1,6 @@
 """GroupNorm + CBAM variant of the P3D saliency model on the B200 engine — public surface of the reference's
 gn/p3d_gn.py: GroupNorm :24, GNReLU :49, conv3d_layers :14, deconv3d_layers :19, Bottleneck :74, make_block :182,
-inference_p3d :214, inference_p3d_concat :279.  Every block ends with cbam_block on the residual
+inference_p3d :214, inference_p3d_concat :279, inference_p3d_decoder_block :489.  Every block ends with cbam_block on the residual
 (gn/p3d_gn.py:175).  Variables: group_norm[_N]/{gamma,beta}, cbam_{id}/ch_at/mlp_{0,1}/{kernel,bias},
 cbam_{id}/sp_at/conv3d/kernel, conv names as in p3d.py.
 
@@ -140,3 +140,36 @@ def inference_p3d(_X, _dropout, batch_size=2, training=True):
 def inference_p3d_concat(_X, _dropout, batch_size=2, training=True):
     """gn/p3d_gn.py:279-324"""
     return _inference(_X, _dropout, training, 512)
+
+
+def inference_p3d_decoder_block(_X, _dropout, batch_size=2, training=True):
+    """gn/p3d_gn.py:489-539: three-scale concat -> conv_concat -> two decoder blocks -> 3x3x3 conv to 1 channel (logits).
+    The whole builder sits inside tf.variable_scope('P3D'), so every variable name carries the 'P3D/' prefix."""
+    eng = _X.eng
+    eng.var_prefix = "P3D/"
+    c = eng.conv([_X], 64, (1, 7, 7), (1, 2, 2), get_conv_weight(eng, "firstconv1", [1, 7, 7, 3, 64]), name="firstconv1", want_stats=False)
+    x = eng.maxpool(GroupNorm(c, relu=True, name="stem"), (2, 3, 3), (2, 2, 2), name="pool1")
+    # (kernel, stride, filters) of the deconv applied to each stage's pooled output, created right after that stage
+    side = (((3, 3, 3), (1, 1, 1), 128), ((2, 3, 3), (2, 2, 2), 256), ((1, 3, 3), (4, 4, 4), 512))
+    ups, cnt = [], 0
+    for si, (planes, num, inplanes, stride) in enumerate(STAGES):
+        blk = make_block(x, planes, num, inplanes, cnt, stride=stride)
+        res = blk.infer()
+        cnt = blk.cnt
+        x = eng.tap(f"pool{si + 2}", eng.maxpool(res, *TEMPORAL_POOL, name=f"pool{si + 2}"))
+        k, s, f = side[si]
+        ups.append(deconv3d_layers(x, f, k, s, f"deconv_pool{si + 2}"))
+    cat = ConcatOp(eng, ups[0], ups[1], name="concat_dp2_dp3").y
+    cc = eng.tap("conv_concat", conv3d_layers(nw.concat([cat, ups[2]]), 1024, 3, 1, "conv_concat"))
+    d = conv3d_layers(cc, 256, 3, 1, "decoder1_conv1")
+    d = deconv3d_layers(d, 256, 3, 2, "decoder1_deconv")
+    d = conv3d_layers(d, 128, 3, 1, "decoder1_conv2")
+    d = conv3d_layers(d, 32, 3, 1, "decoder2_conv1")
+    d = deconv3d_layers(d, 32, 3, 2, "decoder2_deconv")
+    d = eng.tap("decoder2_conv2", conv3d_layers(d, 16, 3, 1, "decoder2_conv2"))
+    if training:
+        d = eng.dropout(d, _dropout, name="final_drop")
+    w = eng.param("results/kernel", [3, 3, 3, 16, 1], "glorot")
+    b = eng.param("results/bias", [1], "zeros")
+    logits = eng.conv([d], 1, (3, 3, 3), (1, 1, 1), w, b, want_stats=False, name="results", out_f32=True)
+    return eng.logits_loss(logits, name="results")

@@ -15,6 +15,7 @@ from typing import Optional
 
 from . import network as nw
 from .engine import ConvOut, Engine, T
+from .engine_gn import ConcatOp
 
 CROP_SIZE = 112
 NUM_FRAMES_PER_CLIP = 16
@@ -190,3 +191,33 @@ def p3d_unet(_X, _dropout, batch_size=2, training=True):
     w = eng.param(eng.names.unique("", "conv3d_transpose") + "/kernel", [3, 3, 3, 1, 32], "glorot_t")
     b = eng.param(w.name.rsplit("/", 1)[0] + "/bias", [1], "zeros")
     return eng.head(c.raw, w, b, (3, 3, 3), 2, sigmoid=True, name="results")
+
+
+def p3d_concat(_X, _dropout, batch_size=2, training=True):
+    """p3d.py:224-276: each stage's pooled output is upsampled to 4x28x28 (deconv 3^3 with stride 1 / 2 / 4), the three
+    maps are concatenated (128+256+512) -> conv_concat -> deconv_revise -> predict_revise.  Returns LOGITS (no sigmoid
+    at p3d.py:275-276)."""
+    eng = _X.eng
+    x = eng.tap("pool1", eng.maxpool(_stem(_X, training), (2, 3, 3), (2, 2, 2), name="pool1"))
+    side = ((1, 128), (2, 256), (4, 512))   # (stride, filters) of deconv_pool{2,3,4}
+    ups, cnt = [], 0
+    for si, (planes, num, inplanes, stride) in enumerate(STAGES):
+        blk = make_block(x, planes, num, inplanes, cnt, stride=stride)
+        res = blk.infer()
+        cnt = blk.cnt
+        x = eng.tap(f"pool{si + 2}", eng.maxpool(res, *TEMPORAL_POOL, name=f"pool{si + 2}"))
+        s, f = side[si]
+        nm = f"deconv_pool{si + 2}"
+        co = nw.layers_conv3d_transpose(x, f, 3, [s, s, s], nm, bias_grad=not training)
+        ups.append(nw.bn_relu(co, training, name=nm + "_bn", tap=nm))
+    cat = ConcatOp(eng, ups[0], ups[1], name="concatenator_01").y
+    cc = nw.bn_relu(nw.layers_conv3d(nw.concat([cat, ups[2]]), 512, 3, 1, "conv_concat", bias_grad=not training), training,
+                    name="conv_concat_bn", tap="conv_concat")
+    eng.tap("conv_concat", cc)
+    dr = nw.bn_relu(nw.layers_conv3d_transpose(cc, 128, 3, 2, "deconv_revise", bias_grad=not training), training,
+                    name="deconv1_revise_bn", tap="deconv_revise")
+    if training:
+        dr = eng.dropout(dr, _dropout, name="deconv_revise_drop")
+    w = eng.param("predict_revise/kernel", [3, 3, 3, 1, 128], "glorot_t")
+    b = eng.param("predict_revise/bias", [1], "zeros")
+    return eng.head(dr, w, b, (3, 3, 3), 2, sigmoid=False, name="predict_revise")

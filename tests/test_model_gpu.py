@@ -93,6 +93,42 @@ def test_training_step_parity_fp32(lib_built):
             assert rel(p, vs.params[name]) < 1e-4, name
 
 
+def test_p3d_concat_parity(lib_built):
+    """p3d.py:224-276 (three-scale concat decoder, returns logits): forward in both storage types, and one fp32 training
+    step (exercises the materialised concat, the stride-1 / stride-4 transposed convs and their gradients)"""
+    graph, batch, size = "p3d_concat", 2, 64
+    x = O.synthetic_clip(batch, 16, size, seed=0)
+    y = O.synthetic_target(batch, 16, size, seed=1)
+    vs = O.VarStore(seed=0)
+    with torch.no_grad():
+        ref = O.forward(graph, x, vs, True)
+    init = {k: v.clone() for k, v in vs.params.items()}
+    # bf16 end-to-end bounds only (raw logits of a batch-statistics network at a 64x64 test extent, see module docstring)
+    for dtype, tol in (("f32", 1e-4), ("bf16", 2e-1)):
+        sess = build(graph, dtype, True, batch, size)
+        assert set(sess.eng.params) == set(vs.params)
+        sess.eng.load_params(init)
+        pred = sess.run(x.cuda())
+        torch.cuda.synchronize()
+        assert rel(pred, ref) < tol, (dtype, rel(pred, ref))
+        assert rel(torch.sigmoid(pred.float().cpu()), torch.sigmoid(ref)) < (1e-4 if dtype == "f32" else 5e-2)
+        if dtype == "f32":
+            loss_ref, grads_ref = O.train_step(graph, x, y, vs, {}, 1)
+            sess.eng.load_params(init)
+            loss = float(sess.train_step(x.cuda(), y.cuda()).item())
+            assert abs(loss - loss_ref) / loss_ref < 1e-4, (loss, loss_ref)
+            gmax = max(float(g.norm()) for g in grads_ref.values())
+            for name, g in sess.gradients().items():
+                gr = grads_ref[name]
+                if float(gr.norm()) < 1e-5 * gmax:
+                    continue
+                a, b = g.float().cpu().reshape(-1), gr.reshape(-1)
+                assert float((a @ b) / (a.norm() * b.norm() + 1e-30)) > 0.995, name
+                assert abs(float(a.norm() / b.norm()) - 1) < 0.05, name
+        del sess
+        torch.cuda.empty_cache()
+
+
 def test_training_reduces_loss_bf16(lib_built):
     """ten Adam steps on one repeated batch through the CUDA-graph path: loss is finite and decreases"""
     graph, batch, size = "p3d_unetplusplus_ds", 2, 64

@@ -133,6 +133,7 @@ PARAM_COUNTS = {
     "p3d_unet": 61_943_105,
     "p3d_concat": 83_472_065,
     "inference_p3d": 152_846_483,
+    "inference_p3d_decoder_block": 103_446_323,
 }
 
 
