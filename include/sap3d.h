@@ -112,6 +112,15 @@ int sap3d_gn_stats(int32_t dtype, const void* x, int32_t N, int64_t S, int32_t C
 int sap3d_affine_act(int32_t dtype, const void* a, const float* s1, const float* t1, int32_t relu1, const void* b,
                      const float* s2, const float* t2, int32_t relu2, int32_t relu_out, void* y, int64_t P, int32_t C,
                      int64_t positions_per_sample, void* stream);
+/* sap3d_bn_finalize (for one or two norms) fused into sap3d_affine_act: y = relu_out?( relu1?(BN1(a)) + relu2?(BN2(b) | b) )
+ * in ONE launch, for layers whose statistics buffers have few rows (the backbone).  scale/shift/mean/rstd are still
+ * published for the backward pass; moving averages are updated when training. */
+int sap3d_bn_apply_fused(int32_t dtype, const void* a, const float* stats1, int32_t rows1, const float* gamma1, const float* beta1,
+                         float* mm1, float* mv1, int32_t training1, float* scale1, float* shift1, float* mean1, float* rstd1,
+                         int32_t relu1, const void* b, int32_t has_norm2, const float* stats2, int32_t rows2, const float* gamma2,
+                         const float* beta2, float* mm2, float* mv2, int32_t training2, float* scale2, float* shift2, float* mean2,
+                         float* rstd2, int32_t relu2, int32_t relu_out, void* y, int64_t P, int32_t C, double count, float momentum,
+                         float eps, void* stream);
 size_t sap3d_affine_act_bwd_workspace(int32_t C);
 /* backward of sap3d_affine_act for per-channel statistics.  mean/rstd non-NULL => that branch is a
  * batch-statistics BatchNorm (full BN backward); NULL => frozen scale.  da/db nullable; d{gamma,beta}
@@ -125,14 +134,16 @@ int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const flo
 /* ------------------------------------------------------------------------------------------------
  * Pooling.  Replaces tf.nn.max_pool3d (p3d.py:347-348,354,360,366) and tf.layers.max_pooling3d
  * (utils/network.py:6-7).  same != 0: TF 'SAME' (padding never wins), else 'VALID'.
+ * argmax (nullable, uint8 [outputs][C]): the forward pass records the window-local index of the FIRST maximum; the
+ * backward pass then gathers (dy, index) pairs instead of re-scanning the windows (the gradient goes to that element).
  * ---------------------------------------------------------------------------------------------- */
 int sap3d_maxpool3d_out_dims(int32_t D, int32_t H, int32_t W, const int32_t* ksize, const int32_t* strides, int32_t same,
                              int32_t* out_dhw);
 int sap3d_maxpool3d_fwd(int32_t dtype, const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,
-                        const int32_t* ksize, const int32_t* strides, int32_t same, void* y, void* stream);
+                        const int32_t* ksize, const int32_t* strides, int32_t same, void* y, uint8_t* argmax, void* stream);
 int sap3d_maxpool3d_bwd(int32_t dtype, const void* x, const void* dy, int32_t N, int32_t D, int32_t H, int32_t W,
-                        int32_t C, const int32_t* ksize, const int32_t* strides, int32_t same, void* dx,
-                        int32_t accumulate, void* stream);
+                        int32_t C, const int32_t* ksize, const int32_t* strides, int32_t same, const uint8_t* argmax,
+                        void* dx, int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Decoder head, loss, dropout, attention gate, optimizer.

@@ -105,13 +105,16 @@ _u64 = C.c_uint64
 _sig("sap3d_bn_finalize", [_vp, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_gn_stats", [_i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_affine_act", [_i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _i64, _vp])
+_sig("sap3d_bn_apply_fused", [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32,
+                              _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _f64, _f32,
+                              _f32, _vp])
 _sig("sap3d_affine_act_bwd_workspace", [_i32], C.c_size_t)
 _sig("sap3d_affine_act_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32,
                               _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp])
 _I3 = C.c_int32 * 3
 _sig("sap3d_maxpool3d_out_dims", [_i32, _i32, _i32, _P(C.c_int32), _P(C.c_int32), _i32, _P(C.c_int32)])
-_sig("sap3d_maxpool3d_fwd", [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int32), _P(C.c_int32), _i32, _vp, _vp])
-_sig("sap3d_maxpool3d_bwd", [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int32), _P(C.c_int32), _i32, _vp, _i32, _vp])
+_sig("sap3d_maxpool3d_fwd", [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int32), _P(C.c_int32), _i32, _vp, _vp, _vp])
+_sig("sap3d_maxpool3d_bwd", [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int32), _P(C.c_int32), _i32, _vp, _vp, _i32, _vp])
 _sig("sap3d_head_fwd", [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int32), _i32, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_head_bwd", [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int32), _i32, _vp, _vp, _i32, _vp, _vp])
 _sig("sap3d_loss_smooth_l1", [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp])

@@ -5,6 +5,7 @@
 // input (moments + ~5 Eigen elementwise kernels), tf.nn.relu and the residual adds
 // (p3d.py:56-81,88,97,114,127,133-134; utils/network.py:65-94).  Bandwidth-bound: 128-bit accesses,
 // one read per operand and one write.
+#include <cooperative_groups.h>
 #include <stdio.h>
 
 #include "../../include/sap3d.h"
@@ -183,6 +184,140 @@ __global__ void __launch_bounds__(256) apply_kernel(const ApplyArgs p) {
       for (int j = 0; j < 8; ++j) r[j] += bv[j];
     }
     if (p.relu_out) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaxf(r[j], 0.f);
+    }
+    Vec8<T>::store(y + e, r);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// fused finalize + apply for layers with few statistics rows (the whole backbone): every block owns one 64-channel
+// chunk and a slab of positions; its prologue reduces the conv epilogue's per-tile sums for those 64 channels
+// (deterministic fp64), block x == 0 of each chunk also publishes scale/shift/mean/rstd (the backward pass reads
+// them) and updates the moving averages.  One launch instead of two (three for two-norm ops), no second grid.
+// ------------------------------------------------------------------------------------------------
+struct FusedNorm {
+  const float* stats; int rows; double count;
+  const float *gamma, *beta;
+  float *mm, *mv;
+  int training;
+  float *scale, *shift, *save_mean, *save_rstd;
+};
+struct FusedApplyArgs {
+  ApplyArgs ap;
+  FusedNorm n[2];
+  int has[2];
+  int prows;        // position slabs (gridDim.x)
+  float momentum, eps;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_fused_kernel(const FusedApplyArgs p) {
+  __shared__ double red[4][2][64];
+  __shared__ float s_scale[2][64], s_shift[2][64];
+  const int C = p.ap.C;
+  const int cbase = blockIdx.y * 64;
+  {
+    const int ch = threadIdx.x & 63, part = threadIdx.x >> 6;
+    const int c = cbase + ch;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!p.has[k]) continue;
+      const FusedNorm& nm = p.n[k];
+      if (nm.training) {
+        double a = 0.0, b = 0.0;
+        if (c < C) {
+          int r = part;
+          for (; r + 12 < nm.rows; r += 16) {   // 4 rows x 2 sums in flight per iteration
+            float va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              va[u] = nm.stats[((long long)(r + 4 * u) * 2 + 0) * C + c];
+              vb[u] = nm.stats[((long long)(r + 4 * u) * 2 + 1) * C + c];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a += (double)va[u]; b += (double)vb[u]; }
+          }
+          for (; r < nm.rows; r += 4) {
+            a += (double)nm.stats[((long long)r * 2 + 0) * C + c];
+            b += (double)nm.stats[((long long)r * 2 + 1) * C + c];
+          }
+        }
+        red[part][0][ch] = a;
+        red[part][1][ch] = b;
+      }
+      __syncthreads();
+      if (part == 0 && c < C) {
+        float mean, var;
+        if (nm.training) {
+          const double ta = red[0][0][ch] + red[1][0][ch] + red[2][0][ch] + red[3][0][ch];
+          const double tb = red[0][1][ch] + red[1][1][ch] + red[2][1][ch] + red[3][1][ch];
+          const double m = ta / nm.count;
+          double v = tb / nm.count - m * m;
+          if (v < 0.0) v = 0.0;
+          mean = (float)m;
+          var = (float)v;
+          if (blockIdx.x == 0 && nm.mm) {
+            nm.mm[c] = nm.mm[c] * p.momentum + mean * (1.f - p.momentum);
+            nm.mv[c] = nm.mv[c] * p.momentum + var * (1.f - p.momentum);
+          }
+        } else {
+          mean = nm.mm[c];
+          var = nm.mv[c];
+        }
+        const float rstd = rsqrtf(var + p.eps);
+        const float g = nm.gamma ? nm.gamma[c] : 1.f, bt = nm.beta ? nm.beta[c] : 0.f;
+        const float sc = g * rstd, sh = bt - mean * g * rstd;
+        s_scale[k][ch] = sc;
+        s_shift[k][ch] = sh;
+        if (blockIdx.x == 0) {
+          nm.scale[c] = sc;
+          nm.shift[c] = sh;
+          if (nm.save_mean) nm.save_mean[c] = mean;
+          if (nm.save_rstd) nm.save_rstd[c] = rstd;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int cv = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = cbase + cv * 8;
+  if (c >= C) return;
+  const T* a = reinterpret_cast<const T*>(p.ap.a);
+  const T* b = reinterpret_cast<const T*>(p.ap.b);
+  T* y = reinterpret_cast<T*>(p.ap.y);
+  const long long per = (p.ap.P + p.prows - 1) / p.prows;
+  const long long pbeg = blockIdx.x * per, pend = pbeg + per < p.ap.P ? pbeg + per : p.ap.P;
+  float s1[8], t1[8], s2[8], t2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[j] = p.has[0] ? s_scale[0][cv * 8 + j] : 1.f;
+    t1[j] = p.has[0] ? s_shift[0][cv * 8 + j] : 0.f;
+    s2[j] = p.has[1] ? s_scale[1][cv * 8 + j] : 1.f;
+    t2[j] = p.has[1] ? s_shift[1][cv * 8 + j] : 0.f;
+  }
+  for (long long pos = pbeg + pl; pos < pend; pos += 32) {
+    const long long e = pos * C + c;
+    float av[8], r[8];
+    Vec8<T>::load(a + e, av);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      r[j] = fmaf(av[j], s1[j], t1[j]);
+      if (p.ap.relu1) r[j] = fmaxf(r[j], 0.f);
+    }
+    if (b) {
+      float bv[8];
+      Vec8<T>::load(b + e, bv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z = p.has[1] ? fmaf(bv[j], s2[j], t2[j]) : bv[j];
+        if (p.ap.relu2) z = fmaxf(z, 0.f);
+        r[j] += z;
+      }
+    }
+    if (p.ap.relu_out) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = fmaxf(r[j], 0.f);
     }
@@ -377,6 +512,133 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// single-launch backward (cooperative grid): reduce -> grid.sync -> per-chunk finalize in shared memory -> apply.
+// grid = (rows, C/64) co-resident blocks; every block owns one 64-channel chunk and one slab of positions in both
+// passes, so the second pass re-reads what the block itself just read (L1/L2 hits for backbone-sized tensors).
+// Replaces the reduce / finalize / apply launch triple (3 launches, 2 dependent grid boundaries per norm op).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_coop_kernel(const ApplyBwdArgs p, const double M, float* dgamma1, float* dbeta1,
+                                                          float* dgamma2, float* dbeta2) {
+  __shared__ float red[8][4][64];
+  __shared__ float coef[4][64];
+  const int cv = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int cbase = blockIdx.y * 64;
+  const int c = cbase + cv * 8;
+  const long long per = (p.P + p.rows - 1) / p.rows;
+  const long long pbeg = blockIdx.x * per, pend = pbeg + per < p.P ? pbeg + per : p.P;
+  {
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    if (c < p.C) {
+      for (long long pos = pbeg + pl; pos < pend; pos += 32) {
+        float g1[8], g2[8], xh1[8], xh2[8];
+        bwd_common<T>(p, pos * p.C + c, c, c, g1, g2, xh1, xh2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += g1[j];
+          acc[1][j] += g1[j] * xh1[j];
+          acc[2][j] += g2[j];
+          acc[3][j] += g2[j] * xh2[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = acc[i][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        acc[i][j] = v;
+      }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < 8) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp][i][lane * 8 + j] = acc[i][j];
+    }
+    __syncthreads();
+    const int i = threadIdx.x >> 6, ch = threadIdx.x & 63;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][i][ch];
+    if (cbase + ch < p.C) p.partial[((long long)blockIdx.x * 4 + i) * p.C + cbase + ch] = v;
+  }
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  {
+    const int i = threadIdx.x >> 6, ch = threadIdx.x & 63;
+    const int cc = cbase + ch;
+    double t = 0.0;
+    if (cc < p.C) {
+      // fixed summation order (deterministic); 8 independent loads in flight per iteration hide the L2 latency
+      const float* src = p.partial + (long long)i * p.C + cc;
+      const long long rs = 4ll * p.C;
+      int r = 0;
+      for (; r + 8 <= p.rows; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (r + u) * rs);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t += (double)v[u];
+      }
+      for (; r < p.rows; ++r) t += (double)__ldcg(src + r * rs);
+    }
+    coef[i][ch] = (float)(t / M);
+    if (blockIdx.x == 0 && cc < p.C) {
+      float* dst = i == 0 ? dbeta1 : (i == 1 ? dgamma1 : (i == 2 ? dbeta2 : dgamma2));
+      if (dst) dst[cc] += (float)t;
+    }
+  }
+  __syncthreads();
+  if (c >= p.C || (!p.da && !p.db)) return;
+  T* da = reinterpret_cast<T*>(p.da);
+  T* db = reinterpret_cast<T*>(p.db);
+  for (long long pos = pbeg + pl; pos < pend; pos += 32) {
+    const long long e = pos * p.C + c;
+    float g1[8], g2[8], xh1[8], xh2[8];
+    bwd_common<T>(p, e, c, c, g1, g2, xh1, xh2);
+    if (da) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sc = p.s1 ? p.s1[c + j] : 1.f;
+        o[j] = p.batch_stats1 ? sc * (g1[j] - coef[0][cv * 8 + j] - xh1[j] * coef[1][cv * 8 + j]) : sc * g1[j];
+      }
+      if (p.acc_a) {
+        float old[8];
+        Vec8<T>::load(da + e, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += old[j];
+      }
+      Vec8<T>::store(da + e, o);
+    }
+    if (db) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sc = p.s2 ? p.s2[c + j] : 1.f;
+        o[j] = p.batch_stats2 ? sc * (g2[j] - coef[2][cv * 8 + j] - xh2[j] * coef[3][cv * 8 + j]) : sc * g2[j];
+      }
+      if (p.acc_b) {
+        float old[8];
+        Vec8<T>::load(db + e, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += old[j];
+      }
+      Vec8<T>::store(db + e, o);
+    }
+  }
+}
+
+constexpr long long COOP_MAX_ELEMS = 4ll << 20;   // above this the three-launch form streams better (more blocks per SM)
+
 int ew_grid(long long nvec) {
   long long b = (nvec + 255) / 256;
   if (b > 148 * 8) b = 148 * 8;
@@ -429,6 +691,38 @@ int sap3d_affine_act(int32_t dtype, const void* a, const float* s1, const float*
   return check_launch("affine_act");
 }
 
+int sap3d_bn_apply_fused(int32_t dtype, const void* a, const float* stats1, int32_t rows1, const float* gamma1, const float* beta1,
+                         float* mm1, float* mv1, int32_t training1, float* scale1, float* shift1, float* mean1, float* rstd1,
+                         int32_t relu1, const void* b, int32_t has_norm2, const float* stats2, int32_t rows2, const float* gamma2,
+                         const float* beta2, float* mm2, float* mv2, int32_t training2, float* scale2, float* shift2, float* mean2,
+                         float* rstd2, int32_t relu2, int32_t relu_out, void* y, int64_t P, int32_t C, double count, float momentum,
+                         float eps, void* stream) {
+  if (require_device()) return 1;
+  if (C % 8 != 0) return set_error("bn_apply_fused: C must be a multiple of 8 (got %d)", C);
+  if (!a || !y || !scale1 || !shift1) return set_error("bn_apply_fused: NULL argument");
+  if (training1 ? !stats1 : (!mm1 || !mv1)) return set_error("bn_apply_fused: norm 1 needs statistics");
+  if (has_norm2 && (!b || !scale2 || !shift2 || (training2 ? !stats2 : (!mm2 || !mv2)))) return set_error("bn_apply_fused: norm 2 needs statistics");
+  FusedApplyArgs p;
+  memset(&p, 0, sizeof(p));
+  p.ap.a = a; p.ap.b = b; p.ap.y = y; p.ap.P = P; p.ap.C = C; p.ap.psp = 0;
+  p.ap.relu1 = relu1; p.ap.relu2 = relu2; p.ap.relu_out = relu_out;
+  p.has[0] = 1; p.has[1] = has_norm2;
+  p.n[0] = FusedNorm{stats1, rows1, count, gamma1, beta1, mm1, mv1, training1, scale1, shift1, mean1, rstd1};
+  p.n[1] = FusedNorm{stats2, rows2, count, gamma2, beta2, mm2, mv2, training2, scale2, shift2, mean2, rstd2};
+  p.momentum = momentum; p.eps = eps;
+  const int chunks = (C + 63) / 64;
+  long long prows = (4 * 148 + chunks - 1) / chunks;
+  const long long max_rows = (P + 31) / 32;
+  if (prows > max_rows) prows = max_rows;
+  if (prows < 1) prows = 1;
+  p.prows = (int)prows;
+  dim3 grid((unsigned)prows, (unsigned)chunks);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == SAP3D_BF16) bn_apply_fused_kernel<bf16><<<grid, 256, 0, st>>>(p);
+  else bn_apply_fused_kernel<float><<<grid, 256, 0, st>>>(p);
+  return check_launch("bn_apply_fused");
+}
+
 size_t sap3d_affine_act_bwd_workspace(int32_t C) { return (size_t)(296 * 4 + 4) * (size_t)C * sizeof(float); }
 
 int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
@@ -460,6 +754,28 @@ int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const flo
     p.rows = (int)rows;
     p.partial = ws + 4 * C;
     dim3 rgrid((unsigned)rows, (unsigned)chunks);
+    // backbone-sized tensors: ONE cooperative launch (reduce -> grid.sync -> finalize -> apply) instead of three
+    if ((long long)P * C <= COOP_MAX_ELEMS) {
+      static int max_blocks[2] = {0, 0};
+      int& mb = max_blocks[dtype == SAP3D_BF16 ? 0 : 1];
+      if (mb == 0) {
+        int per_sm = 0, dev = 0, sms = 0;
+        const void* fn = dtype == SAP3D_BF16 ? (const void*)bn_bwd_coop_kernel<bf16> : (const void*)bn_bwd_coop_kernel<float>;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0) != cudaSuccess) per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        mb = per_sm * sms;
+        if (mb < 1) mb = 1;
+      }
+      if ((long long)rows * chunks <= mb) {
+        double M = (double)P;
+        void* args[] = {(void*)&p, (void*)&M, (void*)&dgamma1, (void*)&dbeta1, (void*)&dgamma2, (void*)&dbeta2};
+        const void* fn = dtype == SAP3D_BF16 ? (const void*)bn_bwd_coop_kernel<bf16> : (const void*)bn_bwd_coop_kernel<float>;
+        cudaError_t e = cudaLaunchCooperativeKernel(fn, rgrid, dim3(256), args, 0, st);
+        if (e != cudaSuccess) return set_error("affine_act_bwd cooperative launch: %s", cudaGetErrorString(e));
+        return 0;
+      }
+    }
     if (dtype == SAP3D_BF16) apply_bwd_reduce_kernel<bf16><<<rgrid, 256, 0, st>>>(p);
     else apply_bwd_reduce_kernel<float><<<rgrid, 256, 0, st>>>(p);
     if (check_launch("affine_act_bwd reduce")) return 1;

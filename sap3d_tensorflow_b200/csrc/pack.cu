@@ -22,18 +22,38 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const sap3d_pack_entry*
       else hi = mid - 1;
     }
     const sap3d_pack_entry en = tab[lo];
-    long long i = e0 - en.start;
-    float v[8];
+    if (en.cols % 8 != 0) {              // odd inner extents (stem: cin = 3): element-wise indexing
+      const long long i = e0 - en.start;
+      float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const long long idx = i + j;
-      const int c = (int)(idx % en.cols);
-      const long long t = idx / en.cols;
-      const int tap = (int)(t % en.taps);
-      const int r = (int)(t / en.taps);
-      v[j] = r < en.rows ? __ldg(en.src + tap * en.s_tap + r * en.s_r + c * en.s_c) : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const long long idx = i + j;
+        const int c = (int)(idx % en.cols);
+        const long long t = idx / en.cols;
+        const int tap = (int)(t % en.taps);
+        const int r = (int)(t / en.taps);
+        v[j] = r < en.rows ? __ldg(en.src + tap * en.s_tap + r * en.s_r + c * en.s_c) : 0.f;
+      }
+      Vec8<bf16>::store(reinterpret_cast<bf16*>(en.dst) + i, v);
+      continue;
     }
-    Vec8<bf16>::store(reinterpret_cast<bf16*>(en.dst) + i, v);
+    long long q = (e0 - en.start) / 8;   // chunk within the entry
+    const int c8n = en.cols / 8;
+    int r, tap, c;
+    if (en.s_c == 1) {                   // source contiguous along the destination's inner axis: chunk order = destination order
+      c = (int)(q % c8n) * 8; q /= c8n;
+      tap = (int)(q % en.taps);
+      r = (int)(q / en.taps);
+    } else {                             // transposing entry (s_r == 1): consecutive threads walk the SOURCE-contiguous axis r,
+      r = (int)(q % en.rows_pad); q /= en.rows_pad;   // so every one of the 8 loads is coalesced across the warp
+      c = (int)(q % c8n) * 8;
+      tap = (int)(q / c8n);
+    }
+    float v[8];
+    const float* src = en.src + tap * en.s_tap + r * en.s_r + c * en.s_c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = r < en.rows ? __ldg(src + j * en.s_c) : 0.f;
+    Vec8<bf16>::store(reinterpret_cast<bf16*>(en.dst) + ((long long)r * en.taps + tap) * en.cols + c, v);
   }
 }
 

@@ -15,6 +15,8 @@ struct PoolArgs {
   int Do, Ho, Wo;
   int kd, kh, kw, sd, sh, sw, pd, ph, pw;
   int accumulate;
+  unsigned char* amax;        // forward: window-local index of the first maximum, [outputs][C] (nullable)
+  const unsigned char* amax_in;  // backward: the same tensor (nullable -> re-scan the windows)
 };
 
 template <typename T>
@@ -31,8 +33,9 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const PoolArgs p) {
     const int od = (int)(r % p.Do);
     const int n = (int)(r / p.Do);
     float m[8];
+    unsigned am[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; am[j] = 255u; }
     for (int a = 0; a < p.kd; ++a) {
       const int id = od * p.sd + a - p.pd;
       if (id < 0 || id >= p.D) continue;
@@ -44,12 +47,21 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const PoolArgs p) {
           if (iw < 0 || iw >= p.W) continue;
           float v[8];
           Vec8<T>::load(x + ((((long long)n * p.D + id) * p.H + ih) * p.W + iw) * p.C + c, v);
+          const unsigned li = (unsigned)((a * p.kh + b) * p.kw + e);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+          for (int j = 0; j < 8; ++j)
+            if (v[j] > m[j] || am[j] == 255u) { m[j] = v[j]; am[j] = li; }   // strict '>' keeps the FIRST maximum
         }
       }
     }
-    Vec8<T>::store(y + ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.C + c, m);
+    const long long yoff = ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.C + c;
+    Vec8<T>::store(y + yoff, m);
+    if (p.amax) {
+      uint2 u;
+      u.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+      u.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+      *reinterpret_cast<uint2*>(p.amax + yoff) = u;
+    }
   }
 }
 
@@ -123,6 +135,51 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const PoolArgs p) {
   }
 }
 
+// backward with the arg-max saved by the forward pass: one (dy, index) vector pair per covering window
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_idx_kernel(const PoolArgs p) {
+  const int cv = p.C / 8;
+  const long long total = (long long)p.N * p.D * p.H * p.W * cv;
+  const T* dy = reinterpret_cast<const T*>(p.dy);
+  T* dx = reinterpret_cast<T*>(p.dx);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    long long r = i / cv;
+    const int iw = (int)(r % p.W); r /= p.W;
+    const int ih = (int)(r % p.H); r /= p.H;
+    const int id = (int)(r % p.D);
+    const int n = (int)(r / p.D);
+    const long long xoff = ((((long long)n * p.D + id) * p.H + ih) * p.W + iw) * p.C + c;
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    const int od_lo = max(0, (id + p.pd - p.kd + p.sd) / p.sd), od_hi = min(p.Do - 1, (id + p.pd) / p.sd);
+    const int oh_lo = max(0, (ih + p.ph - p.kh + p.sh) / p.sh), oh_hi = min(p.Ho - 1, (ih + p.ph) / p.sh);
+    const int ow_lo = max(0, (iw + p.pw - p.kw + p.sw) / p.sw), ow_hi = min(p.Wo - 1, (iw + p.pw) / p.sw);
+    for (int od = od_lo; od <= od_hi; ++od)
+      for (int oh = oh_lo; oh <= oh_hi; ++oh)
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+          const unsigned li = (unsigned)(((id - (od * p.sd - p.pd)) * p.kh + (ih - (oh * p.sh - p.ph))) * p.kw + (iw - (ow * p.sw - p.pw)));
+          const long long yoff = ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.C + c;
+          const uint2 u = *reinterpret_cast<const uint2*>(p.amax_in + yoff);
+          float d[8];
+          Vec8<T>::load(dy + yoff, d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const unsigned a = ((j < 4 ? u.x : u.y) >> (8 * (j & 3))) & 255u;
+            if (a == li) g[j] += d[j];
+          }
+        }
+    if (p.accumulate) {
+      float old[8];
+      Vec8<T>::load(dx + xoff, old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += old[j];
+    }
+    Vec8<T>::store(dx + xoff, g);
+  }
+}
+
 int fill(PoolArgs& p, int N, int D, int H, int W, int C, const int32_t* k, const int32_t* s, int same) {
   p.N = N; p.D = D; p.H = H; p.W = W; p.C = C;
   p.kd = k[0]; p.kh = k[1]; p.kw = k[2];
@@ -166,12 +223,13 @@ int sap3d_maxpool3d_out_dims(int32_t D, int32_t H, int32_t W, const int32_t* ksi
 }
 
 int sap3d_maxpool3d_fwd(int32_t dtype, const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,
-                        const int32_t* ksize, const int32_t* strides, int32_t same, void* y, void* stream) {
+                        const int32_t* ksize, const int32_t* strides, int32_t same, void* y, uint8_t* argmax, void* stream) {
   if (require_device()) return 1;
   if (C % 8 != 0) return set_error("maxpool3d: C must be a multiple of 8");
   PoolArgs p;
   if (fill(p, N, D, H, W, C, ksize, strides, same)) return set_error("maxpool3d: empty output");
-  p.x = x; p.y = y; p.dy = nullptr; p.dx = nullptr; p.accumulate = 0;
+  if (argmax && ksize[0] * ksize[1] * ksize[2] > 254) return set_error("maxpool3d: window too large for the arg-max encoding");
+  p.x = x; p.y = y; p.dy = nullptr; p.dx = nullptr; p.accumulate = 0; p.amax = argmax; p.amax_in = nullptr;
   const long long total = (long long)N * p.Do * p.Ho * p.Wo * (C / 8);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == SAP3D_BF16) maxpool_fwd_kernel<bf16><<<grid_for(total), 256, 0, st>>>(p);
@@ -180,16 +238,19 @@ int sap3d_maxpool3d_fwd(int32_t dtype, const void* x, int32_t N, int32_t D, int3
 }
 
 int sap3d_maxpool3d_bwd(int32_t dtype, const void* x, const void* dy, int32_t N, int32_t D, int32_t H, int32_t W,
-                        int32_t C, const int32_t* ksize, const int32_t* strides, int32_t same, void* dx,
+                        int32_t C, const int32_t* ksize, const int32_t* strides, int32_t same, const uint8_t* argmax, void* dx,
                         int32_t accumulate, void* stream) {
   if (require_device()) return 1;
   if (C % 8 != 0) return set_error("maxpool3d: C must be a multiple of 8");
   PoolArgs p;
   if (fill(p, N, D, H, W, C, ksize, strides, same)) return set_error("maxpool3d: empty output");
-  p.x = x; p.y = nullptr; p.dy = dy; p.dx = dx; p.accumulate = accumulate;
+  p.x = x; p.y = nullptr; p.dy = dy; p.dx = dx; p.accumulate = accumulate; p.amax = nullptr; p.amax_in = argmax;
   const long long total = (long long)N * D * H * W * (C / 8);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == SAP3D_BF16) maxpool_bwd_kernel<bf16><<<grid_for(total), 256, 0, st>>>(p);
+  if (argmax) {
+    if (dtype == SAP3D_BF16) maxpool_bwd_idx_kernel<bf16><<<grid_for(total), 256, 0, st>>>(p);
+    else maxpool_bwd_idx_kernel<float><<<grid_for(total), 256, 0, st>>>(p);
+  } else if (dtype == SAP3D_BF16) maxpool_bwd_kernel<bf16><<<grid_for(total), 256, 0, st>>>(p);
   else maxpool_bwd_kernel<float><<<grid_for(total), 256, 0, st>>>(p);
   return check_launch("maxpool3d_bwd");
 }

@@ -451,8 +451,31 @@ class _NormActOp:
                                         A.ptr(ns.shift), A.ptr(ns.mean), A.ptr(ns.rstd), e.stream), "bn_finalize " + self.name)
         e._count()
 
+    FUSE_MAX_ROWS = 128   # statistics rows up to which finalize is folded into the apply launch (whole backbone)
+
+    def _fwd_fused(self) -> bool:
+        n1, n2, a, e = self.n1, self.n2, self.a, self.eng
+        if n1 is None or (self.train1 and a.rows > self.FUSE_MAX_ROWS):
+            return False
+        b_co = self.b if isinstance(self.b, ConvOut) else None
+        if n2 is not None and (b_co is None or (self.train2 and b_co.rows > self.FUSE_MAX_ROWS)):
+            return False
+        A.check(A.lib.sap3d_bn_apply_fused(
+            e.dt, A.ptr(a.raw.buf), A.ptr(a.stats), a.rows, A.ptr(n1.gamma.w), A.ptr(n1.beta.w), A.ptr(n1.mm.w), A.ptr(n1.mv.w),
+            int(self.train1), A.ptr(n1.scale), A.ptr(n1.shift), A.ptr(n1.mean), A.ptr(n1.rstd), int(self.relu1),
+            A.ptr(self.b_t.buf) if self.b_t is not None else None, int(n2 is not None),
+            A.ptr(b_co.stats) if n2 else None, b_co.rows if n2 else 0, A.ptr(n2.gamma.w) if n2 else None,
+            A.ptr(n2.beta.w) if n2 else None, A.ptr(n2.mm.w) if n2 else None, A.ptr(n2.mv.w) if n2 else None, int(self.train2),
+            A.ptr(n2.scale) if n2 else None, A.ptr(n2.shift) if n2 else None, A.ptr(n2.mean) if n2 else None,
+            A.ptr(n2.rstd) if n2 else None, int(self.relu2), int(self.relu_out), A.ptr(self.y.buf), self.y.positions, self.y.C,
+            float(a.raw.positions), BN_MOMENTUM, BN_EPS, e.stream), "bn_apply_fused " + self.name)
+        e._count()
+        return True
+
     def fwd(self):
         e = self.eng
+        if self._fwd_fused():
+            return
         if self.n1 is not None:
             self._finalize(self.a, self.n1, self.train1)
         if self.n2 is not None:
@@ -503,12 +526,14 @@ class _PoolOp:
         A.check(A.lib.sap3d_maxpool3d_out_dims(D, H, W, self.k, self.s, self.same, out), "maxpool dims")
         self.y = eng.tensor((N, out[0], out[1], out[2], Cc), name, needs_grad=x.needs_grad)
         self.name = name
+        # window-local arg-max (uint8) recorded by the forward pass of training graphs for the gather-form backward
+        self.amax = torch.empty(self.y.shape, device=eng.device, dtype=torch.uint8) if (eng.training_graph and x.needs_grad) else None
 
     def fwd(self):
         e, x = self.eng, self.x
         N, D, H, W, Cc = x.shape
         A.check(A.lib.sap3d_maxpool3d_fwd(e.dt, A.ptr(x.buf), N, D, H, W, Cc, self.k, self.s, self.same, A.ptr(self.y.buf),
-                                          e.stream), "maxpool_fwd " + self.name)
+                                          A.ptr(self.amax), e.stream), "maxpool_fwd " + self.name)
         e._count()
 
     def bwd(self):
@@ -518,7 +543,7 @@ class _PoolOp:
         N, D, H, W, Cc = x.shape
         acc = x.take_acc()
         A.check(A.lib.sap3d_maxpool3d_bwd(e.dt, A.ptr(x.buf), A.ptr(self.y.grad), N, D, H, W, Cc, self.k, self.s, self.same,
-                                          A.ptr(x.ensure_grad()), acc, e.stream), "maxpool_bwd " + self.name)
+                                          A.ptr(self.amax), A.ptr(x.ensure_grad()), acc, e.stream), "maxpool_bwd " + self.name)
         e._count()
 
 

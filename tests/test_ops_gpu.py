@@ -36,11 +36,15 @@ def _stats(x):
 
 @pytest.mark.parametrize("dtn,tdt,tol", DT)
 @pytest.mark.parametrize("pattern", ["relu_bn", "bn_plus_relu_bn", "act_plus_relu_bn", "relu_bn_plus_t", "relu_bn_plus_bn"])
-def test_affine_act_fwd_bwd(A, dtn, tdt, tol, pattern):
+@pytest.mark.parametrize("shape", [(2, 3, 5, 6, 64), (2, 4, 40, 64, 256)], ids=["coop", "three_launch"])
+def test_affine_act_fwd_bwd(A, dtn, tdt, tol, pattern, shape):
+    """small tensors take the single cooperative backward launch, > 4 M elements the reduce/finalize/apply triple"""
+    if shape[-1] == 256 and pattern not in ("bn_plus_relu_bn", "relu_bn_plus_t"):
+        pytest.skip("large shape: two representative patterns")
     torch.manual_seed(0)
     dev = "cuda"
     dt = A.BF16 if dtn == "bf16" else A.F32
-    N, D, H, W, Cc = 2, 3, 5, 6, 64
+    N, D, H, W, Cc = shape
     P = N * D * H * W
     a = (torch.randn(N, D, H, W, Cc, device=dev) * 1.5 + 0.7).to(tdt)
     b = (torch.randn(N, D, H, W, Cc, device=dev) * 0.8 - 0.2).to(tdt)
@@ -89,12 +93,64 @@ def test_affine_act_fwd_bwd(A, dtn, tdt, tol, pattern):
                                        A.ptr(da), 0, A.ptr(db) if use_b else None, 0, A.ptr(dg1), A.ptr(db1),
                                        A.ptr(dg2) if bn2 else None, A.ptr(db2) if bn2 else None, A.ptr(ws), stream()), "bwd")
     torch.cuda.synchronize()
+    if Cc == 256:   # 5.2 M elements: ONE ReLU-mask flip at a |z| ~ 1e-7 element is sqrt(1/5e6) = 4e-4 relative
+        tol = max(tol, 1e-3)
     assert rel(da, af.grad) < 3 * tol
     assert rel(dg1, g1r.grad) < 3 * tol and rel(db1, b1r.grad) < 3 * tol
     if use_b:
         assert rel(db, bf.grad) < 3 * tol
     if bn2:
         assert rel(dg2, g2r.grad) < 3 * tol and rel(db2, b2r.grad) < 3 * tol
+
+
+@pytest.mark.parametrize("dtn,tdt,tol", DT)
+@pytest.mark.parametrize("two_norms,training", [(False, True), (True, True), (True, False)])
+def test_bn_apply_fused_matches_finalize_plus_apply(A, dtn, tdt, tol, two_norms, training):
+    """the one-launch form (finalize folded into apply) is bit-identical to sap3d_bn_finalize + sap3d_affine_act"""
+    torch.manual_seed(5)
+    dev = "cuda"
+    dt = A.BF16 if dtn == "bf16" else A.F32
+    P, Cc, rows = 7 * 11 * 3, 192, 5
+    a = (torch.randn(P, Cc, device=dev) * 1.5 + 0.7).to(tdt)
+    b = (torch.randn(P, Cc, device=dev) * 0.8 - 0.2).to(tdt)
+
+    def split_stats(x):   # per-"tile" partial sums as a conv epilogue would write them
+        xf = x.float()
+        parts = torch.chunk(xf, rows, 0)
+        return torch.stack([torch.stack([q.sum(0), (q * q).sum(0)], 0) for q in parts], 0).contiguous()
+
+    sa, sb = split_stats(a), split_stats(b)
+    gam = [torch.rand(Cc, device=dev) + 0.5 for _ in range(2)]
+    bet = [torch.randn(Cc, device=dev) * 0.1 for _ in range(2)]
+    outs = []
+    for fused in (False, True):
+        mm = [torch.randn(Cc, device=dev) * 0.1 for _ in range(2)]
+        mv = [torch.rand(Cc, device=dev) + 0.5 for _ in range(2)]
+        torch.manual_seed(6)
+        mm = [torch.full((Cc,), 0.05, device=dev), torch.full((Cc,), -0.02, device=dev)]
+        mv = [torch.full((Cc,), 0.9, device=dev), torch.full((Cc,), 1.1, device=dev)]
+        f = lambda: torch.zeros(Cc, device=dev)  # noqa: E731
+        sc, sh, me, rs = [f(), f()], [f(), f()], [f(), f()], [f(), f()]
+        y = torch.empty_like(a)
+        tr = int(training)
+        if fused:
+            A.check(A.lib.sap3d_bn_apply_fused(dt, A.ptr(a), A.ptr(sa), rows, A.ptr(gam[0]), A.ptr(bet[0]), A.ptr(mm[0]), A.ptr(mv[0]), tr,
+                                               A.ptr(sc[0]), A.ptr(sh[0]), A.ptr(me[0]), A.ptr(rs[0]), 1, A.ptr(b), int(two_norms),
+                                               A.ptr(sb) if two_norms else None, rows, A.ptr(gam[1]), A.ptr(bet[1]), A.ptr(mm[1]), A.ptr(mv[1]),
+                                               tr, A.ptr(sc[1]), A.ptr(sh[1]), A.ptr(me[1]), A.ptr(rs[1]), int(two_norms), 1, A.ptr(y), P, Cc,
+                                               float(P), 0.99, 1e-3, stream()), "fused")
+        else:
+            A.check(A.lib.sap3d_bn_finalize(A.ptr(sa), rows, Cc, float(P), A.ptr(gam[0]), A.ptr(bet[0]), A.ptr(mm[0]), A.ptr(mv[0]), tr, 0.99,
+                                            1e-3, A.ptr(sc[0]), A.ptr(sh[0]), A.ptr(me[0]), A.ptr(rs[0]), stream()), "fin1")
+            if two_norms:
+                A.check(A.lib.sap3d_bn_finalize(A.ptr(sb), rows, Cc, float(P), A.ptr(gam[1]), A.ptr(bet[1]), A.ptr(mm[1]), A.ptr(mv[1]), tr,
+                                                0.99, 1e-3, A.ptr(sc[1]), A.ptr(sh[1]), A.ptr(me[1]), A.ptr(rs[1]), stream()), "fin2")
+            A.check(A.lib.sap3d_affine_act(dt, A.ptr(a), A.ptr(sc[0]), A.ptr(sh[0]), 1, A.ptr(b), A.ptr(sc[1]) if two_norms else None,
+                                           A.ptr(sh[1]) if two_norms else None, int(two_norms), 1, A.ptr(y), P, Cc, 0, stream()), "apply")
+        torch.cuda.synchronize()
+        outs.append((y, sc[0], sh[0], me[0], rs[0], mm[0], mv[0], sc[1], mm[1]))
+    for u, v in zip(*outs):
+        assert rel(u, v) < 1e-6
 
 
 @pytest.mark.parametrize("dtn,tdt,tol", DT)
@@ -107,14 +163,40 @@ def test_maxpool(A, dtn, tdt, tol, k, s, same):
     xr = x.float().requires_grad_(True)
     ref = tfs.max_pool3d_same(xr, k, s) if same else tfs.max_pool3d_valid(xr, 2)
     y = torch.empty(ref.shape, device="cuda", dtype=tdt)
-    A.check(A.lib.sap3d_maxpool3d_fwd(dt, A.ptr(x), N, D, H, W, Cc, A.i3(k), A.i3(s), same, A.ptr(y), stream()), "pool")
+    amax = torch.empty(ref.shape, device="cuda", dtype=torch.uint8)
+    A.check(A.lib.sap3d_maxpool3d_fwd(dt, A.ptr(x), N, D, H, W, Cc, A.i3(k), A.i3(s), same, A.ptr(y), A.ptr(amax), stream()), "pool")
     assert rel(y, ref) == 0.0
     dy = torch.randn_like(ref).to(tdt)
     ref.backward(dy.float())
-    dx = torch.empty_like(x)
-    A.check(A.lib.sap3d_maxpool3d_bwd(dt, A.ptr(x), A.ptr(dy), N, D, H, W, Cc, A.i3(k), A.i3(s), same, A.ptr(dx), 0, stream()), "poolb")
+    for idx in (None, amax):   # window re-scan and saved-arg-max forms of the backward pass
+        dx = torch.empty_like(x)
+        A.check(A.lib.sap3d_maxpool3d_bwd(dt, A.ptr(x), A.ptr(dy), N, D, H, W, Cc, A.i3(k), A.i3(s), same, A.ptr(idx), A.ptr(dx), 0,
+                                          stream()), "poolb")
+        torch.cuda.synchronize()
+        assert rel(dx, xr.grad) < tol
+
+
+def test_maxpool_ties_go_to_the_first_maximum(A):
+    """post-ReLU activations are full of exact ties (zeros): both backward forms route a window's gradient to the first
+    maximal element in (d, h, w) scan order, as torch's max_pool3d backward does"""
+    N, D, H, W, Cc = 1, 4, 8, 8, 8
+    x = torch.relu(torch.randn(N, D, H, W, Cc, device="cuda") - 0.8).to(torch.bfloat16)
+    k, s = (2, 3, 3), (2, 2, 2)
+    xr = x.float().requires_grad_(True)
+    ref = tfs.max_pool3d_same(xr, k, s)
+    y = torch.empty(ref.shape, device="cuda", dtype=torch.bfloat16)
+    amax = torch.empty(ref.shape, device="cuda", dtype=torch.uint8)
+    A.check(A.lib.sap3d_maxpool3d_fwd(A.BF16, A.ptr(x), N, D, H, W, Cc, A.i3(k), A.i3(s), 1, A.ptr(y), A.ptr(amax), stream()), "pool")
+    dy = torch.randn_like(ref).to(torch.bfloat16)
+    outs = []
+    for idx in (None, amax):
+        dx = torch.empty_like(x)
+        A.check(A.lib.sap3d_maxpool3d_bwd(A.BF16, A.ptr(x), A.ptr(dy), N, D, H, W, Cc, A.i3(k), A.i3(s), 1, A.ptr(idx), A.ptr(dx), 0,
+                                          stream()), "poolb")
+        outs.append(dx)
     torch.cuda.synchronize()
-    assert rel(dx, xr.grad) < tol
+    assert torch.equal(outs[0], outs[1])
+    assert rel(outs[0].float().sum(), dy.float().sum()) < 1e-2   # every window's gradient lands exactly once
 
 
 @pytest.mark.parametrize("dtn,tdt,tol", DT)
