@@ -177,6 +177,11 @@ int sap3d_attention_fwd(int32_t dtype, const void* g, const void* f, const void*
 int sap3d_attention_bwd(int32_t dtype, const void* g, const void* f, const void* h, const void* beta, const void* d_o, void* ds,
                         void* dg, void* df, void* dh, int32_t B, int32_t Nq, int32_t Nk, int32_t dk, int32_t dv, int32_t ldq,
                         int32_t ldk, int32_t ldv, int32_t ldb, int32_t ldo, void* stream);
+/* fused (flash-style) tcgen05 path: o[b] = softmax(q[b] k[b]^T) v[b] without materialising the [Nq][Nk] scores.
+ * q [B][Nq][64], k [B][Nk][64] (d_k zero-padded to 64), v [B][Nk][dv], o [B][Nq][dv], all bf16 and dense; dv in {128, 256};
+ * lse (nullable) [B][Nq] = log-sum-exp of every score row, kept for the backward kernels. */
+int sap3d_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t Nq, int32_t Nk,
+                         int32_t dk, int32_t dv, void* stream);
 /* bf16 tensor-core GEMMs: C[M][N] (+)= A[M][K] B[N][K]^T  (K % 64 == 0, ldb == K, N % 8 == 0); B has rows_b <= N
  * rows, the remaining output columns are computed against zeros */
 int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t rows_b, void* C, int64_t ldc, int32_t M,

@@ -730,8 +730,13 @@ class _AttnCoreOp:
         self.use_tc = eng.dt == A.BF16 and self.dv % 64 == 0 and self.dk % 8 == 0
         self.Nkp = (self.Nk + 63) // 64 * 64 if self.use_tc else self.Nk   # keys padded (zero probabilities) for K % 64
         self.ldb = self.Nkp
-        self.beta = torch.zeros(B, self.Nq, self.ldb, device=dev, dtype=eng.tdt)
         tr = eng.training_graph
+        # fused flash-style kernels (csrc/flash_attn.cu): the [Nq][Nk] score / probability matrices are never materialised
+        self.use_flash = self.use_tc and self.dk == 64 and self.dv in (128, 256) and self.FLASH and (not tr or self.FLASH_BWD)
+        if self.use_flash:
+            self.lse = torch.empty(B, self.Nq, device=dev, dtype=torch.float32)
+            return
+        self.beta = torch.zeros(B, self.Nq, self.ldb, device=dev, dtype=eng.tdt)
         if self.use_tc:
             self.dkp = (self.dk + 63) // 64 * 64
             self.pad = self.dkp != self.dk   # (network.attention hands over 64-padded projections: no pad kernels)
@@ -749,6 +754,15 @@ class _AttnCoreOp:
                 self.dfp = torch.empty(B, self.Nk, self.dkp, device=dev, dtype=bf) if self.pad else None
         elif tr:
             self.ds = torch.empty_like(self.beta)
+
+    FLASH = True
+    FLASH_BWD = False
+
+    def _fwd_flash(self):
+        e = self.eng
+        A.check(A.lib.sap3d_flash_attn_fwd(A.ptr(self.g.buf), A.ptr(self.f.buf), A.ptr(self.h.buf), A.ptr(self.o.buf), A.ptr(self.lse),
+                                           self.B, self.Nq, self.Nk, self.dk, self.dv, e.stream), "flash_attn_fwd " + self.name)
+        e._count()
 
     # -- tensor-core path -------------------------------------------------------------------------
     def _fwd_tc(self):
@@ -800,6 +814,8 @@ class _AttnCoreOp:
     # -- dispatch ---------------------------------------------------------------------------------
     def fwd(self):
         e = self.eng
+        if self.use_flash:
+            return self._fwd_flash()
         if self.use_tc:
             return self._fwd_tc()
         A.check(A.lib.sap3d_attention_fwd(e.dt, A.ptr(self.g.buf), A.ptr(self.f.buf), A.ptr(self.h.buf), A.ptr(self.beta),
