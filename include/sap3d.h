@@ -182,6 +182,12 @@ int sap3d_attention_bwd(int32_t dtype, const void* g, const void* f, const void*
  * lse (nullable) [B][Nq] = log-sum-exp of every score row, kept for the backward kernels. */
 int sap3d_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t Nq, int32_t Nk,
                          int32_t dk, int32_t dv, void* stream);
+/* backward of sap3d_flash_attn_fwd (dv == 128): dq [B][Nq][64], dk [B][Nk][64], dv [B][Nk][dv] (bf16) from o, d_o and lse;
+ * the probabilities are recomputed on chip.  workspace: sap3d_flash_attn_bwd_workspace(B, Nq, Nk, dv) bytes. */
+size_t sap3d_flash_attn_bwd_workspace(int32_t B, int32_t Nq, int32_t Nk, int32_t dv);
+int sap3d_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse, void* dq,
+                         void* dk, void* dv_out, int32_t B, int32_t Nq, int32_t Nk, int32_t dk_dim, int32_t dv, void* workspace,
+                         void* stream);
 /* bf16 tensor-core GEMMs: C[M][N] (+)= A[M][K] B[N][K]^T  (K % 64 == 0, ldb == K, N % 8 == 0); B has rows_b <= N
  * rows, the remaining output columns are computed against zeros */
 int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t rows_b, void* C, int64_t ldc, int32_t M,

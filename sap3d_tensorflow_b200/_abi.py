@@ -128,6 +128,8 @@ _i32x = _i32
 _sig("sap3d_attention_fwd", [_i32, _vp, _vp, _vp, _vp, _vp] + [_i32] * 10 + [_vp])
 _sig("sap3d_attention_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 10 + [_vp])
 _sig("sap3d_flash_attn_fwd", [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp])
+_sig("sap3d_flash_attn_bwd_workspace", [_i32, _i32, _i32, _i32], C.c_size_t)
+_sig("sap3d_flash_attn_bwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp])
 _sig("sap3d_gemm_nt", [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp])
 _sig("sap3d_gemm_tn", [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp])
 _sig("sap3d_softmax_rows", [_i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp])

@@ -234,6 +234,427 @@ __global__ void __launch_bounds__(192, (DV == 128 ? 2 : 1)) flash_fwd_kernel(con
   }
 }
 
+
+// =================================================================================================
+// Backward.  With P = exp(S - lse), D = rowsum(dO * O):
+//   dV = P^T dO,   dP = dO V^T,   dS = P * (dP - D),   dQ = dS K,   dK = dS^T Q
+// Kernel A (one CTA per 128 queries) recomputes S and produces dQ; kernel B (one CTA per 128 keys and a slice of the
+// query tiles) recomputes S^T = K Q^T directly (so P^T / dS^T come out of TMEM already transposed) and accumulates
+// dV, dK in TMEM, reduced across query slices with red.global.add.v4.f32 into fp32 buffers.
+// =================================================================================================
+
+// D[row] = sum_c dO[row][c] * O[row][c]    (one warp per row)
+__global__ void __launch_bounds__(256) flash_dsum_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, long long rows, int dv,
+                                                         float* __restrict__ dsum) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = w; r < rows; r += nw) {
+    float acc = 0.f;
+    for (int c = lane * 8; c < dv; c += 256) {
+      float a[8], b[8];
+      Vec8<bf16>::load(o + r * dv + c, a);
+      Vec8<bf16>::load(d_o + r * dv + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(a[j], b[j], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dsum[r] = acc;
+  }
+}
+
+template <int DV>
+__global__ void __launch_bounds__(192) flash_bwd_dq_kernel(const __grid_constant__ FlashParams p) {
+  constexpr int KST = 2;
+  constexpr int VCH = DV / 64;
+  constexpr uint32_t Q_OFF = 0, DO_OFF = 16384, K_OFF = DO_OFF + VCH * 16384, V_OFF = K_OFF + KST * 16384, DS_OFF = V_OFF + VCH * 16384,
+                     BAR_OFF = DS_OFF + 32768;
+  constexpr uint32_t TMEM_COLS = 512;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  if ((base & 1023u) != 0) __trap();
+  // 0 qdo_full, 1-2 k_full, 3-4 k_empty, 5 v_full, 6 v_empty, 7-8 s_full, 9-10 s_empty, 11 dp_full, 12 dp_empty, 13 ds_full,
+  // 14 ds_empty, 15 dq_full
+  const uint32_t bar = base + BAR_OFF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, b = blockIdx.y;
+  const int nkb = p.nkb;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 16; ++i) mbar_init(bar + i * 8, (i == 9 || i == 10 || i == 12 || i == 13) ? 128 : 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); tma_prefetch_desc(&p.domap);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 256, tmem_dq = tmem_base + 384;   // S double-buffered: +0, +128
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar + 0, 16384 + VCH * 16384);
+      tma_load_3d(base + Q_OFF, &p.qmap, bar + 0, 0, qt * 128, b);
+#pragma unroll
+      for (int j = 0; j < VCH; ++j) tma_load_3d(base + DO_OFF + j * 16384, &p.domap, bar + 0, j * 64, qt * 128, b);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int ks = kb & 1;
+        mbar_wait(bar + (3 + ks) * 8, ((static_cast<uint32_t>(kb) >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(bar + (1 + ks) * 8, 16384);
+        tma_load_3d(base + K_OFF + ks * 16384, &p.kmap, bar + (1 + ks) * 8, 0, kb * 128, b);
+        mbar_wait(bar + 6 * 8, (static_cast<uint32_t>(kb) & 1u) ^ 1u);
+        mbar_expect_tx(bar + 5 * 8, VCH * 16384);
+#pragma unroll
+        for (int j = 0; j < VCH; ++j) tma_load_3d(base + V_OFF + j * 16384, &p.vmap, bar + 5 * 8, j * 64, kb * 128, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, 0, 1);   // B = K tile, MN-major (N = d_k, K = keys)
+      mbar_wait(bar + 0, 0);
+      tc_fence_after();
+      const uint64_t qdesc = umma_desc_sw128(base + Q_OFF, 16, 1024);
+      auto issue_s = [&](int kb) {
+        const int ks = kb & 1;
+        const uint32_t use = static_cast<uint32_t>(kb) >> 1;
+        mbar_wait(bar + (1 + ks) * 8, use & 1u);
+        mbar_wait(bar + (9 + ks) * 8, (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint64_t kdesc = umma_desc_sw128(base + K_OFF + ks * 16384, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_s + ks * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(bar + (7 + ks) * 8);
+      };
+      issue_s(0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        // dP(kb) = dO V_kb^T
+        mbar_wait(bar + 5 * 8, static_cast<uint32_t>(kb) & 1u);
+        mbar_wait(bar + 12 * 8, (static_cast<uint32_t>(kb) & 1u) ^ 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < VCH; ++c) {
+          const uint64_t ad = umma_desc_sw128(base + DO_OFF + c * 16384, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(base + V_OFF + c * 16384, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_dp, ad + 2 * k, bd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(bar + 11 * 8);
+        tc_commit(bar + 6 * 8);
+        if (kb + 1 < nkb) issue_s(kb + 1);
+        // dQ += dS(kb) K_kb
+        mbar_wait(bar + 13 * 8, static_cast<uint32_t>(kb) & 1u);
+        tc_fence_after();
+        const uint64_t kd = umma_desc_sw128(base + K_OFF + (kb & 1) * 16384, 16384, 1024);
+#pragma unroll
+        for (int c64 = 0; c64 < 2; ++c64) {
+          const uint64_t ad = umma_desc_sw128(base + DS_OFF + c64 * 16384, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_dq, ad + 2 * k, kd + 128 * (c64 * 4 + k), idesc_dq, (kb | c64 | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(bar + 14 * 8);
+        tc_commit(bar + (3 + (kb & 1)) * 8);
+      }
+      tc_commit(bar + 15 * 8);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t trow = static_cast<uint32_t>(q * 32) << 16;
+    const int qrow = qt * 128 + row;
+    const bool valid = qrow < p.Nq;
+    const float lneg = valid ? -p.lse[(long long)b * p.Nq + qrow] * LOG2E : -INFINITY;
+    const float dsum = valid ? p.dsum[(long long)b * p.Nq + qrow] : 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int sb = kb & 1;
+      uint32_t pp[64];   // the 128 probabilities of this row, bf16x2
+      mbar_wait(bar + (7 + sb) * 8, (static_cast<uint32_t>(kb) >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_s + sb * 128 + trow + c * 32, rr);
+        tmem_ld_wait();
+        const int col0 = kb * 128 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float e0 = ex2_approx(fmaf(__uint_as_float(rr[j]), LOG2E, lneg));
+          float e1 = ex2_approx(fmaf(__uint_as_float(rr[j + 1]), LOG2E, lneg));
+          if (col0 + j >= p.Nk) e0 = 0.f;
+          if (col0 + j + 1 >= p.Nk) e1 = 0.f;
+          pp[c * 16 + j / 2] = pack_bf16x2(e0, e1);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar + (9 + sb) * 8);
+      mbar_wait(bar + 11 * 8, static_cast<uint32_t>(kb) & 1u);
+      tc_fence_after();
+      mbar_wait(bar + 14 * 8, (static_cast<uint32_t>(kb) & 1u) ^ 1u);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_dp + trow + c * 32, rr);
+        tmem_ld_wait();
+        float ds[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float2 pr = unpack_bf16x2(pp[c * 16 + j / 2]);
+          ds[j] = pr.x * (__uint_as_float(rr[j]) - dsum);
+          ds[j + 1] = pr.y * (__uint_as_float(rr[j + 1]) - dsum);
+        }
+        store_row_chunk_bf16(base + DS_OFF, row, c, ds);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar + 12 * 8);
+      mbar_arrive(bar + 13 * 8);
+    }
+    mbar_wait(bar + 15 * 8, 0);
+    tc_fence_after();
+    bf16* dq = reinterpret_cast<bf16*>(p.dq) + ((long long)b * p.Nq + qrow) * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t rr[32];
+      tmem_ld_32x32(tmem_dq + trow + c * 32, rr);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float w8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w8[j] = __uint_as_float(rr[g * 8 + j]);
+          Vec8<bf16>::store(dq + c * 32 + g * 8, w8);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+struct FlashDkvExtra {
+  int splits, tiles_per_split;
+  float* dk32;   // [B][Nk][64]
+  float* dv32;   // [B][Nk][DV]
+};
+
+template <int DV>
+__global__ void __launch_bounds__(192) flash_bwd_dkv_kernel(const __grid_constant__ FlashParams p, const FlashDkvExtra x) {
+  constexpr int VCH = DV / 64;
+  constexpr uint32_t K_OFF = 0, V_OFF = 16384, Q_OFF = V_OFF + VCH * 16384, DO_OFF = Q_OFF + 2 * 16384, PT_OFF = DO_OFF + 2 * VCH * 16384,
+                     DST_OFF = PT_OFF + 32768, STAT_OFF = DST_OFF + 32768, BAR_OFF = STAT_OFF + 2 * 2 * 128 * 4;
+  constexpr uint32_t TMEM_COLS = 512;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  if ((base & 1023u) != 0) __trap();
+  // 0 kv_full, 1-2 q_full, 3-4 q_empty, 5 st_full, 6 st_empty, 7 dpt_full, 8 dpt_empty, 9 pt_full, 10 pt_empty, 11 dst_full,
+  // 12 dst_empty, 13 acc_full
+  const uint32_t bar = base + BAR_OFF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 14 * 8);
+  float* s_stat = reinterpret_cast<float*>(smem + STAT_OFF);   // [2 stages][lse | dsum][128]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kbk = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
+  const int t_begin = split * x.tiles_per_split;
+  const int t_end = min(p.nqb, t_begin + x.tiles_per_split);
+  const int nt = max(0, t_end - t_begin);
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 14; ++i) mbar_init(bar + i * 8, (i == 6 || i == 8 || i == 9 || i == 11) ? 128 : 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); tma_prefetch_desc(&p.domap);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_st = tmem_base, tmem_dpt = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 256 + DV;
+
+  if (warp == 0) {
+    if (lane == 0 && nt > 0) {
+      mbar_expect_tx(bar + 0, 16384 + VCH * 16384);
+      tma_load_3d(base + K_OFF, &p.kmap, bar + 0, 0, kbk * 128, b);
+#pragma unroll
+      for (int j = 0; j < VCH; ++j) tma_load_3d(base + V_OFF + j * 16384, &p.vmap, bar + 0, j * 64, kbk * 128, b);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i & 1;
+        mbar_wait(bar + (3 + s) * 8, ((static_cast<uint32_t>(i) >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(bar + (1 + s) * 8, 16384 + VCH * 16384);
+        tma_load_3d(base + Q_OFF + s * 16384, &p.qmap, bar + (1 + s) * 8, 0, (t_begin + i) * 128, b);
+#pragma unroll
+        for (int j = 0; j < VCH; ++j)
+          tma_load_3d(base + DO_OFF + (s * VCH + j) * 16384, &p.domap, bar + (1 + s) * 8, j * 64, (t_begin + i) * 128, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && nt > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_dv = umma_idesc_bf16(128, DV, 0, 1);   // B = dO tile, MN-major (N = d_v, K = queries)
+      constexpr uint32_t idesc_dk = umma_idesc_bf16(128, 64, 0, 1);   // B = Q tile,  MN-major (N = d_k, K = queries)
+      mbar_wait(bar + 0, 0);
+      tc_fence_after();
+      const uint64_t kdesc = umma_desc_sw128(base + K_OFF, 16, 1024);
+      auto issue_scores = [&](int i) {   // S^T(i) = K Q_i^T and dP^T(i) = V dO_i^T
+        const int s = i & 1;
+        mbar_wait(bar + (1 + s) * 8, (static_cast<uint32_t>(i) >> 1) & 1u);
+        mbar_wait(bar + 6 * 8, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint64_t qd = umma_desc_sw128(base + Q_OFF + s * 16384, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_st, kdesc + 2 * k, qd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(bar + 5 * 8);
+        mbar_wait(bar + 8 * 8, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < VCH; ++c) {
+          const uint64_t ad = umma_desc_sw128(base + V_OFF + c * 16384, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(base + DO_OFF + (s * VCH + c) * 16384, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_dpt, ad + 2 * k, bd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(bar + 7 * 8);
+      };
+      issue_scores(0);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i & 1;
+        if (i + 1 < nt) issue_scores(i + 1);
+        // dV += P^T(i) dO_i
+        mbar_wait(bar + 9 * 8, static_cast<uint32_t>(i) & 1u);
+        tc_fence_after();
+        const uint64_t dod = umma_desc_sw128(base + DO_OFF + s * VCH * 16384, 16384, 1024);
+#pragma unroll
+        for (int c64 = 0; c64 < 2; ++c64) {
+          const uint64_t ad = umma_desc_sw128(base + PT_OFF + c64 * 16384, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_dv, ad + 2 * k, dod + 128 * (c64 * 4 + k), idesc_dv, (i | c64 | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(bar + 10 * 8);
+        // dK += dS^T(i) Q_i
+        mbar_wait(bar + 11 * 8, static_cast<uint32_t>(i) & 1u);
+        tc_fence_after();
+        const uint64_t qd = umma_desc_sw128(base + Q_OFF + s * 16384, 16384, 1024);
+#pragma unroll
+        for (int c64 = 0; c64 < 2; ++c64) {
+          const uint64_t ad = umma_desc_sw128(base + DST_OFF + c64 * 16384, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_dk, ad + 2 * k, qd + 128 * (c64 * 4 + k), idesc_dk, (i | c64 | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(bar + 12 * 8);
+        tc_commit(bar + (3 + s) * 8);
+      }
+      tc_commit(bar + 13 * 8);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;           // key row of this thread
+    const int et = threadIdx.x - 64;         // 0..127
+    const uint32_t trow = static_cast<uint32_t>(q * 32) << 16;
+    const int krow = kbk * 128 + row;
+    for (int i = 0; i < nt; ++i) {
+      const int s = i & 1;
+      {   // per-query statistics of this tile -> shared memory (queries are the COLUMNS here)
+        const int qg = (t_begin + i) * 128 + et;
+        const bool qv = qg < p.Nq;
+        s_stat[(s * 2 + 0) * 128 + et] = qv ? -p.lse[(long long)b * p.Nq + qg] * LOG2E : -INFINITY;
+        s_stat[(s * 2 + 1) * 128 + et] = qv ? p.dsum[(long long)b * p.Nq + qg] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float* lneg = s_stat + (s * 2 + 0) * 128;
+      const float* dsm = s_stat + (s * 2 + 1) * 128;
+      uint32_t pp[64];
+      mbar_wait(bar + 5 * 8, static_cast<uint32_t>(i) & 1u);
+      tc_fence_after();
+      mbar_wait(bar + 10 * 8, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_st + trow + c * 32, rr);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pv[j] = ex2_approx(fmaf(__uint_as_float(rr[j]), LOG2E, lneg[c * 32 + j]));
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) pp[c * 16 + j / 2] = pack_bf16x2(pv[j], pv[j + 1]);
+        store_row_chunk_bf16(base + PT_OFF, row, c, pv);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar + 6 * 8);
+      mbar_arrive(bar + 9 * 8);
+      mbar_wait(bar + 7 * 8, static_cast<uint32_t>(i) & 1u);
+      tc_fence_after();
+      mbar_wait(bar + 12 * 8, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_dpt + trow + c * 32, rr);
+        tmem_ld_wait();
+        float ds[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float2 pr = unpack_bf16x2(pp[c * 16 + j / 2]);
+          ds[j] = pr.x * (__uint_as_float(rr[j]) - dsm[c * 32 + j]);
+          ds[j + 1] = pr.y * (__uint_as_float(rr[j + 1]) - dsm[c * 32 + j + 1]);
+        }
+        store_row_chunk_bf16(base + DST_OFF, row, c, ds);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar + 8 * 8);
+      mbar_arrive(bar + 11 * 8);
+    }
+    if (nt > 0) {
+      mbar_wait(bar + 13 * 8, 0);
+      tc_fence_after();
+      const bool valid = krow < p.Nk;
+      float* dv = x.dv32 + ((long long)b * p.Nk + krow) * DV;
+      float* dk = x.dk32 + ((long long)b * p.Nk + krow) * 64;
+#pragma unroll 1
+      for (int c = 0; c < DV / 32 + 2; ++c) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_dv + trow + c * 32, rr);   // dK's 64 columns follow dV's in TMEM
+        tmem_ld_wait();
+        if (valid) {
+          float* out = c < DV / 32 ? dv + c * 32 : dk + (c - DV / 32) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + j), "f"(__uint_as_float(rr[j])),
+                         "f"(__uint_as_float(rr[j + 1])), "f"(__uint_as_float(rr[j + 2])), "f"(__uint_as_float(rr[j + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+__global__ void __launch_bounds__(256) flash_cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    Vec8<float>::load(src + i * 8, v);
+    Vec8<bf16>::store(dst + i * 8, v);
+  }
+}
+
 // ---- host ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -276,6 +697,24 @@ static int launch_fwd(const FlashParams& prm, int B, cudaStream_t st) {
   return check_launch("flash_attn_fwd");
 }
 
+
+template <int DV>
+static int launch_bwd(const FlashParams& prm, const FlashDkvExtra& ex, int B, cudaStream_t st) {
+  constexpr int SMEM_DQ = 16384 + (DV / 64) * 16384 + 2 * 16384 + (DV / 64) * 16384 + 32768 + 16 * 8 + 32;
+  constexpr int SMEM_DKV = 16384 + (DV / 64) * 16384 + 2 * 16384 + 2 * (DV / 64) * 16384 + 32768 + 32768 + 2 * 2 * 128 * 4 + 14 * 8 + 32;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(flash_bwd_dq_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_bwd_dkv_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(flash_bwd): %s", cudaGetErrorString(e));
+    done = true;
+  }
+  flash_bwd_dq_kernel<DV><<<dim3(prm.nqb, B), 192, SMEM_DQ, st>>>(prm);
+  if (check_launch("flash_attn_bwd dq")) return 1;
+  flash_bwd_dkv_kernel<DV><<<dim3(prm.nkb, B, ex.splits), 192, SMEM_DKV, st>>>(prm, ex);
+  return check_launch("flash_attn_bwd dkv");
+}
+
 }  // namespace sap3d
 
 using namespace sap3d;
@@ -292,4 +731,57 @@ extern "C" int sap3d_flash_attn_fwd(const void* q, const void* k, const void* v,
   prm.o = o; prm.lse = lse;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return dv == 128 ? launch_fwd<128>(prm, B, st) : launch_fwd<256>(prm, B, st);
+}
+
+extern "C" size_t sap3d_flash_attn_bwd_workspace(int32_t B, int32_t Nq, int32_t Nk, int32_t dv) {
+  return ((size_t)B * Nq + (size_t)B * Nk * (64 + dv)) * sizeof(float) + 256;
+}
+
+extern "C" int sap3d_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                                    void* dq, void* dk, void* dv_out, int32_t B, int32_t Nq, int32_t Nk, int32_t dk_dim, int32_t dv,
+                                    void* workspace, void* stream) {
+  if (require_device()) return 1;
+  if (dk_dim != 64 || dv != 128) return set_error("flash_attn_bwd: needs d_k == 64 (zero-padded) and d_v == 128 (got %d, %d)", dk_dim, dv);
+  if (!workspace || !lse) return set_error("flash_attn_bwd: NULL workspace / lse");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static thread_local FlashParams prm;
+  memset(&prm, 0, sizeof(prm));
+  if (encode_rows(&prm.qmap, q, B, Nq, 64) || encode_rows(&prm.kmap, k, B, Nk, 64) || encode_rows(&prm.vmap, v, B, Nk, dv) ||
+      encode_rows(&prm.domap, d_o, B, Nq, dv))
+    return 1;
+  float* ws = reinterpret_cast<float*>(workspace);
+  float* dsum = ws;
+  float* dk32 = ws + (((size_t)B * Nq + 63) / 64) * 64;
+  float* dv32 = dk32 + (size_t)B * Nk * 64;
+  prm.Nq = Nq; prm.Nk = Nk; prm.nkb = (Nk + 127) / 128; prm.nqb = (Nq + 127) / 128;
+  prm.lse = const_cast<float*>(lse); prm.dsum = dsum; prm.dq = dq; prm.dk = dk; prm.dv = dv_out;
+  const long long rows = (long long)B * Nq;
+  {
+    long long blocks = (rows * 32 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    flash_dsum_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), rows, dv, dsum);
+    if (check_launch("flash_attn_bwd dsum")) return 1;
+  }
+  if (cudaMemsetAsync(dk32, 0, (size_t)B * Nk * (64 + dv) * sizeof(float), st) != cudaSuccess) return set_error("flash_attn_bwd: memset failed");
+  FlashDkvExtra ex;
+  // split the query tiles so that (key blocks x samples x splits) fills the 148 SMs about evenly
+  const long long base_ctas = (long long)prm.nkb * B;
+  int splits = 1;
+  double best = 0.0;
+  for (int s = 1; s <= 8 && s <= prm.nqb; ++s) {
+    const double waves = (double)(base_ctas * s) / 148.0;
+    const double eff = waves / (double)((long long)(waves + 0.999999));
+    if (eff > best + 0.02) { best = eff; splits = s; }
+  }
+  ex.splits = splits;
+  ex.tiles_per_split = (prm.nqb + splits - 1) / splits;
+  ex.dk32 = dk32; ex.dv32 = dv32;
+  if (launch_bwd<128>(prm, ex, B, st)) return 1;
+  {
+    const long long n8k = (long long)B * Nk * 64 / 8, n8v = (long long)B * Nk * dv / 8;
+    flash_cast_kernel<<<(unsigned)((n8k + 255) / 256 > 1184 ? 1184 : (n8k + 255) / 256), 256, 0, st>>>(dk32, reinterpret_cast<bf16*>(dk), n8k);
+    flash_cast_kernel<<<(unsigned)((n8v + 255) / 256 > 1184 ? 1184 : (n8v + 255) / 256), 256, 0, st>>>(dv32, reinterpret_cast<bf16*>(dv_out), n8v);
+    if (check_launch("flash_attn_bwd cast")) return 1;
+  }
+  return 0;
 }

@@ -732,9 +732,12 @@ class _AttnCoreOp:
         self.ldb = self.Nkp
         tr = eng.training_graph
         # fused flash-style kernels (csrc/flash_attn.cu): the [Nq][Nk] score / probability matrices are never materialised
-        self.use_flash = self.use_tc and self.dk == 64 and self.dv in (128, 256) and self.FLASH and (not tr or self.FLASH_BWD)
+        self.use_flash = self.use_tc and self.dk == 64 and self.dv in (128, 256) and self.FLASH and (not tr or self.dv == 128)
         if self.use_flash:
             self.lse = torch.empty(B, self.Nq, device=dev, dtype=torch.float32)
+            if tr:
+                self.flash_ws = torch.empty(A.lib.sap3d_flash_attn_bwd_workspace(B, self.Nq, self.Nk, self.dv) // 4 + 16, device=dev,
+                                            dtype=torch.float32)
             return
         self.beta = torch.zeros(B, self.Nq, self.ldb, device=dev, dtype=eng.tdt)
         if self.use_tc:
@@ -756,7 +759,14 @@ class _AttnCoreOp:
             self.ds = torch.empty_like(self.beta)
 
     FLASH = True
-    FLASH_BWD = False
+
+    def _bwd_flash(self):
+        e = self.eng
+        A.check(A.lib.sap3d_flash_attn_bwd(A.ptr(self.g.buf), A.ptr(self.f.buf), A.ptr(self.h.buf), A.ptr(self.o.buf), A.ptr(self.o.grad),
+                                           A.ptr(self.lse), A.ptr(self.g.ensure_grad()), A.ptr(self.f.ensure_grad()),
+                                           A.ptr(self.h.ensure_grad()), self.B, self.Nq, self.Nk, self.dk, self.dv, A.ptr(self.flash_ws),
+                                           e.stream), "flash_attn_bwd " + self.name)
+        e._count(6)
 
     def _fwd_flash(self):
         e = self.eng
@@ -830,6 +840,8 @@ class _AttnCoreOp:
         for t in (self.g, self.f, self.h):
             if t.take_acc():
                 raise A.Sap3dError("attention operands must have a single consumer")
+        if self.use_flash:
+            return self._bwd_flash()
         if self.use_tc:
             return self._bwd_tc()
         A.check(A.lib.sap3d_attention_bwd(e.dt, A.ptr(self.g.buf), A.ptr(self.f.buf), A.ptr(self.h.buf), A.ptr(self.beta),

@@ -49,3 +49,31 @@ def test_flash_fwd(A, B, Nq, Nk, dk, dv, scale):
     assert torch.isfinite(o.float()).all()
     assert rel(o, ref) < 1e-2, rel(o, ref)
     assert rel(lse, torch.logsumexp(s, -1)) < 1e-4
+
+
+@pytest.mark.parametrize("B,Nq,Nk,dk", [(2, 300, 200, 16), (1, 512, 3136, 16), (2, 130, 129, 64), (1, 2000, 128, 16), (3, 2, 3, 16)])
+@pytest.mark.parametrize("scale", [1.0, 2.5])
+def test_flash_bwd(A, B, Nq, Nk, dk, scale):
+    """dq, dk, dv of o = softmax(q k^T) v against torch autograd in fp32 on the same bf16 inputs (2e-2: bf16 P and dS)"""
+    dv = 128
+    q, k, v = make(B, Nq, Nk, dk, dv, scale, seed=3)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    d_o = torch.randn(B, Nq, dv, device="cuda", generator=g).bfloat16()
+    o = torch.empty(B, Nq, dv, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, Nq, device="cuda")
+    A.check(A.lib.sap3d_flash_attn_fwd(A.ptr(q), A.ptr(k), A.ptr(v), A.ptr(o), A.ptr(lse), B, Nq, Nk, 64, dv, stream()), "flash fwd")
+    dq = torch.full((B, Nq, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dkk = torch.full((B, Nk, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dvv = torch.full((B, Nk, dv), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ws = torch.empty(A.lib.sap3d_flash_attn_bwd_workspace(B, Nq, Nk, dv) // 4 + 16, device="cuda")
+    A.check(A.lib.sap3d_flash_attn_bwd(A.ptr(q), A.ptr(k), A.ptr(v), A.ptr(o), A.ptr(d_o), A.ptr(lse), A.ptr(dq), A.ptr(dkk), A.ptr(dvv),
+                                       B, Nq, Nk, 64, dv, A.ptr(ws), stream()), "flash bwd")
+    torch.cuda.synchronize()
+    qf, kf, vf = [t.float().requires_grad_(True) for t in (q, k, v)]
+    ref = torch.softmax(qf @ kf.transpose(1, 2), -1) @ vf
+    ref.backward(d_o.float())
+    for name, got, want in (("dq", dq, qf.grad), ("dk", dkk, kf.grad), ("dv", dvv, vf.grad)):
+        assert torch.isfinite(got.float()).all(), name
+        assert rel(got, want) < 2e-2, (name, rel(got, want))
+    if dk < 64:   # padded d_k columns stay exactly zero
+        assert float(dq[..., dk:].float().abs().max()) == 0.0 and float(dkk[..., dk:].float().abs().max()) == 0.0
