@@ -154,6 +154,14 @@ int sap3d_head_fwd(int32_t dtype, const void* x, int32_t N, int32_t D, int32_t H
                    int32_t stride, const float* w, const float* bias, float* logits, float* pred, void* stream);
 int sap3d_head_bwd(int32_t dtype, const float* dlogits, const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C,
                    const int32_t* ksize, int32_t stride, const float* w, void* dx, int32_t accumulate, float* dw, void* stream);
+/* tensor-core form of the k3 s2 head for bf16 activations with C % 64 == 0: [positions x C] x [C x 27] GEMM + col2im gather
+ * (forward), GEMMs over the im2col of dlogits (backward).  workspace: sap3d_head_tc_workspace(N,D,H,W,C) bytes, shared by
+ * forward and backward of one head. */
+size_t sap3d_head_tc_workspace(int32_t N, int32_t D, int32_t H, int32_t W, int32_t C);
+int sap3d_head_tc_fwd(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, const float* w, const float* bias,
+                      float* logits, float* pred, void* workspace, void* stream);
+int sap3d_head_tc_bwd(const float* dlogits, const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, void* dx,
+                      int32_t accumulate, float* dw, void* workspace, void* stream, void* wgrad_stream);
 /* smooth_l1_loss(sigma=1, weights 1) summed over all elements (utils/network.py:49-62, train.py:159):
  * loss_sum[0] += loss; dlogits = dLoss/dlogits; dbias[0] += sum(dlogits); pred = sigmoid(logits). */
 int sap3d_loss_smooth_l1(const float* logits, const float* target, int64_t n, int32_t apply_sigmoid, float* pred,

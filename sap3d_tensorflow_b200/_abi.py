@@ -117,6 +117,9 @@ _sig("sap3d_maxpool3d_fwd", [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int
 _sig("sap3d_maxpool3d_bwd", [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int32), _P(C.c_int32), _i32, _vp, _vp, _i32, _vp])
 _sig("sap3d_head_fwd", [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int32), _i32, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_head_bwd", [_i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int32), _i32, _vp, _vp, _i32, _vp, _vp])
+_sig("sap3d_head_tc_workspace", [_i32, _i32, _i32, _i32, _i32], C.c_size_t)
+_sig("sap3d_head_tc_fwd", [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp])
+_sig("sap3d_head_tc_bwd", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp])
 _sig("sap3d_loss_smooth_l1", [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_dropout", [_i32, _vp, _vp, _i64, _f32, _u64, _vp, _i32, _vp])
 _sig("sap3d_gate_fwd", [_i32, _vp, _vp, _vp, _vp, _i64, _vp])

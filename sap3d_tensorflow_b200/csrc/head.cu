@@ -170,6 +170,86 @@ __global__ void __launch_bounds__(256) head_fwd_k3s2_kernel(const HeadArgs p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core head (k3 s2, C % 64 == 0, bf16): the Cout = 1 transposed conv is a [positions x C] x [C x 27] GEMM
+// followed by a col2im gather; its gradients are GEMMs over the im2col of dlogits (run through sap3d_gemm_nt/_tn).
+// ------------------------------------------------------------------------------------------------
+// w [27][C] fp32 -> wf [32][C] bf16 (rows >= 27 zero) and wd [C][64] bf16 (wd[c][k] = w[k][c], k >= 27 zero)
+__global__ void __launch_bounds__(256) head_pack_w_kernel(const float* __restrict__ w, int C, bf16* __restrict__ wf, bf16* __restrict__ wd) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 32 * C; i += gridDim.x * blockDim.x) {
+    const int k = i / C;
+    wf[i] = __float2bfloat16_rn(k < 27 ? w[i] : 0.f);
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 64 * C; i += gridDim.x * blockDim.x) {
+    const int c = i / 64, k = i % 64;
+    wd[i] = __float2bfloat16_rn(k < 27 ? w[k * C + c] : 0.f);
+  }
+}
+
+// (input index, tap) pairs of a k3 s2 'same' transposed conv that land on output index o: 2i + k = o
+SAP3D_DEVINL int head_contrib(int o, int (&i)[2], int (&k)[2]) {
+  if (o & 1) { i[0] = o >> 1; k[0] = 1; return 1; }
+  i[0] = o >> 1; k[0] = 0;
+  i[1] = (o >> 1) - 1; k[1] = 2;
+  return (o >> 1) >= 1 ? 2 : 1;
+}
+
+// logits[n, o] = bias + sum over (i, k) with 2i + k = o of t[i][k]   (per dim: o even -> (o/2, 0), (o/2 - 1, 2); o odd -> ((o-1)/2, 1))
+__global__ void __launch_bounds__(256) head_col2im_kernel(const float* __restrict__ t, int N, int D, int H, int W, const float* bias,
+                                                           float* __restrict__ logits, float* __restrict__ pred) {
+  const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)N * Do * Ho * Wo;
+  const float b0 = bias ? bias[0] : 0.f;
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    long long r = o;
+    const int ow = (int)(r % Wo); r /= Wo;
+    const int oh = (int)(r % Ho); r /= Ho;
+    const int od = (int)(r % Do);
+    const int n = (int)(r / Do);
+    int id[2], kd[2], ih[2], kh[2], iw[2], kw[2];
+    const int nd = head_contrib(od, id, kd), nh = head_contrib(oh, ih, kh), nw = head_contrib(ow, iw, kw);
+    float acc = b0;
+    for (int a = 0; a < nd; ++a)
+      for (int b = 0; b < nh; ++b)
+        for (int e = 0; e < nw; ++e)
+          acc += __ldg(t + ((((long long)n * D + id[a]) * H + ih[b]) * W + iw[e]) * 32 + (kd[a] * 3 + kh[b]) * 3 + kw[e]);
+    logits[o] = acc;
+    if (pred) pred[o] = 1.f / (1.f + __expf(-acc));
+  }
+}
+
+// col[pos][k] = dlogits[n, 2i + k] (k < 27; 0 beyond the output extent and for the 37 padding columns), bf16 [positions][64]
+__global__ void __launch_bounds__(256) head_im2col_kernel(const float* __restrict__ dlog, int N, int D, int H, int W, bf16* __restrict__ col) {
+  const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)N * D * H * W * 8;   // 8 threads per position, 8 columns each
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int part = (int)(i & 7);
+    long long r = i >> 3;
+    const long long pos = r;
+    const int iw = (int)(r % W); r /= W;
+    const int ih = (int)(r % H); r /= H;
+    const int id = (int)(r % D);
+    const int n = (int)(r / D);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = part * 8 + j;
+      float x = 0.f;
+      if (k < 27) {
+        const int od = 2 * id + k / 9, oh = 2 * ih + (k / 3) % 3, ow = 2 * iw + k % 3;
+        if (od < Do && oh < Ho && ow < Wo) x = __ldg(dlog + (((long long)n * Do + od) * Ho + oh) * Wo + ow);
+      }
+      v[j] = x;
+    }
+    Vec8<bf16>::store(col + pos * 64 + part * 8, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) head_wgrad_fold_kernel(const float* __restrict__ d64, int C, float* dw) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 27 * C; i += gridDim.x * blockDim.x) dw[i] += d64[i];
+}
+
 // dx[n,i,c] (+)= sum_k dlog[n, s*i + k - pb] * w[k][c] ; thread = (voxel, 8 channels)
 struct HeadBwdArgs {
   const float* dlog; const void* x; const float* w; void* dx; float* dw;
@@ -526,6 +606,62 @@ int sap3d_head_bwd(int32_t dtype, const float* dlogits, const void* x, int32_t N
     if (dtype == SAP3D_BF16) head_wgrad_kernel<bf16><<<grid, lanes * cv, smem2, st>>>(p);
     else head_wgrad_kernel<float><<<grid, lanes * cv, smem2, st>>>(p);
     if (check_launch("head_wgrad")) return 1;
+  }
+  return 0;
+}
+
+
+/* workspace layout of the tensor-core head: wf [32][C] bf16 | wd [C][64] bf16 | d64 [64][C] f32 | t27 [P][32] f32 | col [P][64] bf16 */
+static size_t head_tc_offsets(long long P, int C, size_t* o_wd, size_t* o_d64, size_t* o_t27, size_t* o_col) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) / 256 * 256; return r; };
+  take((size_t)32 * C * 2);
+  *o_wd = take((size_t)C * 64 * 2);
+  *o_d64 = take((size_t)64 * C * 4);
+  *o_t27 = take((size_t)P * 32 * 4);
+  *o_col = take((size_t)P * 64 * 2);
+  return off;
+}
+
+size_t sap3d_head_tc_workspace(int32_t N, int32_t D, int32_t H, int32_t W, int32_t C) {
+  size_t a, b, c, d;
+  return head_tc_offsets((long long)N * D * H * W, C, &a, &b, &c, &d);
+}
+
+int sap3d_head_tc_fwd(const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, const float* w, const float* bias,
+                      float* logits, float* pred, void* workspace, void* stream) {
+  if (require_device()) return 1;
+  if (C % 64 != 0 || !workspace) return set_error("head_tc_fwd: needs C %% 64 == 0 and a workspace");
+  const long long P = (long long)N * D * H * W;
+  size_t o_wd, o_d64, o_t27, o_col;
+  head_tc_offsets(P, C, &o_wd, &o_d64, &o_t27, &o_col);
+  char* ws = reinterpret_cast<char*>(workspace);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  head_pack_w_kernel<<<32, 256, 0, st>>>(w, C, reinterpret_cast<bf16*>(ws), reinterpret_cast<bf16*>(ws + o_wd));
+  if (check_launch("head_pack_w")) return 1;
+  if (sap3d_gemm_nt(x, C, ws, C, 32, ws + o_t27, 32, (int32_t)P, 32, C, 1, 0, stream)) return 1;
+  head_col2im_kernel<<<egrid(P * 8), 256, 0, st>>>(reinterpret_cast<const float*>(ws + o_t27), N, D, H, W, bias, logits, pred);
+  return check_launch("head_col2im");
+}
+
+int sap3d_head_tc_bwd(const float* dlogits, const void* x, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, void* dx,
+                      int32_t accumulate, float* dw, void* workspace, void* stream, void* wgrad_stream) {
+  if (require_device()) return 1;
+  if (C % 64 != 0 || !workspace) return set_error("head_tc_bwd: needs C %% 64 == 0 and a workspace");
+  const long long P = (long long)N * D * H * W;
+  size_t o_wd, o_d64, o_t27, o_col;
+  head_tc_offsets(P, C, &o_wd, &o_d64, &o_t27, &o_col);
+  char* ws = reinterpret_cast<char*>(workspace);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  head_im2col_kernel<<<egrid(P * 8), 256, 0, st>>>(dlogits, N, D, H, W, reinterpret_cast<bf16*>(ws + o_col));
+  if (check_launch("head_im2col")) return 1;
+  if (dx && sap3d_gemm_nt(ws + o_col, 64, ws + o_wd, 64, C, dx, C, (int32_t)P, C, 64, 0, accumulate, stream)) return 1;
+  if (dw) {
+    (void)wgrad_stream;
+    if (cudaMemsetAsync(ws + o_d64, 0, (size_t)64 * C * 4, st) != cudaSuccess) return set_error("head_tc_bwd: memset failed");
+    if (sap3d_gemm_tn(ws + o_col, 64, x, C, reinterpret_cast<float*>(ws + o_d64), C, 64, C, (int32_t)P, stream)) return 1;
+    head_wgrad_fold_kernel<<<16, 256, 0, st>>>(reinterpret_cast<const float*>(ws + o_d64), C, dw);
+    if (check_launch("head_wgrad_fold")) return 1;
   }
   return 0;
 }

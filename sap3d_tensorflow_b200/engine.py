@@ -584,10 +584,19 @@ class _HeadOp:
         self.pred = torch.empty(shp, device=eng.device, dtype=torch.float32)
         self.target = torch.zeros(shp[:-1], device=eng.device, dtype=torch.float32) if eng.training_graph else None
         self.dlogits = torch.empty(shp, device=eng.device, dtype=torch.float32) if eng.training_graph else None
+        # tensor-core form ([positions x C] x [C x 27] GEMM + col2im) for the k3 s2 heads of the bf16 graphs
+        self.use_tc = eng.dt == A.BF16 and x.C % 64 == 0 and tuple(ksize) == (3, 3, 3) and self.stride == 2
+        if self.use_tc:
+            self.ws = torch.empty(A.lib.sap3d_head_tc_workspace(N, D, H, W, x.C) // 4 + 16, device=eng.device, dtype=torch.float32)
 
     def fwd(self):
         e, x = self.eng, self.x
         N, D, H, W, Cc = x.shape
+        if self.use_tc:
+            A.check(A.lib.sap3d_head_tc_fwd(A.ptr(x.buf), N, D, H, W, Cc, A.ptr(self.w.w), A.ptr(self.b.w), A.ptr(self.logits),
+                                            A.ptr(self.pred) if self.sigmoid else None, A.ptr(self.ws), e.stream), "head_tc_fwd " + self.name)
+            e._count(3)
+            return
         A.check(A.lib.sap3d_head_fwd(e.dt, A.ptr(x.buf), N, D, H, W, Cc, self.k, self.stride, A.ptr(self.w.w), A.ptr(self.b.w),
                                      A.ptr(self.logits), A.ptr(self.pred) if self.sigmoid else None, e.stream),
                 "head_fwd " + self.name)
@@ -599,6 +608,11 @@ class _HeadOp:
         A.check(A.lib.sap3d_loss_smooth_l1(A.ptr(self.logits), A.ptr(self.target), self.logits.numel(), int(self.sigmoid), None,
                                            A.ptr(self.dlogits), A.ptr(e.loss_buf), A.ptr(self.b.g), e.stream), "loss")
         acc = x.take_acc()
+        if self.use_tc:
+            A.check(A.lib.sap3d_head_tc_bwd(A.ptr(self.dlogits), A.ptr(x.buf), N, D, H, W, Cc, A.ptr(x.ensure_grad()), acc, A.ptr(self.w.g),
+                                            A.ptr(self.ws), e.stream, None), "head_tc_bwd " + self.name)
+            e._count(6)
+            return
         A.check(A.lib.sap3d_head_bwd(e.dt, A.ptr(self.dlogits), A.ptr(x.buf), N, D, H, W, Cc, self.k, self.stride,
                                      A.ptr(self.w.w), A.ptr(x.ensure_grad()), acc, A.ptr(self.w.g), e.stream),
                 "head_bwd " + self.name)

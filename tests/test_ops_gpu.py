@@ -199,6 +199,33 @@ def test_maxpool_ties_go_to_the_first_maximum(A):
     assert rel(outs[0].float().sum(), dy.float().sum()) < 1e-2   # every window's gradient lands exactly once
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 5, 6, 128), (1, 4, 7, 9, 64), (2, 2, 8, 8, 256)])
+def test_head_tensor_core_form(A, shape):
+    """k3 s2 head as GEMM + col2im (forward) and GEMMs over im2col(dlogits) (backward) vs the oracle's conv3d_transpose
+    (p3d.py:393) on the same bf16 inputs; weights and dlogits are rounded to bf16 on this path (tolerance 1e-2)"""
+    torch.manual_seed(4)
+    N, D, H, W, Cc = shape
+    x = torch.randn(N, D, H, W, Cc, device="cuda").bfloat16()
+    w = torch.randn(3, 3, 3, 1, Cc, device="cuda") * 0.05
+    b = torch.randn(1, device="cuda")
+    logits = torch.empty(N, 2 * D, 2 * H, 2 * W, 1, device="cuda")
+    pred = torch.empty_like(logits)
+    ws = torch.empty(A.lib.sap3d_head_tc_workspace(N, D, H, W, Cc) // 4 + 16, device="cuda")
+    A.check(A.lib.sap3d_head_tc_fwd(A.ptr(x), N, D, H, W, Cc, A.ptr(w), A.ptr(b), A.ptr(logits), A.ptr(pred), A.ptr(ws), stream()), "head tc")
+    xr, wr = x.float().requires_grad_(True), w.clone().requires_grad_(True)
+    lref = tfs.conv3d_transpose_same(xr, wr, (2, 2, 2), b)
+    assert rel(logits, lref) < 1e-2
+    assert rel(pred, torch.sigmoid(lref)) < 1e-2
+    dl = torch.randn_like(lref)
+    lref.backward(dl)
+    dx = torch.ones_like(x)
+    dw = torch.zeros_like(w)
+    A.check(A.lib.sap3d_head_tc_bwd(A.ptr(dl), A.ptr(x), N, D, H, W, Cc, A.ptr(dx), 1, A.ptr(dw), A.ptr(ws), stream(), None), "head tc bwd")
+    torch.cuda.synchronize()
+    assert rel(dx.float() - 1.0, xr.grad) < 2e-2     # accumulated onto ones in bf16
+    assert rel(dw, wr.grad) < 1e-2
+
+
 @pytest.mark.parametrize("dtn,tdt,tol", DT)
 def test_head_loss(A, dtn, tdt, tol):
     torch.manual_seed(2)
