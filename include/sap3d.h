@@ -70,7 +70,8 @@ typedef struct sap3d_conv_desc {
 int sap3d_conv_out_dims(const sap3d_conv_desc* d, int32_t* out_dhw);
 /* number of rows of the per-tile statistics buffer conv_fwd writes (stats is [rows][2][cout] f32) */
 int sap3d_conv_stats_rows(const sap3d_conv_desc* d);
-/* element count of the packed bf16 weights used by the tcgen05 path; which: 0 = forward, 1 = data-gradient */
+/* element count (bf16) of the operand buffers of the tcgen05 path; which: 0 = forward (packed filter; for small-Cin
+ * convolutions such as the Cin = 3 stem also the im2col matrix and a scratch block), 1 = data-gradient */
 size_t sap3d_conv_packed_elems(const sap3d_conv_desc* d, int32_t which);
 
 /* w_tf (fp32, TF layout) -> bf16 K-major matrices for the tensor-core path:
@@ -88,8 +89,10 @@ int sap3d_conv_dgrad(const sap3d_conv_desc* d, int32_t seg, const void* dy, cons
                      const void* w_dgrad_packed, void* dx, int32_t accumulate, void* stream);
 /* dw (fp32, TF layout) += filter gradient; db (nullable, [cout]) += bias gradient.
  * The caller zeroes dw/db at the start of a step (gradients accumulate across calls). */
+/* fwd_operand (nullable): the packed forward operand buffer given to sap3d_conv_fwd; small-Cin convolutions (the stem)
+ * keep their im2col matrix there and reuse it for the filter gradient. */
 int sap3d_conv_wgrad(const sap3d_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw,
-                     float* db, void* stream);
+                     float* db, const void* fwd_operand, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Normalisation.  Replaces tf.layers.batch_normalization (p3d.py:58-127,344; utils/network.py:91),

@@ -63,7 +63,7 @@ _sig("sap3d_conv_packed_elems", [_P(ConvDesc), _i32], C.c_size_t)
 _sig("sap3d_conv_pack_weights", [_P(ConvDesc), _vp, _vp, _vp, _vp])
 _sig("sap3d_conv_fwd", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_conv_dgrad", [_P(ConvDesc), _i32, _vp, _vp, _vp, _vp, _i32, _vp])
-_sig("sap3d_conv_wgrad", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp])
+_sig("sap3d_conv_wgrad", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp])
 
 
 def check(rc: int, what: str = "") -> None:

@@ -1,6 +1,7 @@
 // C-ABI entry points of the convolution family (see include/sap3d.h).  Lowers a TF-semantics conv /
 // transposed-conv descriptor to (a) the tcgen05 implicit-GEMM "form F" problem of conv_tc.cu or
 // (b) the CUDA-core gather kernels of conv_simt.cu.
+#include <cuda_bf16.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -13,6 +14,9 @@
 #include "conv_tc.cuh"
 
 using namespace sap3d;
+
+extern "C" int sap3d_gemm_tn(const void* P, int64_t ldp, const void* Q, int64_t ldq, float* D, int64_t ldd, int32_t M, int32_t N,
+                             int32_t Kpos, void* stream);
 
 namespace {
 
@@ -221,6 +225,81 @@ int simt_stats_rows(const sap3d_conv_desc* c, const ConvGeom& g) {
   return (int)rows;
 }
 
+// ---- small-Cin convolutions (the 1x7x7 stem, Cin = 3) on the tensor cores ------------------------------------------
+// im2col into a bf16 [positions][Kp] buffer (K = taps*cin zero-padded to a multiple of 64) -> plain tcgen05 GEMM with the
+// usual bias / statistics epilogue; the filter gradient is the position-contracted GEMM col^T dy.  The buffer lives in the
+// caller's "packed forward operand" allocation (sap3d_conv_packed_elems sizes it), so the ABI needs no extra workspace.
+bool im2col_eligible(const sap3d_conv_desc* c) {
+  if (c->impl == SAP3D_IMPL_SIMT || c->dtype != SAP3D_BF16 || c->transposed || c->nseg != 1 || c->out_f32) return false;
+  if (c->cin[0] % 64 == 0 || c->cin[0] > 32 || c->cout % 64 != 0) return false;
+  return (long long)c->kd * c->kh * c->kw * c->cin[0] <= 1024;
+}
+struct Im2colLayout {
+  int K, Kp;
+  long long P;
+  size_t off_d, off_col, total;   // in bf16 elements: [wB: co_pad*Kp][D: Kp*cout fp32][col: P*Kp]
+};
+Im2colLayout im2col_layout(const sap3d_conv_desc* c, const ConvGeom& g) {
+  Im2colLayout L;
+  L.K = g.taps * g.cin_total;
+  L.Kp = (L.K + 63) / 64 * 64;
+  L.P = (long long)c->N * g.d[0].O * g.d[1].O * g.d[2].O;
+  const size_t co_pad = (size_t)(c->cout + 63) / 64 * 64;
+  auto up = [](size_t v) { return (v + 127) / 128 * 128; };
+  L.off_d = up(co_pad * L.Kp);
+  L.off_col = L.off_d + up((size_t)2 * L.Kp * c->cout);
+  L.total = L.off_col + (size_t)L.P * L.Kp;
+  return L;
+}
+
+struct Im2colArgs {
+  const __nv_bfloat16* x; __nv_bfloat16* col;
+  int N, D, H, W, C, oD, oH, oW, kd, kh, kw, sd, sh, sw, pd, ph, pw, K, Kp;
+  long long P;
+};
+__global__ void __launch_bounds__(256) im2col_kernel(const Im2colArgs p) {
+  const int kv = p.Kp / 8;
+  const long long total = p.P * kv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k0 = (int)(i % kv) * 8;
+    long long r = i / kv;
+    const long long pos = r;
+    const int ow = (int)(r % p.oW); r /= p.oW;
+    const int oh = (int)(r % p.oH); r /= p.oH;
+    const int od = (int)(r % p.oD);
+    const int n = (int)(r / p.oD);
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      __nv_bfloat16 val = __float2bfloat16_rn(0.f);
+      if (k < p.K) {
+        const int c = k % p.C;
+        int t = k / p.C;
+        const int e = t % p.kw; t /= p.kw;
+        const int b = t % p.kh;
+        const int a = t / p.kh;
+        const int id = od * p.sd + a - p.pd, ih = oh * p.sh + b - p.ph, iw = ow * p.sw + e - p.pw;
+        if (id >= 0 && id < p.D && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+          val = p.x[((((long long)n * p.D + id) * p.H + ih) * p.W + iw) * p.C + c];
+      }
+      v[j] = val;
+    }
+    *reinterpret_cast<uint4*>(p.col + pos * p.Kp + k0) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+// wB[n][k] = w_tf[k][n] (k < K), zero padding to [co_pad][Kp]
+__global__ void __launch_bounds__(256) im2col_pack_w_kernel(const float* __restrict__ w, int K, int Kp, int co, int co_pad,
+                                                             __nv_bfloat16* __restrict__ wb) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < co_pad * Kp; i += gridDim.x * blockDim.x) {
+    const int n = i / Kp, k = i % Kp;
+    wb[i] = __float2bfloat16_rn((n < co && k < K) ? w[(long long)k * co + n] : 0.f);
+  }
+}
+__global__ void __launch_bounds__(256) im2col_fold_dw_kernel(const float* __restrict__ d, long long n, float* dw) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dw[i] += d[i];
+}
+
 void fill_simt_common(SimtGeom& sg, const ConvGeom& g, bool gather_is_conv_like) {
   for (int i = 0; i < 3; ++i) {
     if (gather_is_conv_like) {
@@ -254,6 +333,7 @@ int sap3d_conv_stats_rows(const sap3d_conv_desc* d) {
     build_fwd_problem(d, g, nullptr, nullptr, pb);
     return (int)pb.classes.size() * tc_plan_tiles(pb);
   }
+  if (im2col_eligible(d)) return (int)((im2col_layout(d, g).P + 127) / 128);
   return simt_stats_rows(d, g);
 }
 
@@ -262,6 +342,7 @@ size_t sap3d_conv_packed_elems(const sap3d_conv_desc* d, int32_t which) {
   ConvGeom g;
   make_geom(d, g);
   const size_t co_pad = (size_t)(d->cout + 63) / 64 * 64, ci_pad = (size_t)(g.cin_total + 63) / 64 * 64;
+  if (which == 0 && im2col_eligible(d)) return im2col_layout(d, g).total;   // packed filter + scratch + im2col buffer
   if (which == 0) return co_pad * (size_t)g.taps * (size_t)g.cin_total;
   return ci_pad * (size_t)g.taps * (size_t)d->cout;
 }
@@ -309,6 +390,42 @@ int sap3d_conv_fwd(const sap3d_conv_desc* d, const void* x0, const void* x1, con
     pb.accumulate = 0;
     pb.out_f32 = d->out_f32;
     pb.force_block_n = 0;
+    if (tc_launch(pb, st, err, sizeof(err))) return set_error("%s", err);
+    return 0;
+  }
+  if (im2col_eligible(d) && w_fwd_packed && w_tf) {
+    const Im2colLayout L = im2col_layout(d, g);
+    __nv_bfloat16* ws = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(w_fwd_packed));
+    const int co_pad = (d->cout + 63) / 64 * 64;
+    im2col_pack_w_kernel<<<32, 256, 0, st>>>(w_tf, L.K, L.Kp, d->cout, co_pad, ws);
+    Im2colArgs a;
+    a.x = reinterpret_cast<const __nv_bfloat16*>(x0); a.col = ws + L.off_col;
+    a.N = d->N; a.D = d->D; a.H = d->H; a.W = d->W; a.C = g.cin_total;
+    a.oD = g.d[0].O; a.oH = g.d[1].O; a.oW = g.d[2].O;
+    a.kd = d->kd; a.kh = d->kh; a.kw = d->kw; a.sd = d->sd; a.sh = d->sh; a.sw = d->sw;
+    a.pd = g.d[0].pb; a.ph = g.d[1].pb; a.pw = g.d[2].pb; a.K = L.K; a.Kp = L.Kp; a.P = L.P;
+    long long blocks = (L.P * (L.Kp / 8) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    im2col_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    if (cudaGetLastError() != cudaSuccess) return set_error("conv_fwd: im2col launch failed");
+    TcProblem pb;
+    TcView v;
+    v.base = ws + L.off_col;
+    v.C = L.Kp;
+    v.dim[0] = (int)L.P; v.dim[1] = 1; v.dim[2] = 1; v.dim[3] = 1;
+    v.stride[0] = L.Kp; v.stride[1] = 0; v.stride[2] = 0; v.stride[3] = 0;
+    pb.views.push_back(v);
+    TcClassH cls;
+    cls.out_ofs = 0;
+    TcTapH t;
+    t.view = 0; t.off[0] = t.off[1] = t.off[2] = t.off[3] = 0; t.kofs = 0; t.c_begin = 0; t.nch = L.Kp;
+    cls.taps.push_back(t);
+    pb.classes.push_back(cls);
+    pb.ext[0] = (int)L.P; pb.ext[1] = 1; pb.ext[2] = 1; pb.ext[3] = 1;
+    pb.so[0] = d->cout; pb.so[1] = 0; pb.so[2] = 0; pb.so[3] = 0;
+    pb.B = ws; pb.Ktot = L.Kp; pb.rowsB = co_pad; pb.cout = d->cout; pb.out = y;
+    pb.bias = d->has_bias ? bias : nullptr; pb.stats = stats; pb.scale = pb.shift = nullptr;
+    pb.relu = 0; pb.accumulate = 0; pb.out_f32 = 0; pb.force_block_n = 0;
     if (tc_launch(pb, st, err, sizeof(err))) return set_error("%s", err);
     return 0;
   }
@@ -488,7 +605,7 @@ int sap3d_conv_dgrad(const sap3d_conv_desc* d, int32_t seg, const void* dy, cons
 }
 
 int sap3d_conv_wgrad(const sap3d_conv_desc* d, const void* x0, const void* x1, const void* dy, float* dw, float* db,
-                     void* stream) {
+                     const void* fwd_operand, void* stream) {
   if (check_desc(d)) return 1;
   if (!x0 || !dy || !dw) return set_error("conv_wgrad: NULL pointer");
   if (require_device()) return 1;
@@ -496,6 +613,20 @@ int sap3d_conv_wgrad(const sap3d_conv_desc* d, const void* x0, const void* x1, c
   make_geom(d, g);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   char err[512];
+  if (im2col_eligible(d) && fwd_operand) {
+    // the forward pass left im2col(x) in the operand buffer: dW[k][co] = sum_pos col[pos][k] dy[pos][co]
+    const Im2colLayout L = im2col_layout(d, g);
+    __nv_bfloat16* ws = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(fwd_operand));
+    float* dsc = reinterpret_cast<float*>(ws + L.off_d);
+    if (cudaMemsetAsync(dsc, 0, (size_t)L.Kp * d->cout * sizeof(float), st) != cudaSuccess) return set_error("conv_wgrad: memset failed");
+    if (sap3d_gemm_tn(ws + L.off_col, L.Kp, dy, d->cout, dsc, d->cout, L.Kp, d->cout, (int32_t)L.P, stream)) return 1;
+    im2col_fold_dw_kernel<<<64, 256, 0, st>>>(dsc, (long long)L.K * d->cout, dw);
+    if (cudaGetLastError() != cudaSuccess) return set_error("conv_wgrad: fold launch failed");
+    if (db) {
+      if (col_sum_accum_launch(dy, d->dtype, L.P, d->cout, db, st)) return set_error("bias-grad launch failed");
+    }
+    return 0;
+  }
   const void* xs[2] = {x0, x1};
   const bool use_tc = tc_dgrad_eligible(d);  // same constraints: bf16, channels % 64, <= 10 parity views
   for (int s = 0; s < d->nseg; ++s) {
@@ -705,6 +836,7 @@ extern "C" int sap3d_conv_pack_entries(const sap3d_conv_desc* d, const float* w_
     e.src = w_tf; e.dst = dst; e.taps = taps; e.rows = rows; e.rows_pad = rows_pad; e.cols = cols;
     e.s_tap = (long long)ci * co; e.s_r = s_r; e.s_c = s_c; e.start = 0;
   };
+  if (im2col_eligible(d)) w_fwd = nullptr;   // packed inside sap3d_conv_fwd ([cout][Kp], K zero-padded)
   if (!d->transposed) {
     if (w_fwd) add(w_fwd, co, co_pad, ci, 1, co);
     if (w_dgrad) add(w_dgrad, ci, ci_pad, co, co, 1);

@@ -424,7 +424,7 @@ class _ConvOp:
         else:
             st = e.stream
         A.check(A.lib.sap3d_conv_wgrad(C.byref(self.desc), A.ptr(self.xs[0].buf), A.ptr(x1), A.ptr(dy), A.ptr(self.w.g),
-                                       A.ptr(self.b.g) if (self.b is not None and self.bias_grad) else None, st),
+                                       A.ptr(self.b.g) if (self.b is not None and self.bias_grad) else None, A.ptr(self.wf), st),
                 "conv_wgrad " + self.name)
         e._count(len(self.xs) + (1 if (self.b is not None and self.bias_grad) else 0))
 

@@ -75,7 +75,7 @@ def run_case(A, N, D, H, W, cin, cout, k, s, transposed, dtype, impl):
         assert rel(dx, 2 * xcat.grad[..., off:off + c]) < 2 * tol
         off += c
     dw, db = torch.zeros_like(w), torch.zeros(cout, device=dev)
-    A.check(A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(x1), A.ptr(dyd), A.ptr(dw), A.ptr(db), st), "wgrad")
+    A.check(A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(x1), A.ptr(dyd), A.ptr(dw), A.ptr(db), A.ptr(wf), st), "wgrad")
     torch.cuda.synchronize()
     assert rel(dw, wr.grad) < 1e-3
     assert rel(db, dy.float().sum(dim=(0, 1, 2, 3))) < 1e-3
@@ -105,6 +105,14 @@ TC_CASES = [
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_tensor_core_conv(A, case):
     run_case(A, *case[1:], dtype=A.BF16, impl=A.IMPL_TC)
+
+
+@pytest.mark.parametrize("case", [("stem 1x7x7 s(1,2,2) 3->64", 2, 4, 32, 32, [3], 64, (1, 7, 7), (1, 2, 2), False),
+                                  ("ragged stem-like 5->128, k(2,3,3) s(1,2,1)", 1, 3, 9, 10, [5], 128, (2, 3, 3), (1, 2, 1), False)],
+                         ids=["stem", "ragged"])
+def test_small_cin_conv_on_tensor_cores(A, case):
+    """Cin = 3 stem: im2col -> tcgen05 GEMM (forward + statistics), col^T dy GEMM (filter gradient); data gradient on CUDA cores"""
+    run_case(A, *case[1:], dtype=A.BF16, impl=A.IMPL_AUTO)
 
 
 def test_auto_dispatch_mixed_paths(A):

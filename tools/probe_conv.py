@@ -85,7 +85,7 @@ def run_case(name, N, D, H, W, cin, cout, k, s, transposed=False, bias=True, imp
             off += c
         dw = torch.zeros_like(w)
         db = torch.zeros(cout, device=dev)
-        A.check(A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(x1), A.ptr(dy), A.ptr(dw), A.ptr(db), stream), "wgrad")
+        A.check(A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(x1), A.ptr(dy), A.ptr(dw), A.ptr(db), None, stream), "wgrad")
         torch.cuda.synchronize()
         rw, _ = rel(dw, wq.grad)
         rb, _ = rel(db, dy.float().sum(dim=(0, 1, 2, 3)))
@@ -115,7 +115,7 @@ def run_case(name, N, D, H, W, cin, cout, k, s, transposed=False, bias=True, imp
                     for si in range(len(cin)):
                         A.lib.sap3d_conv_dgrad(C.byref(d), si, A.ptr(dy), A.ptr(w), A.ptr(wd), A.ptr(dxs[si]), 0, stream)
                 else:
-                    A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(x1), A.ptr(dy), A.ptr(dw), None, stream)
+                    A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(x1), A.ptr(dy), A.ptr(dw), None, None, stream)
             for _ in range(2):
                 run()
             e0.record()

@@ -32,6 +32,6 @@ for _ in range(4):
     elif which == "dgrad":
         A.check(A.lib.sap3d_conv_dgrad(C.byref(d), 0, A.ptr(dy), A.ptr(w), A.ptr(wd), A.ptr(dx), 0, st), "dgrad")
     else:
-        A.check(A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(xs[1]), A.ptr(dy), A.ptr(dw), None, st), "wgrad")
+        A.check(A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(xs[1]), A.ptr(dy), A.ptr(dw), None, None, st), "wgrad")
 torch.cuda.synchronize()
 print("done", which)
