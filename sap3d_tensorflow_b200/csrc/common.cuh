@@ -214,6 +214,27 @@ SAP3D_DEVINL constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, in
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ----------------------------------------------------------------------------------------------
+// thread-block clusters: rank, distributed shared memory stores, cluster barrier
+// ----------------------------------------------------------------------------------------------
+SAP3D_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+SAP3D_DEVINL uint32_t mapa_shared(uint32_t cta_addr, uint32_t rank) {   // own-CTA shared address -> the same offset in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+SAP3D_DEVINL void st_cluster_v4(uint32_t cluster_addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+SAP3D_DEVINL void cluster_sync_all() {   // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 SAP3D_DEVINL bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -78,11 +78,19 @@ SAP3D_DEVINL float warp_transpose_sum32(float (&v)[32], int lane) {
 
 // MT = number of 128-row M sub-tiles per CTA (each with its own TMEM accumulator) that share every B tile:
 // MT = 2 cuts the L2->SM bytes per MAC by 25 % (the kernel is L2-bandwidth bound at 128x128 tiles).
-template <int BLOCK_N, int STAGES, int MT>
+// SPLIT > 1 (cluster of SPLIT CTAs along K, layers with few output tiles): every CTA of the cluster accumulates the
+// same [128 x BLOCK_N] tile over 1/SPLIT of the k-blocks, then the partial accumulators are reduce-scattered through
+// distributed shared memory (each CTA owns BLOCK_N/SPLIT columns, receives its peers' fp32 slices with
+// st.shared::cluster, and runs the normal epilogue for its columns).  One SM's L2->SMEM ingest (~85 GB/s) is what bounds
+// the K loop of the 16-CTA backbone layers; the split spreads it over SPLIT SMs with no extra global traffic or launch.
+template <int BLOCK_N, int STAGES, int MT, int SPLIT = 1>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
+  static_assert(SPLIT == 1 || (MT == 1 && BLOCK_N == 128 && (SPLIT == 2 || SPLIT == 4)), "split-K clusters: 128-column tiles, 2 or 4 CTAs");
   constexpr int A_BYTES = 128 * 128;
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+  constexpr int OWN_CHUNKS = SPLIT > 1 ? 4 / SPLIT : 4;                   // 32-column chunks owned per CTA
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -90,12 +98,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const uint32_t bar_base = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8);
   float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16);  // [4][2][BLOCK_N]
+  const uint32_t recv_base = (base + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 4 * 2 * BLOCK_N * 4 + 127u) & ~127u;
+  const uint32_t rank = SPLIT > 1 ? cluster_ctarank() : 0u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   // ---- tile decode -------------------------------------------------------------------------
-  int tile = blockIdx.x;
+  int tile = blockIdx.x / SPLIT;
   const int nt = tile % p.n_tiles;
   tile /= p.n_tiles;
   const int m_groups = (p.m_tiles + MT - 1) / MT;
@@ -119,7 +129,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     w0s[sub] = tw * p.box[0]; h0s[sub] = th * p.box[1]; d0s[sub] = td * p.box[2]; n0s[sub] = tn * p.box[3];
   }
   const TcClass cls = p.cls[cls_id];
-  const int nkb = cls.nkb;
+  const int kb_per = (cls.nkb + SPLIT - 1) / SPLIT;
+  const int kb_begin = min(cls.nkb, (int)rank * kb_per);
+  const int nkb = min(cls.nkb, kb_begin + kb_per) - kb_begin;   // k-blocks of THIS CTA
 
   // ---- one-time setup ----------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -146,10 +158,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = MT * p.box_rows * 128 + B_BYTES;
+      int kbi = 0;
       for (int ti = 0; ti < cls.tap_count; ++ti) {
         const TcTap tap = p.taps[cls.tap_begin + ti];
         const void* amap = &p.amap[tap.map];
-        for (int ch = 0; ch < tap.nchunk; ++ch) {
+        if (SPLIT > 1 && (kbi + tap.nchunk <= kb_begin || kbi >= kb_begin + nkb)) { kbi += tap.nchunk; continue; }
+        for (int ch = 0; ch < tap.nchunk; ++ch, ++kbi) {
+          if (SPLIT > 1 && (kbi < kb_begin || kbi >= kb_begin + nkb)) continue;
           mbar_wait(bar_base + (STAGES + stage) * 8, phase ^ 1u);
           const uint32_t full = bar_base + stage * 8;
           const uint32_t sa = base + stage * STAGE_BYTES;
@@ -196,12 +211,44 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       if (nkb > 0) tc_commit(bar_base + 2 * STAGES * 8);  // accumulator ready
     }
     __syncwarp();
-  } else {
+  } else if (SPLIT > 1) {
+    // ================= split-K phase A: ship the chunks owned by peer CTAs =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait(bar_base + 2 * STAGES * 8, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t owner = SPLIT == 4 ? (uint32_t)c : (uint32_t)(c >> 1);
+      if (owner == rank) continue;
+      uint32_t rr[32];
+      if (nkb > 0) {
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rr[j] = 0u;
+      }
+      const uint32_t slot = rank < owner ? rank : rank - 1;                       // my index among the owner's peers
+      const uint32_t local = recv_base + ((slot * OWN_CHUNKS + (SPLIT == 4 ? 0 : (c & 1))) * 128 + row) * 128;
+      const uint32_t remote = mapa_shared(local, owner);
+#pragma unroll
+      for (int g = 0; g < 8; ++g)   // 16-byte groups swizzled by the row: conflict-free at the destination
+        st_cluster_v4(remote + (static_cast<uint32_t>(g ^ (row & 7)) << 4), __uint_as_float(rr[g * 4]), __uint_as_float(rr[g * 4 + 1]),
+                      __uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3]));
+    }
+    tc_fence_before();
+  }
+  if (SPLIT > 1) cluster_sync_all();
+  if (warp >= 2) {
     // ================= epilogue (warps 2..5) =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const bool want_stats = p.stats != nullptr;
-    if (nkb > 0) {
+    if (SPLIT > 1) tc_fence_after();
+    if (SPLIT == 1 && nkb > 0) {
       mbar_wait(bar_base + 2 * STAGES * 8, 0);
       tc_fence_after();
     }
@@ -223,6 +270,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     for (int c = 0; c < BLOCK_N / 32; ++c) {
       const int col0 = nt * BLOCK_N + c * 32;
       if (col0 >= p.cout) break;  // warp-uniform
+      if (SPLIT > 1 && (SPLIT == 4 ? (uint32_t)c : (uint32_t)(c >> 1)) != rank) continue;   // a peer CTA owns these columns
       uint32_t rr[32];
       if (nkb > 0) {
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sub * BLOCK_N + c * 32, rr);
@@ -234,6 +282,17 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+      if (SPLIT > 1) {   // add the partial accumulators the peers left in my receive buffer
+#pragma unroll
+        for (int sl = 0; sl < SPLIT - 1; ++sl) {
+          const float* rb = reinterpret_cast<const float*>(smem + (recv_base - base)) + ((sl * OWN_CHUNKS + (SPLIT == 4 ? 0 : (c & 1))) * 128 + row) * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 f = *reinterpret_cast<const float4*>(rb + ((g ^ (row & 7)) << 2));
+            v[g * 4] += f.x; v[g * 4 + 1] += f.y; v[g * 4 + 2] += f.z; v[g * 4 + 3] += f.w;
+          }
+        }
+      }
       if (p.bias != nullptr) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -301,7 +360,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       const long long srow = static_cast<long long>(cls_id) * p.m_tiles + mt;
       for (int cc = et; cc < BLOCK_N; cc += 128) {
         const int col = nt * BLOCK_N + cc;
-        if (col < p.cout) {
+        const bool mine = SPLIT == 1 || (SPLIT == 4 ? (uint32_t)(cc >> 5) : (uint32_t)(cc >> 6)) == rank;
+        if (col < p.cout && mine) {
           float a = 0.f, b = 0.f;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
@@ -495,6 +555,38 @@ static int launch_t(const TcConvParams& prm, int grid, cudaStream_t stream, char
   return 0;
 }
 
+template <int SPLIT>
+static int launch_split(const TcConvParams& prm, int grid, cudaStream_t stream, char* err, size_t errlen) {
+  constexpr int SMEM = 4 * (128 * 128 + 128 * 128) + (2 * 4 + 1) * 8 + 16 + 4 * 2 * 128 * 4 + (SPLIT - 1) * (4 / SPLIT) * 16384 + 128 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128, 4, 1, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "cudaFuncSetAttribute(conv_tc split) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid * SPLIT);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = SPLIT;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 4, 1, SPLIT>, prm);
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "conv_tc split-K cluster launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
 int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen) {
   Merged m;
   merge_dims(pb, m);
@@ -584,6 +676,18 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
   if (grid <= 0 || grid > 0x7fffffffll) {
     snprintf(err, errlen, "tc_launch: bad grid %lld", grid);
     return 1;
+  }
+  // few output tiles and a long K loop (stage-2/3 backbone layers): split K over a cluster of 2 or 4 CTAs
+  if (block_n == 128 && mt == 1 && pb.force_split >= 0) {
+    int min_nkb = 1 << 30;
+    for (int c = 0; c < prm.ncls; ++c) min_nkb = std::min(min_nkb, prm.cls[c].nkb);
+    int split = pb.force_split;
+    if (split == 0) {
+      if (grid <= 37 && min_nkb >= 8) split = 4;
+      else if (grid <= 74 && min_nkb >= 8) split = 2;
+    }
+    if (split == 4 && min_nkb >= 4) return launch_split<4>(prm, (int)grid, stream, err, errlen);
+    if (split == 2 && min_nkb >= 2) return launch_split<2>(prm, (int)grid, stream, err, errlen);
   }
   switch (block_n) {
     case 64: return mt == 2 ? launch_t<64, 4, 2>(prm, (int)grid, stream, err, errlen) : launch_t<64, 6, 1>(prm, (int)grid, stream, err, errlen);

@@ -43,6 +43,7 @@ struct TcProblem {
   int relu, accumulate, out_f32;
   int force_block_n;  // 0 = auto
   int force_mt = 0;   // 0 = auto, 1 / 2 = M sub-tiles per CTA
+  int force_split = 0;// 0 = auto, 2 / 4 = split-K cluster size, -1 = never
 };
 
 // number of M tiles (per class) the launcher will use for these extents (after dim merging)
