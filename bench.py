@@ -400,12 +400,15 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e, ms_inf = [float(v) for v in t.tolist()]
+    # kernels per step, counted by CUPTI on EVERY rank (the step contains the gradient all-reduce: all ranks must take it)
+    launches_per_step = count_launches(lambda: sess.train_step(x_dev, y_dev, graph=use_graph))
+    barrier()
 
     if rank == 0:
         burst, sustained, hbm, src = peaks()
         kms, kflops = time_dominant_kernel(8, 112)
         achieved = kflops / (kms * 1e-3) / 1e12
-        launches = count_launches(lambda: sess.train_step(x_dev, y_dev, graph=use_graph)) * args.steps
+        launches = launches_per_step * args.steps
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")   # dram bytes per launch from the ncu --set full capture
         if os.path.exists(tp):
