@@ -136,6 +136,9 @@ class Engine:
         self._pack_table = None
         self.pre_pack_ops: List = []
         self.var_prefix = ""   # tf.variable_scope wrapped around a whole builder (gn/p3d_gn.py:490 'P3D')
+        self._split_ops: Optional[int] = None      # data-parallel overlap: backward is cut here (see mark_dp_split)
+        self._split_param: Optional[str] = None
+        self.dp_split_offset: Optional[int] = None
         self.side_stream = torch.cuda.Stream(device=self.device)   # filter gradients run here, off the critical path
         self.use_side_stream = True
 
@@ -164,6 +167,13 @@ class Engine:
         self.params[name] = p
         return p
 
+    def mark_dp_split(self):
+        """called by the builders right before stage 3 of the backbone: everything created AFTER this point (stage 3, decoder,
+        head = ~88 % of the parameters, laid out at the END of the flat gradient buffer) finishes its backward FIRST, so the
+        data-parallel exchange of that tail can run while the gradients of stages 1-2 and the stem are still being computed."""
+        self._split_ops = len(self.bwd_ops)
+        self._split_param = next(reversed(self.params)) if self.params else None
+
     def _count(self, n=1):
         if self._counting == "fwd":
             self.launches_fwd += n
@@ -184,6 +194,16 @@ class Engine:
             if p.trainable:
                 n_train = off
         self.n_train = n_train
+        if self._split_ops is not None:
+            trainable = [p for p in ordered if p.trainable]
+            names = [p.name for p in trainable]
+            # first trainable parameter created after the mark
+            created = list(self.params)
+            k = created.index(self._split_param) + 1 if self._split_param in created else 0
+            later = [n for n in created[k:] if self.params[n].trainable]
+            self.dp_split_offset = self.params[later[0]].offset if later else None
+            if self.dp_split_offset is None or names.index(later[0]) == 0:
+                self._split_ops = None
         self.flat_w = torch.zeros(off, device=self.device, dtype=torch.float32)
         self.flat_g = torch.zeros(max(n_train, 1), device=self.device, dtype=torch.float32) if self.training_graph else None
         self.flat_m = torch.zeros(max(n_train, 1), device=self.device, dtype=torch.float32) if self.training_graph else None
@@ -343,15 +363,20 @@ class Engine:
             f()
         self._counting = None
 
-    def backward(self):
+    def backward(self, part: Optional[int] = None):
+        """part None: the whole backward pass; 0: the ops created after mark_dp_split (head, decoder, stage 3); 1: the rest.
+        Each part ends by joining the filter-gradient side stream, so its share of the flat gradient buffer is complete."""
         assert self.training_graph
         self._counting = "bwd"
-        self.launches_bwd = 0
-        for t in self.tensors:
-            t.gflag = False
-        self.flat_g.zero_()
-        self._count()
-        for f in reversed(self.bwd_ops):
+        split = self._split_ops if (part is not None and self._split_ops is not None) else 0
+        if part in (None, 0):
+            self.launches_bwd = 0
+            for t in self.tensors:
+                t.gflag = False
+            self.flat_g.zero_()
+            self._count()
+        ops = self.bwd_ops if part is None else (self.bwd_ops[split:] if part == 0 else self.bwd_ops[:split])
+        for f in reversed(ops):
             f()
         if self.use_side_stream:
             torch.cuda.current_stream(self.device).wait_stream(self.side_stream)   # join the filter-gradient branch

@@ -43,14 +43,48 @@ def reduce_metric_sums(sums: torch.Tensor, counts: torch.Tensor):
     return sums / counts
 
 
+def split_buckets(n: int, per: int, split: int):
+    """buckets of the tail [split, n) (exchanged while backward is still running) and of the head [0, split)"""
+    tail = [(lo + split, hi + split) for lo, hi in make_buckets(n - split, per)]
+    head = make_buckets(split, per)
+    return tail, head
+
+
 class GradientExchange:
     def __init__(self, eng, bucket_mb: int = 32):
         self.eng = eng
         n = eng.n_train
         self.n = n
         self.buf = torch.zeros(n, device=eng.device, dtype=torch.bfloat16)
-        self.buckets = make_buckets(n, bucket_mb * 1024 * 1024 // 2)
+        per = bucket_mb * 1024 * 1024 // 2
+        self.buckets = make_buckets(n, per)
+        self.split = eng.dp_split_offset if eng._split_ops is not None else None
+        if self.split is not None:
+            self.tail, self.head = split_buckets(n, per, self.split)
         self.comm_stream = torch.cuda.Stream(device=eng.device)
+        self._works = []
+
+    # -- overlapped form: start() after the backward of stage 3 + decoder, finish() after the rest -------------------
+    def _reduce(self, eng, lo, hi, buckets):
+        cur = torch.cuda.current_stream(eng.device)
+        A.check(A.lib.sap3d_cast(A.F32, A.ptr(eng.flat_g[lo:hi]), A.ptr(self.buf[lo:hi]), hi - lo, cur.cuda_stream), "grad cast")
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            self._works += [dist.all_reduce(self.buf[a:b], op=dist.ReduceOp.SUM, async_op=True) for a, b in buckets]
+
+    def start(self, eng):
+        self._works = []
+        self._reduce(eng, self.split, self.n, self.tail)
+
+    def finish(self, eng):
+        cur = torch.cuda.current_stream(eng.device)
+        if self.split > 0:
+            self._reduce(eng, 0, self.split, self.head)
+        with torch.cuda.stream(self.comm_stream):
+            for w in self._works:
+                w.wait()
+        cur.wait_stream(self.comm_stream)
+        A.check(A.lib.sap3d_cast(A.BF16, A.ptr(self.buf), A.ptr(eng.flat_g), self.n, cur.cuda_stream), "grad uncast")
 
     def __call__(self, eng):
         cur = torch.cuda.current_stream(eng.device)

@@ -61,12 +61,17 @@ class Session:
         self._stage_input()
         self.eng.forward()
 
-    def _train_front(self):
+    def _train_front(self, split: bool = False):
         e = self.eng
         self._stage_input()
         e.begin_step()
         e.forward()
-        e.backward()
+        e.backward(0 if split else None)
+
+    def _overlap(self) -> bool:
+        """data-parallel exchange overlapped with the tail of backward: needs the builder's split mark and a hook that can
+        start on a partial gradient buffer"""
+        return self.eng._split_ops is not None and self.grad_hook is not None and hasattr(self.grad_hook, "start")
 
     def _train_back(self):
         self.eng.adam(self.lr, grad_scale=self.grad_scale)
@@ -100,11 +105,17 @@ class Session:
         torch.cuda.synchronize()
         if train:
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            split = self._overlap()
             with torch.cuda.graph(ga):
-                self._train_front()
+                self._train_front(split)
+            gm = None
+            if split:   # backward of stages 1-2 + stem: replayed while the tail of the gradient buffer is being all-reduced
+                gm = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gm, pool=ga.pool()):
+                    e.backward(1)
             with torch.cuda.graph(gb, pool=ga.pool()):
                 self._train_back()
-            self.graph_train = (ga, gb)
+            self.graph_train = (ga, gb, gm)
         else:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -135,10 +146,15 @@ class Session:
         if graph:
             if self.graph_train is None:
                 self.capture(train=True)
-            self.graph_train[0].replay()
-            if self.grad_hook is not None:
+            ga, gb, gm = self.graph_train
+            ga.replay()
+            if gm is not None:
+                self.grad_hook.start(e)      # all-reduce of the finished tail (stage 3 + decoder) starts on the comm stream
+                gm.replay()                  # ... while stages 1-2 and the stem run their backward
+                self.grad_hook.finish(e)
+            elif self.grad_hook is not None:
                 self.grad_hook(e)
-            self.graph_train[1].replay()
+            gb.replay()
         else:
             self.train_eager()
         return e.loss_buf

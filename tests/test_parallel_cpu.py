@@ -19,6 +19,19 @@ def test_buckets_cover_exactly_once():
         assert all(0 < hi - lo <= per for lo, hi in b)
 
 
+def test_split_buckets_cover_tail_then_head():
+    """overlapped exchange: the tail [split, n) (stage 3 + decoder gradients, finished first) and the head [0, split)
+    are bucketed separately and together cover the flat gradient buffer exactly once"""
+    from sap3d_tensorflow_b200.parallel import split_buckets
+
+    for n, per, split in [(100, 16, 37), (85_000_000, 16 * 1024 * 1024, 10_700_000), (50, 8, 0), (50, 8, 50)]:
+        tail, head = split_buckets(n, per, split)
+        cover = sorted(tail + head)
+        assert cover[0][0] == 0 and cover[-1][1] == n if n else True
+        assert all(cover[i][1] == cover[i + 1][0] for i in range(len(cover) - 1))
+        assert all(lo >= split for lo, _ in tail) and all(hi <= split for _, hi in head)
+
+
 def test_clip_sharding_partitions_the_evaluation_set():
     from sap3d_tensorflow_b200.parallel import shard_clips
 
