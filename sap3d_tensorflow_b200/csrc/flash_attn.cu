@@ -54,6 +54,15 @@ SAP3D_DEVINL void store_row_chunk_bf16(uint32_t tile_base, int row, int c /* 32-
   }
 }
 
+// same, from 16 already-packed bf16x2 words
+SAP3D_DEVINL void store_row_chunk_packed(uint32_t tile_base, int row, int c, const uint32_t* w) {
+  const uint32_t rbase = tile_base + (c >> 1) * 16384 + row * 128;
+  const int unit0 = (c & 1) * 4;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    st_shared_v4(rbase + (static_cast<uint32_t>((unit0 + u) ^ (row & 7)) << 4), w[u * 4], w[u * 4 + 1], w[u * 4 + 2], w[u * 4 + 3]);
+}
+
 template <int DV>
 __global__ void __launch_bounds__(192, (DV == 128 ? 2 : 1)) flash_fwd_kernel(const __grid_constant__ FlashParams p) {
   constexpr int KST = 2;
@@ -182,26 +191,43 @@ __global__ void __launch_bounds__(192, (DV == 128 ? 2 : 1)) flash_fwd_kernel(con
     for (int kb = 0; kb < nkb; ++kb) {               // pass 2: probabilities -> shared memory -> O += P V
       mbar_wait(bar + 7 * 8, sfph); sfph ^= 1u;
       tc_fence_after();
-      mbar_wait(bar + 10 * 8, (static_cast<uint32_t>(kb) & 1u) ^ 1u);   // P buffer free (previous PV retired)
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t rr[32];
-        tmem_ld_32x32(tmem_s + trow + c * 32, rr);
-        tmem_ld_wait();
-        const int col0 = kb * 128 + c * 32;
-        float pv[32];
+      // The scores are pulled out of TMEM in two halves and the S buffer is released right after the second load, so the
+      // next Q K^T runs under this tile's exponentials; the P buffer is only waited for once the probabilities sit packed
+      // in registers, so the previous P V runs under them as well.
+      uint32_t pp[64];
+      const bool last = (kb + 1) * 128 > p.Nk;       // only the last key block needs the column mask
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float e = ex2_approx(fmaf(__uint_as_float(rr[j]), LOG2E, mneg));
-          if (col0 + j >= p.Nk) e = 0.f;
-          pv[j] = e;
-          l += e;
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(tmem_s + trow + (2 * h) * 32, r0);
+        tmem_ld_32x32(tmem_s + trow + (2 * h + 1) * 32, r1);
+        tmem_ld_wait();
+        if (h == 1) {
+          tc_fence_before();
+          mbar_arrive(bar + 8 * 8);
         }
-        store_row_chunk_bf16(base + P_OFF, row, c, pv);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const uint32_t* rr = cc == 0 ? r0 : r1;
+          const int c = 2 * h + cc;
+          const int col0 = kb * 128 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float e0 = ex2_approx(fmaf(__uint_as_float(rr[j]), LOG2E, mneg));
+            float e1 = ex2_approx(fmaf(__uint_as_float(rr[j + 1]), LOG2E, mneg));
+            if (last) {
+              if (col0 + j >= p.Nk) e0 = 0.f;
+              if (col0 + j + 1 >= p.Nk) e1 = 0.f;
+            }
+            l += e0 + e1;
+            pp[c * 16 + j / 2] = pack_bf16x2(e0, e1);
+          }
+        }
       }
+      mbar_wait(bar + 10 * 8, (static_cast<uint32_t>(kb) & 1u) ^ 1u);   // P buffer free (previous PV retired)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) store_row_chunk_packed(base + P_OFF, row, c, pp + c * 16);
       fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(bar + 8 * 8);
       mbar_arrive(bar + 9 * 8);
     }
     mbar_wait(bar + 11 * 8, 0);
@@ -374,6 +400,7 @@ __global__ void __launch_bounds__(192) flash_bwd_dq_kernel(const __grid_constant
     for (int kb = 0; kb < nkb; ++kb) {
       const int sb = kb & 1;
       uint32_t pp[64];   // the 128 probabilities of this row, bf16x2
+      const bool last = (kb + 1) * 128 > p.Nk;
       mbar_wait(bar + (7 + sb) * 8, (static_cast<uint32_t>(kb) >> 1) & 1u);
       tc_fence_after();
 #pragma unroll
@@ -386,8 +413,10 @@ __global__ void __launch_bounds__(192) flash_bwd_dq_kernel(const __grid_constant
         for (int j = 0; j < 32; j += 2) {
           float e0 = ex2_approx(fmaf(__uint_as_float(rr[j]), LOG2E, lneg));
           float e1 = ex2_approx(fmaf(__uint_as_float(rr[j + 1]), LOG2E, lneg));
-          if (col0 + j >= p.Nk) e0 = 0.f;
-          if (col0 + j + 1 >= p.Nk) e1 = 0.f;
+          if (last) {
+            if (col0 + j >= p.Nk) e0 = 0.f;
+            if (col0 + j + 1 >= p.Nk) e1 = 0.f;
+          }
           pp[c * 16 + j / 2] = pack_bf16x2(e0, e1);
         }
       }
@@ -584,12 +613,17 @@ __global__ void __launch_bounds__(192) flash_bwd_dkv_kernel(const __grid_constan
         uint32_t rr[32];
         tmem_ld_32x32(tmem_st + trow + c * 32, rr);
         tmem_ld_wait();
-        float pv[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pv[j] = ex2_approx(fmaf(__uint_as_float(rr[j]), LOG2E, lneg[c * 32 + j]));
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) pp[c * 16 + j / 2] = pack_bf16x2(pv[j], pv[j + 1]);
-        store_row_chunk_bf16(base + PT_OFF, row, c, pv);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 ln = *reinterpret_cast<const float4*>(lneg + c * 32 + j);   // broadcast LDS.128
+          const float e0 = ex2_approx(fmaf(__uint_as_float(rr[j]), LOG2E, ln.x));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(rr[j + 1]), LOG2E, ln.y));
+          const float e2 = ex2_approx(fmaf(__uint_as_float(rr[j + 2]), LOG2E, ln.z));
+          const float e3 = ex2_approx(fmaf(__uint_as_float(rr[j + 3]), LOG2E, ln.w));
+          pp[c * 16 + j / 2] = pack_bf16x2(e0, e1);
+          pp[c * 16 + j / 2 + 1] = pack_bf16x2(e2, e3);
+        }
+        store_row_chunk_packed(base + PT_OFF, row, c, pp + c * 16);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -605,10 +639,13 @@ __global__ void __launch_bounds__(192) flash_bwd_dkv_kernel(const __grid_constan
         tmem_ld_wait();
         float ds[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float2 pr = unpack_bf16x2(pp[c * 16 + j / 2]);
-          ds[j] = pr.x * (__uint_as_float(rr[j]) - dsm[c * 32 + j]);
-          ds[j + 1] = pr.y * (__uint_as_float(rr[j + 1]) - dsm[c * 32 + j + 1]);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 dm = *reinterpret_cast<const float4*>(dsm + c * 32 + j);
+          const float2 p0 = unpack_bf16x2(pp[c * 16 + j / 2]), p1 = unpack_bf16x2(pp[c * 16 + j / 2 + 1]);
+          ds[j] = p0.x * (__uint_as_float(rr[j]) - dm.x);
+          ds[j + 1] = p0.y * (__uint_as_float(rr[j + 1]) - dm.y);
+          ds[j + 2] = p1.x * (__uint_as_float(rr[j + 2]) - dm.z);
+          ds[j + 3] = p1.y * (__uint_as_float(rr[j + 3]) - dm.w);
         }
         store_row_chunk_bf16(base + DST_OFF, row, c, ds);
       }
