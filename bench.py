@@ -40,6 +40,8 @@ def parse():
                     help="train: BASELINE configs[1] (default, the headline line); gn160: configs[2] (GN+CBAM, batch 16, 160x160, "
                          "fwd+bwd+Adam); eval: configs[4] (1024 clips sharded over the ranks, forward + CC/SIM/NSS/KLdiv)")
     ap.add_argument("--clips", type=int, default=1024, help="evaluation set size of --workload eval")
+    ap.add_argument("--full-res", action="store_true",
+                    help="--workload eval: test.py convention (upsample the last frame to 1080x960, CC/SIM/AUC_Judd/AUC_Borji/NSS)")
     ap.add_argument("--eager", action="store_true", help="no CUDA-graph replay (debug)")
     return ap.parse_args()
 
@@ -242,21 +244,24 @@ def run_eval(args):
     pool = 4
     xs = [((torch.randint(0, 256, (B, 16, size, size, 3), generator=g).float() - torch.tensor([90.0, 102.0, 98.0])) / 255.0).pin_memory()
           for _ in range(pool)]
-    dens = [torch.rand(B, size, size, generator=g).pin_memory() for _ in range(pool)]
-    fixs = [(torch.rand(B, size, size, generator=g) < 0.01).float().pin_memory() for _ in range(pool)]
+    gh, gw = (1080, 960) if args.full_res else (size, size)
+    dens = [torch.rand(B, gh, gw, generator=g).pin_memory() for _ in range(pool)]
+    fixs = [(torch.rand(B, gh, gw, generator=g) < (4e-5 if args.full_res else 0.01)).float().pin_memory() for _ in range(pool)]
+    nmet = 5 if args.full_res else 4
+    score = metrics.evaluate_clips_test_time if args.full_res else metrics.evaluate_clips
     for f in fixs:
         f[:, 0, 0] = 1.0   # at least one fixation per map
 
     def one_pass(host: bool):
-        sums = torch.zeros(4, device=dev, dtype=torch.float64)
-        cnts = torch.zeros(4, device=dev, dtype=torch.float64)
+        sums = torch.zeros(nmet, device=dev, dtype=torch.float64)
+        cnts = torch.zeros(nmet, device=dev, dtype=torch.float64)
         for i in range(nb):
             j = i % pool
             x = xs[j] if host else xs_dev[j]
             d = dens[j].to(dev, non_blocking=True) if host else dens_dev[j]
             f = fixs[j].to(dev, non_blocking=True) if host else fixs_dev[j]
             pred = sess.run(x, graph=True)
-            r = metrics.evaluate_clips(pred, d, f)
+            r = score(pred, d, f)
             sums += r["sum"]
             cnts += r["count"]
         return parallel.reduce_metric_sums(sums, cnts)
@@ -298,14 +303,15 @@ def run_eval(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = [float(v) for v in t.tolist()]
     if rank == 0:
-        launches = count_launches(lambda: (sess.run(xs_dev[0], graph=True), metrics.evaluate_clips(sess.head.output, dens_dev[0], fixs_dev[0])))
+        launches = count_launches(lambda: (sess.run(xs_dev[0], graph=True), score(sess.head.output, dens_dev[0], fixs_dev[0])))
         out = {
-            "metric": "clips/sec (16x112x112, bf16) inference + CC/SIM/NSS/KLdiv", "value": args.clips / (ms * 1e-3), "unit": UNIT,
+            "metric": "clips/sec (16x112x112, bf16) inference + " + ("CC/SIM/AUC_Judd/AUC_Borji/NSS at 1080x960" if args.full_res else "CC/SIM/NSS/KLdiv"), "value": args.clips / (ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": reps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{graph} inference (training=False) + saliency metrics over {args.clips} clips 16x{size}x{size}, "
                                    f"batch {B} per iteration, clips sharded contiguously over {world} rank(s)",
-                       "parallelism": f"dp{world}", "cuda_graph": True, "metric_means_CC_SIM_NSS_KLdiv": [float(v) for v in means_host.tolist()],
+                       "parallelism": f"dp{world}", "cuda_graph": True, "metric_means": [float(v) for v in means_host.tolist()],
+                       "metric_names": ["CC", "SIM", "AUC_Judd", "AUC_Borji", "NSS"] if args.full_res else ["CC", "SIM", "NSS", "KLdiv"],
                        "l2": "every batch's activations (> 1 GB) exceed the 126 MB L2"},
             "e2e": {"value": args.clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(nb * (xs[0].numel() + 2 * dens[0].numel()) * 4),
                     "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e},

@@ -224,6 +224,15 @@ int sap3d_saliency_metrics(const float* pred, const float* density, const float*
                            int64_t elems_per_map, int64_t pred_stride, int64_t density_stride, int64_t fixation_stride,
                            double* out, void* stream);
 
+/* Test-time evaluation (test.py:164-183): cv2.resize(map, (W, H)) with INTER_LINEAR semantics for n float32 maps, and the
+ * fixation-based AUC_Judd / AUC_Borji (utils/metrics.py:25-154): out[n][2].  jitter != 0 adds a counter-hash jitter of
+ * 1e-7 (the reference draws np.random noise); AUC_Borji's random locations are splitmix64(seed, fixation, repetition) % elems
+ * (the reference accepts any rand_sampler).  workspace: sap3d_saliency_auc_workspace(n_maps, n_rep) bytes. */
+int sap3d_resize_bilinear(const float* src, int32_t n, int32_t h, int32_t w, float* dst, int32_t H, int32_t W, void* stream);
+size_t sap3d_saliency_auc_workspace(int32_t n_maps, int32_t n_rep);
+int sap3d_saliency_auc(const float* sal, const float* fix, int32_t n_maps, int64_t elems, int32_t jitter, int32_t n_rep, double step,
+                       uint64_t seed, double* out, void* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm + CBAM of the GN model variant (gn/p3d_gn.py:24-46,175; utils/network.py:65-87,198-274).
  * ---------------------------------------------------------------------------------------------- */

@@ -50,6 +50,53 @@ def KLdiv(saliencyMap, fixationMap) -> float:
     return float(saliency_metrics(saliencyMap, fixationMap)[0, 3])
 
 
+def resize_bilinear(maps, out_hw) -> torch.Tensor:
+    """cv2.resize(map, (W, H)) (INTER_LINEAR) for [n, h, w] float maps — the upsampling test.py:168 applies to every
+    predicted frame before scoring (112 x 112 -> 1080 x 960)"""
+    m = _dev(maps)
+    m = m[None] if m.dim() == 2 else m
+    n, h, w = m.shape
+    H, W = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty(n, H, W, device=m.device, dtype=torch.float32)
+    A.check(A.lib.sap3d_resize_bilinear(A.ptr(m), n, h, w, A.ptr(out), H, W, torch.cuda.current_stream().cuda_stream), "resize_bilinear")
+    return out
+
+
+def saliency_auc(saliency, fixation, jitter: bool = False, n_rep: int = 100, step_size: float = 0.1, seed: int = 0) -> torch.Tensor:
+    """[n, 2] (fp64): AUC_Judd, AUC_Borji of n (saliency, fixation) map pairs (utils/metrics.py:25-154).  NaN without
+    fixations.  Borji's random locations and the optional jitter are counter hashes of `seed` (reproducible)."""
+    s, f = _dev(saliency), _dev(fixation)
+    if s.dim() == 2:
+        s, f = s[None], f[None]
+    n, elems = s.shape[0], s[0].numel()
+    ws = torch.empty(A.lib.sap3d_saliency_auc_workspace(n, n_rep) // 4 + 16, device=s.device, dtype=torch.float32)
+    out = torch.empty(n, 2, device=s.device, dtype=torch.float64)
+    A.check(A.lib.sap3d_saliency_auc(A.ptr(s), A.ptr(f), n, elems, int(jitter), n_rep, float(step_size), int(seed), A.ptr(out), A.ptr(ws),
+                                     torch.cuda.current_stream().cuda_stream), "saliency_auc")
+    return out
+
+
+def AUC_Judd(saliency_map, fixation_map, jitter=False, seed=0) -> float:
+    return float(saliency_auc(saliency_map, fixation_map, jitter=jitter, seed=seed)[0, 0])
+
+
+def AUC_Borji(saliency_map, fixation_map, n_rep=100, step_size=0.1, seed=0) -> float:
+    return float(saliency_auc(saliency_map, fixation_map, n_rep=n_rep, step_size=step_size, seed=seed)[0, 1])
+
+
+def evaluate_clips_test_time(pred: torch.Tensor, density: torch.Tensor, fixation: torch.Tensor, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """test.py:164-183: the last frame of every clip is upsampled to the ground-truth resolution (cv2.resize) and scored
+    with CC, SIM, AUC_Judd, AUC_Borji, NSS.  pred [B,16,h,w,1]; density / fixation [B,H,W].  Returns the [B,5] values
+    (CC, SIM, AUC_Judd, AUC_Borji, NSS) and the NaN-filtered (sum, count) pairs a sharded evaluation all-reduces."""
+    p = pred.reshape(pred.shape[0], pred.shape[1], pred.shape[2], pred.shape[3])[:, -1].contiguous()
+    up = resize_bilinear(p, density.shape[-2:])
+    base = saliency_metrics(up, density, fixation)
+    auc = saliency_auc(up, fixation, seed=seed)
+    vals = torch.stack([base[:, 0], base[:, 1], auc[:, 0], auc[:, 1], base[:, 2]], dim=1)
+    ok = ~torch.isnan(vals)
+    return {"values": vals, "sum": torch.where(ok, vals, torch.zeros_like(vals)).sum(0), "count": ok.sum(0).to(torch.float64)}
+
+
 def evaluate_clips(pred: torch.Tensor, density: torch.Tensor, fixation: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """pred [B,16,H,W,1] (Session.run output), density/fixation [B,16,H,W] or [B,H,W]: metrics of the last frame of
     every clip.  Returns per-metric (sum over non-NaN clips, count) pairs — the quantities a sharded evaluation

@@ -58,6 +58,32 @@ def main():
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "metrics_golden.npz")
     np.savez_compressed(out, pred=np.stack(preds), density=np.stack(denss), fixation=np.stack(fixs), values=np.array(vals, dtype=np.float64))
     print("wrote", out, np.array(vals)[:3])
+    make_auc_golden()
+
+
+def make_auc_golden():
+    """AUC_Judd (jitter off) / AUC_Borji (rand_sampler = the counter hash of oracle.metrics_oracle.hash_sampler) from the
+    REFERENCE's own functions, and cv2.resize itself for the test-time upsampling (test.py:168)."""
+    import cv2
+
+    if not hasattr(np, "trapz"):
+        np.trapz = np.trapezoid
+    rng = np.random.RandomState(4321)
+    sal, fix, vals = [], [], []
+    for i in range(8):
+        p, _, f = make_case(rng, 56, 64, ["blobs", "uniform", "sigmoid"][i % 3])
+        if i == 3:
+            p = np.round(p * 8) / 8          # heavy ties in the saliency values
+        judd = ref.AUC_Judd(p.copy(), f, jitter=False)
+        borji = ref.AUC_Borji(p.copy(), f, n_rep=100, step_size=0.1, rand_sampler=MO.hash_sampler(5))
+        sal.append(p.astype(np.float32)); fix.append(f); vals.append([judd, borji])
+    small = np.stack([make_case(rng, 28, 28, "sigmoid")[0] for _ in range(3)])
+    big = np.stack([cv2.resize(m, (120, 135)) for m in small])          # (W, H) = (120, 135): same 4.29 / 4.82 ratios as 112 -> 960 x 1080
+    big2 = cv2.resize(small[0], (45, 17))                               # downscale path
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "metrics_auc_golden.npz")
+    np.savez_compressed(out, sal=np.stack(sal), fix=np.stack(fix), values=np.array(vals, dtype=np.float64), resize_src=small,
+                        resize_135x120=big, resize_17x45=big2)
+    print("wrote", out, np.array(vals))
 
 
 if __name__ == "__main__":

@@ -47,6 +47,25 @@ def test_oracle_against_live_reference_when_present():
         assert abs(ref.NSS(p, f) - MO.NSS(p, f)) < 1e-6
 
 
+AUC_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_auc_golden.npz")
+
+
+def test_auc_oracle_matches_reference_golden_vectors():
+    """AUC_Judd (jitter off) and AUC_Borji (hash sampler) golden values were produced by the reference's own functions"""
+    g = np.load(AUC_GOLD)
+    for i in range(g["values"].shape[0]):
+        assert abs(MO.AUC_Judd(g["sal"][i], g["fix"][i]) - g["values"][i, 0]) < 1e-12
+        assert abs(MO.AUC_Borji(g["sal"][i], g["fix"][i], seed=5) - g["values"][i, 1]) < 1e-12
+    assert np.isnan(MO.AUC_Judd(g["sal"][0], np.zeros_like(g["fix"][0])))
+
+
+def test_resize_oracle_matches_cv2_golden_vectors():
+    g = np.load(AUC_GOLD)
+    for i in range(g["resize_src"].shape[0]):
+        np.testing.assert_allclose(MO.resize_bilinear(g["resize_src"][i], (135, 120)), g["resize_135x120"][i], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(MO.resize_bilinear(g["resize_src"][0], (17, 45)), g["resize_17x45"], rtol=0, atol=2e-6)
+
+
 def test_metric_properties():
     rng = np.random.RandomState(0)
     p = rng.rand(32, 32)
@@ -78,3 +97,32 @@ def test_cuda_metrics_match_golden_and_oracle(lib_built):
     assert np.isnan(v[0])
     ev = M.evaluate_clips(torch.rand(3, 16, 8, 8, 1, device="cuda"), torch.rand(3, 16, 8, 8, device="cuda"), (torch.rand(3, 16, 8, 8, device="cuda") > 0.7).float())
     assert ev["values"].shape == (3, 4) and float(ev["count"][0]) == 3
+
+
+@pytest.mark.gpu
+def test_cuda_auc_and_resize_match_golden(lib_built):
+    """test-time path (test.py:164-183): resize + AUC kernels against the reference-generated golden vectors"""
+    import torch
+
+    from sap3d_tensorflow_b200 import metrics as M
+
+    g = np.load(AUC_GOLD)
+    vals = M.saliency_auc(torch.tensor(g["sal"]), torch.tensor(g["fix"]), seed=5).cpu().numpy()
+    np.testing.assert_allclose(vals, g["values"], rtol=0, atol=1e-9)
+    assert abs(M.AUC_Judd(g["sal"][3], g["fix"][3]) - g["values"][3, 0]) < 1e-9          # the heavy-ties case
+    assert np.isnan(M.AUC_Judd(g["sal"][0], np.zeros_like(g["fix"][0])))
+    up = M.resize_bilinear(torch.tensor(g["resize_src"]), (135, 120)).cpu().numpy()
+    np.testing.assert_allclose(up, g["resize_135x120"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(M.resize_bilinear(torch.tensor(g["resize_src"][0]), (17, 45)).cpu().numpy()[0], g["resize_17x45"], rtol=0, atol=2e-6)
+    # full-size path: 112 x 112 -> 1080 x 960, scored against the oracle on the upsampled map
+    rng = np.random.RandomState(3)
+    pred = torch.tensor(rng.rand(2, 16, 112, 112, 1).astype(np.float32))
+    dens = torch.tensor(rng.rand(2, 1080, 960).astype(np.float32))
+    fix = torch.tensor((rng.rand(2, 1080, 960) < 4e-5).astype(np.float32))
+    fix[:, 5, 7] = 1
+    r = M.evaluate_clips_test_time(pred.cuda(), dens.cuda(), fix.cuda(), seed=1)["values"].cpu().numpy()
+    for b in range(2):
+        up_ref = MO.resize_bilinear(pred[b, -1, :, :, 0].numpy(), (1080, 960))
+        want = [MO.CC(up_ref, dens[b].numpy()), MO.SIM(up_ref, dens[b].numpy()), MO.AUC_Judd(up_ref, fix[b].numpy()),
+                MO.AUC_Borji(up_ref, fix[b].numpy(), seed=1), MO.NSS(up_ref, fix[b].numpy())]
+        np.testing.assert_allclose(r[b], want, rtol=1e-3, atol=1e-5)
