@@ -228,6 +228,11 @@ int sap3d_saliency_metrics(const float* pred, const float* density, const float*
  * fixation-based AUC_Judd / AUC_Borji (utils/metrics.py:25-154): out[n][2].  jitter != 0 adds a counter-hash jitter of
  * 1e-7 (the reference draws np.random noise); AUC_Borji's random locations are splitmix64(seed, fixation, repetition) % elems
  * (the reference accepts any rand_sampler).  workspace: sap3d_saliency_auc_workspace(n_maps, n_rep) bytes. */
+/* Input preprocessing of dataflow.py:194-209 / gen_pred.py:113-118 for n decoded BGR uint8 frames [n][h][w][3] (device):
+ * RGB order, minus mean_rgb (HOST pointer to 3 floats: [90, 102, 98]), cv2.resize to W x H on the float image, / 255;
+ * dst [n][H][W][3] in out_dtype (SAP3D_F32 / SAP3D_BF16) = one frame of the NDHWC network input each. */
+int sap3d_preprocess_frames(const uint8_t* bgr, int32_t n, int32_t h, int32_t w, const float* mean_rgb_host, int32_t out_dtype,
+                            void* dst, int32_t H, int32_t W, void* stream);
 int sap3d_resize_bilinear(const float* src, int32_t n, int32_t h, int32_t w, float* dst, int32_t H, int32_t W, void* stream);
 size_t sap3d_saliency_auc_workspace(int32_t n_maps, int32_t n_rep);
 int sap3d_saliency_auc(const float* sal, const float* fix, int32_t n_maps, int64_t elems, int32_t jitter, int32_t n_rep, double step,

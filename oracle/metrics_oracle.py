@@ -95,7 +95,7 @@ def resize_bilinear(src, out_hw):
     H, W = out_hw
 
     def coords(n_out, n_in):
-        f = ((np.arange(n_out) + 0.5) * (n_in / n_out) - 0.5).astype(np.float32)
+        f = (np.arange(n_out) + 0.5) * (n_in / n_out) - 0.5          # float64 coordinate; the FRACTION is rounded to float32
         i0 = np.floor(f).astype(np.int64)
         f = (f - i0).astype(np.float32)
         lo = i0 < 0
@@ -177,3 +177,11 @@ def AUC_Borji(saliency_map, fixation_map, n_rep=100, step_size=0.1, seed=0):
             fp[k + 1] = np.sum(S_rand[:, rep] >= th) / float(n_fix)
         auc[rep] = _trapz(tp, fp)
     return float(np.mean(auc))
+
+
+def preprocess_frame(frame_bgr_u8, size=112):
+    """gen_pred.py:113-118 / dataflow.py:194-209: BGR uint8 -> RGB, minus [90, 102, 98], cv2.resize (INTER_LINEAR) on the
+    float image, / 255 (restated with resize_bilinear per channel; pinned against cv2 in metrics_auc_golden.npz)"""
+    rgb = np.asarray(frame_bgr_u8)[:, :, ::-1].astype(np.float32) - np.array([90.0, 102.0, 98.0], dtype=np.float32)
+    out = np.stack([resize_bilinear(rgb[:, :, c], (size, size)) for c in range(3)], axis=-1)
+    return (out / np.float32(255.0)).astype(np.float32)

@@ -34,9 +34,9 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __res
     long long r = i / W;
     const int dy = (int)(r % H);
     const int m = (int)(r / H);
-    float fx = (float)((dx + 0.5) * sx - 0.5), fy = (float)((dy + 0.5) * sy - 0.5);
-    int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
-    fx -= x0; fy -= y0;
+    const double cx = (dx + 0.5) * sx - 0.5, cy = (dy + 0.5) * sy - 0.5;   // fp64 coordinate, fp32 fraction (what cv2 4.x does)
+    int x0 = (int)floor(cx), y0 = (int)floor(cy);
+    float fx = (float)(cx - x0), fy = (float)(cy - y0);
     if (x0 < 0) { x0 = 0; fx = 0.f; }
     if (x0 >= w - 1) { x0 = w - 1; fx = 0.f; }
     if (y0 < 0) { y0 = 0; fy = 0.f; }
@@ -259,3 +259,54 @@ int sap3d_saliency_auc(const float* sal, const float* fix, int32_t n_maps, int64
 }
 
 }  // extern "C"
+
+// ---- input preprocessing (dataflow.py:194-209 `mapf`, gen_pred.py:113-118): BGR uint8 frame -> RGB, minus the per-channel
+// mean, cv2.resize(frame, (112, 112)) on the float image (INTER_LINEAR), divided by 255 -> NDHWC network input --------
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) preprocess_frames_kernel(const unsigned char* __restrict__ bgr, int n, int h, int w, float m0, float m1,
+                                                                 float m2, T* __restrict__ dst, int H, int W) {
+  const double sx = (double)w / W, sy = (double)h / H;
+  const long long total = (long long)n * H * W;
+  const float mean[3] = {m0, m1, m2};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int dx = (int)(i % W);
+    long long r = i / W;
+    const int dy = (int)(r % H);
+    const int f = (int)(r / H);
+    const double cx = (dx + 0.5) * sx - 0.5, cy = (dy + 0.5) * sy - 0.5;   // fp64 coordinate, fp32 fraction (what cv2 4.x does)
+    int x0 = (int)floor(cx), y0 = (int)floor(cy);
+    float fx = (float)(cx - x0), fy = (float)(cy - y0);
+    if (x0 < 0) { x0 = 0; fx = 0.f; }
+    if (x0 >= w - 1) { x0 = w - 1; fx = 0.f; }
+    if (y0 < 0) { y0 = 0; fy = 0.f; }
+    if (y0 >= h - 1) { y0 = h - 1; fy = 0.f; }
+    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+    const unsigned char* s = bgr + (long long)f * h * w * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {   // output channel c (RGB) = input channel 2 - c (BGR)
+      const int ci = 2 - c;
+      const float p00 = (float)s[(y0 * w + x0) * 3 + ci] - mean[c], p01 = (float)s[(y0 * w + x1) * 3 + ci] - mean[c];
+      const float p10 = (float)s[(y1 * w + x0) * 3 + ci] - mean[c], p11 = (float)s[(y1 * w + x1) * 3 + ci] - mean[c];
+      const float r0 = __fadd_rn(__fmul_rn(p00, 1.f - fx), __fmul_rn(p01, fx));
+      const float r1 = __fadd_rn(__fmul_rn(p10, 1.f - fx), __fmul_rn(p11, fx));
+      dst[i * 3 + c] = from_f32<T>(__fadd_rn(__fmul_rn(r0, 1.f - fy), __fmul_rn(r1, fy)) / 255.f);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int sap3d_preprocess_frames(const uint8_t* bgr, int32_t n, int32_t h, int32_t w, const float* mean_rgb_host, int32_t out_dtype,
+                                       void* dst, int32_t H, int32_t W, void* stream) {
+  if (require_device()) return 1;
+  if (!bgr || !dst || !mean_rgb_host || n < 1 || h < 1 || w < 1 || H < 1 || W < 1) return set_error("preprocess_frames: bad argument");
+  const long long total = (long long)n * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_dtype == SAP3D_BF16)
+    preprocess_frames_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>(bgr, n, h, w, mean_rgb_host[0], mean_rgb_host[1], mean_rgb_host[2], reinterpret_cast<bf16*>(dst), H, W);
+  else
+    preprocess_frames_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(bgr, n, h, w, mean_rgb_host[0], mean_rgb_host[1], mean_rgb_host[2], reinterpret_cast<float*>(dst), H, W);
+  return check_launch("preprocess_frames");
+}

@@ -1,0 +1,52 @@
+"""Whole-video inference as gen_pred.py:88-168 does it: frames are preprocessed (BGR -> RGB, minus the channel mean,
+cv2.resize to 112 x 112, / 255; gen_pred.py:113-118 == dataflow.py:194-209), every window of 16 consecutive frames is one
+clip, the FIRST window contributes all 16 saliency maps and every later window only its last map (gen_pred.py:152-166).
+The reference runs one window per sess.run; here consecutive windows are stacked into batches of the Session's size and
+go through the captured CUDA graph, and the preprocessing is one kernel over all frames (sap3d_preprocess_frames)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterator, Tuple
+
+import numpy as np
+import torch
+
+from . import _abi as A
+
+MEAN_RGB = (90.0, 102.0, 98.0)   # gen_pred.py MEAN_VALUE = [98, 102, 90] (BGR) reversed
+WINDOW = 16
+
+
+def preprocess_frames(frames_bgr_u8, size: int = 112, dtype: str = "f32") -> torch.Tensor:
+    """[T, h, w, 3] uint8 BGR (cv2.imread order) -> [T, size, size, 3] network-input frames on the device"""
+    f = frames_bgr_u8 if isinstance(frames_bgr_u8, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(frames_bgr_u8))
+    f = f.to(device="cuda", dtype=torch.uint8).contiguous()
+    T, h, w, c = f.shape
+    assert c == 3
+    out = torch.empty(T, size, size, 3, device=f.device, dtype=torch.bfloat16 if dtype == "bf16" else torch.float32)
+    mean = (C.c_float * 3)(*MEAN_RGB)
+    A.check(A.lib.sap3d_preprocess_frames(A.ptr(f), T, h, w, mean, A.BF16 if dtype == "bf16" else A.F32, A.ptr(out), size, size,
+                                          torch.cuda.current_stream().cuda_stream), "preprocess_frames")
+    return out
+
+
+def window_starts(n_frames: int) -> range:
+    """start indices of the windows gen_pred.py runs (name_index <= len - 15, 1-based)"""
+    return range(0, max(0, n_frames - WINDOW + 1))
+
+
+def predict_video(sess, frames: torch.Tensor, graph: bool = True) -> Iterator[Tuple[int, torch.Tensor]]:
+    """frames [T, H, W, 3] preprocessed (device, fp32).  Yields (frame index, saliency map [H, W]) in the order and with
+    the selection rule of gen_pred.py: frames 0..15 from the first window, then the last frame of every later window."""
+    B = sess.eng.input.shape[0]
+    starts = list(window_starts(frames.shape[0]))
+    for lo in range(0, len(starts), B):
+        chunk = starts[lo:lo + B]
+        batch = torch.stack([frames[s:s + WINDOW] for s in chunk] + [frames[chunk[-1]:chunk[-1] + WINDOW]] * (B - len(chunk)))
+        sal = sess.run(batch.float(), graph=graph)          # [B, 16, H, W, 1]
+        for j, s in enumerate(chunk):
+            if s == 0:
+                for k in range(WINDOW):
+                    yield k, sal[j, k, :, :, 0].clone()
+            else:
+                yield s + WINDOW - 1, sal[j, WINDOW - 1, :, :, 0].clone()

@@ -80,9 +80,18 @@ def make_auc_golden():
     small = np.stack([make_case(rng, 28, 28, "sigmoid")[0] for _ in range(3)])
     big = np.stack([cv2.resize(m, (120, 135)) for m in small])          # (W, H) = (120, 135): same 4.29 / 4.82 ratios as 112 -> 960 x 1080
     big2 = cv2.resize(small[0], (45, 17))                               # downscale path
+    # input preprocessing exactly as gen_pred.py:113-118 writes it (cv2.resize on the mean-subtracted float image)
+    frames = rng.randint(0, 256, (2, 90, 160, 3)).astype(np.uint8)          # 16:9 frames, BGR as cv2.imread returns them
+    mean_value = np.array([98, 102, 90], dtype=np.float32)[::-1][None, ...]
+    pre = []
+    for fr in frames:
+        im = fr[:, :, ::-1]
+        im = im - mean_value
+        im = cv2.resize(im, (112, 112))
+        pre.append((im / 255.).astype(np.float32))
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "metrics_auc_golden.npz")
     np.savez_compressed(out, sal=np.stack(sal), fix=np.stack(fix), values=np.array(vals, dtype=np.float64), resize_src=small,
-                        resize_135x120=big, resize_17x45=big2)
+                        resize_135x120=big, resize_17x45=big2, frames_bgr=frames, frames_pre=np.stack(pre))
     print("wrote", out, np.array(vals))
 
 
