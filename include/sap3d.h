@@ -84,6 +84,13 @@ int sap3d_conv_pack_weights(const sap3d_conv_desc* d, const float* w_tf, void* w
  * fp32 results, [stats_rows][2][cout] f32, reduced by sap3d_bn_finalize. */
 int sap3d_conv_fwd(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf,
                    const void* w_fwd_packed, const float* bias, void* y, float* stats, void* stream);
+/* inference-mode fusion: y = relu?((conv(x0 ++ x1, w) + bias) * scale[c] + shift[c]) — tf.layers.batch_normalization with
+ * training=False (moving statistics; scale/shift from sap3d_bn_finalize(training = 0)) and tf.nn.relu folded into the conv
+ * epilogue (utils/network.py:100-110 with training=False, p3d.py:343-345).  Tensor-core paths only: query with
+ * sap3d_conv_fwd_on_tensor_cores(). */
+int sap3d_conv_fwd_on_tensor_cores(const sap3d_conv_desc* d);
+int sap3d_conv_fwd_affine(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf, const void* w_fwd_packed,
+                          const float* bias, const float* scale, const float* shift, int32_t relu, void* y, void* stream);
 /* dx_seg = data gradient w.r.t. segment `seg`; accumulate != 0 adds into dx */
 int sap3d_conv_dgrad(const sap3d_conv_desc* d, int32_t seg, const void* dy, const float* w_tf,
                      const void* w_dgrad_packed, void* dx, int32_t accumulate, void* stream);

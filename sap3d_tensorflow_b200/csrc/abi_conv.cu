@@ -381,8 +381,32 @@ int sap3d_conv_pack_weights(const sap3d_conv_desc* d, const float* w_tf, void* w
   return 0;
 }
 
+static int conv_fwd_impl(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf, const void* w_fwd_packed,
+                         const float* bias, void* y, float* stats, const float* ep_scale, const float* ep_shift, int ep_relu, void* stream);
+
 int sap3d_conv_fwd(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf, const void* w_fwd_packed,
                    const float* bias, void* y, float* stats, void* stream) {
+  return conv_fwd_impl(d, x0, x1, w_tf, w_fwd_packed, bias, y, stats, nullptr, nullptr, 0, stream);
+}
+
+/* 1 when conv_fwd runs on the tensor cores for this descriptor (implicit GEMM or the small-Cin im2col form) */
+int sap3d_conv_fwd_on_tensor_cores(const sap3d_conv_desc* d) {
+  if (check_desc(d)) return 0;
+  return (tc_eligible(d) || im2col_eligible(d)) ? 1 : 0;
+}
+
+/* y = relu?((conv(x) + bias) * scale[c] + shift[c]): inference-mode BatchNorm (+ ReLU) folded into the conv epilogue
+ * (tensor-core paths only; scale/shift from sap3d_bn_finalize with training = 0) */
+int sap3d_conv_fwd_affine(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf, const void* w_fwd_packed,
+                          const float* bias, const float* scale, const float* shift, int32_t relu, void* y, void* stream) {
+  if (check_desc(d)) return 1;
+  if (!scale || !shift) return set_error("conv_fwd_affine: NULL scale / shift");
+  if (!(tc_eligible(d) || im2col_eligible(d))) return set_error("conv_fwd_affine: descriptor does not run on the tensor-core path");
+  return conv_fwd_impl(d, x0, x1, w_tf, w_fwd_packed, bias, y, nullptr, scale, shift, relu, stream);
+}
+
+static int conv_fwd_impl(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf, const void* w_fwd_packed,
+                         const float* bias, void* y, float* stats, const float* ep_scale, const float* ep_shift, int ep_relu, void* stream) {
   if (check_desc(d)) return 1;
   if (!x0 || !y || (d->nseg > 1 && !x1)) return set_error("conv_fwd: NULL tensor pointer");
   if (require_device()) return 1;
@@ -398,8 +422,8 @@ int sap3d_conv_fwd(const sap3d_conv_desc* d, const void* x0, const void* x1, con
     pb.out = y;
     pb.bias = d->has_bias ? bias : nullptr;
     pb.stats = stats;
-    pb.scale = pb.shift = nullptr;
-    pb.relu = 0;
+    pb.scale = ep_scale; pb.shift = ep_shift;
+    pb.relu = ep_relu;
     pb.accumulate = 0;
     pb.out_f32 = d->out_f32;
     pb.force_block_n = 0;
@@ -437,8 +461,8 @@ int sap3d_conv_fwd(const sap3d_conv_desc* d, const void* x0, const void* x1, con
     pb.ext[0] = (int)L.P; pb.ext[1] = 1; pb.ext[2] = 1; pb.ext[3] = 1;
     pb.so[0] = d->cout; pb.so[1] = 0; pb.so[2] = 0; pb.so[3] = 0;
     pb.B = ws; pb.Ktot = L.Kp; pb.rowsB = co_pad; pb.cout = d->cout; pb.out = y;
-    pb.bias = d->has_bias ? bias : nullptr; pb.stats = stats; pb.scale = pb.shift = nullptr;
-    pb.relu = 0; pb.accumulate = 0; pb.out_f32 = 0; pb.force_block_n = 0;
+    pb.bias = d->has_bias ? bias : nullptr; pb.stats = stats; pb.scale = ep_scale; pb.shift = ep_shift;
+    pb.relu = ep_relu; pb.accumulate = 0; pb.out_f32 = 0; pb.force_block_n = 0;
     if (tc_launch(pb, st, err, sizeof(err))) return set_error("%s", err);
     return 0;
   }

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const uint32_t bar_base = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8);
   float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16);  // [4][2][BLOCK_N]
-  const uint32_t recv_base = (base + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 4 * 2 * BLOCK_N * 4 + 127u) & ~127u;
+  float* s_ep = s_stats + 4 * 2 * BLOCK_N;   // [3][BLOCK_N]: bias, scale, shift of this tile's columns (staged under the K loop)
+  const uint32_t recv_base = (base + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 127u) & ~127u;
   const uint32_t rank = SPLIT > 1 ? cluster_ctarank() : 0u;
 
   const int warp = threadIdx.x >> 5;
@@ -247,6 +248,17 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const bool want_stats = p.stats != nullptr;
+    {   // per-column epilogue vectors -> shared memory once per CTA (overlaps the K loop; the chunk loop reads broadcasts)
+      const int et0 = threadIdx.x - 64;
+      for (int cc = et0; cc < BLOCK_N; cc += 128) {
+        const int col = nt * BLOCK_N + cc;
+        const bool in = col < p.cout;
+        s_ep[cc] = (in && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
+        s_ep[BLOCK_N + cc] = (in && p.scale != nullptr) ? __ldg(p.scale + col) : 1.f;
+        s_ep[2 * BLOCK_N + cc] = (in && p.scale != nullptr) ? __ldg(p.shift + col) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     if (SPLIT > 1) tc_fence_after();
     if (SPLIT == 1 && nkb > 0) {
       mbar_wait(bar_base + 2 * STAGES * 8, 0);
@@ -295,8 +307,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       }
       if (p.bias != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.cout) v[j] += __ldg(p.bias + col0 + j);
+        for (int j = 0; j < 32; ++j) v[j] += s_ep[c * 32 + j];
       }
       if (want_stats) {
         float s1[32], s2[32];
@@ -313,8 +324,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       }
       if (p.scale != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.cout) v[j] = fmaf(v[j], __ldg(p.scale + col0 + j), __ldg(p.shift + col0 + j));
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_ep[BLOCK_N + c * 32 + j], s_ep[2 * BLOCK_N + c * 32 + j]);
       }
       if (p.relu) {
 #pragma unroll
@@ -536,7 +546,7 @@ int tc_plan_tiles(const TcProblem& pb) {
 
 template <int BLOCK_N, int STAGES, int MT>
 static int launch_t(const TcConvParams& prm, int grid, cudaStream_t stream, char* err, size_t errlen) {
-  constexpr int SMEM = STAGES * (MT * 128 * 128 + BLOCK_N * 128) + (2 * STAGES + 1) * 8 + 16 + 4 * 2 * BLOCK_N * 4 + 1024;
+  constexpr int SMEM = STAGES * (MT * 128 * 128 + BLOCK_N * 128) + (2 * STAGES + 1) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -557,7 +567,7 @@ static int launch_t(const TcConvParams& prm, int grid, cudaStream_t stream, char
 
 template <int SPLIT>
 static int launch_split(const TcConvParams& prm, int grid, cudaStream_t stream, char* err, size_t errlen) {
-  constexpr int SMEM = 4 * (128 * 128 + 128 * 128) + (2 * 4 + 1) * 8 + 16 + 4 * 2 * 128 * 4 + (SPLIT - 1) * (4 / SPLIT) * 16384 + 128 + 1024;
+  constexpr int SMEM = 4 * (128 * 128 + 128 * 128) + (2 * 4 + 1) * 8 + 16 + (4 * 2 + 3) * 128 * 4 + (SPLIT - 1) * (4 / SPLIT) * 16384 + 128 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128, 4, 1, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);

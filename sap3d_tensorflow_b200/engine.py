@@ -94,10 +94,11 @@ class NameScope:
 class ConvOut:
     """raw (pre-normalisation) conv output plus the per-tile statistics its epilogue produced"""
 
-    def __init__(self, raw: T, stats: Optional[torch.Tensor], rows: int):
+    def __init__(self, raw: T, stats: Optional[torch.Tensor], rows: int, op=None):
         self.raw = raw
         self.stats = stats
         self.rows = rows
+        self.op = op      # the producing _ConvOp (lets an inference-mode norm fold itself into the conv epilogue)
 
 
 class NormState:
@@ -407,7 +408,8 @@ class _ConvOp:
         raw = eng.tensor((N, Do, Ho, Wo, cout), name + "/raw", torch_dtype=torch.float32 if out_f32 else None)
         rows = A.lib.sap3d_conv_stats_rows(C.byref(self.desc)) if want_stats else 0
         stats = torch.zeros(rows, 2, cout, device=eng.device, dtype=torch.float32) if want_stats else None
-        self.out = ConvOut(raw, stats, rows)
+        self.out = ConvOut(raw, stats, rows, self)
+        self.fused_affine = None   # (NormState, relu): inference-mode BN (+ReLU) applied in the conv epilogue
         self.use_tc = eng.dt == A.BF16
         nf = A.lib.sap3d_conv_packed_elems(C.byref(self.desc), 0)
         nd = A.lib.sap3d_conv_packed_elems(C.byref(self.desc), 1)
@@ -422,6 +424,16 @@ class _ConvOp:
     def fwd(self):
         e = self.eng
         x1 = self.xs[1].buf if len(self.xs) > 1 else None
+        if self.fused_affine is not None:
+            ns, relu = self.fused_affine
+            A.check(A.lib.sap3d_bn_finalize(None, 0, self.out.raw.C, 1.0, A.ptr(ns.gamma.w), A.ptr(ns.beta.w), A.ptr(ns.mm.w),
+                                            A.ptr(ns.mv.w), 0, BN_MOMENTUM, BN_EPS, A.ptr(ns.scale), A.ptr(ns.shift), A.ptr(ns.mean),
+                                            A.ptr(ns.rstd), e.stream), "bn_finalize(moving) " + self.name)
+            A.check(A.lib.sap3d_conv_fwd_affine(C.byref(self.desc), A.ptr(self.xs[0].buf), A.ptr(x1), A.ptr(self.w.w), A.ptr(self.wf),
+                                                A.ptr(self.b.w) if self.b is not None else None, A.ptr(ns.scale), A.ptr(ns.shift),
+                                                int(relu), A.ptr(self.out.raw.buf), e.stream), "conv_fwd_affine " + self.name)
+            e._count(2)
+            return
         A.check(A.lib.sap3d_conv_fwd(C.byref(self.desc), A.ptr(self.xs[0].buf), A.ptr(x1), A.ptr(self.w.w), A.ptr(self.wf),
                                      A.ptr(self.b.w) if self.b is not None else None, A.ptr(self.out.raw.buf),
                                      A.ptr(self.out.stats), e.stream), "conv_fwd " + self.name)
@@ -464,6 +476,16 @@ class _NormActOp:
         self.relu_out = relu_out
         self.name = name
         self.b_t: Optional[T] = None if b is None else (b.raw if isinstance(b, ConvOut) else b)
+        # inference graphs: a moving-statistics BatchNorm (+ReLU) with no second operand folds into the conv epilogue
+        # (the raw tensor then IS the normalised output; nothing is launched here)
+        self.folded = (not eng.training_graph and n1 is not None and not train1 and b is None and n2 is None and not relu_out
+                       and a.op is not None and a.op.fused_affine is None and not a.raw.shape[-1] % 8
+                       and all(t is not a.raw for t in eng.taps.values())
+                       and A.lib.sap3d_conv_fwd_on_tensor_cores(C.byref(a.op.desc)) == 1 and not a.op.desc.out_f32)
+        if self.folded:
+            a.op.fused_affine = (n1, relu1)
+            self.y = a.raw
+            return
         self.y = eng.tensor(a.raw.shape, name)
         if eng.training_graph:
             a.raw.ensure_grad()
@@ -499,6 +521,8 @@ class _NormActOp:
 
     def fwd(self):
         e = self.eng
+        if self.folded:
+            return
         if self._fwd_fused():
             return
         if self.n1 is not None:
@@ -516,7 +540,7 @@ class _NormActOp:
 
     def bwd(self):
         e = self.eng
-        if not self.y.gflag:
+        if self.folded or not self.y.gflag:
             return
         n1, n2 = self.n1, self.n2
         a_raw = self.a.raw
