@@ -103,22 +103,26 @@ class Session:
                 self.forward_eager()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        # the critical path (forward, data gradients, norms) is captured on a HIGH-priority stream; the filter-gradient
+        # branch forks onto the engine's default-priority side stream, so its many-CTA kernels only fill SMs the
+        # few-CTA backbone kernels of the main chain leave idle instead of queueing in front of them
+        cap = torch.cuda.Stream(device=e.device, priority=-1)
         if train:
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             split = self._overlap()
-            with torch.cuda.graph(ga):
+            with torch.cuda.graph(ga, stream=cap):
                 self._train_front(split)
             gm = None
             if split:   # backward of stages 1-2 + stem: replayed while the tail of the gradient buffer is being all-reduced
                 gm = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gm, pool=ga.pool()):
+                with torch.cuda.graph(gm, pool=ga.pool(), stream=cap):
                     e.backward(1)
-            with torch.cuda.graph(gb, pool=ga.pool()):
+            with torch.cuda.graph(gb, pool=ga.pool(), stream=cap):
                 self._train_back()
             self.graph_train = (ga, gb, gm)
         else:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=cap):
                 self.forward_eager()
             self.graph_fwd = g
         torch.cuda.synchronize()
