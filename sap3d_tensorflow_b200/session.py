@@ -142,11 +142,14 @@ class Session:
     def train_step(self, x: torch.Tensor, y: torch.Tensor, graph: bool = False) -> torch.Tensor:
         """one iteration of train.py:217: returns the (device, fp64) loss scalar tensor."""
         e = self.eng
-        if x.device.type != "cuda":
-            e.input_f32.copy_(x, non_blocking=True)
-        elif x.data_ptr() != e.input_f32.data_ptr():
-            e.input_f32.copy_(x)
-        self.head.target.copy_(y.reshape(self.head.target.shape), non_blocking=True)
+        if x is None:
+            self._take_prefetched(True)      # batch staged by prefetch()
+        else:
+            if x.device.type != "cuda":
+                e.input_f32.copy_(x, non_blocking=True)
+            elif x.data_ptr() != e.input_f32.data_ptr():
+                e.input_f32.copy_(x)
+            self.head.target.copy_(y.reshape(self.head.target.shape), non_blocking=True)
         if graph:
             if self.graph_train is None:
                 self.capture(train=True)
@@ -162,6 +165,34 @@ class Session:
         else:
             self.train_eager()
         return e.loss_buf
+
+    # ---- input prefetch (the reference's tensorpack PrefetchDataZMQ / BatchData pipeline, train.py:120-135) -------------
+    def prefetch(self, x: torch.Tensor, y: Optional[torch.Tensor] = None):
+        """starts the host->device copy of the NEXT batch (pinned host tensors) on a copy stream, so that it overlaps the
+        step that is currently running; `train_step(None, None)` / `run(None)` then consume the staged batch."""
+        e = self.eng
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=e.device)
+            self._stage_x = torch.empty_like(e.input_f32)
+            self._stage_y = torch.empty_like(self.head.target) if getattr(self.head, "target", None) is not None else None
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(e.device))
+        self._copy_stream.wait_event(self._consumed)           # the previous staged batch has been copied out
+        with torch.cuda.stream(self._copy_stream):
+            self._stage_x.copy_(x, non_blocking=True)
+            if y is not None and self._stage_y is not None:
+                self._stage_y.copy_(y.reshape(self._stage_y.shape), non_blocking=True)
+            self._staged.record(self._copy_stream)
+
+    def _take_prefetched(self, with_target: bool):
+        e = self.eng
+        cur = torch.cuda.current_stream(e.device)
+        cur.wait_event(self._staged)
+        e.input_f32.copy_(self._stage_x)                        # device-to-device, ~10 us
+        if with_target and self._stage_y is not None:
+            self.head.target.copy_(self._stage_y)
+        self._consumed.record(cur)
 
     def tap(self, name: str) -> torch.Tensor:
         return self.eng.taps[name].buf

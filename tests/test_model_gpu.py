@@ -223,3 +223,26 @@ def test_split_backward_graphs_match_single_graph(lib_built):
     print("split vs single graph: grad rel", rel(res[1][0], res[0][0]), "weights rel", rel(res[1][1], res[0][1]))
     assert rel(res[1][0], res[0][0]) < 1e-4
     assert rel(res[1][1], res[0][1]) < 1e-4
+
+
+def test_prefetched_inputs_give_the_same_step(lib_built):
+    """Session.prefetch() (H2D of the next batch on a copy stream) + train_step(None, None) == train_step(x, y)"""
+    graph, batch, size = "p3d_unet", 2, 64
+    x = O.synthetic_clip(batch, 16, size, seed=0).pin_memory()
+    y = O.synthetic_target(batch, 16, size, seed=1).pin_memory()
+    losses = []
+    for mode in ("direct", "prefetch"):
+        sess = build(graph, "bf16", True, batch, size, dropout=0.0)
+        out = []
+        if mode == "prefetch":
+            sess.prefetch(x, y)
+        for _ in range(3):
+            if mode == "direct":
+                out.append(float(sess.train_step(x, y, graph=True).item()))
+            else:
+                l = sess.train_step(None, None, graph=True)
+                sess.prefetch(x, y)
+                out.append(float(l.item()))
+        losses.append(out)
+        del sess
+    assert all(abs(a - b) / a < 1e-4 for a, b in zip(*losses)), losses
