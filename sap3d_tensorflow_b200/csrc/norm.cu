@@ -342,6 +342,7 @@ struct ApplyBwdArgs {
   int relu1, relu2, relu_out;
   // pass 1
   float* partial;     // [rows][4][C]
+  double* totals;     // [4][C] (cooperative kernel, two-level reduction)
   int rows;
   // pass 2
   const float* coef;  // [4][C] (BN) or [4][N*C] (GN): S1a/M, S1b/M, S2a/M, S2b/M
@@ -572,7 +573,38 @@ __global__ void __launch_bounds__(256) bn_bwd_coop_kernel(const ApplyBwdArgs p, 
   }
   __threadfence();
   cooperative_groups::this_grid().sync();
-  {
+  const int nb = gridDim.x * gridDim.y;
+  const bool two_level = p.rows > 96;   // few channels, many rows (stage 1/2 inner layers)
+  if (two_level) {
+    // the row reduction itself is spread over the grid: block j sums ALL rows of one (sum, channel) pair with a fixed
+    // tree, a second grid.sync publishes the 4*C totals (instead of every thread walking `rows` values serially)
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    __shared__ double sred[8];
+    for (int pair = bid; pair < 4 * p.C; pair += nb) {   // block-uniform trip count
+      const int i = pair / p.C, cc = pair % p.C;
+      double t = 0.0;
+      for (int r = threadIdx.x; r < p.rows; r += 256) t += (double)__ldcg(p.partial + ((long long)r * 4 + i) * p.C + cc);
+      t = warp_sum(t);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = t;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tt = 0.0;
+        for (int w = 0; w < 8; ++w) tt += sred[w];
+        p.totals[pair] = tt;
+      }
+    }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    const int i = threadIdx.x >> 6, ch = threadIdx.x & 63;
+    const int cc = cbase + ch;
+    double t = cc < p.C ? __ldcg(p.totals + i * p.C + cc) : 0.0;
+    coef[i][ch] = (float)(t / M);
+    if (blockIdx.x == 0 && cc < p.C) {
+      float* dst = i == 0 ? dbeta1 : (i == 1 ? dgamma1 : (i == 2 ? dbeta2 : dgamma2));
+      if (dst) dst[cc] += (float)t;
+    }
+  } else {
     const int i = threadIdx.x >> 6, ch = threadIdx.x & 63;
     const int cc = cbase + ch;
     double t = 0.0;
@@ -723,7 +755,7 @@ int sap3d_bn_apply_fused(int32_t dtype, const void* a, const float* stats1, int3
   return check_launch("bn_apply_fused");
 }
 
-size_t sap3d_affine_act_bwd_workspace(int32_t C) { return (size_t)(296 * 4 + 4) * (size_t)C * sizeof(float); }
+size_t sap3d_affine_act_bwd_workspace(int32_t C) { return (size_t)(296 * 4 + 4 + 8) * (size_t)C * sizeof(float) + 64; }
 
 int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
                          const float* rstd1, int32_t relu1, const void* b, const float* s2, const float* t2,
@@ -753,6 +785,7 @@ int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const flo
     if (rows < 1) rows = 1;
     p.rows = (int)rows;
     p.partial = ws + 4 * C;
+    p.totals = reinterpret_cast<double*>(ws + (size_t)(296 * 4 + 4) * C + (((size_t)(296 * 4 + 4) * C) & 1));   // 8-byte aligned tail
     dim3 rgrid((unsigned)rows, (unsigned)chunks);
     // backbone-sized tensors: ONE cooperative launch (reduce -> grid.sync -> finalize -> apply) instead of three
     if ((long long)P * C <= COOP_MAX_ELEMS) {

@@ -36,11 +36,11 @@ def _stats(x):
 
 @pytest.mark.parametrize("dtn,tdt,tol", DT)
 @pytest.mark.parametrize("pattern", ["relu_bn", "bn_plus_relu_bn", "act_plus_relu_bn", "relu_bn_plus_t", "relu_bn_plus_bn"])
-@pytest.mark.parametrize("shape", [(2, 3, 5, 6, 64), (2, 4, 40, 64, 256)], ids=["coop", "three_launch"])
+@pytest.mark.parametrize("shape", [(2, 3, 5, 6, 64), (2, 8, 28, 28, 64), (2, 4, 40, 64, 256)], ids=["coop", "coop_two_level", "three_launch"])
 def test_affine_act_fwd_bwd(A, dtn, tdt, tol, pattern, shape):
     """small tensors take the single cooperative backward launch, > 4 M elements the reduce/finalize/apply triple"""
-    if shape[-1] == 256 and pattern not in ("bn_plus_relu_bn", "relu_bn_plus_t"):
-        pytest.skip("large shape: two representative patterns")
+    if shape != (2, 3, 5, 6, 64) and pattern not in ("bn_plus_relu_bn", "relu_bn_plus_t"):
+        pytest.skip("large shapes: two representative patterns")
     torch.manual_seed(0)
     dev = "cuda"
     dt = A.BF16 if dtn == "bf16" else A.F32
@@ -93,7 +93,7 @@ def test_affine_act_fwd_bwd(A, dtn, tdt, tol, pattern, shape):
                                        A.ptr(da), 0, A.ptr(db) if use_b else None, 0, A.ptr(dg1), A.ptr(db1),
                                        A.ptr(dg2) if bn2 else None, A.ptr(db2) if bn2 else None, A.ptr(ws), stream()), "bwd")
     torch.cuda.synchronize()
-    if Cc == 256:   # 5.2 M elements: ONE ReLU-mask flip at a |z| ~ 1e-7 element is sqrt(1/5e6) = 4e-4 relative
+    if P > 10000:   # 0.8 - 5.2 M elements: ONE ReLU-mask flip at a |z| ~ 1e-7 element is sqrt(1/5e6) = 4e-4 relative
         tol = max(tol, 1e-3)
     assert rel(da, af.grad) < 3 * tol
     assert rel(dg1, g1r.grad) < 3 * tol and rel(db1, b1r.grad) < 3 * tol
