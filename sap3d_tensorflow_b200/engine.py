@@ -141,6 +141,7 @@ class Engine:
         self._split_param: Optional[str] = None
         self.dp_split_offset: Optional[int] = None
         self.side_stream = torch.cuda.Stream(device=self.device)   # filter gradients run here, off the critical path
+        self.aux_stream = torch.cuda.Stream(device=self.device, priority=-1)   # forward: the second of two independent convs
         self.use_side_stream = True
 
     # ------------------------------------------------------------------------------------------
@@ -410,6 +411,7 @@ class _ConvOp:
         stats = torch.zeros(rows, 2, cout, device=eng.device, dtype=torch.float32) if want_stats else None
         self.out = ConvOut(raw, stats, rows, self)
         self.fused_affine = None   # (NormState, relu): inference-mode BN (+ReLU) applied in the conv epilogue
+        self.aux = False           # forward launch on the aux stream (independent sibling branch, joined by its consumer)
         self.use_tc = eng.dt == A.BF16
         nf = A.lib.sap3d_conv_packed_elems(C.byref(self.desc), 0)
         nd = A.lib.sap3d_conv_packed_elems(C.byref(self.desc), 1)
@@ -422,6 +424,18 @@ class _ConvOp:
                                                   self.eng.stream), "pack " + self.name)
 
     def fwd(self):
+        e = self.eng
+        if self.aux and e.use_side_stream:
+            # fork: this conv and the next op on the main stream both only depend on what has been enqueued so far; the
+            # few-CTA backbone convs of parallel branches (ST_B's S and T, the projection shortcut) then share the GPU
+            main = torch.cuda.current_stream(e.device)
+            e.aux_stream.wait_stream(main)
+            with torch.cuda.stream(e.aux_stream):
+                self._fwd()
+            return
+        self._fwd()
+
+    def _fwd(self):
         e = self.eng
         x1 = self.xs[1].buf if len(self.xs) > 1 else None
         if self.fused_affine is not None:
@@ -523,6 +537,8 @@ class _NormActOp:
         e = self.eng
         if self.folded:
             return
+        if isinstance(self.b, ConvOut) and self.b.op is not None and self.b.op.aux and e.use_side_stream:
+            torch.cuda.current_stream(e.device).wait_stream(e.aux_stream)   # join the sibling branch
         if self._fwd_fused():
             return
         if self.n1 is not None:

@@ -71,6 +71,7 @@ class Bottleneck:
             o = nw.bn_relu(convT(nm + "_T", o, pl, pl), tr, tap=nm + "_T")
         elif self.ST == "B":    # relu(bn(T(o))) + relu(bn(S(o))) in one fused pass
             s_raw = convS(nm + "_S", o, pl, pl)
+            s_raw.op.aux = True     # S and T are independent: S runs on the aux stream, the fused norm op joins them
             ns_s = nw._bn_state(eng, pl)
             t_raw = convT(nm + "_T", o, pl, pl)
             ns_t = nw._bn_state(eng, pl)
@@ -86,6 +87,7 @@ class Bottleneck:
             r = eng.conv([x], pl * BLOCK_EXPANSION, one, s,
                          get_conv_weight(eng, f"dw3d_{i}", [1, 1, 1, self.inplanes, pl * BLOCK_EXPANSION]), name=f"dw3d_{i}")
             nsr = nw._bn_state(eng, pl * BLOCK_EXPANSION)
+            r.op.aux = True         # the projection shortcut only needs the block input
             y = eng.norm_act(c3, ns3, tr, False, b=r, n2=nsr, train2=tr, relu2=False, relu_out=True, name=f"b{i}")
         else:
             y = eng.norm_act(c3, ns3, tr, False, b=x, relu_out=True, name=f"b{i}")

