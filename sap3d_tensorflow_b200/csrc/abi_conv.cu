@@ -90,7 +90,7 @@ bool tc_dgrad_eligible(const sap3d_conv_desc* c) {
   if (!tc_eligible(c)) return false;
   if (c->cout % 64 != 0) return false;
   if (c->transposed) {
-    // parity views of dy: at most 10 tensor maps
+    // parity views of dy: at most 27 tensor maps (k3 s4: deconv_pool4 of the concat decoders)
     ConvGeom g;
     make_geom(c, g);
     int nv = 1;
@@ -99,7 +99,7 @@ bool tc_dgrad_eligible(const sap3d_conv_desc* c) {
       for (int k = 0; k < g.d[i].k; ++k) rs[((k - g.d[i].pb) % g.d[i].s + g.d[i].s) % g.d[i].s] = 1;
       nv *= (int)rs.size();
     }
-    if (nv > 10) return false;
+    if (nv > 27) return false;
   }
   return true;
 }

@@ -25,7 +25,7 @@
 
 namespace sap3d {
 
-constexpr int TC_MAX_MAPS = 10;
+constexpr int TC_MAX_MAPS = 28;   // 27 parity views of dy (transposed conv k3 s4 data gradient) + slack
 constexpr int TC_MAX_TAPS = 128;
 constexpr int TC_MAX_CLS = 64;
 constexpr int TC_THREADS = 192;

@@ -94,15 +94,16 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
 
 // CBAM channel attention: part (sum, -, max over positions) -> shared MLP -> sigmoid -> cscale [N][C]
 // one block per sample (utils/network.py:208-249)
-__global__ void __launch_bounds__(256) cbam_channel_mlp_kernel(const float* __restrict__ part, int rows, int C, int hidden, long long S,
-                                                                const float* __restrict__ w0, const float* __restrict__ b0,
-                                                                const float* __restrict__ w1, const float* __restrict__ b1,
-                                                                float* __restrict__ cscale, float* __restrict__ save) {
-  extern __shared__ float sm[];  // avg[C], mx[C], h_avg[hidden], h_max[hidden]
+__global__ void __launch_bounds__(1024) cbam_channel_mlp_kernel(const float* __restrict__ part, int rows, int C, int hidden, long long S,
+                                                                 const float* __restrict__ w0, const float* __restrict__ b0,
+                                                                 const float* __restrict__ w1, const float* __restrict__ b1,
+                                                                 float* __restrict__ cscale, float* __restrict__ save) {
+  extern __shared__ float sm[];  // avg[C], mx[C], h_avg[hidden], h_max[hidden], scratch[2][8][hidden]
   float* avg = sm;
   float* mx = sm + C;
   float* ha = sm + 2 * C;
   float* hm = ha + hidden;
+  float* scr = hm + hidden;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f, m = -INFINITY;
@@ -114,15 +115,30 @@ __global__ void __launch_bounds__(256) cbam_channel_mlp_kernel(const float* __re
     mx[c] = m;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < hidden; j += blockDim.x) {
-    float sa = b0[j], sx = b0[j];
-    for (int c = 0; c < C; ++c) {
-      const float w = w0[(long long)c * hidden + j];
-      sa = fmaf(avg[c], w, sa);
-      sx = fmaf(mx[c], w, sx);
+  // hidden layer: the C-long dot products are split over 8 slices of the block (thread = (slice, j)); w0 rows are read
+  // coalesced along j; slices are combined in a fixed order
+  {
+    const int nsl = blockDim.x / hidden >= 8 ? 8 : (blockDim.x / hidden >= 1 ? blockDim.x / hidden : 1);
+    const int j = threadIdx.x % hidden, sl = threadIdx.x / hidden;
+    if (sl < nsl) {
+      float sa = 0.f, sx = 0.f;
+      const int per = (C + nsl - 1) / nsl;
+      const int c1 = min(C, (sl + 1) * per);
+      for (int c = sl * per; c < c1; ++c) {
+        const float w = w0[(long long)c * hidden + j];
+        sa = fmaf(avg[c], w, sa);
+        sx = fmaf(mx[c], w, sx);
+      }
+      scr[(0 * 8 + sl) * hidden + j] = sa;
+      scr[(1 * 8 + sl) * hidden + j] = sx;
     }
-    ha[j] = fmaxf(sa, 0.f);
-    hm[j] = fmaxf(sx, 0.f);
+    __syncthreads();
+    if (threadIdx.x < hidden) {
+      float sa = b0[threadIdx.x], sx = b0[threadIdx.x];
+      for (int q = 0; q < nsl; ++q) { sa += scr[(0 * 8 + q) * hidden + threadIdx.x]; sx += scr[(1 * 8 + q) * hidden + threadIdx.x]; }
+      ha[threadIdx.x] = fmaxf(sa, 0.f);
+      hm[threadIdx.x] = fmaxf(sx, 0.f);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -296,8 +312,10 @@ int sap3d_cbam_fwd(int32_t dtype, const void* r, int32_t N, int32_t D, int32_t H
   const long long S = (long long)D * H * W;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (sap3d_sample_channel_partials(dtype, r, nullptr, N, S, C, rows, part, stream)) return 1;
-  const size_t sm = (size_t)(2 * C + 2 * hidden) * sizeof(float);
-  cbam_channel_mlp_kernel<<<N, 256, sm, st>>>(part, rows, C, hidden, S, w0, b0, w1, b1, cscale, save);
+  if (hidden > 1024) return set_error("cbam_fwd: hidden > 1024");
+  const size_t sm = (size_t)(2 * C + 2 * hidden + 16 * hidden) * sizeof(float);
+  const int threads = hidden * 8 <= 1024 ? (hidden * 8 < 256 ? 256 : hidden * 8) : 1024;
+  cbam_channel_mlp_kernel<<<N, threads, sm, st>>>(part, rows, C, hidden, S, w0, b0, w1, b1, cscale, save);
   if (check_launch("cbam_channel_mlp")) return 1;
   const long long total = (long long)N * S;
   const int blocks = (int)((total * 32 + 255) / 256 > 148 * 8 ? 148 * 8 : (total * 32 + 255) / 256);

@@ -142,42 +142,46 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs p) {
   block_fold_4x64(acc, red, p.partial + ((long long)n * p.rows + blockIdx.x) * 4 * p.C, p.C, blockIdx.y * 64);
 }
 
-// one block per group: per sample, rows -> per-channel sums -> group sums weighted by gamma -> coef [N][4][C];
-// dgamma / dbeta accumulate over samples in registers (deterministic).  nsum = 2 (one norm) or 4 (two norms).
+// one block per (group, sample): rows -> per-channel sums (kept in vsum [N][4][C]) -> group sums weighted by gamma ->
+// coef [N][4][C].  nsum = 2 (one norm) or 4 (two norms).  dgamma / dbeta are folded over the samples by gn_bwd_param_kernel
+// in a fixed order (deterministic).
 __global__ void __launch_bounds__(128) gn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int N, int C, int G, double M,
                                                                const float* __restrict__ gamma1, const float* __restrict__ rstd1,
                                                                const float* __restrict__ gamma2, const float* __restrict__ rstd2,
-                                                               int nsum, float* __restrict__ coef, float* dgamma1, float* dbeta1,
-                                                               float* dgamma2, float* dbeta2) {
+                                                               int nsum, float* __restrict__ coef, float* __restrict__ vsum) {
   __shared__ float v[4][32];
   __shared__ float gs[4];
-  const int g = blockIdx.x, cpg = C / G, t = threadIdx.x;
+  const int g = blockIdx.x, n = blockIdx.y, cpg = C / G, t = threadIdx.x;
   const bool mine = t < nsum * cpg;
   const int i = mine ? t / cpg : 0, cl = mine ? t % cpg : 0;
   const int c = g * cpg + cl;
-  float accum = 0.f;
-  for (int n = 0; n < N; ++n) {
-    if (mine) {
-      float s = 0.f;
-      for (int r = 0; r < rows; ++r) s += partial[(((long long)n * rows + r) * 4 + i) * C + c];
-      v[i][cl] = s;
-      accum += s;
-    }
-    __syncthreads();
-    if (t < nsum) {
-      const float* gm = t < 2 ? gamma1 : gamma2;
-      double s = 0.0;
-      for (int k = 0; k < cpg; ++k) s += (double)gm[g * cpg + k] * (double)v[t][k];
-      const float rs = (t < 2 ? rstd1 : rstd2)[n * G + g];
-      gs[t] = (float)(s / M) * rs;
-    }
-    __syncthreads();
-    if (mine) coef[((long long)n * 4 + i) * C + c] = gs[i];
-  }
   if (mine) {
-    float* dst = i == 0 ? dbeta1 : (i == 1 ? dgamma1 : (i == 2 ? dbeta2 : dgamma2));
-    if (dst) dst[c] += accum;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += partial[(((long long)n * rows + r) * 4 + i) * C + c];
+    v[i][cl] = s;
+    vsum[((long long)n * 4 + i) * C + c] = s;
   }
+  __syncthreads();
+  if (t < nsum) {
+    const float* gm = t < 2 ? gamma1 : gamma2;
+    double s = 0.0;
+    for (int k = 0; k < cpg; ++k) s += (double)gm[g * cpg + k] * (double)v[t][k];
+    const float rs = (t < 2 ? rstd1 : rstd2)[n * G + g];
+    gs[t] = (float)(s / M) * rs;
+  }
+  __syncthreads();
+  if (mine) coef[((long long)n * 4 + i) * C + c] = gs[i];
+}
+__global__ void __launch_bounds__(256) gn_bwd_param_kernel(const float* __restrict__ vsum, int N, int C, int nsum, float* dgamma1, float* dbeta1,
+                                                            float* dgamma2, float* dbeta2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nsum * C) return;
+  const int i = idx / C, c = idx % C;
+  float* dst = i == 0 ? dbeta1 : (i == 1 ? dgamma1 : (i == 2 ? dbeta2 : dgamma2));
+  if (!dst) return;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s += vsum[((long long)n * 4 + i) * C + c];
+  dst[c] += s;
 }
 
 template <typename T>
@@ -316,18 +320,18 @@ __global__ void __launch_bounds__(256) cbam_bwd_spw_kernel(const float* __restri
                                                             int W, float* dw) {
   const int tap = blockIdx.x;
   const int a = tap / 49 - 3, b = (tap / 7) % 7 - 3, e = tap % 7 - 3;
-  const long long total = (long long)N * D * H * W;
+  const int total = N * D * H * W;   // < 2^31 (checked by the launcher): 32-bit index arithmetic, no 64-bit divisions
   float a0 = 0.f, a1 = 0.f;
-  for (long long o = threadIdx.x; o < total; o += blockDim.x) {
-    long long q = o;
-    const int ow = (int)(q % W); q /= W;
-    const int oh = (int)(q % H); q /= H;
-    const int od = (int)(q % D);
-    const int n = (int)(q / D);
+  for (int o = threadIdx.x; o < total; o += blockDim.x) {
+    int q = o;
+    const int ow = q % W; q /= W;
+    const int oh = q % H; q /= H;
+    const int od = q % D;
+    const int n = q / D;
     const int zd = od + a, zh = oh + b, zw = ow + e;
     if (zd < 0 || zd >= D || zh < 0 || zh >= H || zw < 0 || zw >= W) continue;
     const float d = dpre[o];
-    const float* s = sp + ((((long long)n * D + zd) * H + zh) * W + zw) * 2;
+    const float* s = sp + (((n * D + zd) * H + zh) * W + zw) * 2;
     a0 = fmaf(d, s[0], a0);
     a1 = fmaf(d, s[1], a1);
   }
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(256) cbam_bwd_reduce_kernel(const TailArgs p) 
 // channel-attention MLP backward, one block per sample.
 //   save [N][2C+2h] = avg, max, ha, hm ;  out: coef[n][2][c] = d avg / S, coef[n][3][c] = d max / ties,
 //   mlpg [N][C + 2h] = d pre-sigmoid, d ha, d hm (for the weight-gradient kernel)
-__global__ void __launch_bounds__(256) cbam_bwd_mlp_kernel(const float* __restrict__ partial, int rows, int C, int hidden, long long S,
+__global__ void __launch_bounds__(1024) cbam_bwd_mlp_kernel(const float* __restrict__ partial, int rows, int C, int hidden, long long S,
                                                             const float* __restrict__ cscale, const float* __restrict__ save,
                                                             const float* __restrict__ w0, const float* __restrict__ w1,
                                                             float* __restrict__ coef, float* __restrict__ mlpg) {
@@ -422,8 +426,8 @@ __global__ void __launch_bounds__(256) cbam_bwd_mlp_kernel(const float* __restri
     mg[c] = d;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < hidden; j += 8) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int j = warp; j < hidden; j += nwarp) {
     float s = 0.f;
     for (int c = lane; c < C; c += 32) s = fmaf(w1[(long long)j * C + c], dp[c], s);
     s = warp_sum(s);
@@ -434,15 +438,25 @@ __global__ void __launch_bounds__(256) cbam_bwd_mlp_kernel(const float* __restri
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float da = 0.f, dm = 0.f;
-    for (int j = 0; j < hidden; ++j) {
-      const float w = w0[(long long)c * hidden + j];
-      da = fmaf(w, dha[j], da);
-      dm = fmaf(w, dhm[j], dm);
+  for (int c0 = warp * 4; c0 < C; c0 += nwarp * 4) {   // one warp per 4 channels: rows of w0 are read coalesced, 4 rows in flight
+    float da[4] = {0.f, 0.f, 0.f, 0.f}, dm[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < hidden; j += 32) {
+      const float a = dha[j], b = dhm[j];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float w = c0 + u < C ? w0[(long long)(c0 + u) * hidden + j] : 0.f;
+        da[u] = fmaf(w, a, da[u]);
+        dm[u] = fmaf(w, b, dm[u]);
+      }
     }
-    coef[((long long)n * 4 + 2) * C + c] = da / (float)S;
-    coef[((long long)n * 4 + 3) * C + c] = dm / cnt[c];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float x = warp_sum(da[u]), y = warp_sum(dm[u]);
+      if (lane == 0 && c0 + u < C) {
+        coef[((long long)n * 4 + 2) * C + c0 + u] = x / (float)S;
+        coef[((long long)n * 4 + 3) * C + c0 + u] = y / cnt[c0 + u];
+      }
+    }
   }
 }
 
@@ -551,7 +565,7 @@ extern "C" {
 size_t sap3d_gn_bwd_workspace(int32_t N, int64_t S, int32_t C) {
   const size_t rows = (size_t)sap3d_sample_stats_rows(S, C, N);
   // partial [N][rows][4][C] + coef [N][4][C] + (CBAM tail) dpre, tinv [N*S], dsp [N*S][2], mlpg [N][C + 2*(C/8)]
-  return ((size_t)N * rows * 4 * C + (size_t)N * 4 * C + (size_t)N * S * 4 + (size_t)N * (C + 2 * (C / 8 + 1)) + 64) * sizeof(float);
+  return ((size_t)N * rows * 4 * C + (size_t)N * 8 * C + (size_t)N * S * 4 + (size_t)N * (C + 2 * (C / 8 + 1)) + 64) * sizeof(float);
 }
 
 int sap3d_gn_act_bwd(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
@@ -581,9 +595,11 @@ int sap3d_gn_act_bwd(int32_t dtype, const void* dy, const void* a, const float* 
   else gn_bwd_reduce_kernel<float><<<rgrid, 256, 0, st>>>(p);
   if (check_launch("gn_act_bwd reduce")) return 1;
   const bool norm2 = b && s2;
-  gn_bwd_finalize_kernel<<<G, 128, 0, st>>>(p.partial, p.rows, N, C, G, (double)S * p.cpg, gamma1, rstd1, norm2 ? gamma2 : gamma1,
-                                            norm2 ? rstd2 : rstd1, norm2 ? 4 : 2, coef, dgamma1, dbeta1, norm2 ? dgamma2 : nullptr,
-                                            norm2 ? dbeta2 : nullptr);
+  float* vsum = coef + (size_t)N * 4 * C;
+  gn_bwd_finalize_kernel<<<dim3(G, N), 128, 0, st>>>(p.partial, p.rows, N, C, G, (double)S * p.cpg, gamma1, rstd1, norm2 ? gamma2 : gamma1,
+                                                     norm2 ? rstd2 : rstd1, norm2 ? 4 : 2, coef, vsum);
+  gn_bwd_param_kernel<<<((norm2 ? 4 : 2) * C + 255) / 256, 256, 0, st>>>(vsum, N, C, norm2 ? 4 : 2, dgamma1, dbeta1, norm2 ? dgamma2 : nullptr,
+                                                                        norm2 ? dbeta2 : nullptr);
   if (check_launch("gn_act_bwd finalize")) return 1;
   if (da || db) {
     const long long nvec = (long long)N * S * C / 8;
@@ -610,6 +626,7 @@ int sap3d_cbam_tail_bwd(int32_t dtype, const void* dy, const void* y, const void
   float* ws = reinterpret_cast<float*>(workspace);
   float* partial = ws;               ws += (size_t)N * rows * 4 * C;
   float* coef = ws;                  ws += (size_t)N * 4 * C;
+  float* vsum = ws;                  ws += (size_t)N * 4 * C;
   float* dpre = ws;                  ws += total;
   float* tinv = ws;                  ws += total;
   float* dsp = ws;                   ws += 2 * total;
@@ -646,10 +663,10 @@ int sap3d_cbam_tail_bwd(int32_t dtype, const void* dy, const void* y, const void
   if (bf) cbam_bwd_reduce_kernel<bf16><<<rgrid, 256, 0, st>>>(p);
   else cbam_bwd_reduce_kernel<float><<<rgrid, 256, 0, st>>>(p);
   if (check_launch("cbam_bwd reduce")) return 1;
-  gn_bwd_finalize_kernel<<<G, 128, 0, st>>>(partial, rows, N, C, G, (double)S * p.cpg, gamma3, rstd3, gamma3, rstd3, 2, coef, dgamma3, dbeta3,
-                                            nullptr, nullptr);
+  gn_bwd_finalize_kernel<<<dim3(G, N), 128, 0, st>>>(partial, rows, N, C, G, (double)S * p.cpg, gamma3, rstd3, gamma3, rstd3, 2, coef, vsum);
+  gn_bwd_param_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(vsum, N, C, 2, dgamma3, dbeta3, nullptr, nullptr);
   if (check_launch("cbam_bwd gn finalize")) return 1;
-  cbam_bwd_mlp_kernel<<<N, 256, (size_t)(2 * C + 2 * hidden) * sizeof(float), st>>>(partial, rows, C, hidden, S, cscale, save, w0, w1, coef, mlpg);
+  cbam_bwd_mlp_kernel<<<N, C >= 512 ? 1024 : 256, (size_t)(2 * C + 2 * hidden) * sizeof(float), st>>>(partial, rows, C, hidden, S, cscale, save, w0, w1, coef, mlpg);
   if (check_launch("cbam_bwd mlp")) return 1;
   if (dw0 && db0 && dw1 && db1) {
     cbam_bwd_mlp_wgrad_kernel<<<ew_grid((long long)C * hidden), 256, 0, st>>>(save, mlpg, N, C, hidden, dw0, db0, dw1, db1);

@@ -22,7 +22,7 @@
 
 namespace sap3d {
 
-constexpr int WG_MAX_MAPS = 10;
+constexpr int WG_MAX_MAPS = 28;
 constexpr int WG_MAX_TAPS = 32;
 constexpr int WG_THREADS = 192;
 

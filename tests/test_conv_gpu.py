@@ -99,6 +99,8 @@ TC_CASES = [
     ("upx_4_0 deconv k(1,3,3) s2", 2, 1, 7, 7, [1024], 512, (1, 3, 3), (2, 2, 2), True),
     ("ragged extents", 1, 3, 9, 11, [64], 128, (3, 3, 3), (1, 1, 1), False),
     ("deconv k3 s1 (p3d_concat)", 1, 2, 6, 6, [64], 64, (3, 3, 3), (1, 1, 1), True),
+    ("deconv_pool4 k3 s4 (64 output classes, 27 parity views of dy)", 2, 1, 5, 5, [128], 64, (3, 3, 3), (4, 4, 4), True),
+    ("deconv_pool4 k(1,3,3) s4 (decoder_block)", 1, 1, 5, 5, [64], 64, (1, 3, 3), (4, 4, 4), True),
 ]
 
 
