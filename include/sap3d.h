@@ -240,6 +240,8 @@ int sap3d_saliency_metrics(const float* pred, const float* density, const float*
  * dst [n][H][W][3] in out_dtype (SAP3D_F32 / SAP3D_BF16) = one frame of the NDHWC network input each. */
 int sap3d_preprocess_frames(const uint8_t* bgr, int32_t n, int32_t h, int32_t w, const float* mean_rgb_host, int32_t out_dtype,
                             void* dst, int32_t H, int32_t W, void* stream);
+/* NaN-filtered column sums and counts of values [n][m] (fp64): the per-metric (sum, count) pairs of test.py:177-181 */
+int sap3d_nan_sum_count(const double* values, int32_t n, int32_t m, double* sums, double* counts, void* stream);
 int sap3d_resize_bilinear(const float* src, int32_t n, int32_t h, int32_t w, float* dst, int32_t H, int32_t W, void* stream);
 size_t sap3d_saliency_auc_workspace(int32_t n_maps, int32_t n_rep);
 int sap3d_saliency_auc(const float* sal, const float* fix, int32_t n_maps, int64_t elems, int32_t jitter, int32_t n_rep, double step,

@@ -310,3 +310,25 @@ extern "C" int sap3d_preprocess_frames(const uint8_t* bgr, int32_t n, int32_t h,
     preprocess_frames_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(bgr, n, h, w, mean_rgb_host[0], mean_rgb_host[1], mean_rgb_host[2], reinterpret_cast<float*>(dst), H, W);
   return check_launch("preprocess_frames");
 }
+
+// NaN-filtered column sums / counts of a small [n][m] table of per-clip metric values (test.py:177-181 drops NaN scores
+// before averaging); the (sum, count) pairs are what a sharded evaluation all-reduces.
+namespace {
+__global__ void nan_sum_count_kernel(const double* __restrict__ v, int n, int m, double* __restrict__ sums, double* __restrict__ counts) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  double s = 0.0, c = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double x = v[(long long)i * m + j];
+    if (x == x) { s += x; c += 1.0; }
+  }
+  sums[j] = s;
+  counts[j] = c;
+}
+}  // namespace
+extern "C" int sap3d_nan_sum_count(const double* values, int32_t n, int32_t m, double* sums, double* counts, void* stream) {
+  if (require_device()) return 1;
+  if (!values || !sums || !counts || n < 0 || m < 1) return set_error("nan_sum_count: bad argument");
+  nan_sum_count_kernel<<<(m + 63) / 64, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(values, n, m, sums, counts);
+  return check_launch("nan_sum_count");
+}

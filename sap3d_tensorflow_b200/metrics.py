@@ -50,6 +50,15 @@ def KLdiv(saliencyMap, fixationMap) -> float:
     return float(saliency_metrics(saliencyMap, fixationMap)[0, 3])
 
 
+def _nan_sum_count(vals: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """NaN-filtered per-metric (sum, count) of a [B, m] fp64 table (test.py:177-181)"""
+    n, m = vals.shape
+    sums = torch.empty(m, device=vals.device, dtype=torch.float64)
+    cnts = torch.empty(m, device=vals.device, dtype=torch.float64)
+    A.check(A.lib.sap3d_nan_sum_count(A.ptr(vals), n, m, A.ptr(sums), A.ptr(cnts), torch.cuda.current_stream().cuda_stream), "nan_sum_count")
+    return {"values": vals, "sum": sums, "count": cnts}
+
+
 def resize_bilinear(maps, out_hw) -> torch.Tensor:
     """cv2.resize(map, (W, H)) (INTER_LINEAR) for [n, h, w] float maps — the upsampling test.py:168 applies to every
     predicted frame before scoring (112 x 112 -> 1080 x 960)"""
@@ -92,9 +101,9 @@ def evaluate_clips_test_time(pred: torch.Tensor, density: torch.Tensor, fixation
     up = resize_bilinear(p, density.shape[-2:])
     base = saliency_metrics(up, density, fixation)
     auc = saliency_auc(up, fixation, seed=seed)
-    vals = torch.stack([base[:, 0], base[:, 1], auc[:, 0], auc[:, 1], base[:, 2]], dim=1)
-    ok = ~torch.isnan(vals)
-    return {"values": vals, "sum": torch.where(ok, vals, torch.zeros_like(vals)).sum(0), "count": ok.sum(0).to(torch.float64)}
+    vals = torch.empty(base.shape[0], 5, device=base.device, dtype=torch.float64)      # column gather = memory plumbing
+    vals[:, 0], vals[:, 1], vals[:, 2], vals[:, 3], vals[:, 4] = base[:, 0], base[:, 1], auc[:, 0], auc[:, 1], base[:, 2]
+    return _nan_sum_count(vals)
 
 
 def evaluate_clips(pred: torch.Tensor, density: torch.Tensor, fixation: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
@@ -104,7 +113,4 @@ def evaluate_clips(pred: torch.Tensor, density: torch.Tensor, fixation: Optional
     p = pred.reshape(pred.shape[0], pred.shape[1], pred.shape[2], pred.shape[3])[:, -1]
     d = density[:, -1] if density.dim() == 4 else density
     f = None if fixation is None else (fixation[:, -1] if fixation.dim() == 4 else fixation)
-    vals = saliency_metrics(p, d, f)
-    ok = ~torch.isnan(vals)
-    sums = torch.where(ok, vals, torch.zeros_like(vals)).sum(0)
-    return {"values": vals, "sum": sums, "count": ok.sum(0).to(torch.float64)}
+    return _nan_sum_count(saliency_metrics(p, d, f))
