@@ -394,6 +394,283 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   }
 }
 
+
+// =================================================================================================
+// Persistent form for layers with more work units than SMs (the decoder): one CTA per SM walks the units
+// u = blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulators are DOUBLE-BUFFERED in TMEM (2 x MT x BLOCK_N columns
+// when that fits in 512), so the epilogue of unit i (tcgen05.ld, bias, statistics, stores) runs under the MMAs of
+// unit i+1, the TMA ring never drains between units, and the wave-quantisation tail of a 5.3-wave launch disappears
+// (every SM gets floor or ceil of units/SMs).
+// =================================================================================================
+template <int BLOCK_N, int STAGES, int MT>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __grid_constant__ TcConvParams p, const int total_units) {
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+  constexpr int NBUF = 2 * MT * BLOCK_N <= 512 ? 2 : 1;
+  constexpr int TCOLS = NBUF * MT * BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  constexpr int NBAR = 2 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + NBAR * 8);
+  float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + NBAR * 8 + 16);  // [4][2][BLOCK_N]
+  float* s_ep = s_stats + 4 * 2 * BLOCK_N;                                                  // [3][BLOCK_N]
+  const uint32_t tfull = bar_base + 2 * STAGES * 8, tempty = tfull + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_groups = (p.m_tiles + MT - 1) / MT;
+
+  struct Unit { int nt, cls_id; int mts[MT], w0s[MT], h0s[MT], d0s[MT], n0s[MT]; bool live[MT]; };
+  auto decode = [&](int u, Unit& t) {
+    t.nt = u % p.n_tiles;
+    u /= p.n_tiles;
+    t.cls_id = u / m_groups;
+    const int mg = u - t.cls_id * m_groups;
+#pragma unroll
+    for (int sub = 0; sub < MT; ++sub) {
+      int mt = mg * MT + sub;
+      t.live[sub] = mt < p.m_tiles;
+      if (!t.live[sub]) mt = p.m_tiles - 1;
+      t.mts[sub] = mt;
+      int r = mt;
+      const int tw = r % p.tiles[0]; r /= p.tiles[0];
+      const int th = r % p.tiles[1]; r /= p.tiles[1];
+      const int td = r % p.tiles[2];
+      const int tn = r / p.tiles[2];
+      t.w0s[sub] = tw * p.box[0]; t.h0s[sub] = th * p.box[1]; t.d0s[sub] = td * p.box[2]; t.n0s[sub] = tn * p.box[3];
+    }
+  };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_base + s * 8, 1);
+      mbar_init(bar_base + (STAGES + s) * 8, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b * 8, 1);
+      mbar_init(tempty + b * 8, 128);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&p.bmap);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), TCOLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: one continuous ring over all units =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = MT * p.box_rows * 128 + B_BYTES;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        Unit t;
+        decode(u, t);
+        const TcClass cls = p.cls[t.cls_id];
+        for (int ti = 0; ti < cls.tap_count; ++ti) {
+          const TcTap tap = p.taps[cls.tap_begin + ti];
+          const void* amap = &p.amap[tap.map];
+          for (int ch = 0; ch < tap.nchunk; ++ch) {
+            mbar_wait(bar_base + (STAGES + stage) * 8, phase ^ 1u);
+            const uint32_t full = bar_base + stage * 8;
+            const uint32_t sa = base + stage * STAGE_BYTES;
+            mbar_expect_tx(full, tx_bytes);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub)
+              tma_load_5d(sa + sub * A_BYTES, amap, full, (tap.c0 + ch) * 64, t.w0s[sub] + tap.dw, t.h0s[sub] + tap.dh, t.d0s[sub] + tap.dd,
+                          t.n0s[sub]);
+            tma_load_2d(sa + MT * A_BYTES, &p.bmap, full, tap.kofs + ch * 64, t.nt * BLOCK_N);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+        const int buf = it % NBUF;
+        const uint32_t use = static_cast<uint32_t>(it / NBUF);
+        const int cls_id = (u / p.n_tiles) / m_groups;
+        const int nkb = p.cls[cls_id].nkb;
+        mbar_wait(tempty + buf * 8, (use & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * MT * BLOCK_N;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar_base + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint64_t bdesc = umma_desc_sw128(sa + MT * A_BYTES, 16, 1024);
+#pragma unroll
+          for (int sub = 0; sub < MT; ++sub) {
+            const uint64_t adesc = umma_desc_sw128(sa + sub * A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_bf16(tacc + sub * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(bar_base + (STAGES + stage) * 8);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (nkb > 0) tc_commit(tfull + buf * 8);
+        else mbar_arrive(tfull + buf * 8);               // bias-only class: nothing to wait for
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5), overlapped with the next unit's MMAs =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool want_stats = p.stats != nullptr;
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+      Unit t;
+      decode(u, t);
+      const TcClass cls = p.cls[t.cls_id];
+      const int nkb = cls.nkb;
+      const int buf = it % NBUF;
+      const uint32_t use = static_cast<uint32_t>(it / NBUF);
+      for (int cc = et; cc < BLOCK_N; cc += 128) {     // per-column epilogue vectors of this unit
+        const int col = t.nt * BLOCK_N + cc;
+        const bool in = col < p.cout;
+        s_ep[cc] = (in && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
+        s_ep[BLOCK_N + cc] = (in && p.scale != nullptr) ? __ldg(p.scale + col) : 1.f;
+        s_ep[2 * BLOCK_N + cc] = (in && p.scale != nullptr) ? __ldg(p.shift + col) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull + buf * 8, use & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * MT * BLOCK_N;
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+        if (!t.live[sub]) break;
+        int r = row;
+        const int iw = r % p.box[0]; r /= p.box[0];
+        const int ih = r % p.box[1]; r /= p.box[1];
+        const int id = r % p.box[2];
+        const int in = r / p.box[2];
+        const int ow = t.w0s[sub] + iw, oh = t.h0s[sub] + ih, od = t.d0s[sub] + id, on = t.n0s[sub] + in;
+        const bool valid = row < p.box_rows && ow < p.ext[0] && oh < p.ext[1] && od < p.ext[2] && on < p.ext[3];
+        const long long row_off = cls.out_ofs + ow * p.so[0] + oh * p.so[1] + od * p.so[2] + on * p.so[3];
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          const int col0 = t.nt * BLOCK_N + c * 32;
+          if (col0 >= p.cout) break;
+          uint32_t rr[32];
+          if (nkb > 0) {
+            tmem_ld_32x32(tacc + (static_cast<uint32_t>(q * 32) << 16) + sub * BLOCK_N + c * 32, rr);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rr[j] = 0u;
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += s_ep[c * 32 + j];
+          }
+          if (want_stats) {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float m = valid ? v[j] : 0.f;
+              s1[j] = m;
+              s2[j] = m * m;
+            }
+            const float c1 = warp_transpose_sum32(s1, lane);
+            const float c2 = warp_transpose_sum32(s2, lane);
+            s_stats[(q * 2 + 0) * BLOCK_N + c * 32 + lane] = c1;
+            s_stats[(q * 2 + 1) * BLOCK_N + c * 32 + lane] = c2;
+          }
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_ep[BLOCK_N + c * 32 + j], s_ep[2 * BLOCK_N + c * 32 + j]);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (valid) {
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (col0 + g * 4 < p.cout) {
+                  float4 f = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                  if (p.accumulate) {
+                    const float4 e = *reinterpret_cast<const float4*>(o + g * 4);
+                    f.x += e.x; f.y += e.y; f.z += e.z; f.w += e.w;
+                  }
+                  *reinterpret_cast<float4*>(o + g * 4) = f;
+                }
+              }
+            } else {
+              bf16* o = reinterpret_cast<bf16*>(p.out) + row_off + col0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (col0 + g * 8 < p.cout) {
+                  float w8[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) w8[j] = v[g * 8 + j];
+                  if (p.accumulate) {
+                    float e[8];
+                    Vec8<bf16>::load(o + g * 8, e);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w8[j] += e[j];
+                  }
+                  Vec8<bf16>::store(o + g * 8, w8);
+                }
+              }
+            }
+          }
+        }
+        if (sub + 1 == MT || !t.live[sub + 1 < MT ? sub + 1 : sub]) {
+          // last sub-tile of the unit has been read out of TMEM: hand the buffer back before the statistics tail
+          tc_fence_before();
+          mbar_arrive(tempty + buf * 8);
+        }
+        if (want_stats) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const long long srow = static_cast<long long>(t.cls_id) * p.m_tiles + t.mts[sub];
+          for (int cc = et; cc < BLOCK_N; cc += 128) {
+            const int col = t.nt * BLOCK_N + cc;
+            if (col < p.cout) {
+              float a = 0.f, b = 0.f;
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) {
+                a += s_stats[(qq * 2 + 0) * BLOCK_N + cc];
+                b += s_stats[(qq * 2 + 1) * BLOCK_N + cc];
+              }
+              p.stats[(srow * 2 + 0) * p.cout + col] = a;
+              p.stats[(srow * 2 + 1) * p.cout + col] = b;
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");   // s_stats / s_ep are reused by the next sub-tile / unit
+        }
+      }
+      if (!want_stats) asm volatile("bar.sync 1, 128;" ::: "memory");   // s_ep is rewritten at the top of the next unit
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TCOLS);
+  }
+}
+
 // =================================================================================================
 // host side
 // =================================================================================================
@@ -597,6 +874,32 @@ static int launch_split(const TcConvParams& prm, int grid, cudaStream_t stream, 
   return 0;
 }
 
+template <int BLOCK_N, int STAGES, int MT>
+static int launch_persist(const TcConvParams& prm, int units, cudaStream_t stream, char* err, size_t errlen) {
+  constexpr int SMEM = STAGES * (MT * 128 * 128 + BLOCK_N * 128) + (2 * STAGES + 4) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
+  static bool attr_done = false;
+  static int sms = 0;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "cudaFuncSetAttribute(conv_tc_persist) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) sms = 148;
+    attr_done = true;
+  }
+  conv_tc_persist_kernel<BLOCK_N, STAGES, MT><<<units < sms ? units : sms, TC_THREADS, SMEM, stream>>>(prm, units);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "conv_tc_persist launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
 int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen) {
   Merged m;
   merge_dims(pb, m);
@@ -698,6 +1001,14 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
     }
     if (split == 4 && min_nkb >= 4) return launch_split<4>(prm, (int)grid, stream, err, errlen);
     if (split == 2 && min_nkb >= 2) return launch_split<2>(prm, (int)grid, stream, err, errlen);
+  }
+  // more work units than SMs (decoder layers): persistent CTAs with double-buffered accumulators
+  if (grid > 148 && pb.force_split >= 0) {
+    switch (block_n) {
+      case 64: return mt == 2 ? launch_persist<64, 4, 2>(prm, (int)grid, stream, err, errlen) : launch_persist<64, 6, 1>(prm, (int)grid, stream, err, errlen);
+      case 128: return mt == 2 ? launch_persist<128, 4, 2>(prm, (int)grid, stream, err, errlen) : launch_persist<128, 4, 1>(prm, (int)grid, stream, err, errlen);
+      case 256: return mt == 2 ? launch_persist<256, 3, 2>(prm, (int)grid, stream, err, errlen) : launch_persist<256, 4, 1>(prm, (int)grid, stream, err, errlen);
+    }
   }
   switch (block_n) {
     case 64: return mt == 2 ? launch_t<64, 4, 2>(prm, (int)grid, stream, err, errlen) : launch_t<64, 6, 1>(prm, (int)grid, stream, err, errlen);

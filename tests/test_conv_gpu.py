@@ -104,6 +104,21 @@ TC_CASES = [
 ]
 
 
+# more work units than SMs: the persistent form (one CTA per SM walks the units, double-buffered TMEM accumulators)
+PERSIST_CASES = [
+    ("200 units, 64 cols (MT=1)", 2, 8, 40, 40, [64], 64, (1, 3, 3), (1, 1, 1), False),
+    ("200 units, 128 cols, concat", 2, 8, 40, 40, [64, 64], 128, (3, 1, 1), (1, 1, 1), False),
+    ("784 tiles, two M sub-tiles per unit", 4, 8, 56, 56, [64], 64, (1, 1, 1), (1, 1, 1), False),
+    ("deconv k3 s2: 8 parity classes x 25 tiles", 2, 4, 20, 20, [64], 64, (3, 3, 3), (2, 2, 2), True),
+    ("256 cols", 2, 8, 40, 40, [64], 256, (1, 1, 1), (1, 1, 1), False),
+]
+
+
+@pytest.mark.parametrize("case", PERSIST_CASES, ids=[c[0] for c in PERSIST_CASES])
+def test_persistent_tensor_core_conv(A, case):
+    run_case(A, *case[1:], dtype=A.BF16, impl=A.IMPL_TC)
+
+
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_tensor_core_conv(A, case):
     run_case(A, *case[1:], dtype=A.BF16, impl=A.IMPL_TC)
