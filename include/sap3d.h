@@ -94,6 +94,11 @@ int sap3d_conv_fwd_affine(const sap3d_conv_desc* d, const void* x0, const void* 
 /* dx_seg = data gradient w.r.t. segment `seg`; accumulate != 0 adds into dx */
 int sap3d_conv_dgrad(const sap3d_conv_desc* d, int32_t seg, const void* dy, const float* w_tf,
                      const void* w_dgrad_packed, void* dx, int32_t accumulate, void* stream);
+/* both segment gradients of a fused-concat conv (two equal, 64-aligned segments, tensor-core path) in ONE launch: dy is read
+ * once per tap instead of once per segment */
+int sap3d_conv_dgrad2_supported(const sap3d_conv_desc* d);
+int sap3d_conv_dgrad2(const sap3d_conv_desc* d, const void* dy, const float* w_tf, const void* w_dgrad_packed, void* dx0,
+                      int32_t accumulate0, void* dx1, int32_t accumulate1, void* stream);
 /* dw (fp32, TF layout) += filter gradient; db (nullable, [cout]) += bias gradient.
  * The caller zeroes dw/db at the start of a step (gradients accumulate across calls). */
 /* fwd_operand (nullable): the packed forward operand buffer given to sap3d_conv_fwd; small-Cin convolutions (the stem)

@@ -65,6 +65,8 @@ _sig("sap3d_conv_fwd", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_conv_fwd_on_tensor_cores", [_P(ConvDesc)])
 _sig("sap3d_conv_fwd_affine", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp])
 _sig("sap3d_conv_dgrad", [_P(ConvDesc), _i32, _vp, _vp, _vp, _vp, _i32, _vp])
+_sig("sap3d_conv_dgrad2_supported", [_P(ConvDesc)])
+_sig("sap3d_conv_dgrad2", [_P(ConvDesc), _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp])
 _sig("sap3d_conv_wgrad", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp])
 
 

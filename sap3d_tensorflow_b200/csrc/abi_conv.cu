@@ -496,8 +496,31 @@ static int conv_fwd_impl(const sap3d_conv_desc* d, const void* x0, const void* x
   return 0;
 }
 
+static int conv_dgrad_impl(const sap3d_conv_desc* d, int32_t seg, const void* dy, const float* w_tf, const void* w_dgrad_packed,
+                           void* dx, int32_t accumulate, void* dx2, int32_t accumulate2, void* stream);
+
 int sap3d_conv_dgrad(const sap3d_conv_desc* d, int32_t seg, const void* dy, const float* w_tf, const void* w_dgrad_packed,
                      void* dx, int32_t accumulate, void* stream) {
+  return conv_dgrad_impl(d, seg, dy, w_tf, w_dgrad_packed, dx, accumulate, nullptr, 0, stream);
+}
+
+/* 1 when both segment gradients of a fused-concat conv can come out of ONE launch (sap3d_conv_dgrad2) */
+int sap3d_conv_dgrad2_supported(const sap3d_conv_desc* d) {
+  if (check_desc(d)) return 0;
+  return (d->nseg == 2 && d->cin[0] == d->cin[1] && d->cin[0] % 64 == 0 && tc_dgrad_eligible(d)) ? 1 : 0;
+}
+
+/* data gradients of BOTH segments of a fused-concat conv in one launch: dy is read once per tap instead of once per
+ * segment (N = cin0 + cin1 output columns; columns >= cin0 are written to dx1) */
+int sap3d_conv_dgrad2(const sap3d_conv_desc* d, const void* dy, const float* w_tf, const void* w_dgrad_packed, void* dx0,
+                      int32_t accumulate0, void* dx1, int32_t accumulate1, void* stream) {
+  if (!sap3d_conv_dgrad2_supported(d)) return set_error("conv_dgrad2: needs two equal 64-aligned segments on the tensor-core path");
+  if (!dx1) return set_error("conv_dgrad2: NULL tensor pointer");
+  return conv_dgrad_impl(d, 0, dy, w_tf, w_dgrad_packed, dx0, accumulate0, dx1, accumulate1, stream);
+}
+
+static int conv_dgrad_impl(const sap3d_conv_desc* d, int32_t seg, const void* dy, const float* w_tf, const void* w_dgrad_packed,
+                           void* dx, int32_t accumulate, void* dx2, int32_t accumulate2, void* stream) {
   if (check_desc(d)) return 1;
   if (seg < 0 || seg >= d->nseg) return set_error("conv_dgrad: bad segment");
   if (!dy || !dx) return set_error("conv_dgrad: NULL tensor pointer");
@@ -522,6 +545,9 @@ int sap3d_conv_dgrad(const sap3d_conv_desc* d, int32_t seg, const void* dy, cons
     if (!d->transposed) {
       if (strided_scatter && !accumulate) {
         if (cudaMemsetAsync(dx, 0, (size_t)si[3] * d->N * esize, st) != cudaSuccess) return set_error("conv_dgrad: memset failed");
+      }
+      if (strided_scatter && dx2 && !accumulate2) {
+        if (cudaMemsetAsync(dx2, 0, (size_t)si[3] * d->N * esize, st) != cudaSuccess) return set_error("conv_dgrad: memset failed");
       }
       TcView v;
       v.base = dy;
@@ -605,6 +631,13 @@ int sap3d_conv_dgrad(const sap3d_conv_desc* d, int32_t seg, const void* dy, cons
     pb.rowsB = (cseg + 63) / 64 * 64;
     pb.cout = cseg;
     pb.out = dx;
+    if (dx2) {   // both segments: N = cin0 + cin1 columns of the packed data-gradient filter, split at cin0
+      pb.rowsB = (g.cin_total + 63) / 64 * 64;
+      pb.cout = g.cin_total;
+      pb.out2 = dx2;
+      pb.seg_split = d->cin[0];
+      pb.accumulate2 = accumulate2;
+    }
     pb.bias = nullptr;
     pb.stats = nullptr;
     pb.scale = pb.shift = nullptr;

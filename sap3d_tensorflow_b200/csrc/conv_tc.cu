@@ -53,6 +53,8 @@ struct alignas(64) TcConvParams {
   long long so[4];
   int cout, box_rows;
   void* out;
+  void* out2;          // merged two-segment data gradient: columns >= seg_split go to out2 (same row strides)
+  int seg_split, accumulate2;
   const float* bias;
   float* stats;
   const float* scale;
@@ -331,13 +333,17 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
       if (valid) {
+        const bool second = p.out2 != nullptr && col0 >= p.seg_split;
+        void* const outp = second ? p.out2 : p.out;
+        const int colx = second ? col0 - p.seg_split : col0;
+        const int accum = second ? p.accumulate2 : p.accumulate;
         if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
+          float* o = reinterpret_cast<float*>(outp) + row_off + colx;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             if (col0 + g * 4 < p.cout) {
               float4 f = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-              if (p.accumulate) {
+              if (accum) {
                 const float4 e = *reinterpret_cast<const float4*>(o + g * 4);
                 f.x += e.x; f.y += e.y; f.z += e.z; f.w += e.w;
               }
@@ -345,14 +351,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             }
           }
         } else {
-          bf16* o = reinterpret_cast<bf16*>(p.out) + row_off + col0;
+          bf16* o = reinterpret_cast<bf16*>(outp) + row_off + colx;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (col0 + g * 8 < p.cout) {
               float w8[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) w8[j] = v[g * 8 + j];
-              if (p.accumulate) {
+              if (accum) {
                 float e[8];
                 Vec8<bf16>::load(o + g * 8, e);
 #pragma unroll
@@ -603,13 +609,17 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (valid) {
+            const bool second = p.out2 != nullptr && col0 >= p.seg_split;
+            void* const outp = second ? p.out2 : p.out;
+            const int colx = second ? col0 - p.seg_split : col0;
+            const int accum = second ? p.accumulate2 : p.accumulate;
             if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + row_off + col0;
+              float* o = reinterpret_cast<float*>(outp) + row_off + colx;
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
                 if (col0 + g * 4 < p.cout) {
                   float4 f = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                  if (p.accumulate) {
+                  if (accum) {
                     const float4 e = *reinterpret_cast<const float4*>(o + g * 4);
                     f.x += e.x; f.y += e.y; f.z += e.z; f.w += e.w;
                   }
@@ -617,14 +627,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
                 }
               }
             } else {
-              bf16* o = reinterpret_cast<bf16*>(p.out) + row_off + col0;
+              bf16* o = reinterpret_cast<bf16*>(outp) + row_off + colx;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 if (col0 + g * 8 < p.cout) {
                   float w8[8];
 #pragma unroll
                   for (int j = 0; j < 8; ++j) w8[j] = v[g * 8 + j];
-                  if (p.accumulate) {
+                  if (accum) {
                     float e[8];
                     Vec8<bf16>::load(o + g * 8, e);
 #pragma unroll
@@ -980,6 +990,9 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
   prm.shift = pb.shift;
   prm.relu = pb.relu;
   prm.accumulate = pb.accumulate;
+  prm.out2 = pb.out2;
+  prm.seg_split = pb.seg_split;
+  prm.accumulate2 = pb.accumulate2;
   prm.out_f32 = pb.out_f32;
   // two M sub-tiles per CTA when the problem still fills the GPU several times over
   const long long ctas1 = (long long)prm.ncls * prm.m_tiles * prm.n_tiles;

@@ -36,6 +36,8 @@ struct TcProblem {
   int Ktot, rowsB;
   int cout;           // valid output columns (multiple of 8)
   void* out;          // bf16 (or f32 when out_f32)
+  void* out2 = nullptr;   // optional second output tensor for columns >= seg_split (merged two-segment data gradient)
+  int seg_split = 0, accumulate2 = 0;
   const float* bias;  // nullable, [cout]
   float* stats;       // nullable, [ncls*m_tiles][2][cout]
   const float* scale; // nullable epilogue affine (inference-folded norm)

@@ -459,13 +459,21 @@ class _ConvOp:
         if not raw.gflag:
             return
         dy = raw.grad
-        for si, x in enumerate(self.xs):
-            if not x.needs_grad:
-                continue
-            acc = x.take_acc()
-            A.check(A.lib.sap3d_conv_dgrad(C.byref(self.desc), si, A.ptr(dy), A.ptr(self.w.w), A.ptr(self.wd),
-                                           A.ptr(x.ensure_grad()), acc, e.stream), "conv_dgrad " + self.name)
+        if (len(self.xs) == 2 and all(x.needs_grad for x in self.xs) and self.xs[0] is not self.xs[1]
+                and A.lib.sap3d_conv_dgrad2_supported(C.byref(self.desc)) == 1):
+            # fused-concat conv with two equal segments: both data gradients from ONE launch (dy read once per tap)
+            a0, a1 = self.xs[0].take_acc(), self.xs[1].take_acc()
+            A.check(A.lib.sap3d_conv_dgrad2(C.byref(self.desc), A.ptr(dy), A.ptr(self.w.w), A.ptr(self.wd), A.ptr(self.xs[0].ensure_grad()),
+                                            a0, A.ptr(self.xs[1].ensure_grad()), a1, e.stream), "conv_dgrad2 " + self.name)
             e._count()
+        else:
+            for si, x in enumerate(self.xs):
+                if not x.needs_grad:
+                    continue
+                acc = x.take_acc()
+                A.check(A.lib.sap3d_conv_dgrad(C.byref(self.desc), si, A.ptr(dy), A.ptr(self.w.w), A.ptr(self.wd),
+                                               A.ptr(x.ensure_grad()), acc, e.stream), "conv_dgrad " + self.name)
+                e._count()
         x1 = self.xs[1].buf if len(self.xs) > 1 else None
         main = torch.cuda.current_stream(e.device)
         if e.use_side_stream:

@@ -74,6 +74,14 @@ def run_case(A, N, D, H, W, cin, cout, k, s, transposed, dtype, impl):
         torch.cuda.synchronize()
         assert rel(dx, 2 * xcat.grad[..., off:off + c]) < 2 * tol
         off += c
+    if len(cin) == 2 and A.lib.sap3d_conv_dgrad2_supported(C.byref(d)) == 1:
+        # both segment gradients from one launch, one of them accumulating onto existing data
+        dx0 = torch.full_like(xs[0], float("nan"))
+        dx1 = torch.ones_like(xs[1])
+        A.check(A.lib.sap3d_conv_dgrad2(C.byref(d), A.ptr(dyd), A.ptr(w), A.ptr(wd), A.ptr(dx0), 0, A.ptr(dx1), 1, st), "dgrad2")
+        torch.cuda.synchronize()
+        assert rel(dx0, xcat.grad[..., :cin[0]]) < tol
+        assert rel(dx1.float() - 1.0, xcat.grad[..., cin[0]:].to(dev)) < 2 * tol + (2e-2 if dtype == A.BF16 else 0)
     dw, db = torch.zeros_like(w), torch.zeros(cout, device=dev)
     A.check(A.lib.sap3d_conv_wgrad(C.byref(d), A.ptr(xs[0]), A.ptr(x1), A.ptr(dyd), A.ptr(dw), A.ptr(db), A.ptr(wf), st), "wgrad")
     torch.cuda.synchronize()
@@ -111,6 +119,7 @@ PERSIST_CASES = [
     ("784 tiles, two M sub-tiles per unit", 4, 8, 56, 56, [64], 64, (1, 1, 1), (1, 1, 1), False),
     ("deconv k3 s2: 8 parity classes x 25 tiles", 2, 4, 20, 20, [64], 64, (3, 3, 3), (2, 2, 2), True),
     ("256 cols", 2, 8, 40, 40, [64], 256, (1, 1, 1), (1, 1, 1), False),
+    ("x_1_2-like concat 128+128 (merged two-segment data gradient)", 2, 8, 40, 40, [128, 128], 128, (1, 3, 3), (1, 1, 1), False),
 ]
 
 
