@@ -441,7 +441,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
-                         "traffic": traffic, "kernel": "conv_tc_kernel<128,4,2> (x_1_2/x_1_3 3x3x3 conv, 128+128->128, B=8)",
+                         "traffic": traffic, "kernel": "conv_tc_persist_kernel<128,4,2> (x_1_2/x_1_3 3x3x3 conv, 128+128->128, B=8)",
                          "ms_per_launch": kms, "flops_per_launch": kflops, "peak_source": f"{src} bf16 burst (kernel timed alone)"},
         }
         if gn:

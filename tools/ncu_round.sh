@@ -11,7 +11,7 @@ python tools/profile_step.py $G 8 112 infer > $O/plain_infer.log 2>&1 &&
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_infer.csv \
     python tools/profile_step.py $G 8 112 infer > $O/ncu_infer.log 2>&1
 python tools/run_dominant_kernel.py fwd > $O/plain_dom.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 1 -c 2 -f -o $O/full_conv_fwd \
+ncu --set full --clock-control none --import-source on -k regex:conv_tc_ -s 1 -c 2 -f -o $O/full_conv_fwd \
     python tools/run_dominant_kernel.py fwd > $O/ncu_dom.log 2>&1
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:flash_ -c 3 -f -o $O/full_flash \
     python tools/profile_step.py $G 8 112 train > $O/ncu_flash.log 2>&1

@@ -46,7 +46,7 @@ for f, desc in names.items():
             l2sm = float(r[i2]) * scale[units[i2]]
 open(os.path.join(P, f"{tag}_ncu_full_summary.txt"), "w").write("\n".join(lines) + "\n")
 if traffic is not None:
-    json.dump({"kernel": "conv_tc_kernel<128,4,2,1> x_1_2 fwd B=8", "dram_bytes_per_launch": traffic,
+    json.dump({"kernel": "conv_tc_persist_kernel<128,4,2> x_1_2 fwd B=8", "dram_bytes_per_launch": traffic,
                "algorithmic_bytes_per_launch": 2 * 51380224 + 1769472 + 51380224, "l2_to_sm_bytes_per_launch": l2sm,
                "source": f"profiles/{tag}_ncu_full_summary.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
               open(os.path.join(P, "dominant_kernel_traffic.json"), "w"), indent=1)
