@@ -86,14 +86,16 @@ torch.cuda.synchronize()
 def time_graphs(label):
     sess.graph_train = None
     sess.capture(train=True)
-    ga, gb = sess.graph_train
+    graphs = [g for g in (sess.graph_train[0], sess.graph_train[2], sess.graph_train[1]) if g is not None]
     for _ in range(2):
-        ga.replay(); gb.replay()
+        for g in graphs:
+            g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(args.iters):
-        ga.replay(); gb.replay()
+        for g in graphs:
+            g.replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
