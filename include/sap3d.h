@@ -318,6 +318,12 @@ int sap3d_step_increment(int32_t* step, void* stream);
 /* f32 -> bf16 (src_dtype == SAP3D_F32) or bf16 -> f32 */
 int sap3d_cast(int32_t src_dtype, const void* src, void* dst, int64_t n, void* stream);
 
+
+/* HOST helper (no device needed): CRC-32C of n bytes, continuing from `crc` (0 to start).  The checksum of TensorFlow's
+ * tensor-bundle checkpoint files, which tf.train.Saver writes/reads at train.py:184,267 and gen_pred.py:57-64; used by the
+ * checkpoint reader/writer of the Python host (sap3d_tensorflow_b200/checkpoint.py). */
+uint32_t sap3d_crc32c(uint32_t crc, const void* data, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

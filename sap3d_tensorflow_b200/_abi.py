@@ -165,6 +165,7 @@ _sig("sap3d_cbam_tail_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
 _sig("sap3d_cbam_merge", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp])
 _sig("sap3d_concat_channels", [_i32, _vp, _vp, _vp, _i64, _i32, _i32, _vp])
 _sig("sap3d_preprocess_frames", [_vp, _i32, _i32, _i32, _P(C.c_float), _i32, _vp, _i32, _i32, _vp])
+_sig("sap3d_crc32c", [C.c_uint32, _vp, C.c_size_t], C.c_uint32)
 _sig("sap3d_nan_sum_count", [_vp, _i32, _i32, _vp, _vp, _vp])
 _sig("sap3d_resize_bilinear", [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp])
 _sig("sap3d_saliency_auc_workspace", [_i32, _i32], C.c_size_t)

@@ -9,6 +9,7 @@ gen_pred.py:45-46,151, test.py:157-160), backed by the static engine and CUDA gr
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -202,3 +203,69 @@ class Session:
 
     def gradients(self) -> Dict[str, torch.Tensor]:
         return {n: p.g for n, p in self.eng.params.items() if p.trainable}
+
+    # ---- checkpoints (tf.train.Saver of train.py:180-185,266-267; gen_pred.py:57-64) -------------------------------------
+    def save(self, prefix: str, include_optimizer: bool = False, max_to_keep: int = 10) -> str:
+        """writes a TensorFlow tensor-bundle checkpoint of the reference's Saver var_list -- the trainable variables plus every
+        moving_mean / moving_variance, under the reference's variable names -- and updates the directory's `checkpoint` file.
+        `include_optimizer` adds tf.train.AdamOptimizer's slots (`<var>/Adam`, `<var>/Adam_1`, beta1_power, beta2_power),
+        which the reference's saver leaves out (its resumed runs restart Adam)."""
+        from . import checkpoint as ckpt
+        e = self.eng
+        torch.cuda.synchronize(e.device)
+        tensors = {n: p.w.detach().cpu().numpy() for n, p in e.params.items()}
+        if include_optimizer:
+            if e.flat_m is None:
+                raise RuntimeError("include_optimizer needs a training graph")
+            m, v = e.flat_m.cpu().numpy(), e.flat_v.cpu().numpy()
+            for n, p in e.params.items():
+                if p.trainable:
+                    sm, sv = ckpt.adam_slot_names(n)
+                    tensors[sm] = m[p.offset:p.offset + p.numel].reshape(p.shape)
+                    tensors[sv] = v[p.offset:p.offset + p.numel].reshape(p.shape)
+            t = int(e.step.item())
+            tensors["beta1_power"] = np.float32(0.9 ** (t + 1))      # TF multiplies the accumulators AFTER each apply
+            tensors["beta2_power"] = np.float32(0.999 ** (t + 1))
+            tensors["sap3d/adam_step"] = np.int64(t)                 # exact step; beta1_power underflows fp32 resolution late
+        return ckpt.save(prefix, tensors, update_state=True, max_to_keep=max_to_keep)
+
+    def restore(self, prefix_or_dir: str, strict: bool = True) -> str:
+        """`saver.restore(sess, path)`: loads every variable of this graph by name from a tensor-bundle checkpoint (a prefix, or
+        a directory whose `checkpoint` file names the newest one).  Adam slots are restored when present; otherwise the
+        optimiser state is left as it is (the reference's behaviour).  Invalidates nothing: the graphs read the same buffers."""
+        from . import checkpoint as ckpt
+        e = self.eng
+        prefix = prefix_or_dir
+        if os.path.isdir(prefix_or_dir):
+            prefix = ckpt.latest_checkpoint(prefix_or_dir)
+            if prefix is None:
+                raise ckpt.CheckpointError(f"no checkpoint state in {prefix_or_dir}")
+        avail = {n for n, _ in ckpt.list_variables(prefix)}
+        missing = [n for n in e.params if n not in avail]
+        if strict and missing:
+            raise KeyError(f"checkpoint {prefix} lacks {len(missing)} variables, e.g. {missing[:3]}")
+        want = [n for n in e.params if n in avail]
+        slots = []
+        if e.flat_m is not None:
+            for n, p in e.params.items():
+                if p.trainable:
+                    sm, sv = ckpt.adam_slot_names(n)
+                    if sm in avail and sv in avail:
+                        slots.append((p, sm, sv))
+        extra = [s for _, a, b in slots for s in (a, b)] + [n for n in ("beta1_power", "sap3d/adam_step") if n in avail]
+        vals = ckpt.load(prefix, want + extra)
+        torch.cuda.synchronize(e.device)
+        e.load_params({n: vals[n] for n in want}, strict=False)
+        if slots and len(slots) == sum(1 for p in e.params.values() if p.trainable):
+            for p, sm, sv in slots:
+                e.flat_m[p.offset:p.offset + p.numel].copy_(torch.from_numpy(vals[sm].reshape(-1).copy()))
+                e.flat_v[p.offset:p.offset + p.numel].copy_(torch.from_numpy(vals[sv].reshape(-1).copy()))
+            if "sap3d/adam_step" in vals:
+                t = int(vals["sap3d/adam_step"])
+            elif "beta1_power" in vals:
+                t = max(int(round(np.log(float(vals["beta1_power"])) / np.log(0.9))) - 1, 0)
+            else:
+                t = 0
+            e.step.fill_(t)
+        torch.cuda.synchronize(e.device)
+        return prefix

@@ -6,6 +6,8 @@ bf16 path: saliency map within 1e-2 relative in inference mode (BASELINE.json to
 random-weight network amplifies ANY bf16 storage rounding ~100x across its 47 batch-statistics blocks
 (measured with a bf16-rounding simulation inside the oracle); per-layer bf16 parity is
 asserted op by op in test_conv_gpu.py / test_ops_gpu.py instead."""
+import os
+
 import pytest
 import torch
 
@@ -249,3 +251,44 @@ def test_prefetched_inputs_give_the_same_step(lib_built):
     # fp32-atomic filter gradients through Adam's sign-like first updates, so they are only compared loosely
     assert abs(losses[0][0] - losses[1][0]) / losses[0][0] < 1e-6, losses
     assert all(abs(a - b) / a < 1e-2 for a, b in zip(*losses)), losses
+
+
+def test_checkpoint_save_restore_resumes_training(lib_built, tmp_path):
+    """Session.save / Session.restore (TF tensor-bundle files, the reference's tf.train.Saver at train.py:180-185,266-267 and
+    gen_pred.py:57-64): variables come back bit-exactly under the reference's names; with the Adam slots saved too, a restored
+    session continues exactly where the first one was; an inference graph restores the same file by name."""
+    from sap3d_tensorflow_b200 import checkpoint as ck
+    graph, batch, size = "p3d_unet", 2, 64
+    x = O.synthetic_clip(batch, 16, size, seed=0).cuda()
+    y = O.synthetic_target(batch, 16, size, seed=1).cuda()
+    a = build(graph, "bf16", True, batch, size, dropout=0.0)
+    for _ in range(2):
+        a.train_step(x, y, graph=True)
+    d = str(tmp_path / "model")
+    prefix = a.save(os.path.join(d, "p3d_2.ckpt"), include_optimizer=True)
+    names = dict(ck.list_variables(prefix))
+    assert names["firstconv1"] == (1, 7, 7, 3, 64) and "firstconv1/Adam_1" in names and names["beta1_power"] == ()
+    assert ck.latest_checkpoint(d) == prefix
+    weights_a = {n: v.clone() for n, v in a.variables().items()}
+    b = build(graph, "bf16", True, batch, size, dropout=0.0)
+    b.eng.init_params_tf(seed=7)                                  # different weights before the restore
+    assert b.restore(d) == prefix
+    for n, v in b.variables().items():
+        assert torch.equal(v, weights_a[n]), n
+    assert int(b.eng.step.item()) == 2 and torch.equal(b.eng.flat_m, a.eng.flat_m) and torch.equal(b.eng.flat_v, a.eng.flat_v)
+    la = float(a.train_step(x, y, graph=True).item())
+    lb = float(b.train_step(x, y, graph=True).item())
+    assert abs(la - lb) / la < 1e-5, (la, lb)                     # same state -> same step (atomics: last-bit noise only)
+    # variables-only checkpoint (what the reference's saver writes) into an inference graph
+    prefix2 = a.save(os.path.join(d, "p3d_3.ckpt"))
+    assert not any(n.endswith("/Adam") for n in dict(ck.list_variables(prefix2)))
+    inf_a = build(graph, "bf16", False, batch, size)
+    inf_a.restore(prefix2)
+    for n, v in inf_a.variables().items():
+        assert torch.equal(v, a.variables()[n]), n
+    out = inf_a.run(x).float()
+    assert torch.isfinite(out).all()
+    # a graph with other variables refuses a strict restore
+    other = build("p3d_unetplusplus_nonsa", "bf16", False, 1, 64)
+    with pytest.raises(KeyError):
+        other.restore(prefix2)
