@@ -145,6 +145,16 @@ int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const flo
                          const float* mean2, const float* rstd2, int32_t relu2, int32_t relu_out, int64_t P, int32_t C,
                          void* da, int32_t acc_a, void* db, int32_t acc_b, float* dgamma1, float* dbeta1, float* dgamma2,
                          float* dbeta2, void* workspace, void* stream);
+/* the same backward in two phases, for BatchNorm statistics that span the replicas of a data-parallel job (the
+ * reference normalises over its whole single-device batch, p3d.py:344 / tf.layers.batch_normalization).
+ * phase 1: reductions only -- d{gamma,beta} += LOCAL sums, and workspace[0 .. 4*C) floats = LOCAL sums / global_count;
+ * the caller sums those 4*C floats over the replicas (the forward pass did the same with the statistics rows, finalised by
+ * sap3d_bn_finalize with the global count); phase 2: applies the data gradient from that workspace. */
+int sap3d_affine_act_bwd_sync(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
+                              const float* rstd1, int32_t relu1, const void* b, const float* s2, const float* t2,
+                              const float* mean2, const float* rstd2, int32_t relu2, int32_t relu_out, int64_t P, int32_t C,
+                              void* da, int32_t acc_a, void* db, int32_t acc_b, float* dgamma1, float* dbeta1, float* dgamma2,
+                              float* dbeta2, void* workspace, void* stream, double global_count, int32_t phase);
 
 /* ------------------------------------------------------------------------------------------------
  * Pooling.  Replaces tf.nn.max_pool3d (p3d.py:347-348,354,360,366) and tf.layers.max_pooling3d

@@ -115,6 +115,8 @@ _sig("sap3d_bn_apply_fused", [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _v
 _sig("sap3d_affine_act_bwd_workspace", [_i32], C.c_size_t)
 _sig("sap3d_affine_act_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32,
                               _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp])
+_sig("sap3d_affine_act_bwd_sync", [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32,
+                                   _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32])
 _I3 = C.c_int32 * 3
 _sig("sap3d_maxpool3d_out_dims", [_i32, _i32, _i32, _P(C.c_int32), _P(C.c_int32), _i32, _P(C.c_int32)])
 _sig("sap3d_maxpool3d_fwd", [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _P(C.c_int32), _P(C.c_int32), _i32, _vp, _vp, _vp])

@@ -757,11 +757,13 @@ int sap3d_bn_apply_fused(int32_t dtype, const void* a, const float* stats1, int3
 
 size_t sap3d_affine_act_bwd_workspace(int32_t C) { return (size_t)(296 * 4 + 4 + 8) * (size_t)C * sizeof(float) + 64; }
 
-int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
-                         const float* rstd1, int32_t relu1, const void* b, const float* s2, const float* t2,
-                         const float* mean2, const float* rstd2, int32_t relu2, int32_t relu_out, int64_t P, int32_t C,
-                         void* da, int32_t acc_a, void* db, int32_t acc_b, float* dgamma1, float* dbeta1, float* dgamma2,
-                         float* dbeta2, void* workspace, void* stream) {
+// phase 0: the whole backward.  phase 1: reductions only (coef = LOCAL sums / count at workspace[0 .. 4C)); phase 2: apply
+// only, reading coef from the workspace (the caller has summed it over the replicas in between: synchronised BatchNorm).
+static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
+                               const float* rstd1, int32_t relu1, const void* b, const float* s2, const float* t2,
+                               const float* mean2, const float* rstd2, int32_t relu2, int32_t relu_out, int64_t P, int32_t C,
+                               void* da, int32_t acc_a, void* db, int32_t acc_b, float* dgamma1, float* dbeta1, float* dgamma2,
+                               float* dbeta2, void* workspace, void* stream, double count, int phase) {
   if (require_device()) return 1;
   if (C % 8 != 0 || C > 2048) return set_error("affine_act_bwd: C must be a multiple of 8 and <= 2048 (got %d)", C);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -775,7 +777,10 @@ int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const flo
   p.da = da; p.db = db; p.acc_a = acc_a; p.acc_b = acc_b;
   float* ws = reinterpret_cast<float*>(workspace);
   const bool need_reduce = p.batch_stats1 || p.batch_stats2 || dgamma1 || dbeta1 || dgamma2 || dbeta2;
-  if (need_reduce) {
+  if (phase == 2) {
+    if (!workspace) return set_error("affine_act_bwd: workspace required");
+    p.coef = ws;
+  } else if (need_reduce) {
     if (!workspace) return set_error("affine_act_bwd: workspace required");
     const int chunks = (C + 63) / 64;
     long long rows = (2 * 148 + chunks - 1) / chunks;
@@ -788,7 +793,7 @@ int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const flo
     p.totals = reinterpret_cast<double*>(ws + (size_t)(296 * 4 + 4) * C + (((size_t)(296 * 4 + 4) * C) & 1));   // 8-byte aligned tail
     dim3 rgrid((unsigned)rows, (unsigned)chunks);
     // backbone-sized tensors: ONE cooperative launch (reduce -> grid.sync -> finalize -> apply) instead of three
-    if ((long long)P * C <= COOP_MAX_ELEMS) {
+    if (phase == 0 && (long long)P * C <= COOP_MAX_ELEMS) {
       static int max_blocks[2] = {0, 0};
       int& mb = max_blocks[dtype == SAP3D_BF16 ? 0 : 1];
       if (mb == 0) {
@@ -801,7 +806,7 @@ int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const flo
         if (mb < 1) mb = 1;
       }
       if ((long long)rows * chunks <= mb) {
-        double M = (double)P;
+        double M = count;
         void* args[] = {(void*)&p, (void*)&M, (void*)&dgamma1, (void*)&dbeta1, (void*)&dgamma2, (void*)&dbeta2};
         const void* fn = dtype == SAP3D_BF16 ? (const void*)bn_bwd_coop_kernel<bf16> : (const void*)bn_bwd_coop_kernel<float>;
         cudaError_t e = cudaLaunchCooperativeKernel(fn, rgrid, dim3(256), args, 0, st);
@@ -812,17 +817,37 @@ int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const flo
     if (dtype == SAP3D_BF16) apply_bwd_reduce_kernel<bf16><<<rgrid, 256, 0, st>>>(p);
     else apply_bwd_reduce_kernel<float><<<rgrid, 256, 0, st>>>(p);
     if (check_launch("affine_act_bwd reduce")) return 1;
-    apply_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, st>>>(p.partial, (int)rows, C, (double)P, ws, dgamma1, dbeta1, dgamma2, dbeta2);
+    apply_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, st>>>(p.partial, (int)rows, C, count, ws, dgamma1, dbeta1, dgamma2, dbeta2);
     if (check_launch("affine_act_bwd finalize")) return 1;
     p.coef = ws;
   }
-  if (da || db) {
+  if (phase != 1 && (da || db)) {
     const long long nvec = P * C / 8;
     if (dtype == SAP3D_BF16) apply_bwd_kernel<bf16><<<ew_grid(nvec), 256, 0, st>>>(p);
     else apply_bwd_kernel<float><<<ew_grid(nvec), 256, 0, st>>>(p);
     if (check_launch("affine_act_bwd apply")) return 1;
   }
   return 0;
+}
+
+int sap3d_affine_act_bwd(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
+                         const float* rstd1, int32_t relu1, const void* b, const float* s2, const float* t2,
+                         const float* mean2, const float* rstd2, int32_t relu2, int32_t relu_out, int64_t P, int32_t C,
+                         void* da, int32_t acc_a, void* db, int32_t acc_b, float* dgamma1, float* dbeta1, float* dgamma2,
+                         float* dbeta2, void* workspace, void* stream) {
+  return affine_act_bwd_impl(dtype, dy, a, s1, t1, mean1, rstd1, relu1, b, s2, t2, mean2, rstd2, relu2, relu_out, P, C, da, acc_a,
+                             db, acc_b, dgamma1, dbeta1, dgamma2, dbeta2, workspace, stream, (double)P, 0);
+}
+
+int sap3d_affine_act_bwd_sync(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
+                              const float* rstd1, int32_t relu1, const void* b, const float* s2, const float* t2,
+                              const float* mean2, const float* rstd2, int32_t relu2, int32_t relu_out, int64_t P, int32_t C,
+                              void* da, int32_t acc_a, void* db, int32_t acc_b, float* dgamma1, float* dbeta1, float* dgamma2,
+                              float* dbeta2, void* workspace, void* stream, double global_count, int32_t phase) {
+  if (phase != 1 && phase != 2) return set_error("affine_act_bwd_sync: phase must be 1 (reduce) or 2 (apply)");
+  if (!(global_count >= (double)P)) return set_error("affine_act_bwd_sync: global_count is smaller than the local position count");
+  return affine_act_bwd_impl(dtype, dy, a, s1, t1, mean1, rstd1, relu1, b, s2, t2, mean2, rstd2, relu2, relu_out, P, C, da, acc_a,
+                             db, acc_b, dgamma1, dbeta1, dgamma2, dbeta2, workspace, stream, global_count, phase);
 }
 
 }  // extern "C"

@@ -130,6 +130,7 @@ class Engine:
         self.step = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.loss_buf = torch.zeros(1, device=self.device, dtype=torch.float64)
         self.bwd_ws: Optional[torch.Tensor] = None
+        self.sync_bn = None      # parallel.SyncBatchNorm: batch statistics span the data-parallel replicas (eager mode)
         self._max_c = 8
         self.launches_fwd = 0
         self.launches_bwd = 0
@@ -515,6 +516,11 @@ class _NormActOp:
     def _finalize(self, co: ConvOut, ns: NormState, training: bool):
         e = self.eng
         cnt = float(co.raw.positions)
+        if training and e.sync_bn is not None:
+            # synchronised BatchNorm: the per-tile (sum, sum of squares) rows are summed over the replicas, then finalised
+            # against the global position count -- the statistics of the reference's single-device batch
+            e.sync_bn.all_reduce(co.stats)
+            cnt *= e.sync_bn.world
         A.check(A.lib.sap3d_bn_finalize(A.ptr(co.stats), co.rows, co.raw.C, cnt, A.ptr(ns.gamma.w), A.ptr(ns.beta.w),
                                         A.ptr(ns.mm.w), A.ptr(ns.mv.w), int(training), BN_MOMENTUM, BN_EPS, A.ptr(ns.scale),
                                         A.ptr(ns.shift), A.ptr(ns.mean), A.ptr(ns.rstd), e.stream), "bn_finalize " + self.name)
@@ -524,6 +530,8 @@ class _NormActOp:
 
     def _fwd_fused(self) -> bool:
         n1, n2, a, e = self.n1, self.n2, self.a, self.eng
+        if e.sync_bn is not None and (self.train1 or self.train2):
+            return False
         if n1 is None or (self.train1 and a.rows > self.FUSE_MAX_ROWS):
             return False
         b_co = self.b if isinstance(self.b, ConvOut) else None
@@ -575,7 +583,7 @@ class _NormActOp:
             db_ptr = A.ptr(self.b_t.ensure_grad())
         bs1 = n1 is not None and self.train1
         bs2 = n2 is not None and self.train2
-        A.check(A.lib.sap3d_affine_act_bwd(
+        args = (
             e.dt, A.ptr(self.y.grad), A.ptr(a_raw.buf),
             A.ptr(n1.scale) if n1 else None, A.ptr(n1.shift) if n1 else None,
             A.ptr(n1.mean) if bs1 else None, A.ptr(n1.rstd) if bs1 else None, int(self.relu1),
@@ -586,7 +594,16 @@ class _NormActOp:
             A.ptr(a_raw.ensure_grad()), acc_a, db_ptr, acc_b,
             A.ptr(n1.gamma.g) if n1 else None, A.ptr(n1.beta.g) if n1 else None,
             A.ptr(n2.gamma.g) if n2 else None, A.ptr(n2.beta.g) if n2 else None,
-            A.ptr(e.bwd_ws), e.stream), "affine_act_bwd " + self.name)
+            A.ptr(e.bwd_ws), e.stream)
+        if e.sync_bn is not None and (bs1 or bs2):
+            # the per-channel sums of the BN backward span the replicas too; d(gamma), d(beta) stay LOCAL sums (the gradient
+            # exchange adds them up with every other gradient)
+            cnt = float(self.y.positions) * e.sync_bn.world
+            A.check(A.lib.sap3d_affine_act_bwd_sync(*args, cnt, 1), "affine_act_bwd reduce " + self.name)
+            e.sync_bn.all_reduce(e.bwd_ws[:4 * self.y.C])
+            A.check(A.lib.sap3d_affine_act_bwd_sync(*args, cnt, 2), "affine_act_bwd apply " + self.name)
+        else:
+            A.check(A.lib.sap3d_affine_act_bwd(*args), "affine_act_bwd " + self.name)
         e._count(3)
 
 

@@ -4,7 +4,9 @@ over NVLink 5 + NVSwitch for the plumbing), clips sharded by rank, weights repli
 The reference is single-GPU (train.py:73); DP is new work required by BASELINE.json configs[3].
 The only exchange step is the gradient sum: the loss is a plain SUM over all elements
 (utils/network.py:60), so the global-batch gradient is the sum of the shard gradients — no averaging.
-Gradients travel as bf16 buckets (half the NVLink bytes); BatchNorm statistics stay per replica.
+Gradients travel as bf16 buckets (half the NVLink bytes); BatchNorm statistics stay per replica by default.
+`enable_sync_batch_norm` makes them span the replicas (the reference's single-device batch): an option for
+parity runs -- two small latency-bound collectives per norm layer, eager mode only; throughput is reported without it.
 """
 from __future__ import annotations
 
@@ -99,13 +101,53 @@ class GradientExchange:
         A.check(A.lib.sap3d_cast(A.BF16, A.ptr(self.buf), A.ptr(eng.flat_g), self.n, st), "grad uncast")
 
 
-def attach_data_parallel(sess, bucket_mb: int = 32) -> GradientExchange:
-    """installs the gradient all-reduce between backward and Adam; broadcasts rank 0's variables"""
+class SyncBatchNorm:
+    """sum-all-reduce of the small per-layer statistics buffers (forward: the conv epilogue's [rows][2][C] partial sums;
+    backward: the 4*C per-channel sums of the BN gradient) on the current stream, in fp32"""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise A.Sap3dError("torch.distributed is not initialised")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.calls = 0
+
+    def all_reduce(self, t: torch.Tensor):
+        self.calls += 1
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+
+def enable_sync_batch_norm(sess, group=None) -> SyncBatchNorm:
+    """every batch-statistics BatchNorm of the session's graph normalises over the GLOBAL batch (all replicas must run the same
+    graph with the same per-replica batch).  Eager execution only: Session.train_step(graph=True) refuses it."""
+    sb = SyncBatchNorm(group)
+    sess.eng.sync_bn = sb
+    sess.graph_train = None
+    sess.graph_fwd = None
+    return sb
+
+
+class ExactGradientExchange:
+    """fp32 sum-all-reduce of the whole flat gradient buffer in one call: the parity-test form of GradientExchange"""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def __call__(self, eng):
+        dist.all_reduce(eng.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+
+
+def attach_data_parallel(sess, bucket_mb: int = 32, sync_bn: bool = False, exact: bool = False):
+    """installs the gradient all-reduce between backward and Adam; broadcasts rank 0's variables.
+    sync_bn: BatchNorm statistics over the global batch (parity option).  exact: fp32 un-bucketed exchange."""
     if not dist.is_initialized():
         raise A.Sap3dError("torch.distributed is not initialised")
     eng = sess.eng
     dist.broadcast(eng.flat_w, src=0)
     eng.pack_weights()
-    ex = GradientExchange(eng, bucket_mb)
+    ex = ExactGradientExchange() if exact else GradientExchange(eng, bucket_mb)
     sess.grad_hook = ex
+    if sync_bn:
+        enable_sync_batch_norm(sess)
     return ex

@@ -133,6 +133,8 @@ class Session:
         """forward pass; returns the [B,16,H,W,1] fp32 saliency tensor (device)."""
         self._feed(x)
         if graph:
+            if self.eng.sync_bn is not None:
+                raise A.Sap3dError("synchronised BatchNorm runs in eager mode only (run(graph=False))")
             if self.graph_fwd is None:
                 self.capture(train=False)
             self.graph_fwd.replay()
@@ -152,6 +154,8 @@ class Session:
                 e.input_f32.copy_(x)
             self.head.target.copy_(y.reshape(self.head.target.shape), non_blocking=True)
         if graph:
+            if e.sync_bn is not None:
+                raise A.Sap3dError("synchronised BatchNorm runs in eager mode only (train_step(graph=False))")
             if self.graph_train is None:
                 self.capture(train=True)
             ga, gb, gm = self.graph_train

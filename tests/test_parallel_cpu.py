@@ -66,7 +66,35 @@ def _worker(rank, world, port, q):
     okm = ~torch.isnan(vals)
     means = reduce_metric_sums(torch.where(okm, vals, torch.zeros_like(vals)).sum(0), okm.sum(0).float())
     ok2 = torch.allclose(means, torch.tensor([0.7, 0.4]), atol=1e-6)
-    q.put((rank, bool(ok1), bool(ok2)))
+    # (3) synchronised BatchNorm algebra (engine._NormActOp with parallel.SyncBatchNorm): statistics rows and the backward's
+    # per-channel sums are SUMMED over the replicas and divided by the global count; d(gamma)/d(beta) stay local sums that
+    # the gradient exchange adds up.  Checked against autograd over the whole batch.
+    from sap3d_tensorflow_b200.parallel import SyncBatchNorm
+    sb = SyncBatchNorm()
+    torch.manual_seed(1)
+    xb = torch.randn(4, 5, 3, dtype=torch.float64, requires_grad=True)     # global batch 4, 5 positions, 3 channels
+    gamma = torch.rand(3, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(4, 5, 3, dtype=torch.float64)
+    mean, var = xb.mean((0, 1)), xb.var((0, 1), unbiased=False)
+    ((xb - mean) / torch.sqrt(var + 1e-3) * gamma * dy).sum().backward()
+    xs, dys = xb.detach()[lo:hi], dy[lo:hi]
+    stats = torch.stack([xs.sum((0, 1)), (xs * xs).sum((0, 1))])           # this replica's [2][C] row
+    sb.all_reduce(stats)
+    cnt = xs.shape[0] * xs.shape[1] * sb.world
+    m = stats[0] / cnt
+    v = stats[1] / cnt - m * m
+    rstd = 1.0 / torch.sqrt(v + 1e-3)
+    xhat = (xs - m) * rstd
+    g = dys * gamma.detach()
+    local = torch.stack([g.sum((0, 1)), (g * xhat).sum((0, 1))])
+    dgamma_local = (dys * xhat).sum((0, 1))
+    coef = local / cnt                                                     # phase 1 of sap3d_affine_act_bwd_sync
+    sb.all_reduce(coef)
+    dx = rstd * (g - coef[0] - xhat * coef[1])                             # phase 2
+    dist.all_reduce(dgamma_local)                                          # what the gradient exchange does
+    ok3 = (torch.allclose(m, mean.detach()) and torch.allclose(v, var.detach()) and torch.allclose(dx, xb.grad[lo:hi], atol=1e-10)
+           and torch.allclose(dgamma_local, gamma.grad, atol=1e-10) and sb.calls == 2)
+    q.put((rank, bool(ok1), bool(ok2 and ok3)))
     dist.destroy_process_group()
 
 

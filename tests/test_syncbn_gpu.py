@@ -1,0 +1,87 @@
+"""Synchronised BatchNorm (the reference has ONE device, so its batch statistics span the whole batch; under data
+parallelism that needs the statistics -- forward sums and the backward's per-channel sums -- summed over the replicas).
+Two replicas (gloo, sharing the GPU) each take half of a batch; with sync_bn their predictions, summed loss, exchanged
+gradients and updated variables must equal a single-process run over the whole batch."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import p3d_oracle as O  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def rel(a, b):
+    a, b = a.float().reshape(-1), b.float().reshape(-1)
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 2e-4), ("bf16", 5e-2)])
+def test_two_replicas_with_sync_bn_equal_one_big_batch(lib_built, tmp_path, dtype, tol):
+    import sap3d_tensorflow_b200 as sp
+
+    graph, per, size, world = "p3d_unet", 1, 64, 2
+    env = dict(os.environ, WORLD_SIZE=str(world), SAP3D_PORT=str(free_port()), SAP3D_OUT=str(tmp_path), SAP3D_GRAPH=graph,
+               SAP3D_PER=str(per), SAP3D_SIZE=str(size), SAP3D_DTYPE=dtype)
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_syncbn_worker.py")], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(world)]
+    logs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        logs.append(out.decode(errors="replace")[-3000:])
+    assert all(p.returncode == 0 for p in procs), "\n----\n".join(logs)
+    ranks = [torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in range(world)]
+
+    # the whole batch in one process, per-device statistics (= the reference's single-device semantics)
+    B = per * world
+    xin = sp.placeholder([B, 16, size, size, 3], dtype=dtype, training_graph=True)
+    head = getattr(sp.p3d, graph)(xin, 0.0, B, True)
+    sess = sp.Session(head)
+    x = O.synthetic_clip(B, 16, size, seed=0).cuda()
+    y = O.synthetic_target(B, 16, size, seed=1).cuda()
+    loss = float(sess.train_step(x, y, graph=False).item())
+    torch.cuda.synchronize()
+    pred = head.output.detach().float().cpu()
+
+    assert all(r["graph_refused"] for r in ranks)
+    assert ranks[0]["sync_calls"] > 200                      # ~104 batch-statistics norms, forward + backward
+    for r in range(world):
+        assert rel(ranks[r]["pred"], pred[r * per:(r + 1) * per]) < tol, (r, rel(ranks[r]["pred"], pred[r * per:(r + 1) * per]))
+    assert abs(sum(r["loss"] for r in ranks) - loss) / loss < tol
+    grads = {n: g.detach().cpu() for n, g in sess.gradients().items()}
+    worst = max((rel(ranks[0]["grads"][n], g), n) for n, g in grads.items() if g.norm() > 1e-6 * g.numel() ** 0.5)
+    gtol = 5e-3 if dtype == "f32" else 2.5e-1
+    assert worst[0] < gtol, worst
+    # replicas hold identical gradients and identical variables after the step; moving statistics match the big batch
+    for n in grads:
+        assert torch.equal(ranks[0]["grads"][n], ranks[1]["grads"][n]), n
+    for n, v in sess.variables().items():
+        assert torch.equal(ranks[0]["vars"][n], ranks[1]["vars"][n]), n
+        if "moving_" in n:
+            assert rel(ranks[0]["vars"][n], v.detach().cpu()) < tol, n
+
+    # without sync the same two shards do NOT reproduce the big batch (the option is doing something)
+    xin1 = sp.placeholder([per, 16, size, size, 3], dtype=dtype, training_graph=True)
+    head1 = getattr(sp.p3d, graph)(xin1, 0.0, per, True)
+    s1 = sp.Session(head1)
+    s1.train_step(x[:per], y[:per], graph=False)
+    assert rel(head1.output.detach().float().cpu(), pred[:per]) > 10 * rel(ranks[0]["pred"], pred[:per])
