@@ -104,6 +104,56 @@ def test_affine_act_fwd_bwd(A, dtn, tdt, tol, pattern, shape):
 
 
 @pytest.mark.parametrize("dtn,tdt,tol", DT)
+@pytest.mark.parametrize("P", [2 * 37, 2 * 4 * 28 * 28], ids=["tiny", "stage1"])
+def test_bn_backward_in_two_phases_over_two_replicas(A, dtn, tdt, tol, P):
+    """sap3d_affine_act_bwd_sync (synchronised BatchNorm): two 'replicas' each own half of the positions; phase 1 leaves
+    (local sums / global count) in each workspace, the caller adds them up, phase 2 applies.  The result equals the one-shot
+    backward over all positions, and d(gamma), d(beta) add up to the global ones."""
+    torch.manual_seed(3)
+    dev, Cc = "cuda", 192
+    dt = A.BF16 if dtn == "bf16" else A.F32
+    a = (torch.randn(P, Cc, device=dev) * 1.5 + 0.7).to(tdt)
+    b = (torch.randn(P, Cc, device=dev) * 0.8 - 0.2).to(tdt)
+    dy = torch.randn(P, Cc, device=dev).to(tdt)
+    gam = [torch.rand(Cc, device=dev) + 0.5 for _ in range(2)]
+    bet = [torch.randn(Cc, device=dev) * 0.1 for _ in range(2)]
+    mm, mv = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+    f = lambda: torch.empty(Cc, device=dev)  # noqa: E731
+    sc, sh, me, rs = [f(), f()], [f(), f()], [f(), f()], [f(), f()]
+    for i, x in enumerate((a, b)):   # global statistics (what the all-reduced forward rows finalise to)
+        A.check(A.lib.sap3d_bn_finalize(A.ptr(_stats(x)), 1, Cc, float(P), A.ptr(gam[i]), A.ptr(bet[i]), A.ptr(mm), A.ptr(mv), 1, 0.99,
+                                        1e-3, A.ptr(sc[i]), A.ptr(sh[i]), A.ptr(me[i]), A.ptr(rs[i]), stream()), "fin")
+    nws = A.lib.sap3d_affine_act_bwd_workspace(Cc) // 4 + 16
+
+    def args(lo, hi, da, db, dg, ws):
+        return (dt, A.ptr(dy[lo:hi]), A.ptr(a[lo:hi]), A.ptr(sc[0]), A.ptr(sh[0]), A.ptr(me[0]), A.ptr(rs[0]), 1, A.ptr(b[lo:hi]),
+                A.ptr(sc[1]), A.ptr(sh[1]), A.ptr(me[1]), A.ptr(rs[1]), 0, 1, hi - lo, Cc, A.ptr(da[lo:hi]), 0, A.ptr(db[lo:hi]), 0,
+                A.ptr(dg[0]), A.ptr(dg[1]), A.ptr(dg[2]), A.ptr(dg[3]), A.ptr(ws), stream())
+
+    da0, db0 = torch.empty_like(a), torch.empty_like(b)
+    dg0 = [torch.zeros(Cc, device=dev) for _ in range(4)]
+    A.check(A.lib.sap3d_affine_act_bwd(*args(0, P, da0, db0, dg0, torch.zeros(nws, device=dev))), "one shot")
+    da1, db1 = torch.empty_like(a), torch.empty_like(b)
+    halves = [(0, P // 2), (P // 2, P)]
+    wss = [torch.zeros(nws, device=dev) for _ in halves]
+    dgs = [[torch.zeros(Cc, device=dev) for _ in range(4)] for _ in halves]
+    for (lo, hi), ws, dg in zip(halves, wss, dgs):
+        A.check(A.lib.sap3d_affine_act_bwd_sync(*args(lo, hi, da1, db1, dg, ws), float(P), 1), "phase 1")
+    total = wss[0][:4 * Cc] + wss[1][:4 * Cc]                    # the all-reduce
+    for (lo, hi), ws, dg in zip(halves, wss, dgs):
+        ws[:4 * Cc].copy_(total)
+        A.check(A.lib.sap3d_affine_act_bwd_sync(*args(lo, hi, da1, db1, dg, ws), float(P), 2), "phase 2")
+    torch.cuda.synchronize()
+    assert rel(da1, da0) < 10 * tol * (1e-2 if dtn == "bf16" else 1) + 1e-5, rel(da1, da0)
+    assert rel(db1, db0) < 10 * tol * (1e-2 if dtn == "bf16" else 1) + 1e-5, rel(db1, db0)
+    for k in range(4):
+        assert rel(dgs[0][k] + dgs[1][k], dg0[k]) < 1e-4, k
+    # argument checking
+    assert A.lib.sap3d_affine_act_bwd_sync(*args(0, P, da1, db1, dg0, wss[0]), float(P), 0) != 0
+    assert A.lib.sap3d_affine_act_bwd_sync(*args(0, P, da1, db1, dg0, wss[0]), float(P - 1), 1) != 0
+
+
+@pytest.mark.parametrize("dtn,tdt,tol", DT)
 @pytest.mark.parametrize("two_norms,training", [(False, True), (True, True), (True, False)])
 def test_bn_apply_fused_matches_finalize_plus_apply(A, dtn, tdt, tol, two_norms, training):
     """the one-launch form (finalize folded into apply) is bit-identical to sap3d_bn_finalize + sap3d_affine_act"""
