@@ -12,6 +12,26 @@ sys.path.insert(0, ROOT)
 from oracle import p3d_oracle as O  # noqa: E402  (synthetic inputs only)
 
 
+def build_graph(sp, graph, xin, batch):
+    """a reference builder by name, or "shallow": stem -> pool1 -> the three stage-1 bottlenecks (ST_A with the projection
+    shortcut, ST_B, ST_C) -> conv 3x3x3 + BN + ReLU -> 1-channel head.  Same ops and norm wirings as the full graphs, but 15
+    BatchNorms instead of ~195, so rounding differences are not amplified and gradients can be compared tightly."""
+    if graph != "shallow":
+        return getattr(sp.p3d, graph)(xin, 0.0, batch, True)
+    from sap3d_tensorflow_b200 import network as nw
+    eng = xin.eng
+    x = eng.maxpool(sp.p3d._stem(xin, True), (2, 3, 3), (2, 2, 2), name="pool1")
+    x = sp.p3d.make_block(x, 64, 3, 64, 0).infer()
+    d = nw.bn_relu(nw.layers_conv3d(x, 64, 3, 1, "dec"), True, name="dec_bn")
+    w = eng.param("out/kernel", [3, 3, 3, 1, 64], "glorot_t")
+    b = eng.param("out/bias", [1], "zeros")
+    return eng.head(d, w, b, (3, 3, 3), 2, sigmoid=True, name="out")
+
+
+def targets(graph, batch, size):
+    return O.synthetic_target(batch, 16, size // 2 if graph == "shallow" else size, seed=1)
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     graph, per, size, dtype = os.environ["SAP3D_GRAPH"], int(os.environ["SAP3D_PER"]), int(os.environ["SAP3D_SIZE"]), os.environ["SAP3D_DTYPE"]
@@ -22,11 +42,11 @@ def main():
     from sap3d_tensorflow_b200 import parallel
 
     xin = sp.placeholder([per, 16, size, size, 3], dtype=dtype, training_graph=True, device=dev)
-    head = getattr(sp.p3d, graph)(xin, 0.0, per, True)
+    head = build_graph(sp, graph, xin, per)
     sess = sp.Session(head)
     parallel.attach_data_parallel(sess, sync_bn=True, exact=True)
     x = O.synthetic_clip(per * world, 16, size, seed=0)[rank * per:(rank + 1) * per].to(dev)
-    y = O.synthetic_target(per * world, 16, size, seed=1)[rank * per:(rank + 1) * per].to(dev)
+    y = targets(graph, per * world, size)[rank * per:(rank + 1) * per].to(dev)
     loss = sess.train_step(x, y, graph=False)
     torch.cuda.synchronize()
     out = {
