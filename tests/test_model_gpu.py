@@ -292,3 +292,40 @@ def test_checkpoint_save_restore_resumes_training(lib_built, tmp_path):
     other = build("p3d_unetplusplus_nonsa", "bf16", False, 1, 64)
     with pytest.raises(KeyError):
         other.restore(prefix2)
+
+
+def test_full_size_properties_of_the_baseline_config(lib_built):
+    """BASELINE.json configs[1] at its real size (p3d_unetplusplus_ds, 8 clips of 16 x 112 x 112, bf16), where the CPU oracle
+    takes minutes: size-independent properties instead of an element-wise comparison.
+      inference : eager == CUDA-graph replay bit for bit; replay is idempotent; saliency in [0, 1]; permuting the clips of the
+                  batch permutes the maps (the batch statistics every backbone BN uses are permutation invariant)
+      training  : the loss kernel equals 0.5 * sum (pred - y)^2 recomputed from the prediction (|pred - y| < 1 always, so
+                  smooth-L1 is its quadratic branch, utils/network.py:49-62); every gradient is finite; TF-Adam's first step
+                  moves each weight by at most lr (|m_hat| / sqrt(v_hat) = 1 on step 1)"""
+    graph, batch, size = "p3d_unetplusplus_ds", 8, 112
+    x = O.synthetic_clip(batch, 16, size, seed=0).cuda()
+    y = O.synthetic_target(batch, 16, size, seed=1).cuda()
+    inf = build(graph, "bf16", False, batch, size)
+    eager = inf.run(x, graph=False).clone()
+    replay = inf.run(x, graph=True).clone()
+    assert torch.equal(eager, replay)
+    assert torch.equal(inf.run(x, graph=True), replay)
+    assert tuple(replay.shape) == (batch, 16, size, size, 1) and torch.isfinite(replay).all()
+    assert float(replay.min()) >= 0.0 and float(replay.max()) <= 1.0
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4], device="cuda")
+    permuted = inf.run(x[perm].contiguous(), graph=True)
+    assert rel(permuted, replay[perm]) < 1e-2, rel(permuted, replay[perm])
+    del inf
+    tr = build(graph, "bf16", True, batch, size, dropout=0.0)
+    w0 = tr.eng.flat_w[:tr.eng.n_train].clone()
+    loss = float(tr.train_step(x, y, graph=True).item())
+    torch.cuda.synchronize()
+    pred = tr.head.output.double().reshape(batch, 16, size, size)
+    expect = float(0.5 * ((pred - y.double()) ** 2).sum().item())
+    assert abs(loss - expect) / expect < 1e-6, (loss, expect)
+    g = tr.eng.flat_g
+    assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+    step = (tr.eng.flat_w[:tr.eng.n_train] - w0).abs()
+    assert float(step.max()) <= 1e-4 * 1.002, float(step.max())
+    moved = (step > 0).float().mean().item()
+    assert moved > 0.95, moved      # (conv biases in front of batch-statistics norms keep a zero gradient)
