@@ -328,4 +328,6 @@ def test_full_size_properties_of_the_baseline_config(lib_built):
     step = (tr.eng.flat_w[:tr.eng.n_train] - w0).abs()
     assert float(step.max()) <= 1e-4 * 1.002, float(step.max())
     moved = (step > 0).float().mean().item()
-    assert moved > 0.95, moved      # (conv biases in front of batch-statistics norms keep a zero gradient)
+    # zero gradients by construction: conv biases in front of batch-statistics norms, and the four attention blocks' 3.1 M
+    # parameters while their gate gamma is still at its initial 0 (utils/network.py:191-192) -- 5 % of the variables
+    assert 0.9 < moved < 0.99, moved

@@ -100,4 +100,4 @@ def test_two_replicas_with_sync_bn_equal_one_big_batch(lib_built, tmp_path, grap
     s1.train_step(x[:per], y[:per], graph=False)
     unsynced, synced = rel(head1.output.detach().float().cpu(), pred[:per]), rel(ranks[0]["pred"], pred[:per])
     print("prediction rel err: per-replica statistics", unsynced, "synchronised", synced)
-    assert unsynced > 10 * synced
+    assert unsynced > (10 if dtype == "f32" else 2.5) * synced     # (bf16: the synchronised run sits on the rounding floor)
