@@ -194,3 +194,41 @@ def test_oracle_variables_roundtrip_by_reference_names(ck, tmp_path):
     for n in tensors:
         np.testing.assert_array_equal(back[n], tensors[n])
     assert "firstconv1" in back and any(n.endswith("moving_variance") for n in back)
+
+
+def test_table_and_bundle_roundtrip_properties(ck, tmp_path):
+    """hypothesis: any sorted set of keys/values survives build_table -> read_table at any block size; any dict of tensors
+    (names with '/', '_', digits; ranks 0-4; the dtypes TF stores for this model) survives save -> load."""
+    from hypothesis import given, settings, strategies as st
+
+    keys = st.lists(st.binary(min_size=1, max_size=40), min_size=0, max_size=120, unique=True)
+
+    @settings(max_examples=60, deadline=None)
+    @given(keys, st.integers(min_value=32, max_value=4096), st.data())
+    def table(ks, block_size, data):
+        items = [(k, data.draw(st.binary(max_size=64))) for k in sorted(ks)]
+        assert ck.read_table(ck.build_table(items, block_size=block_size)) == items
+
+    table()
+
+    name = st.text(alphabet="abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789_/", min_size=1, max_size=48)
+    dtype = st.sampled_from([np.float32, np.float64, np.int32, np.int64, np.uint8, np.float16, np.bool_])
+    shape = st.lists(st.integers(min_value=0, max_value=5), min_size=0, max_size=4)
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.dictionaries(name, st.tuples(dtype, shape), min_size=1, max_size=12), st.integers(0, 2 ** 31 - 1))
+    def bundle(spec, seed):
+        rng = np.random.RandomState(seed)
+        tensors = {n: np.asarray(rng.randn(*s) * 100).astype(d) for n, (d, s) in spec.items()}
+        counter[0] += 1
+        prefix = str(tmp_path / f"b{counter[0]}.ckpt")
+        ck.save(prefix, tensors, update_state=False)
+        back = ck.load(prefix)
+        assert set(back) == set(tensors)
+        for n, v in tensors.items():
+            assert back[n].dtype == v.dtype and back[n].shape == v.shape
+            np.testing.assert_array_equal(back[n], v)
+        assert [n for n, _ in ck.list_variables(prefix)] == sorted(tensors, key=lambda s: s.encode())
+
+    bundle()
