@@ -14,7 +14,11 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 size = int(sys.argv[3]) if len(sys.argv) > 3 else 112
 mode = sys.argv[4] if len(sys.argv) > 4 else "train"
 xin = sp.placeholder([B, 16, size, size, 3], dtype="bf16", training_graph=(mode == "train"))
-head = getattr(sp.p3d, graph)(xin, 0.5, B, mode == "train")
+if graph.startswith("gn:"):     # GroupNorm + CBAM graphs: gn:inference_p3d, gn:inference_p3d_decoder_block ...
+    from sap3d_tensorflow_b200.gn import p3d_gn
+    head = getattr(p3d_gn, graph[3:])(xin, 0.5, B, mode == "train")
+else:
+    head = getattr(sp.p3d, graph)(xin, 0.5, B, mode == "train")
 sess = sp.Session(head)
 x = torch.randn(B, 16, size, size, 3, device="cuda") * 0.3
 y = torch.rand(B, 16, size, size, device="cuda")
