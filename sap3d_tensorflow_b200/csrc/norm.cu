@@ -514,6 +514,204 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same two passes for the common big-tensor case y = relu?(norm(a)) with NO second operand (every decoder conv / deconv
+// -> BN -> ReLU, the stem).  The generic apply kernel re-reads ~100 per-channel constants per 8 elements (LSU-bound, 1.4 TB/s
+// in ncu) and the generic reduce kernel keeps one position per thread in flight at 127 registers (2.0 TB/s).  Here a thread
+// owns FOUR fixed channels, so its constants live in 16 registers, and FOUR positions are in flight per thread; at ~64
+// registers four 256-thread blocks are resident per SM (64 KB of loads in flight, what 6.5 TB/s x ~1 us latency needs).
+//   mask  : z = a*s + t;   g = dy unless (relu_out && !(relu?(z) > 0)) or (relu && !(z > 0))
+//   reduce: S_a = sum g, S_b = sum g*xhat,  xhat = a*rstd - mean*rstd
+//   apply : d a = s*g - a*A - B,  A = s*c1*rstd,  B = s*(c0 - c1*mean*rstd)   (== s*(g - c0 - xhat*c1));  frozen: s*g
+// block = 16 channel lanes (64 channels) x 16 position lanes; grid = (position slabs, C/64).
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Vec4;
+template <> struct Vec4<bf16> {
+  typedef uint2 Raw;
+  static SAP3D_DEVINL Raw load(const bf16* p) { return *reinterpret_cast<const uint2*>(p); }
+  static SAP3D_DEVINL void unpack(const Raw& u, float (&v)[4]) {
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static SAP3D_DEVINL void store(bf16* p, const float (&v)[4]) {
+    uint2 u;
+    u.x = pack_bf16x2(v[0], v[1]);
+    u.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+template <> struct Vec4<float> {
+  typedef float4 Raw;
+  static SAP3D_DEVINL Raw load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static SAP3D_DEVINL void unpack(const Raw& u, float (&v)[4]) { v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; }
+  static SAP3D_DEVINL void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+SAP3D_DEVINL void nob_mask(const float (&d)[4], const float (&av)[4], const float (&s)[4], const float (&t)[4], int relu1, int relu_out,
+                           float (&g)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float z = fmaf(av[j], s[j], t[j]);
+    const float r1 = relu1 ? fmaxf(z, 0.f) : z;
+    float u = d[j];
+    if (relu_out && !(r1 > 0.f)) u = 0.f;
+    g[j] = (relu1 && !(z > 0.f)) ? 0.f : u;
+  }
+}
+
+constexpr int NOB_INFLIGHT = 4;    // positions per thread per iteration
+constexpr int NOB_PLANES = 16;     // position lanes per block
+
+template <typename T>
+__global__ void __launch_bounds__(256, 3) apply_bwd_reduce_nob_kernel(const ApplyBwdArgs p) {
+  __shared__ float red[8][2][2][64];   // [warp][position lane pair within the warp][sum][channel]
+  const int cv = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  const int c = blockIdx.y * 64 + cv * 4;
+  const long long per = (p.P + p.rows - 1) / p.rows;
+  const long long pbeg = blockIdx.x * per, pend = pbeg + per < p.P ? pbeg + per : p.P;
+  const T* dy = reinterpret_cast<const T*>(p.dy);
+  const T* a = reinterpret_cast<const T*>(p.a);
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  if (c < p.C) {
+    float s[4], t[4], rs[4], mr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s[j] = p.s1 ? p.s1[c + j] : 1.f;
+      t[j] = p.t1 ? p.t1[c + j] : 0.f;
+      rs[j] = p.mean1 ? p.rstd1[c + j] : 0.f;
+      mr[j] = p.mean1 ? p.mean1[c + j] * rs[j] : 0.f;
+    }
+    const long long step = (long long)NOB_PLANES * p.C;
+    long long pos = pbeg + pl;
+    for (; pos + (NOB_INFLIGHT - 1) * NOB_PLANES < pend; pos += NOB_PLANES * NOB_INFLIGHT) {   // all loads first
+      const T* pd = dy + pos * p.C + c;
+      const T* pa = a + pos * p.C + c;
+      typename Vec4<T>::Raw rd[NOB_INFLIGHT], ra[NOB_INFLIGHT];
+#pragma unroll
+      for (int u = 0; u < NOB_INFLIGHT; ++u) {
+        rd[u] = Vec4<T>::load(pd + u * step);
+        ra[u] = Vec4<T>::load(pa + u * step);
+      }
+#pragma unroll
+      for (int u = 0; u < NOB_INFLIGHT; ++u) {
+        float d[4], av[4], g[4];
+        Vec4<T>::unpack(rd[u], d);
+        Vec4<T>::unpack(ra[u], av);
+        nob_mask(d, av, s, t, p.relu1, p.relu_out, g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[0][j] += g[j];
+          acc[1][j] += g[j] * fmaf(av[j], rs[j], -mr[j]);
+        }
+      }
+    }
+    for (; pos < pend; pos += NOB_PLANES) {   // ragged tail of the slab
+      float d[4], av[4], g[4];
+      Vec4<T>::unpack(Vec4<T>::load(dy + pos * p.C + c), d);
+      Vec4<T>::unpack(Vec4<T>::load(a + pos * p.C + c), av);
+      nob_mask(d, av, s, t, p.relu1, p.relu_out, g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[0][j] += g[j];
+        acc[1][j] += g[j] * fmaf(av[j], rs[j], -mr[j]);
+      }
+    }
+  }
+  // a warp holds two position lanes (lane >> 4) of the same 64 channels
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[warp][lane >> 4][i][(lane & 15) * 4 + j] = acc[i][j];
+  __syncthreads();
+  {
+    const int i = threadIdx.x >> 6, ch = threadIdx.x & 63;  // 4 sums x 64 channels; sums 2, 3 (second operand) are zero
+    float v = 0.f;
+    if (i < 2) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][0][i][ch] + red[w][1][i][ch];
+    }
+    const int cc = blockIdx.y * 64 + ch;
+    if (cc < p.C) p.partial[((long long)blockIdx.x * 4 + i) * p.C + cc] = v;
+  }
+}
+
+// grid = (slabs, C/64); the slab count is independent of the reduce pass
+template <typename T, bool ACC>
+__global__ void __launch_bounds__(256, 3) apply_bwd_nob_kernel(const ApplyBwdArgs p) {
+  const int cv = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  const int c = blockIdx.y * 64 + cv * 4;
+  if (c >= p.C) return;
+  const long long per = (p.P + gridDim.x - 1) / gridDim.x;
+  const long long pbeg = blockIdx.x * per, pend = pbeg + per < p.P ? pbeg + per : p.P;
+  const T* dy = reinterpret_cast<const T*>(p.dy);
+  const T* a = reinterpret_cast<const T*>(p.a);
+  T* da = reinterpret_cast<T*>(p.da);
+  float s[4], t[4], A[4], B[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s[j] = p.s1 ? p.s1[c + j] : 1.f;
+    t[j] = p.t1 ? p.t1[c + j] : 0.f;
+    if (p.batch_stats1) {
+      const float rs = p.rstd1[c + j], mu = p.mean1[c + j];
+      const float c0 = p.coef[c + j], c1 = p.coef[p.C + c + j];
+      A[j] = s[j] * c1 * rs;
+      B[j] = s[j] * (c0 - c1 * mu * rs);
+    } else {
+      A[j] = 0.f;
+      B[j] = 0.f;
+    }
+  }
+  const long long step = (long long)NOB_PLANES * p.C;
+  long long pos = pbeg + pl;
+  for (; pos + (NOB_INFLIGHT - 1) * NOB_PLANES < pend; pos += NOB_PLANES * NOB_INFLIGHT) {   // all loads first
+    const long long e = pos * p.C + c;
+    typename Vec4<T>::Raw rd[NOB_INFLIGHT], ra[NOB_INFLIGHT], ro[NOB_INFLIGHT];
+#pragma unroll
+    for (int u = 0; u < NOB_INFLIGHT; ++u) {
+      rd[u] = Vec4<T>::load(dy + e + u * step);
+      ra[u] = Vec4<T>::load(a + e + u * step);
+      if (ACC) ro[u] = Vec4<T>::load(da + e + u * step);
+    }
+#pragma unroll
+    for (int u = 0; u < NOB_INFLIGHT; ++u) {
+      float d[4], av[4], g[4], o[4];
+      Vec4<T>::unpack(rd[u], d);
+      Vec4<T>::unpack(ra[u], av);
+      nob_mask(d, av, s, t, p.relu1, p.relu_out, g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = fmaf(s[j], g[j], -fmaf(av[j], A[j], B[j]));
+      if (ACC) {
+        float old[4];
+        Vec4<T>::unpack(ro[u], old);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] += old[j];
+      }
+      Vec4<T>::store(da + e + u * step, o);
+    }
+  }
+  for (; pos < pend; pos += NOB_PLANES) {   // ragged tail of the slab
+    const long long e = pos * p.C + c;
+    float d[4], av[4], g[4], o[4];
+    Vec4<T>::unpack(Vec4<T>::load(dy + e), d);
+    Vec4<T>::unpack(Vec4<T>::load(a + e), av);
+    nob_mask(d, av, s, t, p.relu1, p.relu_out, g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaf(s[j], g[j], -fmaf(av[j], A[j], B[j]));
+    if (ACC) {
+      float old[4];
+      Vec4<T>::unpack(Vec4<T>::load(da + e), old);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] += old[j];
+    }
+    Vec4<T>::store(da + e, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // single-launch backward (cooperative grid): reduce -> grid.sync -> per-chunk finalize in shared memory -> apply.
 // grid = (rows, C/64) co-resident blocks; every block owns one 64-channel chunk and one slab of positions in both
 // passes, so the second pass re-reads what the block itself just read (L1/L2 hits for backbone-sized tensors).
@@ -777,6 +975,7 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
   p.da = da; p.db = db; p.acc_a = acc_a; p.acc_b = acc_b;
   float* ws = reinterpret_cast<float*>(workspace);
   const bool need_reduce = p.batch_stats1 || p.batch_stats2 || dgamma1 || dbeta1 || dgamma2 || dbeta2;
+  const bool nob = b == nullptr && db == nullptr && !p.batch_stats2;   // y = relu?(norm(a)): the register-resident kernels
   if (phase == 2) {
     if (!workspace) return set_error("affine_act_bwd: workspace required");
     p.coef = ws;
@@ -814,7 +1013,17 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
         return 0;
       }
     }
-    if (dtype == SAP3D_BF16) apply_bwd_reduce_kernel<bf16><<<rgrid, 256, 0, st>>>(p);
+    if (nob) {   // no second operand: constants in registers, four positions in flight, four blocks per SM
+      long long r3 = (4 * 148 + chunks - 1) / chunks;
+      if (r3 > (P + 63) / 64) r3 = (P + 63) / 64;
+      if (r3 > 296) r3 = 296;
+      if (r3 < 1) r3 = 1;
+      rows = r3;
+      p.rows = (int)rows;
+      dim3 g3((unsigned)rows, (unsigned)chunks);
+      if (dtype == SAP3D_BF16) apply_bwd_reduce_nob_kernel<bf16><<<g3, 256, 0, st>>>(p);
+      else apply_bwd_reduce_nob_kernel<float><<<g3, 256, 0, st>>>(p);
+    } else if (dtype == SAP3D_BF16) apply_bwd_reduce_kernel<bf16><<<rgrid, 256, 0, st>>>(p);
     else apply_bwd_reduce_kernel<float><<<rgrid, 256, 0, st>>>(p);
     if (check_launch("affine_act_bwd reduce")) return 1;
     apply_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, st>>>(p.partial, (int)rows, C, count, ws, dgamma1, dbeta1, dgamma2, dbeta2);
@@ -823,7 +1032,21 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
   }
   if (phase != 1 && (da || db)) {
     const long long nvec = P * C / 8;
-    if (dtype == SAP3D_BF16) apply_bwd_kernel<bf16><<<ew_grid(nvec), 256, 0, st>>>(p);
+    if (nob && da) {
+      const int chunks = (C + 63) / 64;
+      long long slabs = (8 * 148 + chunks - 1) / chunks;           // two waves of four blocks per SM
+      const long long max_slabs = (P + 63) / 64;
+      if (slabs > max_slabs) slabs = max_slabs;
+      if (slabs < 1) slabs = 1;
+      dim3 ag((unsigned)slabs, (unsigned)chunks);
+      if (dtype == SAP3D_BF16) {
+        if (acc_a) apply_bwd_nob_kernel<bf16, true><<<ag, 256, 0, st>>>(p);
+        else apply_bwd_nob_kernel<bf16, false><<<ag, 256, 0, st>>>(p);
+      } else {
+        if (acc_a) apply_bwd_nob_kernel<float, true><<<ag, 256, 0, st>>>(p);
+        else apply_bwd_nob_kernel<float, false><<<ag, 256, 0, st>>>(p);
+      }
+    } else if (dtype == SAP3D_BF16) apply_bwd_kernel<bf16><<<ew_grid(nvec), 256, 0, st>>>(p);
     else apply_bwd_kernel<float><<<ew_grid(nvec), 256, 0, st>>>(p);
     if (check_launch("affine_act_bwd apply")) return 1;
   }

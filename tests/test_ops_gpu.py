@@ -104,6 +104,53 @@ def test_affine_act_fwd_bwd(A, dtn, tdt, tol, pattern, shape):
 
 
 @pytest.mark.parametrize("dtn,tdt,tol", DT)
+@pytest.mark.parametrize("variant", ["relu_bn", "bn", "bn_relu_out", "frozen_relu", "relu_bn_acc"])
+@pytest.mark.parametrize("shape", [(2, 4, 40, 64, 256), (3, 5, 61, 67, 72)], ids=["decoder", "ragged"])
+def test_bn_backward_without_second_operand_large(A, dtn, tdt, tol, variant, shape):
+    """y = relu?(norm(a)) on tensors above the cooperative-launch limit: the register-resident reduce / apply kernels
+    (apply_bwd_reduce_nob / apply_bwd_nob: four fixed channels per thread, four positions in flight).  "ragged": channels not a
+    multiple of 64, positions not a multiple of anything; "frozen": moving-statistics norm (no reductions in d a); "acc": the
+    data gradient is accumulated onto an existing one."""
+    torch.manual_seed(11)
+    dev = "cuda"
+    dt = A.BF16 if dtn == "bf16" else A.F32
+    N, D, H, W, Cc = shape
+    P = N * D * H * W
+    relu1 = int(variant in ("relu_bn", "frozen_relu", "relu_bn_acc"))
+    relu_out = int(variant == "bn_relu_out")
+    training = variant != "frozen_relu"
+    acc = int(variant == "relu_bn_acc")
+    a = (torch.randn(N, D, H, W, Cc, device=dev) * 1.5 + 0.7).to(tdt)
+    dy = torch.randn(N, D, H, W, Cc, device=dev).to(tdt)
+    g1, b1 = torch.rand(Cc, device=dev) + 0.5, torch.randn(Cc, device=dev) * 0.1
+    mm, mv = torch.randn(Cc, device=dev) * 0.3 + 0.6, torch.rand(Cc, device=dev) + 1.5
+    mm0, mv0 = mm.clone(), mv.clone()
+    f = lambda: torch.empty(Cc, device=dev)  # noqa: E731
+    s1, t1, m1, r1 = f(), f(), f(), f()
+    A.check(A.lib.sap3d_bn_finalize(A.ptr(_stats(a)), 1, Cc, float(P), A.ptr(g1), A.ptr(b1), A.ptr(mm), A.ptr(mv), int(training), 0.99,
+                                    1e-3, A.ptr(s1), A.ptr(t1), A.ptr(m1), A.ptr(r1), stream()), "fin")
+    af = a.float().requires_grad_(True)
+    g1r, b1r = g1.clone().requires_grad_(True), b1.clone().requires_grad_(True)
+    z = tfs.batch_norm(af, g1r, b1r, mm0, mv0, training)[0]
+    ref = torch.relu(z) if (relu1 or relu_out) else z
+    ref.backward(dy.float())
+    base = (torch.randn(N, D, H, W, Cc, device=dev) * 0.5).to(tdt)
+    da = base.clone() if acc else torch.empty_like(a)
+    dg1, db1 = torch.zeros(Cc, device=dev), torch.zeros(Cc, device=dev)
+    ws = torch.zeros(A.lib.sap3d_affine_act_bwd_workspace(Cc) // 4 + 16, device=dev)
+    A.check(A.lib.sap3d_affine_act_bwd(dt, A.ptr(dy), A.ptr(a), A.ptr(s1), A.ptr(t1), A.ptr(m1) if training else None,
+                                       A.ptr(r1) if training else None, relu1, None, None, None, None, None, 0, relu_out, P, Cc,
+                                       A.ptr(da), acc, None, 0, A.ptr(dg1), A.ptr(db1), None, None, A.ptr(ws), stream()), "bwd")
+    torch.cuda.synchronize()
+    tol = max(tol, 1e-3)            # millions of elements: single ReLU-mask flips at |z| ~ 1e-7
+    want = af.grad + (base.float() if acc else 0)
+    assert rel(da, want) < 3 * tol, rel(da, want)
+    assert rel(db1, b1r.grad) < 3 * tol
+    if training:        # (a frozen norm's gamma is not trained by any graph: its x-hat is not formed)
+        assert rel(dg1, g1r.grad) < 3 * tol
+
+
+@pytest.mark.parametrize("dtn,tdt,tol", DT)
 @pytest.mark.parametrize("P", [2 * 37, 2 * 4 * 28 * 28], ids=["tiny", "stage1"])
 def test_bn_backward_in_two_phases_over_two_replicas(A, dtn, tdt, tol, P):
     """sap3d_affine_act_bwd_sync (synchronised BatchNorm): two 'replicas' each own half of the positions; phase 1 leaves
