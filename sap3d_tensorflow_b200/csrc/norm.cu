@@ -517,8 +517,8 @@ __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs p) {
 // The same two passes for the common big-tensor case y = relu?(norm(a)) with NO second operand (every decoder conv / deconv
 // -> BN -> ReLU, the stem).  The generic apply kernel re-reads ~100 per-channel constants per 8 elements (LSU-bound, 1.4 TB/s
 // in ncu) and the generic reduce kernel keeps one position per thread in flight at 127 registers (2.0 TB/s).  Here a thread
-// owns FOUR fixed channels, so its constants live in 16 registers, and FOUR positions are in flight per thread; at ~64
-// registers four 256-thread blocks are resident per SM (64 KB of loads in flight, what 6.5 TB/s x ~1 us latency needs).
+// owns FOUR fixed channels, so its constants live in 16 registers, and FOUR positions are in flight per thread; at 80
+// registers three 256-thread blocks are resident per SM (48 KB of loads in flight, what 6.5 TB/s x ~1 us latency needs).
 //   mask  : z = a*s + t;   g = dy unless (relu_out && !(relu?(z) > 0)) or (relu && !(z > 0))
 //   reduce: S_a = sum g, S_b = sum g*xhat,  xhat = a*rstd - mean*rstd
 //   apply : d a = s*g - a*A - B,  A = s*c1*rstd,  B = s*(c0 - c1*mean*rstd)   (== s*(g - c0 - xhat*c1));  frozen: s*g
@@ -1013,8 +1013,8 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
         return 0;
       }
     }
-    if (nob) {   // no second operand: constants in registers, four positions in flight, four blocks per SM
-      long long r3 = (4 * 148 + chunks - 1) / chunks;
+    if (nob) {   // no second operand: constants in registers, four positions in flight, one wave of three blocks per SM
+      long long r3 = (3 * 148 + chunks - 1) / chunks;
       if (r3 > (P + 63) / 64) r3 = (P + 63) / 64;
       if (r3 > 296) r3 = 296;
       if (r3 < 1) r3 = 1;
@@ -1034,7 +1034,7 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
     const long long nvec = P * C / 8;
     if (nob && da) {
       const int chunks = (C + 63) / 64;
-      long long slabs = (8 * 148 + chunks - 1) / chunks;           // two waves of four blocks per SM
+      long long slabs = (6 * 148 + chunks - 1) / chunks;           // two waves of three blocks per SM
       const long long max_slabs = (P + 63) / 64;
       if (slabs > max_slabs) slabs = max_slabs;
       if (slabs < 1) slabs = 1;
