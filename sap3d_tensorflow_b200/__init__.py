@@ -5,7 +5,7 @@ utils/metrics.py); all arithmetic runs in hand-written sm_100a kernels behind th
 include/sap3d.h (lib/libsap3d_b200.so).  There is no CPU or PyTorch fallback path.
 """
 from . import _abi  # noqa: F401  (raises ImportError when the CUDA library has not been built)
-from . import checkpoint, gn, metrics, network, p3d, video  # noqa: F401
+from . import checkpoint, dataflow, gn, metrics, network, p3d, video  # noqa: F401
 from .session import Session, placeholder  # noqa: F401
 
-__all__ = ["Session", "placeholder", "p3d", "network", "metrics", "gn", "video", "checkpoint"]
+__all__ = ["Session", "placeholder", "p3d", "network", "metrics", "gn", "video", "checkpoint", "dataflow"]
