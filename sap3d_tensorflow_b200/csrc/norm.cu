@@ -982,8 +982,8 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
   } else if (need_reduce) {
     if (!workspace) return set_error("affine_act_bwd: workspace required");
     const int chunks = (C + 63) / 64;
-    long long rows = (2 * 148 + chunks - 1) / chunks;
-    const long long max_rows = (P + 31) / 32;
+    long long rows = (2 * 148) / chunks;   // floor: rows x chunks must fit the 2 x 148 co-resident blocks of the cooperative form
+    const long long max_rows = (P + 31) / 32;   // (ceil put C = 1024 at 19 x 16 = 304 blocks: every stage-3 block tail fell back to 3 launches)
     if (rows > max_rows) rows = max_rows;
     if (rows > 296) rows = 296;
     if (rows < 1) rows = 1;
