@@ -1,5 +1,5 @@
 """GPU probe: conv family (tcgen05 + SIMT) against the torch oracle.  Usage (on a B200 box):
-    python tools/probe_conv.py > gpurun_out/probe_conv.log 2>&1
+    python tests/probe_conv.py > gpurun_out/probe_conv.log 2>&1
 Development aid; the real parity tests live in tests/ (pytest -m gpu).
 """
 import ctypes as C

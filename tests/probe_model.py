@@ -1,5 +1,5 @@
 """GPU probe: whole-graph forward / training-step parity against the CPU oracle.
-    python tools/probe_model.py [graph] [size] [batch] > gpurun_out/probe_model.log 2>&1
+    python tests/probe_model.py [graph] [size] [batch] > gpurun_out/probe_model.log 2>&1
 """
 import os
 import sys
