@@ -39,3 +39,18 @@ def test_batched_gemm_nt_matches_bmm(lib_built, case):
     if batch > 1:                                       # and sample n really used B_n, not B_0
         wrong = torch.bmm(a.float(), b[:1].float().expand(batch, -1, -1).transpose(1, 2))
         assert ((got[1:, :, :rows_b] - wrong[1:]).norm() / ref[1:].norm()).item() > 0.5
+
+
+def test_model_parity_with_batched_attention(lib_built):
+    """the engine's attention core with one launch per product for the whole batch (SAP3D_ATTN_BATCHED=1, read at import):
+    the graph-level parity tests of the attention graphs must hold with it switched on (child process)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SAP3D_ATTN_BATCHED="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_model_gpu.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "forward_parity or training_step_parity or reduces_loss or gradcheck"], env=env, cwd=root, capture_output=True,
+                       text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
