@@ -225,6 +225,12 @@ int sap3d_flash_attn_bwd(const void* q, const void* k, const void* v, const void
  * rows, the remaining output columns are computed against zeros */
 int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t rows_b, void* C, int64_t ldc, int32_t M,
                   int32_t N, int32_t K, int32_t out_f32, int32_t accumulate, void* stream);
+/* `batch` independent products in ONE launch: sample n reads A + n*stride_a and B + n*stride_b and writes C + n*stride_c (element
+ * strides, multiples of 8).  Replaces the per-sample loops over tf.matmul(g, f, transpose_b=True) / tf.matmul(beta, h) of
+ * utils/network.py:176-180 for the attention blocks that are not on the fused path. */
+int sap3d_gemm_nt_batched(const void* A, int64_t lda, int64_t stride_a, const void* B, int64_t ldb, int64_t stride_b, int32_t rows_b,
+                          void* C, int64_t ldc, int64_t stride_c, int32_t M, int32_t N, int32_t K, int32_t batch, int32_t out_f32,
+                          int32_t accumulate, void* stream);
 /* D[M][N] (fp32) += sum_pos P[pos][m] Q[pos][n]  (M, N % 64 == 0); the caller zeroes D */
 int sap3d_gemm_tn(const void* P, int64_t ldp, const void* Q, int64_t ldq, float* D, int64_t ldd, int32_t M, int32_t N,
                   int32_t Kpos, void* stream);

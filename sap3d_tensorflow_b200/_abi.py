@@ -140,6 +140,7 @@ _sig("sap3d_flash_attn_fwd", [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _
 _sig("sap3d_flash_attn_bwd_workspace", [_i32, _i32, _i32, _i32], C.c_size_t)
 _sig("sap3d_flash_attn_bwd", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp])
 _sig("sap3d_gemm_nt", [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp])
+_sig("sap3d_gemm_nt_batched", [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp])
 _sig("sap3d_gemm_tn", [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp])
 _sig("sap3d_softmax_rows", [_i32, _vp, _vp, _i64, _i32, _i32, _i32, _vp])
 _sig("sap3d_softmax_bwd_rows", [_vp, _vp, _i64, _i32, _i32, _vp])

@@ -822,19 +822,22 @@ int sap3d_conv_wgrad(const sap3d_conv_desc* d, const void* x0, const void* x1, c
 // ---- plain GEMMs on the same tensor-core kernels (attention matmuls, utils/network.py:184,186) ----
 extern "C" {
 
-int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t rows_b, void* Cout, int64_t ldc, int32_t M,
-                  int32_t N, int32_t K, int32_t out_f32, int32_t accumulate, void* stream) {
+static int gemm_nt_impl(const void* A, int64_t lda, int64_t stride_a, const void* B, int64_t ldb, int64_t stride_b, int32_t rows_b,
+                        void* Cout, int64_t ldc, int64_t stride_c, int32_t M, int32_t N, int32_t K, int32_t batch, int32_t out_f32,
+                        int32_t accumulate, void* stream) {
   if (require_device()) return 1;
   if (!A || !B || !Cout) return set_error("gemm_nt: NULL pointer");
   if (K % 64 != 0 || ldb != K || N % 8 != 0 || lda % 8 != 0 || ldc % 8 != 0 || rows_b < 1 || rows_b > N)
     return set_error("gemm_nt: need K %% 64 == 0, ldb == K, N %% 8 == 0, lda/ldc %% 8 == 0, rows_b <= N (M=%d N=%d K=%d lda=%lld ldb=%lld)",
                      M, N, K, (long long)lda, (long long)ldb);
+  if (batch < 1 || (batch > 1 && (stride_a % 8 != 0 || stride_b % 8 != 0 || stride_c % 8 != 0)))
+    return set_error("gemm_nt: batch >= 1 and batch strides %% 8 == 0 required");
   TcProblem pb;
   TcView v;
   v.base = A;
   v.C = K;
-  v.dim[0] = M; v.dim[1] = 1; v.dim[2] = 1; v.dim[3] = 1;
-  v.stride[0] = lda; v.stride[1] = 0; v.stride[2] = 0; v.stride[3] = 0;
+  v.dim[0] = M; v.dim[1] = 1; v.dim[2] = 1; v.dim[3] = batch;
+  v.stride[0] = lda; v.stride[1] = 0; v.stride[2] = 0; v.stride[3] = batch > 1 ? stride_a : 0;
   pb.views.push_back(v);
   TcClassH cls;
   cls.out_ofs = 0;
@@ -846,8 +849,8 @@ int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int32_
   t.nch = K;
   cls.taps.push_back(t);
   pb.classes.push_back(cls);
-  pb.ext[0] = M; pb.ext[1] = 1; pb.ext[2] = 1; pb.ext[3] = 1;
-  pb.so[0] = ldc; pb.so[1] = 0; pb.so[2] = 0; pb.so[3] = 0;
+  pb.ext[0] = M; pb.ext[1] = 1; pb.ext[2] = 1; pb.ext[3] = batch;
+  pb.so[0] = ldc; pb.so[1] = 0; pb.so[2] = 0; pb.so[3] = batch > 1 ? stride_c : 0;
   pb.B = B;
   pb.Ktot = K;
   pb.rowsB = rows_b;  // rows beyond rows_b are zero-filled by the TMA unit
@@ -855,9 +858,22 @@ int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int32_
   pb.out = Cout;
   pb.bias = nullptr; pb.stats = nullptr; pb.scale = nullptr; pb.shift = nullptr;
   pb.relu = 0; pb.accumulate = accumulate; pb.out_f32 = out_f32; pb.force_block_n = 0;
+  pb.b_batch = batch;
+  pb.b_batch_stride = stride_b;
   char err[512];
   if (tc_launch(pb, reinterpret_cast<cudaStream_t>(stream), err, sizeof(err))) return set_error("%s", err);
   return 0;
+}
+
+int sap3d_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t rows_b, void* Cout, int64_t ldc, int32_t M,
+                  int32_t N, int32_t K, int32_t out_f32, int32_t accumulate, void* stream) {
+  return gemm_nt_impl(A, lda, 0, B, ldb, 0, rows_b, Cout, ldc, 0, M, N, K, 1, out_f32, accumulate, stream);
+}
+
+int sap3d_gemm_nt_batched(const void* A, int64_t lda, int64_t stride_a, const void* B, int64_t ldb, int64_t stride_b, int32_t rows_b,
+                          void* Cout, int64_t ldc, int64_t stride_c, int32_t M, int32_t N, int32_t K, int32_t batch, int32_t out_f32,
+                          int32_t accumulate, void* stream) {
+  return gemm_nt_impl(A, lda, stride_a, B, ldb, stride_b, rows_b, Cout, ldc, stride_c, M, N, K, batch, out_f32, accumulate, stream);
 }
 
 int sap3d_gemm_tn(const void* P, int64_t ldp, const void* Q, int64_t ldq, float* D, int64_t ldd, int32_t M, int32_t N,

@@ -60,6 +60,7 @@ struct alignas(64) TcConvParams {
   const float* scale;
   const float* shift;
   int relu, accumulate, out_f32;
+  int b_batched;       // the weight-side operand is per sample: third TMA coordinate = the tile's batch index
 };
 
 // column sums of a 32(lanes) x 32(values) block: on return lane l holds the sum over all lanes of
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
           for (int sub = 0; sub < MT; ++sub)
             tma_load_5d(sa + sub * A_BYTES, amap, full, (tap.c0 + ch) * 64, w0s[sub] + tap.dw, h0s[sub] + tap.dh, d0s[sub] + tap.dd,
                         n0s[sub]);
-          tma_load_2d(sa + MT * A_BYTES, &p.bmap, full, tap.kofs + ch * 64, nt * BLOCK_N);
+          tma_load_3d(sa + MT * A_BYTES, &p.bmap, full, tap.kofs + ch * 64, nt * BLOCK_N, p.b_batched ? n0s[0] : 0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
             for (int sub = 0; sub < MT; ++sub)
               tma_load_5d(sa + sub * A_BYTES, amap, full, (tap.c0 + ch) * 64, t.w0s[sub] + tap.dw, t.h0s[sub] + tap.dh, t.d0s[sub] + tap.dd,
                           t.n0s[sub]);
-            tma_load_2d(sa + MT * A_BYTES, &p.bmap, full, tap.kofs + ch * 64, t.nt * BLOCK_N);
+            tma_load_3d(sa + MT * A_BYTES, &p.bmap, full, tap.kofs + ch * 64, t.nt * BLOCK_N, p.b_batched ? t.n0s[0] : 0);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -730,17 +731,19 @@ static int encode_view(CUtensorMap* m, const void* base, int C, const int dim[4]
   return 0;
 }
 
-static int encode_b(CUtensorMap* m, const void* base, int Ktot, int rows, int block_n, char* err, size_t errlen) {
+// [batch][rows][Ktot] bf16 (batch = 1 for convolutions) -> rank-3 map {K, rows, batch}, box {64, block_n, 1}
+static int encode_b(CUtensorMap* m, const void* base, int Ktot, int rows, int block_n, int batch, long long batch_stride, char* err,
+                    size_t errlen) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     return 1;
   }
-  cuuint64_t gdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)Ktot * 2};
-  cuuint32_t bdim[2] = {64u, (cuuint32_t)block_n};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, bdim, estr,
+  cuuint64_t gdim[3] = {(cuuint64_t)Ktot, (cuuint64_t)rows, (cuuint64_t)(batch < 1 ? 1 : batch)};
+  cuuint64_t gstr[2] = {(cuuint64_t)Ktot * 2, (cuuint64_t)(batch > 1 ? batch_stride * 2 : (long long)Ktot * 2 * rows)};
+  cuuint32_t bdim[3] = {64u, (cuuint32_t)block_n, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, bdim, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -765,6 +768,7 @@ static void merge_dims(const TcProblem& pb, Merged& m) {
   }
   m.views = pb.views;
   m.classes = pb.classes;
+  if (pb.b_batch > 1) return;   // the batch stays dim 3: a tile's n coordinate selects its B matrix
   // try to fold dim i+1 into dim i (W<-H, then <-D, then <-N) while geometry allows
   int i = 0;
   int live = 4;
@@ -802,13 +806,13 @@ static void merge_dims(const TcProblem& pb, Merged& m) {
   }
 }
 
-static long long choose_box(const int ext[4], int box[4]) {
+static long long choose_box(const int ext[4], int box[4], int max_bn = 128) {
   long long best = -1;
   int bb[4] = {1, 1, 1, 1};
   for (int bw = 1; bw <= std::min(ext[0], 128); ++bw) {
     for (int bh = 1; bh <= std::min(ext[1], 128 / bw); ++bh) {
       for (int bd = 1; bd <= std::min(ext[2], 128 / (bw * bh)); ++bd) {
-        int bn = std::min(ext[3], 128 / (bw * bh * bd));
+        int bn = std::min(std::min(ext[3], max_bn), 128 / (bw * bh * bd));
         if (bn < 1) continue;
         long long tiles = (long long)((ext[0] + bw - 1) / bw) * ((ext[1] + bh - 1) / bh) * ((ext[2] + bd - 1) / bd) *
                           ((ext[3] + bn - 1) / bn);
@@ -828,7 +832,7 @@ int tc_plan_tiles(const TcProblem& pb) {
   Merged m;
   merge_dims(pb, m);
   int box[4];
-  return (int)choose_box(m.ext, box);
+  return (int)choose_box(m.ext, box, pb.b_batch > 1 ? 1 : 128);
 }
 
 template <int BLOCK_N, int STAGES, int MT>
@@ -928,7 +932,11 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
   static thread_local TcConvParams prm;  // ~4 KB, filled per call
   memset(&prm, 0, sizeof(prm));
   int box[4];
-  long long m_tiles = choose_box(m.ext, box);
+  long long m_tiles = choose_box(m.ext, box, pb.b_batch > 1 ? 1 : 128);
+  if (pb.b_batch > 1 && (pb.b_batch != m.ext[3] || m.classes.size() != 1)) {
+    snprintf(err, errlen, "tc_launch: batched B needs ext[3] == b_batch and one class");
+    return 1;
+  }
   int block_n = pb.force_block_n;
   if (block_n == 0) {
     if (pb.cout <= 64) block_n = 64;
@@ -939,7 +947,8 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
   for (size_t v = 0; v < m.views.size(); ++v)
     if (encode_view(&prm.amap[v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, box, err, errlen))
       return 1;
-  if (encode_b(&prm.bmap, pb.B, pb.Ktot, pb.rowsB, block_n, err, errlen)) return 1;
+  if (encode_b(&prm.bmap, pb.B, pb.Ktot, pb.rowsB, block_n, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
+  prm.b_batched = pb.b_batch > 1 ? 1 : 0;
   int ntap = 0;
   for (size_t c = 0; c < m.classes.size(); ++c) {
     TcClass& dc = prm.cls[c];
@@ -997,6 +1006,7 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
   // two M sub-tiles per CTA when the problem still fills the GPU several times over
   const long long ctas1 = (long long)prm.ncls * prm.m_tiles * prm.n_tiles;
   int mt = (pb.force_mt ? pb.force_mt : (ctas1 >= 4 * 148 ? 2 : 1));
+  if (pb.b_batch > 1) mt = 1;   // the sub-tiles of a unit share one B tile, so they must belong to one sample
   const long long m_groups = (prm.m_tiles + mt - 1) / mt;
   long long grid = (long long)prm.ncls * m_groups * prm.n_tiles;
   if (grid <= 0 || grid > 0x7fffffffll) {

@@ -46,6 +46,10 @@ struct TcProblem {
   int force_block_n;  // 0 = auto
   int force_mt = 0;   // 0 = auto, 1 / 2 = M sub-tiles per CTA
   int force_split = 0;// 0 = auto, 2 / 4 = split-K cluster size, -1 = never
+  // batched GEMM (one B matrix per sample): ext[3] is the batch; sample n uses B + n * b_batch_stride.  Row tiles then never
+  // span samples and dims are not merged.  1 = one shared B (every convolution).
+  int b_batch = 1;
+  long long b_batch_stride = 0;   // elements
 };
 
 // number of M tiles (per class) the launcher will use for these extents (after dim merging)

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence
 
@@ -861,8 +862,72 @@ class _AttnCoreOp:
                 self.dfp = torch.empty(B, self.Nk, self.dkp, device=dev, dtype=bf) if self.pad else None
         elif tr:
             self.ds = torch.empty_like(self.beta)
+        if self.use_tc and self.BATCHED:
+            # all samples in one launch per product (sap3d_gemm_nt_batched): score / gradient buffers for the whole batch, and the
+            # transposed operands that turn the two P^T.X products into NT form (query axis zero-padded to a multiple of 64)
+            self.Nqp = (self.Nq + 63) // 64 * 64
+            bf = torch.bfloat16
+            self.logits = torch.empty(B, self.Nq, self.Nkp, device=dev, dtype=torch.float32)
+            if tr:
+                self.ds = torch.empty(B, self.Nq, self.Nkp, device=dev, dtype=bf)
+                self.ft = torch.zeros(B, self.dkp, self.Nkp, device=dev, dtype=bf)
+                self.pt = torch.zeros(B, self.Nkp, self.Nqp, device=dev, dtype=bf)     # beta^T, then dS^T
+                self.dot = torch.zeros(B, self.dv, self.Nqp, device=dev, dtype=bf)     # dO^T
+                self.gt = torch.zeros(B, self.dkp, self.Nqp, device=dev, dtype=bf)     # g^T
+                self.dv32 = self.dk32 = None
 
     FLASH = True
+    BATCHED = os.environ.get("SAP3D_ATTN_BATCHED", "0") == "1"   # opt-in while it is being measured
+
+    def _nt(self, a, lda, sa, b, ldb, sb, rows_b, c, ldc, sc, M, N, K, out_f32, what):
+        A.check(A.lib.sap3d_gemm_nt_batched(A.ptr(a), lda, sa, A.ptr(b), ldb, sb, rows_b, A.ptr(c), ldc, sc, M, N, K, self.B, out_f32, 0,
+                                            self.eng.stream), what + " " + self.name)
+
+    def _fwd_tc_batched(self):
+        e, st = self.eng, self.eng.stream
+        B, Nq, Nk, Nkp, dkp, dv = self.B, self.Nq, self.Nk, self.Nkp, self.dkp, self.dv
+        if self.pad:
+            A.check(A.lib.sap3d_pad_channels(e.dt, A.ptr(self.g.buf), A.ptr(self.gp), B * Nq, self.dk, dkp, 0, 0, st), "pad g")
+            A.check(A.lib.sap3d_pad_channels(e.dt, A.ptr(self.f.buf), A.ptr(self.fp), B * Nk, self.dk, dkp, 0, 0, st), "pad f")
+            e._count(2)
+        gq = self.gp if self.pad else self.g.buf
+        fk = self.fp if self.pad else self.f.buf
+        A.check(A.lib.sap3d_transpose(e.dt, A.ptr(self.h.buf), A.ptr(self.vt), B, Nk, dv, dv, Nkp, Nk * dv, dv * Nkp, st), "transpose h")
+        self._nt(gq, dkp, Nq * dkp, fk, dkp, Nk * dkp, Nk, self.logits, Nkp, Nq * Nkp, Nq, Nkp, dkp, 1, "QK^T")
+        A.check(A.lib.sap3d_softmax_rows(A.F32, A.ptr(self.logits), A.ptr(self.beta), B * Nq, Nk, Nkp, Nkp, st), "softmax")
+        self._nt(self.beta, Nkp, Nq * Nkp, self.vt, Nkp, dv * Nkp, dv, self.o.buf, dv, Nq * dv, Nq, dv, Nkp, 0, "PV")
+        e._count(4)
+
+    def _bwd_tc_batched(self):
+        e, st = self.eng, self.eng.stream
+        B, Nq, Nk, Nkp, Nqp, dkp, dv, dk = self.B, self.Nq, self.Nk, self.Nkp, self.Nqp, self.dkp, self.dv, self.dk
+        gq = self.gp if self.pad else self.g.buf
+        fk = self.fp if self.pad else self.f.buf
+        do = self.o.grad
+        dh = self.h.ensure_grad()
+        dg = self.dgp if self.pad else self.g.ensure_grad()
+        df = self.dfp if self.pad else self.f.ensure_grad()
+        tr = lambda src, dst, R, Cc, ld_in, ld_out, what: A.check(  # noqa: E731
+            A.lib.sap3d_transpose(e.dt, A.ptr(src), A.ptr(dst), B, R, Cc, ld_in, ld_out, R * ld_in, Cc * ld_out, st), what)
+        # dV = P^T dO  as  (P^T)[Nk x Nq] . (dO^T)[dv x Nq]^T
+        tr(self.beta, self.pt, Nq, Nkp, Nkp, Nqp, "transpose P")
+        tr(do, self.dot, Nq, dv, dv, Nqp, "transpose dO")
+        self._nt(self.pt, Nqp, Nkp * Nqp, self.dot, Nqp, dv * Nqp, dv, dh, dv, Nk * dv, Nk, dv, Nqp, 0, "dV")
+        # dP = dO V^T ;  dS = P o (dP - rowsum(dP o P))
+        self._nt(do, dv, Nq * dv, self.h.buf, dv, Nk * dv, Nk, self.ds, Nkp, Nq * Nkp, Nq, Nkp, dv, 0, "dP")
+        A.check(A.lib.sap3d_softmax_bwd_rows(A.ptr(self.beta), A.ptr(self.ds), B * Nq, Nk, Nkp, st), "softmax bwd")
+        # dQ = dS F  as  dS[Nq x Nk] . (F^T)[dk x Nk]^T
+        tr(fk, self.ft, Nk, dkp, dkp, Nkp, "transpose f")
+        self._nt(self.ds, Nkp, Nq * Nkp, self.ft, Nkp, dkp * Nkp, dkp, dg, dkp, Nq * dkp, Nq, dkp, Nkp, 0, "dQ")
+        # dK = dS^T G  as  (dS^T)[Nk x Nq] . (G^T)[dk x Nq]^T
+        tr(self.ds, self.pt, Nq, Nkp, Nkp, Nqp, "transpose dS")
+        tr(gq, self.gt, Nq, dkp, dkp, Nqp, "transpose g")
+        self._nt(self.pt, Nqp, Nkp * Nqp, self.gt, Nqp, dkp * Nqp, dkp, df, dkp, Nk * dkp, Nk, dkp, Nqp, 0, "dK")
+        e._count(10)
+        if self.pad:
+            A.check(A.lib.sap3d_pad_channels(e.dt, A.ptr(self.dgp), A.ptr(self.g.ensure_grad()), B * Nq, dk, dkp, 1, 0, st), "unpad dg")
+            A.check(A.lib.sap3d_pad_channels(e.dt, A.ptr(self.dfp), A.ptr(self.f.ensure_grad()), B * Nk, dk, dkp, 1, 0, st), "unpad df")
+            e._count(2)
 
     def _bwd_flash(self):
         e = self.eng
@@ -931,7 +996,7 @@ class _AttnCoreOp:
         if self.use_flash:
             return self._fwd_flash()
         if self.use_tc:
-            return self._fwd_tc()
+            return self._fwd_tc_batched() if self.BATCHED else self._fwd_tc()
         A.check(A.lib.sap3d_attention_fwd(e.dt, A.ptr(self.g.buf), A.ptr(self.f.buf), A.ptr(self.h.buf), A.ptr(self.beta),
                                           A.ptr(self.o.buf), self.B, self.Nq, self.Nk, self.dk, self.dv, self.dk, self.dk, self.dv,
                                           self.ldb, self.dv, e.stream), "attention_fwd " + self.name)
@@ -947,7 +1012,7 @@ class _AttnCoreOp:
         if self.use_flash:
             return self._bwd_flash()
         if self.use_tc:
-            return self._bwd_tc()
+            return self._bwd_tc_batched() if self.BATCHED else self._bwd_tc()
         A.check(A.lib.sap3d_attention_bwd(e.dt, A.ptr(self.g.buf), A.ptr(self.f.buf), A.ptr(self.h.buf), A.ptr(self.beta),
                                           A.ptr(self.o.grad), A.ptr(self.ds), A.ptr(self.g.ensure_grad()), A.ptr(self.f.ensure_grad()),
                                           A.ptr(self.h.ensure_grad()), self.B, self.Nq, self.Nk, self.dk, self.dv, self.dk, self.dk,
