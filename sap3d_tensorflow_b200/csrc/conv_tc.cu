@@ -45,7 +45,8 @@ struct TcClass {
 struct alignas(64) TcConvParams {
   CUtensorMap amap[TC_MAX_MAPS];
   CUtensorMap bmap;
-  CUtensorMap bmap_half;   // box {64, BLOCK_N / 2}: the weight-tile half one CTA of a 2-CTA cluster multicasts
+  CUtensorMap bmap_half;     // box {64, BLOCK_N / 2}: the part of a weight tile one CTA of a 2-CTA cluster multicasts
+  CUtensorMap bmap_quarter;  // box {64, BLOCK_N / 4}: ... of a 4-CTA cluster
   TcTap taps[TC_MAX_TAPS];
   TcClass cls[TC_MAX_CLS];
   int ncls, m_tiles, n_tiles;
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
 // A stage is refilled only after both CTAs' MMAs have read it: the MMA warp's commit arrives on the `empty` barrier of BOTH
 // CTAs (tcgen05.commit ... multicast::cluster), whose count is 2.
 // -------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES, int MT>
+template <int BLOCK_N, int STAGES, int MT, int CL>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_mc_kernel(const __grid_constant__ TcConvParams p, const int total_pairs) {
   constexpr int A_BYTES = 128 * 128;
   constexpr int B_BYTES = BLOCK_N * 128;
@@ -716,11 +717,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_mc_kernel(const __
   // work is dealt in PAIRS of row groups with the same n-tile: the two CTAs of a cluster walk identical (tap, chunk)
   // schedules on different rows, so every weight tile is fetched once per cluster (each CTA multicasts one half of it)
   const uint32_t crank = cluster_ctarank();
-  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x / CL, cluster_id = blockIdx.x / CL;
+  constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1u);
   auto decode = [&](int q, Unit& t) {
     t.nt = q % p.n_tiles;
     t.cls_id = 0;
-    int mg = (q / p.n_tiles) * 2 + static_cast<int>(crank);
+    int mg = (q / p.n_tiles) * CL + static_cast<int>(crank);
     const bool dummy = mg >= m_groups;      // odd group count: the last pair's second CTA keeps the pipeline in step on a
     if (dummy) mg = m_groups - 1;           // duplicate of the last group and stores nothing
 #pragma unroll
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_mc_kernel(const __
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_base + s * 8, 1);
-      mbar_init(bar_base + (STAGES + s) * 8, 2);   // freed when BOTH CTAs' MMAs have read the stage (the peer writes half of B)
+      mbar_init(bar_base + (STAGES + s) * 8, CL);   // freed when ALL CTAs' MMAs have read the stage (the peers write parts of B)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull + b * 8, 1);
@@ -781,8 +783,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_mc_kernel(const __
             for (int sub = 0; sub < MT; ++sub)
               tma_load_5d(sa + sub * A_BYTES, amap, full, (tap.c0 + ch) * 64, t.w0s[sub] + tap.dw, t.h0s[sub] + tap.dh, t.d0s[sub] + tap.dd,
                           t.n0s[sub]);
-            tma_load_2d_mc(sa + MT * A_BYTES + crank * (B_BYTES / 2), &p.bmap_half, full, tap.kofs + ch * 64,
-                           t.nt * BLOCK_N + static_cast<int>(crank) * (BLOCK_N / 2), static_cast<uint16_t>(3));
+            tma_load_2d_mc(sa + MT * A_BYTES + crank * (B_BYTES / CL), CL == 2 ? &p.bmap_half : &p.bmap_quarter, full, tap.kofs + ch * 64,
+                           t.nt * BLOCK_N + static_cast<int>(crank) * (BLOCK_N / CL), CL_MASK);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -813,7 +815,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_mc_kernel(const __
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc_mma_bf16(tacc + sub * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit_mc(bar_base + (STAGES + stage) * 8, static_cast<uint16_t>(3));
+          tc_commit_mc(bar_base + (STAGES + stage) * 8, CL_MASK);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         if (nkb > 0) tc_commit(tfull + buf * 8);
@@ -1205,13 +1207,13 @@ static int launch_persist(const TcConvParams& prm, int units, cudaStream_t strea
   return 0;
 }
 
-template <int BLOCK_N, int STAGES, int MT>
+template <int BLOCK_N, int STAGES, int MT, int CL>
 static int launch_persist_mc(const TcConvParams& prm, int m_groups, cudaStream_t stream, char* err, size_t errlen) {
   constexpr int SMEM = STAGES * (MT * 128 * 128 + BLOCK_N * 128) + (2 * STAGES + 4) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
   static bool attr_done = false;
   static int sms = 0;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_mc_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_mc_kernel<BLOCK_N, STAGES, MT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
       snprintf(err, errlen, "cudaFuncSetAttribute(conv_tc_persist_mc) failed: %s", cudaGetErrorString(e));
       return 1;
@@ -1222,22 +1224,22 @@ static int launch_persist_mc(const TcConvParams& prm, int m_groups, cudaStream_t
     if (sms < 2) sms = 148;
     attr_done = true;
   }
-  const int pairs = prm.n_tiles * ((m_groups + 1) / 2);
-  int clusters = sms / 2;
+  const int pairs = prm.n_tiles * ((m_groups + CL - 1) / CL);   // groups of CL row groups with the same n-tile
+  int clusters = sms / CL;
   if (clusters > pairs) clusters = pairs;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)clusters * 2);
+  cfg.gridDim = dim3((unsigned)clusters * CL);
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.x = CL;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_persist_mc_kernel<BLOCK_N, STAGES, MT>, prm, pairs);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_persist_mc_kernel<BLOCK_N, STAGES, MT, CL>, prm, pairs);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "conv_tc_persist_mc cluster launch failed: %s", cudaGetErrorString(e));
     return 1;
@@ -1245,14 +1247,14 @@ static int launch_persist_mc(const TcConvParams& prm, int m_groups, cudaStream_t
   return 0;
 }
 
-// opt-in while it is being measured: SAP3D_CONV_MULTICAST=1
-static bool multicast_enabled() {
+// opt-in while it is being measured: SAP3D_CONV_MULTICAST=2 or 4 (cluster size); unset / 0 = off
+static int multicast_cluster() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SAP3D_CONV_MULTICAST");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    v = (e != nullptr && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
   }
-  return v == 1;
+  return v;
 }
 
 int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen) {
@@ -1286,6 +1288,7 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
       return 1;
   if (encode_b(&prm.bmap, pb.B, pb.Ktot, pb.rowsB, block_n, err, errlen)) return 1;
   if (encode_b(&prm.bmap_half, pb.B, pb.Ktot, pb.rowsB, block_n / 2, err, errlen)) return 1;
+  if (encode_b(&prm.bmap_quarter, pb.B, pb.Ktot, pb.rowsB, block_n / 4, err, errlen)) return 1;
   int ntap = 0;
   for (size_t c = 0; c < m.classes.size(); ++c) {
     TcClass& dc = prm.cls[c];
@@ -1362,11 +1365,14 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
     if (split == 2 && min_nkb >= 2) return launch_split<2>(prm, (int)grid, stream, err, errlen);
   }
   // more work units than SMs (decoder layers): persistent CTAs with double-buffered accumulators
-  if (grid > 148 && pb.force_split >= 0 && prm.ncls == 1 && block_n >= 128 && multicast_enabled()) {
-    if (block_n == 128) return mt == 2 ? launch_persist_mc<128, 4, 2>(prm, (int)m_groups, stream, err, errlen)
-                                        : launch_persist_mc<128, 4, 1>(prm, (int)m_groups, stream, err, errlen);
-    return mt == 2 ? launch_persist_mc<256, 3, 2>(prm, (int)m_groups, stream, err, errlen)
-                   : launch_persist_mc<256, 4, 1>(prm, (int)m_groups, stream, err, errlen);
+  if (grid > 148 && pb.force_split >= 0 && prm.ncls == 1 && block_n >= 128 && multicast_cluster() != 0) {
+    const int mg = (int)m_groups;
+    if (multicast_cluster() == 2) {
+      if (block_n == 128) return mt == 2 ? launch_persist_mc<128, 4, 2, 2>(prm, mg, stream, err, errlen) : launch_persist_mc<128, 4, 1, 2>(prm, mg, stream, err, errlen);
+      return mt == 2 ? launch_persist_mc<256, 3, 2, 2>(prm, mg, stream, err, errlen) : launch_persist_mc<256, 4, 1, 2>(prm, mg, stream, err, errlen);
+    }
+    if (block_n == 128) return mt == 2 ? launch_persist_mc<128, 4, 2, 4>(prm, mg, stream, err, errlen) : launch_persist_mc<128, 4, 1, 4>(prm, mg, stream, err, errlen);
+    return mt == 2 ? launch_persist_mc<256, 3, 2, 4>(prm, mg, stream, err, errlen) : launch_persist_mc<256, 4, 1, 4>(prm, mg, stream, err, errlen);
   }
   if (grid > 148 && pb.force_split >= 0) {
     switch (block_n) {
