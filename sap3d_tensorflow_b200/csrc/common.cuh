@@ -146,6 +146,26 @@ SAP3D_DEVINL void tma_load_2d(uint32_t dst, const void* map, uint32_t bar, int c
       : "memory");
 }
 
+// multicast form: the box lands at the same shared-memory offset of every CTA in `mask`, and each of those CTAs' mbarrier
+// (same offset) receives the complete_tx
+SAP3D_DEVINL void tma_load_2d_mc(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+SAP3D_DEVINL void tma_load_3d_mc(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM — SASS: UTCHMMA (mma), LDTM (ld), UTCBAR (commit)
 // ----------------------------------------------------------------------------------------------
@@ -163,6 +183,12 @@ SAP3D_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread
 SAP3D_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 SAP3D_DEVINL void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of `mask` once the MMAs issued so far have completed
+SAP3D_DEVINL void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> f32
 SAP3D_DEVINL void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

@@ -17,6 +17,7 @@
 #include "conv_tc.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -44,6 +45,8 @@ struct TcClass {
 struct alignas(64) TcConvParams {
   CUtensorMap amap[TC_MAX_MAPS];
   CUtensorMap bmap;
+  CUtensorMap bmap_half;     // box {64, BLOCK_N / 2}: the part of a weight tile one CTA of a 2-CTA cluster multicasts
+  CUtensorMap bmap_quarter;  // box {64, BLOCK_N / 4}: ... of a 4-CTA cluster
   TcTap taps[TC_MAX_TAPS];
   TcClass cls[TC_MAX_CLS];
   int ncls, m_tiles, n_tiles;
@@ -682,6 +685,300 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
   }
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// Persistent kernel, 2-CTA cluster with MULTICAST weight tiles (single-class problems = plain convolutions).
+// The persistent kernel above is bound by the L2->SM crossbar (ncu: 4.17 GB per launch of the dominant decoder conv, 14.4
+// TB/s): per 64-channel k-block a CTA pulls MT x 16 KB of activations and BLOCK_N x 128 B of weights, and every CTA pulls
+// the SAME weights.  Here two CTAs of a cluster work on different row groups in lock-step; each issues one TMA multicast for
+// HALF of the weight tile, so the weights cross the fabric once per cluster (-17 % bytes at BLOCK_N = 128, MT = 2).
+// A stage is refilled only after both CTAs' MMAs have read it: the MMA warp's commit arrives on the `empty` barrier of BOTH
+// CTAs (tcgen05.commit ... multicast::cluster), whose count is 2.
+// -------------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES, int MT, int CL>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_mc_kernel(const __grid_constant__ TcConvParams p, const int total_pairs) {
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+  constexpr int NBUF = 2 * MT * BLOCK_N <= 512 ? 2 : 1;
+  constexpr int TCOLS = NBUF * MT * BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  constexpr int NBAR = 2 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + NBAR * 8);
+  float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + NBAR * 8 + 16);  // [4][2][BLOCK_N]
+  float* s_ep = s_stats + 4 * 2 * BLOCK_N;                                                  // [3][BLOCK_N]
+  const uint32_t tfull = bar_base + 2 * STAGES * 8, tempty = tfull + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_groups = (p.m_tiles + MT - 1) / MT;
+
+  struct Unit { int nt, cls_id; int mts[MT], w0s[MT], h0s[MT], d0s[MT], n0s[MT]; bool live[MT]; };
+  // work is dealt in PAIRS of row groups with the same n-tile: the two CTAs of a cluster walk identical (tap, chunk)
+  // schedules on different rows, so every weight tile is fetched once per cluster (each CTA multicasts one half of it)
+  const uint32_t crank = cluster_ctarank();
+  const int n_clusters = gridDim.x / CL, cluster_id = blockIdx.x / CL;
+  constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1u);
+  auto decode = [&](int q, Unit& t) {
+    t.nt = q % p.n_tiles;
+    t.cls_id = 0;
+    int mg = (q / p.n_tiles) * CL + static_cast<int>(crank);
+    const bool dummy = mg >= m_groups;      // odd group count: the last pair's second CTA keeps the pipeline in step on a
+    if (dummy) mg = m_groups - 1;           // duplicate of the last group and stores nothing
+#pragma unroll
+    for (int sub = 0; sub < MT; ++sub) {
+      int mt = mg * MT + sub;
+      t.live[sub] = !dummy && mt < p.m_tiles;
+      if (!t.live[sub]) mt = p.m_tiles - 1;
+      t.mts[sub] = mt;
+      int r = mt;
+      const int tw = r % p.tiles[0]; r /= p.tiles[0];
+      const int th = r % p.tiles[1]; r /= p.tiles[1];
+      const int td = r % p.tiles[2];
+      const int tn = r / p.tiles[2];
+      t.w0s[sub] = tw * p.box[0]; t.h0s[sub] = th * p.box[1]; t.d0s[sub] = td * p.box[2]; t.n0s[sub] = tn * p.box[3];
+    }
+  };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_base + s * 8, 1);
+      mbar_init(bar_base + (STAGES + s) * 8, CL);   // freed when ALL CTAs' MMAs have read the stage (the peers write parts of B)
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b * 8, 1);
+      mbar_init(tempty + b * 8, 128);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&p.bmap);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), TCOLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  cluster_sync_all();      // the peer's barriers exist before anything is multicast at them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: one continuous ring over all units =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = MT * p.box_rows * 128 + B_BYTES;
+      for (int u = cluster_id; u < total_pairs; u += n_clusters) {
+        Unit t;
+        decode(u, t);
+        const TcClass cls = p.cls[t.cls_id];
+        for (int ti = 0; ti < cls.tap_count; ++ti) {
+          const TcTap tap = p.taps[cls.tap_begin + ti];
+          const void* amap = &p.amap[tap.map];
+          for (int ch = 0; ch < tap.nchunk; ++ch) {
+            mbar_wait(bar_base + (STAGES + stage) * 8, phase ^ 1u);
+            const uint32_t full = bar_base + stage * 8;
+            const uint32_t sa = base + stage * STAGE_BYTES;
+            mbar_expect_tx(full, tx_bytes);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub)
+              tma_load_5d(sa + sub * A_BYTES, amap, full, (tap.c0 + ch) * 64, t.w0s[sub] + tap.dw, t.h0s[sub] + tap.dh, t.d0s[sub] + tap.dd,
+                          t.n0s[sub]);
+            tma_load_3d_mc(sa + MT * A_BYTES + crank * (B_BYTES / CL), CL == 2 ? &p.bmap_half : &p.bmap_quarter, full, tap.kofs + ch * 64,
+                           t.nt * BLOCK_N + static_cast<int>(crank) * (BLOCK_N / CL), 0, CL_MASK);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int u = cluster_id; u < total_pairs; u += n_clusters, ++it) {
+        const int buf = it % NBUF;
+        const uint32_t use = static_cast<uint32_t>(it / NBUF);
+        const int nkb = p.cls[0].nkb;
+        mbar_wait(tempty + buf * 8, (use & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * MT * BLOCK_N;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar_base + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint64_t bdesc = umma_desc_sw128(sa + MT * A_BYTES, 16, 1024);
+#pragma unroll
+          for (int sub = 0; sub < MT; ++sub) {
+            const uint64_t adesc = umma_desc_sw128(sa + sub * A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_bf16(tacc + sub * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit_mc(bar_base + (STAGES + stage) * 8, CL_MASK);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (nkb > 0) tc_commit(tfull + buf * 8);
+        else mbar_arrive(tfull + buf * 8);               // bias-only class: nothing to wait for
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5), overlapped with the next unit's MMAs =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool want_stats = p.stats != nullptr;
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    for (int u = cluster_id; u < total_pairs; u += n_clusters, ++it) {
+      Unit t;
+      decode(u, t);
+      const TcClass cls = p.cls[t.cls_id];
+      const int nkb = cls.nkb;
+      const int buf = it % NBUF;
+      const uint32_t use = static_cast<uint32_t>(it / NBUF);
+      for (int cc = et; cc < BLOCK_N; cc += 128) {     // per-column epilogue vectors of this unit
+        const int col = t.nt * BLOCK_N + cc;
+        const bool in = col < p.cout;
+        s_ep[cc] = (in && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
+        s_ep[BLOCK_N + cc] = (in && p.scale != nullptr) ? __ldg(p.scale + col) : 1.f;
+        s_ep[2 * BLOCK_N + cc] = (in && p.scale != nullptr) ? __ldg(p.shift + col) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull + buf * 8, use & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * MT * BLOCK_N;
+      if (!t.live[0]) {   // duplicate unit of an odd tail: nothing to store, only hand the accumulator back
+        tc_fence_before();
+        mbar_arrive(tempty + buf * 8);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        continue;
+      }
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+        if (!t.live[sub]) break;
+        int r = row;
+        const int iw = r % p.box[0]; r /= p.box[0];
+        const int ih = r % p.box[1]; r /= p.box[1];
+        const int id = r % p.box[2];
+        const int in = r / p.box[2];
+        const int ow = t.w0s[sub] + iw, oh = t.h0s[sub] + ih, od = t.d0s[sub] + id, on = t.n0s[sub] + in;
+        const bool valid = row < p.box_rows && ow < p.ext[0] && oh < p.ext[1] && od < p.ext[2] && on < p.ext[3];
+        const long long row_off = cls.out_ofs + ow * p.so[0] + oh * p.so[1] + od * p.so[2] + on * p.so[3];
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          const int col0 = t.nt * BLOCK_N + c * 32;
+          if (col0 >= p.cout) break;
+          uint32_t rr[32];
+          if (nkb > 0) {
+            tmem_ld_32x32(tacc + (static_cast<uint32_t>(q * 32) << 16) + sub * BLOCK_N + c * 32, rr);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rr[j] = 0u;
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += s_ep[c * 32 + j];
+          }
+          if (want_stats) {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float m = valid ? v[j] : 0.f;
+              s1[j] = m;
+              s2[j] = m * m;
+            }
+            const float c1 = warp_transpose_sum32(s1, lane);
+            const float c2 = warp_transpose_sum32(s2, lane);
+            s_stats[(q * 2 + 0) * BLOCK_N + c * 32 + lane] = c1;
+            s_stats[(q * 2 + 1) * BLOCK_N + c * 32 + lane] = c2;
+          }
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_ep[BLOCK_N + c * 32 + j], s_ep[2 * BLOCK_N + c * 32 + j]);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (valid) {
+            const bool second = p.out2 != nullptr && col0 >= p.seg_split;
+            void* const outp = second ? p.out2 : p.out;
+            const int colx = second ? col0 - p.seg_split : col0;
+            const int accum = second ? p.accumulate2 : p.accumulate;
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(outp) + row_off + colx;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (col0 + g * 4 < p.cout) {
+                  float4 f = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                  if (accum) {
+                    const float4 e = *reinterpret_cast<const float4*>(o + g * 4);
+                    f.x += e.x; f.y += e.y; f.z += e.z; f.w += e.w;
+                  }
+                  *reinterpret_cast<float4*>(o + g * 4) = f;
+                }
+              }
+            } else {
+              bf16* o = reinterpret_cast<bf16*>(outp) + row_off + colx;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (col0 + g * 8 < p.cout) {
+                  float w8[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) w8[j] = v[g * 8 + j];
+                  if (accum) {
+                    float e[8];
+                    Vec8<bf16>::load(o + g * 8, e);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w8[j] += e[j];
+                  }
+                  Vec8<bf16>::store(o + g * 8, w8);
+                }
+              }
+            }
+          }
+        }
+        if (sub + 1 == MT || !t.live[sub + 1 < MT ? sub + 1 : sub]) {
+          // last sub-tile of the unit has been read out of TMEM: hand the buffer back before the statistics tail
+          tc_fence_before();
+          mbar_arrive(tempty + buf * 8);
+        }
+        if (want_stats) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const long long srow = static_cast<long long>(t.cls_id) * p.m_tiles + t.mts[sub];
+          for (int cc = et; cc < BLOCK_N; cc += 128) {
+            const int col = t.nt * BLOCK_N + cc;
+            if (col < p.cout) {
+              float a = 0.f, b = 0.f;
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) {
+                a += s_stats[(qq * 2 + 0) * BLOCK_N + cc];
+                b += s_stats[(qq * 2 + 1) * BLOCK_N + cc];
+              }
+              p.stats[(srow * 2 + 0) * p.cout + col] = a;
+              p.stats[(srow * 2 + 1) * p.cout + col] = b;
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");   // s_stats / s_ep are reused by the next sub-tile / unit
+        }
+      }
+      if (!want_stats) asm volatile("bar.sync 1, 128;" ::: "memory");   // s_ep is rewritten at the top of the next unit
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();      // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TCOLS);
+  }
+}
+
 // =================================================================================================
 // host side
 // =================================================================================================
@@ -914,6 +1211,56 @@ static int launch_persist(const TcConvParams& prm, int units, cudaStream_t strea
   return 0;
 }
 
+template <int BLOCK_N, int STAGES, int MT, int CL>
+static int launch_persist_mc(const TcConvParams& prm, int m_groups, cudaStream_t stream, char* err, size_t errlen) {
+  constexpr int SMEM = STAGES * (MT * 128 * 128 + BLOCK_N * 128) + (2 * STAGES + 4) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
+  static bool attr_done = false;
+  static int sms = 0;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_mc_kernel<BLOCK_N, STAGES, MT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "cudaFuncSetAttribute(conv_tc_persist_mc) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 2) sms = 148;
+    attr_done = true;
+  }
+  const int pairs = prm.n_tiles * ((m_groups + CL - 1) / CL);   // groups of CL row groups with the same n-tile
+  int clusters = sms / CL;
+  if (clusters > pairs) clusters = pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)clusters * CL);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_persist_mc_kernel<BLOCK_N, STAGES, MT, CL>, prm, pairs);
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "conv_tc_persist_mc cluster launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+// opt-in while it is being measured: SAP3D_CONV_MULTICAST=2 or 4 (cluster size); unset / 0 = off
+static int multicast_cluster() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAP3D_CONV_MULTICAST");
+    v = (e != nullptr && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
+  }
+  return v;
+}
+
 int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen) {
   Merged m;
   merge_dims(pb, m);
@@ -949,6 +1296,8 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
       return 1;
   if (encode_b(&prm.bmap, pb.B, pb.Ktot, pb.rowsB, block_n, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
   prm.b_batched = pb.b_batch > 1 ? 1 : 0;
+  if (encode_b(&prm.bmap_half, pb.B, pb.Ktot, pb.rowsB, block_n / 2, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
+  if (encode_b(&prm.bmap_quarter, pb.B, pb.Ktot, pb.rowsB, block_n / 4, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
   int ntap = 0;
   for (size_t c = 0; c < m.classes.size(); ++c) {
     TcClass& dc = prm.cls[c];
@@ -1026,6 +1375,15 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
     if (split == 2 && min_nkb >= 2) return launch_split<2>(prm, (int)grid, stream, err, errlen);
   }
   // more work units than SMs (decoder layers): persistent CTAs with double-buffered accumulators
+  if (grid > 148 && pb.force_split >= 0 && prm.ncls == 1 && block_n >= 128 && multicast_cluster() != 0) {
+    const int mg = (int)m_groups;
+    if (multicast_cluster() == 2) {
+      if (block_n == 128) return mt == 2 ? launch_persist_mc<128, 4, 2, 2>(prm, mg, stream, err, errlen) : launch_persist_mc<128, 4, 1, 2>(prm, mg, stream, err, errlen);
+      return mt == 2 ? launch_persist_mc<256, 3, 2, 2>(prm, mg, stream, err, errlen) : launch_persist_mc<256, 4, 1, 2>(prm, mg, stream, err, errlen);
+    }
+    if (block_n == 128) return mt == 2 ? launch_persist_mc<128, 4, 2, 4>(prm, mg, stream, err, errlen) : launch_persist_mc<128, 4, 1, 4>(prm, mg, stream, err, errlen);
+    return mt == 2 ? launch_persist_mc<256, 3, 2, 4>(prm, mg, stream, err, errlen) : launch_persist_mc<256, 4, 1, 4>(prm, mg, stream, err, errlen);
+  }
   if (grid > 148 && pb.force_split >= 0) {
     switch (block_n) {
       case 64: return mt == 2 ? launch_persist<64, 4, 2>(prm, (int)grid, stream, err, errlen) : launch_persist<64, 6, 1>(prm, (int)grid, stream, err, errlen);
