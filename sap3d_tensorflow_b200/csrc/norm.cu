@@ -20,17 +20,21 @@ namespace {
 // finalize: partial [rows][2][C] -> mean/var -> scale/shift (+ moving-average update)
 // block = 32 channels x 32 row lanes, deterministic fp64 reduction
 // ------------------------------------------------------------------------------------------------
+// CPB channels x (1024 / CPB) row lanes per block.  CPB = 32 for few-row layers; CPB = 8 for the decoder's 1000+ statistics rows
+// (4x more blocks, 4x shorter serial walk per lane; a lane still reads 32 contiguous bytes per row and statistic).
+template <int CPB>
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* moving_mean, float* moving_var, int training,
                                                             float momentum, float eps, float* scale, float* shift,
                                                             float* save_mean, float* save_rstd) {
+  constexpr int LANES = 1024 / CPB;
   const int cx = threadIdx.x, ry = threadIdx.y;
-  const int c = blockIdx.x * 32 + cx;
-  __shared__ double s1[32][33], s2[32][33];
+  const int c = blockIdx.x * CPB + cx;
+  __shared__ double s1[LANES][CPB + 1], s2[LANES][CPB + 1];
   double a = 0.0, b = 0.0;
   if (training && c < C) {
-    for (int r = ry; r < rows; r += 32) {
+    for (int r = ry; r < rows; r += LANES) {
       a += (double)stats[((long long)r * 2 + 0) * C + c];
       b += (double)stats[((long long)r * 2 + 1) * C + c];
     }
@@ -42,7 +46,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
     float mean, var;
     if (training) {
       double ta = 0.0, tb = 0.0;
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < LANES; ++i) {      // fixed order: deterministic
         ta += s1[i][cx];
         tb += s2[i][cx];
       }
@@ -887,9 +891,13 @@ int sap3d_bn_finalize(const float* stats, int32_t rows, int32_t C, double count,
   if (!scale || !shift) return set_error("bn_finalize: NULL output");
   if (training && !stats) return set_error("bn_finalize: training mode needs statistics");
   if (!training && (!moving_mean || !moving_var)) return set_error("bn_finalize: inference mode needs moving statistics");
-  dim3 block(32, 32);
-  bn_finalize_kernel<<<(C + 31) / 32, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      stats, rows, C, count, gamma, beta, moving_mean, moving_var, training, momentum, eps, scale, shift, save_mean, save_rstd);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (training && rows >= 256)
+    bn_finalize_kernel<8><<<(C + 7) / 8, dim3(8, 128), 0, st>>>(stats, rows, C, count, gamma, beta, moving_mean, moving_var, training,
+                                                               momentum, eps, scale, shift, save_mean, save_rstd);
+  else
+    bn_finalize_kernel<32><<<(C + 31) / 32, dim3(32, 32), 0, st>>>(stats, rows, C, count, gamma, beta, moving_mean, moving_var, training,
+                                                                  momentum, eps, scale, shift, save_mean, save_rstd);
   return check_launch("bn_finalize");
 }
 

@@ -300,7 +300,21 @@ int tc_wgrad_launch(const TcWgradProblem& pb, cudaStream_t stream, char* err, si
   prm.nblocks = (pb.N + block_n - 1) / block_n;
   prm.m_tiles = (int)m_tiles;
   const long long out_tiles = (long long)prm.ntaps * prm.mblocks * prm.nblocks;
+  // split count: the CTAs are one per SM (197 KB of shared memory), so the grid should fill WHOLE waves of 148.  Among the
+  // splits that give 2.5 .. 4 waves pick the one wasting the least of its last wave; ties go to fewer splits (less fp32
+  // reduction traffic).  (ceil(4*148 / tiles) used to give e.g. 54 tiles x 11 = 594 CTAs = four waves plus two CTAs.)
   long long splits = (4 * 148 + out_tiles - 1) / out_tiles;
+  {
+    const long long lo = std::max(1ll, (5 * 74) / out_tiles), hi = std::max(lo, (4 * 148) / out_tiles);
+    double best_eff = -1.0;
+    long long best = splits;
+    for (long long sp = lo; sp <= hi; ++sp) {
+      const long long g = out_tiles * sp, waves = (g + 147) / 148;
+      const double eff = (double)g / (double)(waves * 148);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
+    }
+    if (best_eff > 0.0) splits = best;
+  }
   splits = std::max(1ll, std::min(splits, m_tiles));
   prm.splits = (int)splits;
   for (int i = 0; i < 4; ++i) {
