@@ -1375,7 +1375,7 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
     if (split == 2 && min_nkb >= 2) return launch_split<2>(prm, (int)grid, stream, err, errlen);
   }
   // more work units than SMs (decoder layers): persistent CTAs with double-buffered accumulators
-  if (grid > 148 && pb.force_split >= 0 && prm.ncls == 1 && block_n >= 128 && multicast_cluster() != 0) {
+  if (grid > 148 && pb.force_split >= 0 && prm.ncls == 1 && block_n >= 128 && pb.b_batch <= 1 && multicast_cluster() != 0) {
     const int mg = (int)m_groups;
     if (multicast_cluster() == 2) {
       if (block_n == 128) return mt == 2 ? launch_persist_mc<128, 4, 2, 2>(prm, mg, stream, err, errlen) : launch_persist_mc<128, 4, 1, 2>(prm, mg, stream, err, errlen);
