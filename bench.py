@@ -46,10 +46,21 @@ def parse():
     return ap.parse_args()
 
 
-def default_graph():
-    import sap3d_tensorflow_b200 as sp
+DEFAULT_GRAPH = "p3d_unetplusplus_ds"     # p3d.py:340 (what gen_pred.py:46 builds); named literally: the reference arm must not
+                                          # import the product package
 
-    return "p3d_unetplusplus_ds" if hasattr(sp.network, "attention") else "p3d_unetplusplus_nonsa"
+
+def default_graph():
+    return DEFAULT_GRAPH
+
+
+def workload_config(graph: str, batch: int, size: int, world: int):
+    """the `config` object both arms print (identical for the same command line)"""
+    return {
+        "workload": f"{graph} training step (fwd + smooth-L1 + bwd + Adam), batch {batch} clips 16x{size}x{size} per GPU",
+        "global_batch": world * batch, "parallelism": f"dp{world}", "weights": "random init (TF initialisers)",
+        "l2": "per-step working set (activations + gradients, several GB) is far larger than the 126 MB L2",
+    }
 
 
 # ------------------------------------------------------------------------------------------------
@@ -136,45 +147,69 @@ def cpu_reference_step(graph: str, size: int, batch: int, steps: int, warmup: in
     return batch / sec, sec, cores
 
 
+REF_SAMPLE_BATCH = 2   # clips per reference-arm step: a bounded sample of the batch-8 step (a full batch is ~17 s per step on
+                       # 16 host cores; K + W = 25 steps of it would take 7 minutes)
+
+
 def run_reference(args):
+    """reference arm: the CPU restatement of the reference's TF graph (TensorFlow cannot be installed in this image, so
+    `oracle/` stands in for the reference's own CPU path; kind = "port"), all host threads, EXACTLY --steps timed steps after
+    --warmup untimed ones.  Each step is a training step on REF_SAMPLE_BATCH clips of the configured workload; the value is
+    clips / second.  Imports nothing from the product package."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    graph = args.graph or default_graph()
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
-    val, sec, cores = cpu_reference_step(graph, args.size, 1, steps, warm)
-    sample = f"{steps} training steps of {graph} on 1 clip 16x{args.size}x{args.size} (fp32, torch-CPU oracle, {cores} threads)"
+    gn = args.workload == "gn160"
+    graph = args.graph or ("inference_p3d" if gn else default_graph())
+    B, size = (16, 160) if gn and args.batch == 8 and args.size == 112 else (args.batch, args.size)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    sb = min(REF_SAMPLE_BATCH, B)
+    val, sec, cores = cpu_reference_step(graph, size, sb, steps, warm)
+    sample = (f"each step = one training step of {graph} on {sb} clip(s) 16x{size}x{size} (a {sb}/{B} sample of the batch-{B} step; "
+              f"fp32, torch-CPU restatement of the reference graph, {cores} threads); {steps} timed steps after {warm} warm-up steps")
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": sec * 1e3 * B / sb, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{graph} training step (fwd + smooth-L1 + bwd + Adam), batch 8 clips 16x{args.size}x{args.size} per GPU",
-                   "note": "reference = CPU restatement of the reference TF graph (TensorFlow unavailable in this image)"},
+        "config": workload_config(graph, B, size, max(1, args.gpus)),
+        "note": "reference = CPU restatement of the reference TF graph (TensorFlow unavailable in this image); ms_per_step is "
+                "scaled from the sample to the full batch",
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if gn:
+        out["metric"] = "clips/sec (16x160x160, bf16) GN+CBAM train step"
     print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
-def time_dominant_kernel(batch: int, size: int, iters: int = 20):
-    """the FLOP-dominant launch: the x_1_2 / x_1_3 decoder conv (3x3x3, 128+128 -> 128 at 8 x size/2 x size/2),
-    timed alone with CUDA events on the launching stream, L2 flushed between launches"""
+DOMINANT = {
+    # workload -> the FLOP-dominant launch of its step: (description, D, H/size, W/size divisor, input segments, cout)
+    "train": ("x_1_2 / x_1_3 decoder conv (3x3x3, 128+128 -> 128 at B x 8 x size/2 x size/2; p3d.py:388-390)", 8, 2, [128, 128], 128, 2),
+    "eval": ("x_1_2 / x_1_3 decoder conv (3x3x3, 128+128 -> 128 at B x 8 x size/2 x size/2; p3d.py:388-390)", 8, 2, [128, 128], 128, 2),
+    "gn160": ("conv_concat (3x3x3, 1536+256 -> 1024 at B x 4 x size/4 x size/4; gn/p3d_gn.py:245)", 4, 4, [1536, 256], 1024, 1),
+}
+
+
+def time_dominant_kernel(workload: str, batch: int, size: int, iters: int = 20):
+    """the FLOP-dominant launch of the workload's step, timed alone with CUDA events on the launching stream, L2 flushed
+    between launches.  Returns (ms per launch, FLOPs per launch, kernel name as CUPTI reports it, launches of it per step)."""
     import ctypes as C
 
     import torch
+    from torch.profiler import ProfilerActivity, profile
     from sap3d_tensorflow_b200 import _abi as A
 
+    desc, D, div, cins, cout, per_step = DOMINANT[workload]
     dev = torch.device("cuda")
-    N, D, H, W = batch, 8, size // 2, size // 2
-    xs = [torch.randn(N, D, H, W, 128, device=dev).to(torch.bfloat16) for _ in range(2)]
-    w = torch.randn(3, 3, 3, 256, 128, device=dev) * 0.02
-    b = torch.zeros(128, device=dev)
-    d = A.make_conv_desc(A.BF16, N, D, H, W, [128, 128], 128, (3, 3, 3), (1, 1, 1), False, True, False, A.IMPL_TC)
-    y = torch.empty(N, D, H, W, 128, device=dev, dtype=torch.bfloat16)
+    N, H, W = batch, size // div, size // div
+    xs = [torch.randn(N, D, H, W, c, device=dev).to(torch.bfloat16) for c in cins]
+    w = torch.randn(3, 3, 3, sum(cins), cout, device=dev) * 0.02
+    b = torch.zeros(cout, device=dev)
+    d = A.make_conv_desc(A.BF16, N, D, H, W, cins, cout, (3, 3, 3), (1, 1, 1), False, True, False, A.IMPL_TC)
+    y = torch.empty(N, D, H, W, cout, device=dev, dtype=torch.bfloat16)
     rows = A.lib.sap3d_conv_stats_rows(C.byref(d))
-    stats = torch.zeros(rows, 2, 128, device=dev)
+    stats = torch.zeros(rows, 2, cout, device=dev)
     wf = torch.zeros(A.lib.sap3d_conv_packed_elems(C.byref(d), 0), device=dev, dtype=torch.bfloat16)
     st = torch.cuda.current_stream().cuda_stream
     A.check(A.lib.sap3d_conv_pack_weights(C.byref(d), A.ptr(w), A.ptr(wf), None, st), "pack")
@@ -195,8 +230,31 @@ def time_dominant_kernel(batch: int, size: int, iters: int = 20):
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
     ms = tot / iters
-    flops = 2.0 * N * D * H * W * 27 * 256 * 128
-    return ms, flops
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        launch()
+        torch.cuda.synchronize()
+    names = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "conv_tc" in e.name]
+    flops = 2.0 * N * D * H * W * 27 * sum(cins) * cout
+    return ms, flops, (names[0] if names else None), per_step, desc
+
+
+def in_graph_kernel_ms(step_fn, kernel_name: str, topk: int):
+    """device durations of the `topk` longest launches of `kernel_name` INSIDE one replay of the step's CUDA graphs (CUPTI
+    activity records): the same launches the stand-alone timing isolates, warm and with their real neighbours."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+
+    if not kernel_name:
+        return None
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step_fn()
+        torch.cuda.synchronize()
+    ds = sorted((e.time_range.end - e.time_range.start for e in prof.events()
+                 if e.device_type == torch.autograd.DeviceType.CUDA and e.name == kernel_name), reverse=True)
+    if len(ds) < topk:
+        return None
+    return sum(ds[:topk]) / topk / 1e3
 
 
 def count_launches(fn):
@@ -317,6 +375,16 @@ def run_eval(args):
                     "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches * nb * reps), "clocks": clocks,
         }
+        burst, sustained, hbm, src = peaks()
+        kms, kflops, kname, per_step, kdesc = time_dominant_kernel("eval", B, size)
+        achieved = kflops / (kms * 1e-3) / 1e12
+        out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
+                           "kernel": f"{kname}: {kdesc}, B={B}", "ms_per_launch": kms, "flops_per_launch": kflops,
+                           "peak_source": f"{src} bf16 burst (kernel timed alone, L2 flushed)"}
+        ig = in_graph_kernel_ms(lambda: sess.run(xs_dev[0], graph=True), kname, per_step)
+        if ig is not None:
+            out["roofline"]["in_graph"] = {"ms_per_launch": ig, "achieved": kflops / (ig * 1e-3) / 1e12, "peak": sustained,
+                                           "frac": kflops / (ig * 1e-3) / 1e12 / sustained}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -377,6 +445,16 @@ def run_ours(args):
     ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(sess.eng.loss_buf.item())
+    # data-parallel correctness: after the timed steps every replica must hold bit-identical weights (same initial broadcast,
+    # same all-reduced gradients, same Adam).  Checksum = exact integer sum of the fp32 bit patterns; min == max over the ranks.
+    replicas_identical = None
+    if world > 1:
+        bits = sess.eng.flat_w[:sess.eng.n_train].view(torch.int32).to(torch.int64)
+        cs = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=dev) % 8191 + 1)).sum()])
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replicas_identical = bool(torch.equal(lo, hi))
 
     # ---- end-to-end timing: pinned host inputs -> H2D -> step -> D2H loss -------------------------
     # Every step's inputs come from pinned host memory and its loss is read back to the host.  As in the reference's
@@ -418,38 +496,44 @@ def run_ours(args):
 
     if rank == 0:
         burst, sustained, hbm, src = peaks()
-        kms, kflops = time_dominant_kernel(8, 112)
+        wl = "gn160" if gn else "train"
+        kms, kflops, kname, per_step, kdesc = time_dominant_kernel(wl, B, size)
         achieved = kflops / (kms * 1e-3) / 1e12
         launches = launches_per_step * args.steps
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")   # dram bytes per launch from the ncu --set full capture
-        if os.path.exists(tp):
+        if os.path.exists(tp) and not gn and B == 8 and size == 112:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        config = workload_config(graph, B, size, world)
+        config["cuda_graph"] = use_graph
         out = {
             "metric": METRIC, "value": world * B / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {
-                "workload": f"{graph} training step (fwd + smooth-L1 + bwd + Adam), batch {B} clips 16x{size}x{size} per GPU",
-                "global_batch": world * B, "parallelism": f"dp{world}", "weights": "random init (TF initialisers)",
-                "cuda_graph": use_graph,
-                "l2": "per-step working set (activations + gradients, several GB) is far larger than the 126 MB L2",
-                "infer_clips_per_s": world * B / (ms_inf * 1e-3), "infer_ms_per_step": ms_inf, "loss": loss_val,
-            },
+            "config": config,
+            "extra": {"infer_clips_per_s": world * B / (ms_inf * 1e-3), "infer_ms_per_step": ms_inf, "loss": loss_val,
+                      "replicas_identical": replicas_identical},
             "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4),
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
-                         "traffic": traffic, "kernel": "conv_tc_persist_kernel<128,4,2> (x_1_2/x_1_3 3x3x3 conv, 128+128->128, B=8)",
-                         "ms_per_launch": kms, "flops_per_launch": kflops, "peak_source": f"{src} bf16 burst (kernel timed alone)"},
+                         "traffic": traffic, "kernel": f"{kname}: {kdesc}, B={B}",
+                         "ms_per_launch": kms, "flops_per_launch": kflops, "peak_source": f"{src} bf16 burst (kernel timed alone, L2 flushed)"},
         }
+        ig = in_graph_kernel_ms(lambda: sess.train_step(x_dev, y_dev, graph=use_graph), kname, per_step) if (use_graph and world == 1) else None
+        if ig is not None:
+            out["roofline"]["in_graph"] = {"ms_per_launch": ig, "achieved": kflops / (ig * 1e-3) / 1e12, "peak": sustained,
+                                           "frac": kflops / (ig * 1e-3) / 1e12 / sustained,
+                                           "what": f"mean of the {per_step} longest launches of this kernel inside one CUDA-graph replay of the "
+                                                   f"step (CUPTI), against the {src} sustained bf16 peak"}
         if gn:
             out["metric"] = "clips/sec (16x160x160, bf16) GN+CBAM train step"
         if not args.no_cpu_baseline and not gn:
             val, sec, cores = cpu_reference_step(graph, size, 1, 2, 1)
             out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": f"2 training steps of {graph} on 1 clip 16x{size}x{size} (fp32 torch-CPU oracle)"}
+                                   "sample": f"2 training steps of {graph} on 1 clip 16x{size}x{size} after 1 warm-up step (fp32 torch-CPU "
+                                             f"restatement of the reference graph, {cores} threads; a 1/{B} sample of the batch-{B} step)"}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

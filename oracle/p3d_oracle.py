@@ -95,10 +95,23 @@ class VarStore:
         return t
 
 
+def _ste_round_bf16(t: torch.Tensor) -> torch.Tensor:
+    """value rounded to bf16 (round-to-nearest-even, what a bf16 store does), gradient passed straight through"""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
 class Ctx:
+    """bf16=True emulates the bf16-STORAGE arithmetic of the CUDA path inside this fp32 oracle: every tensor the CUDA path
+    keeps in HBM as bf16 (conv outputs, normalised activations, attention probabilities, tensor-core weight operands) is
+    rounded to bf16 at the point where it is stored; accumulation, statistics, scale/shift and the loss stay fp32.  This is
+    NOT a different definition of the reference graph -- it is the same graph (same functions below) with storage rounding,
+    used by the tests to (a) compare the bf16 CUDA path against an equal-rounding reference and (b) measure how far ANY
+    bf16-storage implementation is from the fp32 graph (the distance fp32-oracle <-> bf16-oracle)."""
+
     def __init__(self, vs: VarStore, training: bool, dropout: float = 0.0, taps: Optional[dict] = None,
-                 backbone_training: bool = True, dropout_mask_fn: Optional[Callable] = None):
+                 backbone_training: bool = True, dropout_mask_fn: Optional[Callable] = None, bf16: bool = False):
         self.vs = vs
+        self.bf16 = bf16
         self.training = training
         self.dropout = dropout
         self.taps = taps
@@ -110,6 +123,10 @@ class Ctx:
         if self.taps is not None:
             self.taps[name] = x
         return x
+
+    def q(self, t):
+        """storage point of an activation / operand"""
+        return _ste_round_bf16(t) if self.bf16 else t
 
 
 # ------------------------------------------------------------------------------------------------
@@ -123,7 +140,16 @@ def bn(ctx: Ctx, x, training: bool, name: Optional[str] = None, scope: str = "",
     b = ctx.vs.get(nm + "/beta", [c], "beta")
     mm = ctx.vs.get(nm + "/moving_mean", [c], "mean", trainable=False)
     mv = ctx.vs.get(nm + "/moving_variance", [c], "var", trainable=False)
-    y, nmm, nmv = tfs.batch_norm(x, g, b, mm, mv, training)
+    if ctx.bf16 and training:
+        # CUDA path: (sum, sum of squares) come from the conv's fp32 accumulators, the affine pass reads the bf16-stored raw
+        mean = x.mean(dim=(0, 1, 2, 3))
+        var = x.var(dim=(0, 1, 2, 3), unbiased=False)
+        y = (ctx.q(x) - mean) * torch.rsqrt(var + tfs.BN_EPS) * g + b
+        nmm = mm * tfs.BN_MOMENTUM + mean.detach() * (1 - tfs.BN_MOMENTUM)
+        nmv = mv * tfs.BN_MOMENTUM + var.detach() * (1 - tfs.BN_MOMENTUM)
+    else:
+        # (moving-statistics BN of an inference graph is folded into the conv epilogue: applied to the fp32 accumulators)
+        y, nmm, nmv = tfs.batch_norm(x, g, b, mm, mv, training)
     if training:
         ctx.new_moving[nm + "/moving_mean"] = nmm
         ctx.new_moving[nm + "/moving_variance"] = nmv
@@ -137,7 +163,7 @@ def gn_layer(ctx: Ctx, x, scope: str = "", gamma_kind: str = "gamma"):
     c = x.shape[-1]
     g = ctx.vs.get(nm + "/gamma", [c], gamma_kind)
     b = ctx.vs.get(nm + "/beta", [c], "beta")
-    return tfs.group_norm(x, g, b)
+    return tfs.group_norm(ctx.q(x), g, b)   # CUDA path: group statistics are taken from the stored raw tensor
 
 
 def norm(ctx, x, training, mode, scope=""):
@@ -149,11 +175,11 @@ def conv_w(ctx, name, kshape):  # get_conv_weight (p3d.py:10-16)
 
 
 def convS(ctx, name, x, cin, cout):  # p3d.py:18-22
-    return tfs.conv3d_same(x, conv_w(ctx, name, [1, 3, 3, cin, cout]), (1, 1, 1), conv_w(ctx, name + "_bias", [cout]))
+    return tfs.conv3d_same(x, ctx.q(conv_w(ctx, name, [1, 3, 3, cin, cout])), (1, 1, 1), conv_w(ctx, name + "_bias", [cout]))
 
 
 def convT(ctx, name, x, cin, cout):  # p3d.py:23-27
-    return tfs.conv3d_same(x, conv_w(ctx, name, [3, 1, 1, cin, cout]), (1, 1, 1), conv_w(ctx, name + "_bias", [cout]))
+    return tfs.conv3d_same(x, ctx.q(conv_w(ctx, name, [3, 1, 1, cin, cout])), (1, 1, 1), conv_w(ctx, name + "_bias", [cout]))
 
 
 def layers_conv3d(ctx, x, cout, k, s, name=None, scope="", use_bias=True):
@@ -163,7 +189,7 @@ def layers_conv3d(ctx, x, cout, k, s, name=None, scope="", use_bias=True):
     nm = (scope + "/" + name if scope else name) if name is not None else ctx.vs.unique(scope, "conv3d")
     w = ctx.vs.get(nm + "/kernel", [*k, x.shape[-1], cout], "glorot")
     b = ctx.vs.get(nm + "/bias", [cout], "bias") if use_bias else None
-    return tfs.conv3d_same(x, w, s, b)
+    return tfs.conv3d_same(x, ctx.q(w), s, b)
 
 
 def layers_deconv3d(ctx, x, cout, k, s, name=None, scope=""):
@@ -173,24 +199,24 @@ def layers_deconv3d(ctx, x, cout, k, s, name=None, scope=""):
     nm = (scope + "/" + name if scope else name) if name is not None else ctx.vs.unique(scope, "conv3d_transpose")
     w = ctx.vs.get(nm + "/kernel", [*k, cout, x.shape[-1]], "glorot_t")
     b = ctx.vs.get(nm + "/bias", [cout], "bias")
-    return tfs.conv3d_transpose_same(x, w, s, b)
+    return tfs.conv3d_transpose_same(x, ctx.q(w), s, b)
 
 
 def net_conv3d(ctx, x, cout, k, s, training, name, mode="bn"):  # network.py:100-104
-    return torch.relu(norm(ctx, layers_conv3d(ctx, x, cout, k, s, name), training, mode))
+    return ctx.q(torch.relu(norm(ctx, layers_conv3d(ctx, x, cout, k, s, name), training, mode)))
 
 
 def net_deconv3d(ctx, x, cout, k, s, training, name, mode="bn"):  # network.py:106-110
-    return torch.relu(norm(ctx, layers_deconv3d(ctx, x, cout, k, s, name), training, mode))
+    return ctx.q(torch.relu(norm(ctx, layers_deconv3d(ctx, x, cout, k, s, name), training, mode)))
 
 
 def attention(ctx, x, name, training, mode="bn", subsample=False, sub_size=2):
     """network.py:157-193 (Python-2 integer division at :182,187,188)."""
     n, d, h, w, ch = x.shape
     inter = max(1, ch // 8)
-    f = layers_conv3d(ctx, x, inter, 1, 1, scope=name)
-    g = layers_conv3d(ctx, x, inter, 1, 1, scope=name)
-    hh = layers_conv3d(ctx, x, ch, 1, 1, scope=name)
+    f = ctx.q(layers_conv3d(ctx, x, inter, 1, 1, scope=name))
+    g = ctx.q(layers_conv3d(ctx, x, inter, 1, 1, scope=name))
+    hh = ctx.q(layers_conv3d(ctx, x, ch, 1, 1, scope=name))
     if subsample:
         f = tfs.max_pool3d_valid(f, sub_size)
         g = tfs.max_pool3d_valid(g, sub_size // 2)
@@ -199,13 +225,13 @@ def attention(ctx, x, name, training, mode="bn", subsample=False, sub_size=2):
     fk = f.reshape(n, -1, inter)
     hv = hh.reshape(n, -1, ch)
     s = torch.matmul(gq, fk.transpose(1, 2))
-    beta = torch.softmax(s, dim=-1)
-    o = torch.matmul(beta, hv)
+    beta = ctx.q(torch.softmax(s, dim=-1))      # probabilities are a bf16 tensor-core operand
+    o = ctx.q(torch.matmul(beta, hv))
     o = o.reshape(n, d * 2 // sub_size, h * 2 // sub_size, w * 2 // sub_size, ch)
     o = layers_conv3d(ctx, o, ch, 1, sub_size // 2)
-    o = torch.relu(norm(ctx, o, training, mode))
+    o = ctx.q(torch.relu(norm(ctx, o, training, mode)))
     gamma = ctx.vs.get("gamma" + name, [1], "sa_gamma")
-    return o * gamma + x
+    return ctx.q(o * gamma + x)
 
 
 def cbam_block(ctx, x, name, ratio=8):
@@ -238,7 +264,7 @@ def dropout(ctx, x, name):
     if not ctx.training or ctx.dropout <= 0.0:
         return x
     keep = ctx.dropout_mask_fn(name, x.shape).to(x.dtype)
-    return x * keep / (1.0 - ctx.dropout)
+    return ctx.q(x * keep / (1.0 - ctx.dropout))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -249,30 +275,33 @@ def bottleneck(ctx: Ctx, x, inplanes, planes, idx, first_of_stage, mode):
     tr = ctx.backbone_training
     stride_hw = 2 if (first_of_stage and idx != 0) else 1  # p3d.py:45-49
     nrm = (lambda t, gk="gamma": bn(ctx, t, tr, gamma_kind=gk)) if mode == "bn" else (lambda t, gk="gamma": gn_layer(ctx, t, gamma_kind=gk))
+    q = ctx.q
     residual = x
-    out = tfs.conv3d_same(x, conv_w(ctx, f"conv3_{idx}_1", [1, 1, 1, inplanes, planes]), (1, stride_hw, stride_hw))
-    out = torch.relu(nrm(out))
+    out = tfs.conv3d_same(x, q(conv_w(ctx, f"conv3_{idx}_1", [1, 1, 1, inplanes, planes])), (1, stride_hw, stride_hw))
+    out = q(torch.relu(nrm(out)))
     st = "ABC"[idx % 3]
     nm = f"ST{st}_{idx}_2"
     if st == "A":  # serial S -> T
-        out = torch.relu(nrm(convS(ctx, nm + "_S", out, planes, planes)))
-        out = torch.relu(nrm(convT(ctx, nm + "_T", out, planes, planes)))
-    elif st == "B":  # parallel S + T
+        out = q(torch.relu(nrm(convS(ctx, nm + "_S", out, planes, planes))))
+        out = q(torch.relu(nrm(convT(ctx, nm + "_T", out, planes, planes))))
+    elif st == "B":  # parallel S + T  (CUDA path: both norms + ReLUs + the sum are one pass, stored once)
         s_br = torch.relu(nrm(convS(ctx, nm + "_S", out, planes, planes)))
         t_br = torch.relu(nrm(convT(ctx, nm + "_T", out, planes, planes)))
-        out = t_br + s_br
+        out = q(t_br + s_br)
     else:  # C: S then S + T(S)
-        s_br = torch.relu(nrm(convS(ctx, nm + "_S", out, planes, planes)))
+        s_br = q(torch.relu(nrm(convS(ctx, nm + "_S", out, planes, planes))))
         t_br = torch.relu(nrm(convT(ctx, nm + "_T", s_br, planes, planes)))
-        out = s_br + t_br
-    out = nrm(tfs.conv3d_same(out, conv_w(ctx, f"conv3_{idx}_3", [1, 1, 1, planes, planes * BLOCK_EXPANSION])), "gamma_res")
+        out = q(s_br + t_br)
+    out = nrm(tfs.conv3d_same(out, q(conv_w(ctx, f"conv3_{idx}_3", [1, 1, 1, planes, planes * BLOCK_EXPANSION]))), "gamma_res")
     if first_of_stage:  # downsample=['3d', stride_p] (p3d.py:149-155,124-127)
-        residual = tfs.conv3d_same(residual, conv_w(ctx, f"dw3d_{idx}", [1, 1, 1, inplanes, planes * BLOCK_EXPANSION]),
+        residual = tfs.conv3d_same(residual, q(conv_w(ctx, f"dw3d_{idx}", [1, 1, 1, inplanes, planes * BLOCK_EXPANSION])),
                                    (1, stride_hw, stride_hw))
         residual = nrm(residual)
+        if mode == "gn":
+            residual = q(residual)   # GN graphs store the normalised shortcut (it feeds the CBAM kernels); BN graphs fuse it
     if mode == "gn":
         residual = cbam_block(ctx, residual, f"cbam_{idx}")  # gn/p3d_gn.py:175
-    return ctx.tap(f"b{idx}", torch.relu(out + residual))
+    return ctx.tap(f"b{idx}", q(torch.relu(out + residual)))
 
 
 def make_block(ctx, x, planes, num, inplanes, cnt, mode):
@@ -287,13 +316,13 @@ TPOOL = ((2, 1, 1), (2, 1, 1))
 
 def backbone(ctx: Ctx, x, mode="bn", stem_training=None):
     """stem + 3 stages; returns dict of the tensors the decoders consume."""
-    w = conv_w(ctx, "firstconv1", [1, 7, 7, 3, 64])
-    c1 = ctx.tap("firstconv1", tfs.conv3d_same(x, w, (1, 2, 2)))
+    w = ctx.q(conv_w(ctx, "firstconv1", [1, 7, 7, 3, 64]))
+    c1 = ctx.tap("firstconv1", tfs.conv3d_same(ctx.q(x), w, (1, 2, 2)))
     if mode == "bn":
         c1 = bn(ctx, c1, ctx.training if stem_training is None else stem_training)  # p3d.py:344 follows `training`
     else:
         c1 = gn_layer(ctx, c1)
-    c1 = ctx.tap("stem", torch.relu(c1))
+    c1 = ctx.tap("stem", ctx.q(torch.relu(c1)))
     t = {}
     t["x_1_0"] = ctx.tap("x_1_0", tfs.max_pool3d_same(c1, *TPOOL))
     pool1 = ctx.tap("pool1", tfs.max_pool3d_same(c1, (2, 3, 3), (2, 2, 2)))
@@ -351,51 +380,51 @@ def p3d_unet(ctx, x):  # p3d.py:169-221
     tr = ctx.training
     t = backbone(ctx, x)
     cat = lambda a, b: torch.cat([a, b], dim=-1)  # noqa: E731
-    d1 = torch.relu(bn(ctx, layers_deconv3d(ctx, t["x_4_0"], 512, (1, 3, 3), 2), tr, name="deconv1_bn"))
-    d2 = torch.relu(bn(ctx, layers_deconv3d(ctx, cat(d1, t["x_3_0"]), 256, (2, 3, 3), 2), tr, name="deconv2_bn"))
-    d3 = torch.relu(bn(ctx, layers_deconv3d(ctx, cat(d2, t["x_2_0"]), 128, 3, 2), tr, name="deconv3_bn"))
+    d1 = ctx.q(torch.relu(bn(ctx, layers_deconv3d(ctx, t["x_4_0"], 512, (1, 3, 3), 2), tr, name="deconv1_bn")))
+    d2 = ctx.q(torch.relu(bn(ctx, layers_deconv3d(ctx, cat(d1, t["x_3_0"]), 256, (2, 3, 3), 2), tr, name="deconv2_bn")))
+    d3 = ctx.q(torch.relu(bn(ctx, layers_deconv3d(ctx, cat(d2, t["x_2_0"]), 128, 3, 2), tr, name="deconv3_bn")))
     d3 = ctx.tap("deconv3", dropout(ctx, d3, "deconv3_drop"))  # deconv3_concat is computed and ignored (:213-214)
-    c = layers_conv3d(ctx, d3, 32, 1, 1)
+    c = ctx.q(layers_conv3d(ctx, d3, 32, 1, 1))
     logits = ctx.tap("x_0_1", layers_deconv3d(ctx, c, 1, 3, 2))
     return ctx.tap("pred", torch.sigmoid(logits))
 
 
 def p3d_concat(ctx, x):  # p3d.py:224-276 (returns logits: no sigmoid at :275-276)
     tr = ctx.training
-    w = conv_w(ctx, "firstconv1", [1, 7, 7, 3, 64])
-    c1 = torch.relu(bn(ctx, tfs.conv3d_same(x, w, (1, 2, 2)), tr))
+    w = ctx.q(conv_w(ctx, "firstconv1", [1, 7, 7, 3, 64]))
+    c1 = ctx.q(torch.relu(bn(ctx, tfs.conv3d_same(ctx.q(x), w, (1, 2, 2)), tr)))
     pool1 = tfs.max_pool3d_same(c1, (2, 3, 3), (2, 2, 2))
     res1, cnt = make_block(ctx, pool1, 64, 3, 64, 0, "bn")
     pool2 = tfs.max_pool3d_same(res1, *TPOOL)
-    dp2 = torch.relu(bn(ctx, layers_deconv3d(ctx, pool2, 128, 3, 1, "deconv_pool2"), tr, name="deconv_pool2_bn"))
+    dp2 = ctx.q(torch.relu(bn(ctx, layers_deconv3d(ctx, pool2, 128, 3, 1, "deconv_pool2"), tr, name="deconv_pool2_bn")))
     res2, cnt = make_block(ctx, pool2, 128, 8, 256, cnt, "bn")
     pool3 = tfs.max_pool3d_same(res2, *TPOOL)
-    dp3 = torch.relu(bn(ctx, layers_deconv3d(ctx, pool3, 256, 3, 2, "deconv_pool3"), tr, name="deconv_pool3_bn"))
+    dp3 = ctx.q(torch.relu(bn(ctx, layers_deconv3d(ctx, pool3, 256, 3, 2, "deconv_pool3"), tr, name="deconv_pool3_bn")))
     res3, cnt = make_block(ctx, pool3, 256, 36, 512, cnt, "bn")
     pool4 = tfs.max_pool3d_same(res3, *TPOOL)
-    dp4 = torch.relu(bn(ctx, layers_deconv3d(ctx, pool4, 512, 3, 4, "deconv_pool4"), tr, name="deconv_pool4_bn"))
+    dp4 = ctx.q(torch.relu(bn(ctx, layers_deconv3d(ctx, pool4, 512, 3, 4, "deconv_pool4"), tr, name="deconv_pool4_bn")))
     cc = torch.cat([dp2, dp3, dp4], dim=-1)
-    cc = torch.relu(bn(ctx, layers_conv3d(ctx, cc, 512, 3, 1, "conv_concat"), tr, name="conv_concat_bn"))
-    dr = torch.relu(bn(ctx, layers_deconv3d(ctx, cc, 128, 3, 2, "deconv_revise"), tr, name="deconv1_revise_bn"))
+    cc = ctx.q(torch.relu(bn(ctx, layers_conv3d(ctx, cc, 512, 3, 1, "conv_concat"), tr, name="conv_concat_bn")))
+    dr = ctx.q(torch.relu(bn(ctx, layers_deconv3d(ctx, cc, 128, 3, 2, "deconv_revise"), tr, name="deconv1_revise_bn")))
     dr = dropout(ctx, dr, "deconv_revise_drop")
     return ctx.tap("pred", layers_deconv3d(ctx, dr, 1, 3, 2, "predict_revise"))
 
 
 def gn_inference_p3d(ctx, x, pool4_filters=1024):  # gn/p3d_gn.py:214-258 (and :279-324 with 512)
-    w = conv_w(ctx, "firstconv1", [1, 7, 7, 3, 64])
-    c1 = torch.relu(gn_layer(ctx, tfs.conv3d_same(x, w, (1, 2, 2))))
+    w = ctx.q(conv_w(ctx, "firstconv1", [1, 7, 7, 3, 64]))
+    c1 = ctx.q(torch.relu(gn_layer(ctx, tfs.conv3d_same(ctx.q(x), w, (1, 2, 2)))))
     pool1 = tfs.max_pool3d_same(c1, (2, 3, 3), (2, 2, 2))
     res1, cnt = make_block(ctx, pool1, 64, 3, 64, 0, "gn")
     pool2 = ctx.tap("pool2", tfs.max_pool3d_same(res1, *TPOOL))
     res2, cnt = make_block(ctx, pool2, 128, 8, 256, cnt, "gn")
     pool3 = ctx.tap("pool3", tfs.max_pool3d_same(res2, *TPOOL))
-    dp3 = torch.relu(gn_layer(ctx, layers_deconv3d(ctx, pool3, 512, 3, 2, "deconv_pool3")))
+    dp3 = ctx.q(torch.relu(gn_layer(ctx, layers_deconv3d(ctx, pool3, 512, 3, 2, "deconv_pool3"))))
     res3, cnt = make_block(ctx, pool3, 256, 36, 512, cnt, "gn")
     pool4 = ctx.tap("pool4", tfs.max_pool3d_same(res3, *TPOOL))
-    dp4 = torch.relu(gn_layer(ctx, layers_deconv3d(ctx, pool4, pool4_filters, 3, 4, "deconv_pool4")))
+    dp4 = ctx.q(torch.relu(gn_layer(ctx, layers_deconv3d(ctx, pool4, pool4_filters, 3, 4, "deconv_pool4"))))
     cc = torch.cat([dp3, dp4, pool2], dim=-1)
-    cc = ctx.tap("conv_concat", torch.relu(gn_layer(ctx, layers_conv3d(ctx, cc, 1024, 3, 1, "conv_concat"))))
-    dr = torch.relu(gn_layer(ctx, layers_deconv3d(ctx, cc, 256, 3, 2, "deconv_revise")))
+    cc = ctx.tap("conv_concat", ctx.q(torch.relu(gn_layer(ctx, layers_conv3d(ctx, cc, 1024, 3, 1, "conv_concat")))))
+    dr = ctx.q(torch.relu(gn_layer(ctx, layers_deconv3d(ctx, cc, 256, 3, 2, "deconv_revise"))))
     dr = dropout(ctx, dr, "deconv_revise_drop")
     return ctx.tap("pred", layers_deconv3d(ctx, dr, 1, 3, 2, "predict_revise"))
 
@@ -406,9 +435,9 @@ def gn_inference_p3d_concat(ctx, x):
 
 def gn_inference_p3d_decoder_block(ctx, x):  # gn/p3d_gn.py:489-539 (inside tf.variable_scope('P3D'))
     ctx.vs.prefix = "P3D/"
-    gnrelu = lambda t: torch.relu(gn_layer(ctx, t))  # noqa: E731
-    w = conv_w(ctx, "firstconv1", [1, 7, 7, 3, 64])
-    c1 = gnrelu(tfs.conv3d_same(x, w, (1, 2, 2)))
+    gnrelu = lambda t: ctx.q(torch.relu(gn_layer(ctx, t)))  # noqa: E731
+    w = ctx.q(conv_w(ctx, "firstconv1", [1, 7, 7, 3, 64]))
+    c1 = gnrelu(tfs.conv3d_same(ctx.q(x), w, (1, 2, 2)))
     pool1 = tfs.max_pool3d_same(c1, (2, 3, 3), (2, 2, 2))
     res1, cnt = make_block(ctx, pool1, 64, 3, 64, 0, "gn")
     pool2 = ctx.tap("pool2", tfs.max_pool3d_same(res1, *TPOOL))
@@ -458,16 +487,16 @@ def synthetic_target(batch: int, frames: int = 16, size: int = 112, seed: int = 
 
 
 def forward(graph: str, x: torch.Tensor, vs: VarStore, training: bool, dropout_rate: float = 0.0,
-            taps: Optional[dict] = None, dropout_mask_fn=None) -> torch.Tensor:
+            taps: Optional[dict] = None, dropout_mask_fn=None, bf16: bool = False) -> torch.Tensor:
     vs.reset_names()
-    ctx = Ctx(vs, training, dropout_rate, taps, dropout_mask_fn=dropout_mask_fn)
+    ctx = Ctx(vs, training, dropout_rate, taps, dropout_mask_fn=dropout_mask_fn, bf16=bf16)
     out = GRAPHS[graph](ctx, x)
     forward.last_ctx = ctx
     return out
 
 
 def train_step(graph: str, x, y, vs: VarStore, adam_state: dict, step: int, lr: float = 1e-4, dropout_rate: float = 0.0,
-               dropout_mask_fn=None):
+               dropout_mask_fn=None, bf16: bool = False, taps: Optional[dict] = None):
     """One iteration of train.py:156-172,217: smooth-L1 (sum) loss, Adam(lr), BN moving-average updates.
     Returns (loss, grads dict).  Updates vs.params and adam_state in place."""
     names = [n for n in vs.params if vs.trainable.get(n, True)]
@@ -477,7 +506,8 @@ def train_step(graph: str, x, y, vs: VarStore, adam_state: dict, step: int, lr: 
         vs.params[n] = leaves[n]
     was_frozen = vs.frozen
     vs.frozen = True
-    pred = forward(graph, x, vs, True, dropout_rate, dropout_mask_fn=dropout_mask_fn)
+    pred = forward(graph, x, vs, True, dropout_rate, taps=taps, dropout_mask_fn=dropout_mask_fn, bf16=bf16)
+    train_step.last_pred = pred.detach()
     ctx = forward.last_ctx
     loss = tfs.smooth_l1_loss(pred.reshape(y.shape), y, 1.0)
     loss.backward()
