@@ -38,6 +38,9 @@ const char* sap3d_last_error(void);
 int sap3d_abi_version(void);
 /* 1 when a CUDA device of compute capability 10.x is usable */
 int sap3d_device_ok(void);
+/* developer probe, not a reference call-site: per-CTA phase time stamps of the tcgen05 convolution kernel are written to
+ * buf ([cta][16][2] uint64 device memory: clock64, globaltimer); NULL switches the probe off.  Process-global. */
+int sap3d_debug_conv_timing(void* buf);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolution family.  Replaces tf.nn.conv3d (p3d.py:19,24,86,112,125,343), tf.nn.bias_add
@@ -191,6 +194,11 @@ int sap3d_head_tc_bwd(const float* dlogits, const void* x, int32_t N, int32_t D,
  * loss_sum[0] += loss; dlogits = dLoss/dlogits; dbias[0] += sum(dlogits); pred = sigmoid(logits). */
 int sap3d_loss_smooth_l1(const float* logits, const float* target, int64_t n, int32_t apply_sigmoid, float* pred,
                          float* dlogits, double* loss_sum, float* dbias, void* stream);
+/* the general form of utils/network.py:49-62: in = inside_weight * (pred - target); per element
+ * |in| < 1/sigma^2 ? in^2 sigma^2 / 2 : |in| - 0.5/sigma^2, times outside_weight, summed over all elements. */
+int sap3d_loss_smooth_l1_ex(const float* logits, const float* target, int64_t n, int32_t apply_sigmoid, float* pred,
+                            float* dlogits, double* loss_sum, float* dbias, float sigma, float inside_weight, float outside_weight,
+                            void* stream);
 /* tf.layers.dropout (p3d.py:392): y = x*keep/(1-rate), keep = splitmix64(base_seed + *step, index) >= rate.
  * The backward pass is the same call on dy. */
 int sap3d_dropout(int32_t dtype, const void* x, void* y, int64_t n, float rate, uint64_t base_seed, const int32_t* step,

@@ -57,6 +57,7 @@ def _sig(name, argtypes, restype=C.c_int):
 
 
 _P = C.POINTER
+_sig("sap3d_debug_conv_timing", [_vp])
 _sig("sap3d_conv_out_dims", [_P(ConvDesc), _P(C.c_int32)])
 _sig("sap3d_conv_stats_rows", [_P(ConvDesc)])
 _sig("sap3d_conv_packed_elems", [_P(ConvDesc), _i32], C.c_size_t)
@@ -127,6 +128,7 @@ _sig("sap3d_head_tc_workspace", [_i32, _i32, _i32, _i32, _i32], C.c_size_t)
 _sig("sap3d_head_tc_fwd", [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_head_tc_bwd", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp])
 _sig("sap3d_loss_smooth_l1", [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp])
+_sig("sap3d_loss_smooth_l1_ex", [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _vp])
 _sig("sap3d_dropout", [_i32, _vp, _vp, _i64, _f32, _u64, _vp, _i32, _vp])
 _sig("sap3d_gate_fwd", [_i32, _vp, _vp, _vp, _vp, _i64, _vp])
 _sig("sap3d_gate_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp])

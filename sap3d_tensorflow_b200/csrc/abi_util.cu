@@ -1,4 +1,5 @@
 #include "abi_util.cuh"
+#include "conv_tc.cuh"
 
 #include <stdint.h>
 #include <string.h>
@@ -75,6 +76,12 @@ uint32_t sap3d_crc32c(uint32_t crc, const void* data, size_t n) {
   return ~c;
 }
 const char* sap3d_last_error(void) { return sap3d::g_err; }
-int sap3d_abi_version(void) { return 1; }
+int sap3d_abi_version(void) { return 2; }
+// developer probe (tools/conv_phase_probe.py): per-CTA phase time stamps of conv_tc_kernel into `buf` ([cta][16][2] uint64,
+// device memory); NULL switches it off.  Process-global and NOT part of the re-entrant surface.
+int sap3d_debug_conv_timing(void* buf) {
+  sap3d::tc_set_debug_buffer(buf);
+  return 0;
+}
 int sap3d_device_ok(void) { return sap3d::require_device() == 0 ? 1 : 0; }
 }

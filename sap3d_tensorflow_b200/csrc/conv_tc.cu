@@ -64,7 +64,17 @@ struct alignas(64) TcConvParams {
   const float* shift;
   int relu, accumulate, out_f32;
   int b_batched;       // the weight-side operand is per sample: third TMA coordinate = the tile's batch index
+  unsigned long long* dbg;   // phase-timing probe (tools/conv_phase_probe.py): [cta][16][2] = (clock64, globaltimer); normally NULL
 };
+
+SAP3D_DEVINL void dbg_mark(const TcConvParams& p, int i) {
+  if (p.dbg != nullptr) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[(blockIdx.x * 16 + i) * 2] = clock64();
+    p.dbg[(blockIdx.x * 16 + i) * 2 + 1] = g;
+  }
+}
 
 // column sums of a 32(lanes) x 32(values) block: on return lane l holds the sum over all lanes of
 // the caller's v[l].  31 shuffles instead of 160.
@@ -110,6 +120,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) dbg_mark(p, 0);
 
   // ---- tile decode -------------------------------------------------------------------------
   int tile = blockIdx.x / SPLIT;
@@ -158,6 +169,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) dbg_mark(p, 1);
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -181,12 +193,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             tma_load_5d(sa + sub * A_BYTES, amap, full, (tap.c0 + ch) * 64, w0s[sub] + tap.dw, h0s[sub] + tap.dh, d0s[sub] + tap.dd,
                         n0s[sub]);
           tma_load_3d(sa + MT * A_BYTES, &p.bmap, full, tap.kofs + ch * 64, nt * BLOCK_N, p.b_batched ? n0s[0] : 0);
+          if (kbi == kb_begin) dbg_mark(p, 2);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
       }
+      dbg_mark(p, 9);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -198,6 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(bar_base + stage * 8, phase);
         tc_fence_after();
+        if (kb == 0) dbg_mark(p, 3);
         const uint32_t sa = base + stage * STAGE_BYTES;
         const uint64_t bdesc = umma_desc_sw128(sa + MT * A_BYTES, 16, 1024);
 #pragma unroll
@@ -216,6 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         }
       }
       if (nkb > 0) tc_commit(bar_base + 2 * STAGES * 8);  // accumulator ready
+      dbg_mark(p, 4);
     }
     __syncwarp();
   } else if (SPLIT > 1) {
@@ -226,6 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       mbar_wait(bar_base + 2 * STAGES * 8, 0);
       tc_fence_after();
     }
+    if (threadIdx.x == 64) dbg_mark(p, 5);
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       const uint32_t owner = SPLIT == 4 ? (uint32_t)c : (uint32_t)(c >> 1);
@@ -249,6 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     tc_fence_before();
   }
   if (SPLIT > 1) cluster_sync_all();
+  if (threadIdx.x == 64) dbg_mark(p, 6);
   if (warp >= 2) {
     // ================= epilogue (warps 2..5) =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -270,6 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       mbar_wait(bar_base + 2 * STAGES * 8, 0);
       tc_fence_after();
     }
+    if (threadIdx.x == 64) dbg_mark(p, 10);
 #pragma unroll 1
     for (int sub = 0; sub < MT; ++sub) {
     if (!live[sub]) break;
@@ -395,6 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     }
     if (want_stats && sub + 1 < MT) asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats is reused by the next sub-tile
     }  // sub
+    if (threadIdx.x == 64) dbg_mark(p, 7);
     tc_fence_before();
   }
   __syncthreads();
@@ -402,6 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, MT * BLOCK_N);
   }
+  if (threadIdx.x == 0) dbg_mark(p, 8);
 }
 
 
@@ -1251,6 +1272,9 @@ static int launch_persist_mc(const TcConvParams& prm, int m_groups, cudaStream_t
   return 0;
 }
 
+static unsigned long long* g_conv_dbg = nullptr;
+void tc_set_debug_buffer(void* buf) { g_conv_dbg = reinterpret_cast<unsigned long long*>(buf); }
+
 // opt-in while it is being measured: SAP3D_CONV_MULTICAST=2 or 4 (cluster size); unset / 0 = off
 static int multicast_cluster() {
   static int v = -1;
@@ -1352,6 +1376,7 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
   prm.seg_split = pb.seg_split;
   prm.accumulate2 = pb.accumulate2;
   prm.out_f32 = pb.out_f32;
+  prm.dbg = g_conv_dbg;
   // two M sub-tiles per CTA when the problem still fills the GPU several times over
   const long long ctas1 = (long long)prm.ncls * prm.m_tiles * prm.n_tiles;
   int mt = (pb.force_mt ? pb.force_mt : (ctas1 >= 4 * 148 ? 2 : 1));

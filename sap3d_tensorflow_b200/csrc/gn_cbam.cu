@@ -229,13 +229,18 @@ __global__ void __launch_bounds__(256) cbam_merge_kernel(const T* __restrict__ a
     const int c = (int)(e - pos * C);
     const long long n = pos / S;
     float av[8], rv[8], o[8];
-    Vec8<T>::load(a + e, av);
     Vec8<T>::load(r + e, rv);
     const float at = att[pos];
+    if (a == nullptr) {   // stand-alone cbam_block (utils/network.py:198-206): refined feature, no main branch, no ReLU
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const long long si = n * C + c + j;
-      o[j] = fmaxf(fmaf(av[j], s1[si], t1[si]) + rv[j] * cscale[si] * at, 0.f);
+      for (int j = 0; j < 8; ++j) o[j] = rv[j] * cscale[n * C + c + j] * at;
+    } else {
+      Vec8<T>::load(a + e, av);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long si = n * C + c + j;
+        o[j] = fmaxf(fmaf(av[j], s1[si], t1[si]) + rv[j] * cscale[si] * at, 0.f);
+      }
     }
     Vec8<T>::store(y + e, o);
   }
@@ -311,12 +316,15 @@ int sap3d_cbam_fwd(int32_t dtype, const void* r, int32_t N, int32_t D, int32_t H
   if (C % 8 != 0) return set_error("cbam_fwd: C %% 8 != 0");
   const long long S = (long long)D * H * W;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (sap3d_sample_channel_partials(dtype, r, nullptr, N, S, C, rows, part, stream)) return 1;
-  if (hidden > 1024) return set_error("cbam_fwd: hidden > 1024");
-  const size_t sm = (size_t)(2 * C + 2 * hidden + 16 * hidden) * sizeof(float);
-  const int threads = hidden * 8 <= 1024 ? (hidden * 8 < 256 ? 256 : hidden * 8) : 1024;
-  cbam_channel_mlp_kernel<<<N, threads, sm, st>>>(part, rows, C, hidden, S, w0, b0, w1, b1, cscale, save);
-  if (check_launch("cbam_channel_mlp")) return 1;
+  if (w0 != nullptr) {   // channel attention; w0 == NULL: spatial attention alone, the caller keeps cscale == 1
+    if (sap3d_sample_channel_partials(dtype, r, nullptr, N, S, C, rows, part, stream)) return 1;
+    if (hidden > 1024) return set_error("cbam_fwd: hidden > 1024");
+    const size_t sm = (size_t)(2 * C + 2 * hidden + 16 * hidden) * sizeof(float);
+    const int threads = hidden * 8 <= 1024 ? (hidden * 8 < 256 ? 256 : hidden * 8) : 1024;
+    cbam_channel_mlp_kernel<<<N, threads, sm, st>>>(part, rows, C, hidden, S, w0, b0, w1, b1, cscale, save);
+    if (check_launch("cbam_channel_mlp")) return 1;
+  }
+  if (w_sp == nullptr) return 0;   // channel attention alone: the caller keeps att == 1
   const long long total = (long long)N * S;
   const int blocks = (int)((total * 32 + 255) / 256 > 148 * 8 ? 148 * 8 : (total * 32 + 255) / 256);
   if (dtype == SAP3D_BF16) cbam_spatial_pool_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(r), cscale, S, C, total, sp);

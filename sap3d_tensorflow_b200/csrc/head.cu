@@ -368,18 +368,19 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const HeadBwdArgs p) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                     long long n, int apply_sigmoid, float* pred, float* dlogits,
-                                                    double* loss_sum, float* dbias) {
+                                                    double* loss_sum, float* dbias, float sigma2, float w_in, float w_out) {
   double ls = 0.0;
   float ds = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float z = logits[i];
     const float pr = apply_sigmoid ? 1.f / (1.f + __expf(-z)) : z;
     if (pred) pred[i] = pr;
-    const float d = pr - target[i];
+    // utils/network.py:49-62: in = w_in * (pred - target); |in| < 1/sigma^2 ? in^2 sigma^2 / 2 : |in| - 0.5/sigma^2; times w_out
+    const float d = w_in * (pr - target[i]);
     const float a = fabsf(d);
-    const bool quad = a < 1.f;
-    ls += quad ? 0.5f * d * d : a - 0.5f;
-    float g = quad ? d : (d > 0.f ? 1.f : -1.f);
+    const bool quad = a < 1.f / sigma2;
+    ls += w_out * (quad ? 0.5f * sigma2 * d * d : a - 0.5f / sigma2);
+    float g = w_out * w_in * (quad ? sigma2 * d : (d > 0.f ? 1.f : -1.f));
     if (apply_sigmoid) g *= pr * (1.f - pr);
     if (dlogits) dlogits[i] = g;
     ds += g;
@@ -668,10 +669,17 @@ int sap3d_head_tc_bwd(const float* dlogits, const void* x, int32_t N, int32_t D,
 
 int sap3d_loss_smooth_l1(const float* logits, const float* target, int64_t n, int32_t apply_sigmoid, float* pred,
                          float* dlogits, double* loss_sum, float* dbias, void* stream) {
+  return sap3d_loss_smooth_l1_ex(logits, target, n, apply_sigmoid, pred, dlogits, loss_sum, dbias, 1.f, 1.f, 1.f, stream);
+}
+
+int sap3d_loss_smooth_l1_ex(const float* logits, const float* target, int64_t n, int32_t apply_sigmoid, float* pred,
+                            float* dlogits, double* loss_sum, float* dbias, float sigma, float inside_weight, float outside_weight,
+                            void* stream) {
   if (require_device()) return 1;
   if (!logits || !target || !loss_sum) return set_error("loss_smooth_l1: NULL pointer");
+  if (!(sigma > 0.f)) return set_error("loss_smooth_l1: sigma must be positive");
   loss_kernel<<<egrid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, target, n, apply_sigmoid, pred, dlogits,
-                                                                            loss_sum, dbias);
+                                                                            loss_sum, dbias, sigma * sigma, inside_weight, outside_weight);
   return check_launch("loss_smooth_l1");
 }
 

@@ -160,6 +160,77 @@ class CbamBlockTailOp:
         e._count(8)
 
 
+class CbamOp:
+    """stand-alone cbam_block / channel_attention / spatial_attention of utils/network.py:198-274 on an arbitrary feature map
+    (the block tail above is the fused form the GN backbone uses).  mode: 'both' | 'channel' | 'spatial'.
+    Forward: sap3d_cbam_fwd (attention maps) + sap3d_cbam_merge with no main branch (y = x * cscale * att, no ReLU).
+    Backward: the tail kernels with the main branch switched off -- zero main-branch operand, an all-positive stand-in for the
+    ReLU mask -- so the CBAM gradient code is the one the hot path exercises."""
+
+    def __init__(self, eng: Engine, x: T, mode: str, w0=None, b0=None, w1=None, b1=None, w_sp=None, name=""):
+        assert mode in ("both", "channel", "spatial")
+        self.eng, self.x, self.mode, self.name = eng, x, mode, name
+        self.w0, self.b0, self.w1, self.b1, self.w_sp = w0, b0, w1, b1, w_sp
+        N, D, H, W, Cc = x.shape
+        if Cc % 8 != 0:
+            raise A.Sap3dError("cbam_block: channels must be a multiple of 8")
+        dev, S = eng.device, D * H * W
+        self.hidden = Cc // 8
+        self.rows = A.lib.sap3d_sample_stats_rows(S, Cc, N)
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.part = torch.zeros(N, self.rows, 3, Cc, **f32)
+        self.cscale = torch.ones(N, Cc, **f32)          # stays 1 in 'spatial' mode
+        self.sp = torch.zeros(N, S, 2, **f32)
+        self.att = torch.ones(N, S, **f32)              # stays 1 in 'channel' mode
+        self.save = torch.zeros(N, 2 * Cc + 2 * self.hidden, **f32)
+        self.y = eng.tensor(x.shape, name)
+        eng.fwd_ops.append(self.fwd)
+        eng.bwd_ops.append(self.bwd)
+        if eng.training_graph:
+            _reserve_ws(eng, N, S, Cc)
+            G = min(GN_GROUPS, Cc)
+            self.G = G
+            self.zero_act = torch.zeros(x.shape, device=dev, dtype=eng.tdt)      # main-branch operand (none)
+            self.ones_act = torch.ones(x.shape, device=dev, dtype=eng.tdt)       # ReLU mask stand-in: everything passes
+            self.zc = torch.zeros(N, Cc, **f32)
+            self.zg = torch.zeros(N, G, **f32)
+            self.zw = torch.zeros(max(Cc * self.hidden, 686), **f32)             # stand-in weights / gradient sinks
+            self.sink = torch.zeros(max(Cc * self.hidden, 686), **f32)
+
+    def fwd(self):
+        e = self.eng
+        N, D, H, W, Cc = self.x.shape
+        ch = self.mode in ("both", "channel")
+        spt = self.mode in ("both", "spatial")
+        A.check(A.lib.sap3d_cbam_fwd(e.dt, A.ptr(self.x.buf), N, D, H, W, Cc, self.hidden,
+                                     A.ptr(self.w0.w) if ch else None, A.ptr(self.b0.w) if ch else None,
+                                     A.ptr(self.w1.w) if ch else None, A.ptr(self.b1.w) if ch else None,
+                                     A.ptr(self.w_sp.w) if spt else None, A.ptr(self.part), self.rows, A.ptr(self.cscale),
+                                     A.ptr(self.sp), A.ptr(self.att), A.ptr(self.save), e.stream), "cbam_fwd " + self.name)
+        A.check(A.lib.sap3d_cbam_merge(e.dt, None, None, None, A.ptr(self.x.buf), A.ptr(self.cscale), A.ptr(self.att),
+                                       A.ptr(self.y.buf), N, D * H * W, Cc, e.stream), "cbam apply " + self.name)
+        e._count(5)
+
+    def bwd(self):
+        e = self.eng
+        if not self.y.gflag or not self.x.needs_grad:
+            return
+        N, D, H, W, Cc = self.x.shape
+        ch = self.mode in ("both", "channel")
+        spt = self.mode in ("both", "spatial")
+        acc = self.x.take_acc()
+        g = lambda p, on: A.ptr(p.g) if on else A.ptr(self.sink)  # noqa: E731
+        A.check(A.lib.sap3d_cbam_tail_bwd(
+            e.dt, A.ptr(self.y.grad), A.ptr(self.ones_act), A.ptr(self.zero_act), A.ptr(self.zc), A.ptr(self.zg), A.ptr(self.zg),
+            A.ptr(self.zc), A.ptr(self.x.buf), N, D, H, W, Cc, self.G, self.hidden,
+            A.ptr(self.w0.w) if ch else A.ptr(self.zw), A.ptr(self.w1.w) if ch else A.ptr(self.zw),
+            A.ptr(self.w_sp.w) if spt else A.ptr(self.zw), A.ptr(self.cscale), A.ptr(self.sp), A.ptr(self.att), A.ptr(self.save),
+            None, 0, A.ptr(self.x.ensure_grad()), acc, A.ptr(self.sink), A.ptr(self.sink),
+            g(self.w0, ch), g(self.b0, ch), g(self.w1, ch), g(self.b1, ch), A.ptr(self.w_sp.g) if spt else None,
+            A.ptr(_ws(e)), e.stream), "cbam_bwd " + self.name)
+        e._count(8)
+
+
 class ConcatOp:
     """materialised tf.concat([a, b], -1) (only needed for three-way concatenations)"""
 

@@ -23,11 +23,7 @@ def convT(name, l_input, in_channels, out_channels):   # gn/p3d_gn.py:67-70
     return _convT_bn(name, l_input, in_channels, out_channels, bias_grad=True)
 
 
-def _gn_state(t: T) -> GNState:
-    eng = t.eng
-    nm = eng.names.unique("", "group_norm")
-    N, Cc = t.shape[0], t.C
-    return GNState(eng, N, Cc, t.positions // N, eng.param(nm + "/gamma", [Cc], "ones"), eng.param(nm + "/beta", [Cc], "zeros"))
+_gn_state = nw.gn_state
 
 
 def GroupNorm(x: ConvOut, G=32, esp=1e-5, relu=False, name="") -> T:   # gn/p3d_gn.py:24-46

@@ -66,10 +66,39 @@ def bn_relu(co: ConvOut, training: bool, name=None, relu=True, tap: str = "") ->
     return eng.norm_act(co, ns, training, relu, name=tap or (name or "bn"))
 
 
-def normalize(x: ConvOut, training, mode="bn"):  # utils/network.py:89 (without the ReLU)
-    if mode != "bn":
-        raise NotImplementedError("GroupNorm graphs are built by gn/p3d_gn.py")
-    return bn_relu(x, training, relu=False)
+def _as_conv_out(x) -> ConvOut:
+    """normalisation helpers take the raw output of a conv (ConvOut) or any activation tensor"""
+    return x if isinstance(x, ConvOut) else ConvOut(x, None, 0)
+
+
+def gn_state(t: T):
+    """variables + statistics buffers of one GroupNorm call: tf.Variable gamma / beta inside variable_scope('group_norm'),
+    uniquified per graph as group_norm, group_norm_1, ... (utils/network.py:69,78-79)"""
+    from .engine_gn import GNState
+    eng = t.eng
+    nm = eng.names.unique("", "group_norm")
+    N, Cc = t.shape[0], t.C
+    return GNState(eng, N, Cc, t.positions // N, eng.param(nm + "/gamma", [Cc], "ones"), eng.param(nm + "/beta", [Cc], "zeros"))
+
+
+def GroupNorm(x, G=32, esp=1e-5, relu=False, name="") -> T:  # utils/network.py:65-87 (== gn/p3d_gn.py:24-46)
+    """per-sample statistics over (C/G, D, H, W) with G = min(32, C), biased variance, per-channel gamma / beta"""
+    from .engine_gn import GN_EPS, GN_GROUPS, GNActOp
+    if G != GN_GROUPS or abs(esp - GN_EPS) > 1e-12:
+        raise A.Sap3dError("GroupNorm: the kernels implement the reference's only configuration (G = 32, esp = 1e-5)")
+    co = _as_conv_out(x)
+    return GNActOp(co.raw.eng, co, gn_state(co.raw), relu, name=name or "group_norm").y
+
+
+def normalize(x, training, mode="bn"):  # utils/network.py:89-94 (without the ReLU)
+    if mode == "bn":
+        co = _as_conv_out(x)
+        if co.stats is None:
+            raise A.Sap3dError("normalize(mode='bn'): batch statistics come from the producing conv's epilogue; pass the conv output")
+        return bn_relu(co, training, relu=False)
+    if mode == "gn":
+        return GroupNorm(x)
+    raise ValueError(mode)
 
 
 # ---- conv / deconv + norm + relu -----------------------------------------------------------------
@@ -142,5 +171,76 @@ def attention(x: T, name, training, mode="bn", subsample=False, sub_size=2) -> T
     return eng.gate(o, x, gamma, name=name)
 
 
-def smooth_l1_loss(*_args, **_kw):  # utils/network.py:49 — fused into the head's backward (engine._HeadOp)
-    raise NotImplementedError("the smooth-L1 loss is fused into Session.train_step (sap3d_loss_smooth_l1)")
+# ---- CBAM (utils/network.py:198-274) ------------------------------------------------------------------
+def _cbam_params(eng: Engine, name: str, Cc: int, ratio: int, channel: bool, spatial: bool):
+    if ratio != 8:
+        raise A.Sap3dError("cbam_block: the kernels implement the reference's only configuration (ratio = 8)")
+    w0 = b0 = w1 = b1 = w_sp = None
+    if channel:   # channel_attention: tf.layers.dense mlp_0 / mlp_1 inside variable_scope(name + '/ch_at' ...)
+        w0 = eng.param(name + "/mlp_0/kernel", [Cc, Cc // ratio], "vscale")
+        b0 = eng.param(name + "/mlp_0/bias", [Cc // ratio], "zeros")
+        w1 = eng.param(name + "/mlp_1/kernel", [Cc // ratio, Cc], "vscale")
+        b1 = eng.param(name + "/mlp_1/bias", [Cc], "zeros")
+    return w0, b0, w1, b1, w_sp
+
+
+def channel_attention(input_feature: T, name, ratio=8) -> T:  # utils/network.py:208-249
+    """mean & max over D,H,W -> shared MLP C -> C/ratio (ReLU) -> C -> sum -> sigmoid -> scale"""
+    from .engine_gn import CbamOp
+    eng = input_feature.eng
+    w0, b0, w1, b1, _ = _cbam_params(eng, name, input_feature.C, ratio, True, False)
+    return CbamOp(eng, input_feature, "channel", w0, b0, w1, b1, None, name=name).y
+
+
+def spatial_attention(input_feature: T, name) -> T:  # utils/network.py:251-274
+    """mean & max over C -> 7x7x7 conv (2 -> 1, no bias) -> sigmoid -> scale"""
+    from .engine_gn import CbamOp
+    eng = input_feature.eng
+    w_sp = eng.param(name + "/conv3d/kernel", [7, 7, 7, 2, 1], "vscale")
+    return CbamOp(eng, input_feature, "spatial", w_sp=w_sp, name=name).y
+
+
+def cbam_block(input_feature: T, name, ratio=8) -> T:  # utils/network.py:198-206
+    """channel attention then spatial attention on any feature map, as ONE fused op (variables '<name>/ch_at/mlp_{0,1}/...',
+    '<name>/sp_at/conv3d/kernel').  The GN backbone uses the block-tail form that also folds the residual add + ReLU
+    (engine_gn.CbamBlockTailOp); this is the stand-alone call of the reference surface."""
+    from .engine_gn import CbamOp
+    eng = input_feature.eng
+    w0, b0, w1, b1, _ = _cbam_params(eng, name + "/ch_at", input_feature.C, ratio, True, False)
+    w_sp = eng.param(name + "/sp_at/conv3d/kernel", [7, 7, 7, 2, 1], "vscale")
+    return CbamOp(eng, input_feature, "both", w0, b0, w1, b1, w_sp, name=name).y
+
+
+# ---- loss --------------------------------------------------------------------------------------------------
+class Loss:
+    """result of smooth_l1_loss: what `Session` trains on (the reference hands the loss tensor to AdamOptimizer.minimize,
+    train.py:166-168).  `head` is the network output op it was built from."""
+
+    def __init__(self, head, sigma, inside, outside):
+        self.head, self.eng = head, head.eng
+        self.sigma, self.inside, self.outside = sigma, inside, outside
+
+    @property
+    def output(self):
+        return self.head.output
+
+
+def smooth_l1_loss(bbox_pred, bbox_targets, bbox_inside_weights, bbox_outside_weights, sigma=3.0, dim=[0]):  # noqa: B006
+    """utils/network.py:49-62 (call sites train.py:159, gn/train_p3d_gn_dataset.py:186, both with weights 1, sigma 1):
+    in = inside * (pred - target); per element |in| < 1/sigma^2 ? in^2 sigma^2 / 2 : |in| - 0.5/sigma^2; times outside;
+    reduce_sum over everything (the reduce_mean of that scalar is the identity; `dim` is unused in the reference too).
+
+    bbox_pred is the handle a graph builder returned (the tf.reshape the drivers wrap around it is a view: the loss is over
+    all elements either way); bbox_targets is fed per step through Session.train_step(x, y) and may be None here.  The
+    weights are the reference's scalars.  Records the loss configuration on the output op, whose backward launch is the fused
+    loss + gradient kernel (sap3d_loss_smooth_l1_ex)."""
+    head = bbox_pred.head if isinstance(bbox_pred, Loss) else bbox_pred
+    if not hasattr(head, "loss_sigma"):
+        raise A.Sap3dError("smooth_l1_loss: the first argument must be the output handle of a graph builder")
+    if not head.eng.training_graph:
+        raise A.Sap3dError("smooth_l1_loss needs a training graph (placeholder(..., training_graph=True))")
+    for wgt in (bbox_inside_weights, bbox_outside_weights):
+        if not isinstance(wgt, (int, float)):
+            raise A.Sap3dError("smooth_l1_loss: inside / outside weights are scalars (the reference passes 1, 1)")
+    head.loss_sigma, head.loss_w_in, head.loss_w_out = float(sigma), float(bbox_inside_weights), float(bbox_outside_weights)
+    return Loss(head, float(sigma), float(bbox_inside_weights), float(bbox_outside_weights))

@@ -31,6 +31,7 @@ def placeholder(shape, dtype: str = "bf16", training_graph: bool = False, conv_i
 
 class Session:
     def __init__(self, head, lr: float = 1e-4):
+        head = getattr(head, "head", head)     # a network.Loss (smooth_l1_loss(pred, y, 1, 1, sigma)) wraps the output op
         self.head = head
         self.eng: Engine = head.eng
         self.lr = lr
