@@ -2,6 +2,7 @@
 #include "conv_tc.cuh"
 
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/sap3d.h"
@@ -30,6 +31,15 @@ int require_device() {
   if (major != 10) return set_error("device compute capability %d.x is not sm_100 (B200 required)", major);
   ok = 1;
   return 0;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAP3D_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int check_launch(const char* what) {

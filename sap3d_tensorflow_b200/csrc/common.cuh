@@ -261,6 +261,26 @@ SAP3D_DEVINL void cluster_sync_all() {   // every thread of every CTA of the clu
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// split arrive / wait (no .aligned: the callers sit behind warp-role branches)
+SAP3D_DEVINL void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+SAP3D_DEVINL void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+// DSMEM bulk copy (SASS: UBLKCP): `bytes` from this CTA's shared memory to a peer CTA's shared memory (shared::cluster
+// address from mapa); completion is signalled as complete_tx on the PEER's mbarrier (shared::cluster address)
+SAP3D_DEVINL void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+               "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (and
+// run its set-up: barrier init, TMEM allocation, tensor-map prefetch) while its predecessor in the stream is still running;
+// pdl_wait() blocks until the predecessor has completed and its memory operations are visible, pdl_launch_dependents() lets
+// the successor start its own set-up.  Both are no-ops for ordinary launches.
+// ----------------------------------------------------------------------------------------------
+SAP3D_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+SAP3D_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 SAP3D_DEVINL bool elect_one() {
   uint32_t pred;
   asm volatile(

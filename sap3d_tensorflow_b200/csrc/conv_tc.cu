@@ -22,6 +22,7 @@
 
 #include <algorithm>
 
+#include "abi_util.cuh"
 #include "common.cuh"
 
 namespace sap3d {
@@ -111,11 +112,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8);
-  float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16);  // [4][2][BLOCK_N]
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full, recv (split-K exchange)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 2) * 8);
+  float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 2) * 8 + 16);  // [4][2][BLOCK_N]
   float* s_ep = s_stats + 4 * 2 * BLOCK_N;   // [3][BLOCK_N]: bias, scale, shift of this tile's columns (staged under the K loop)
-  const uint32_t recv_base = (base + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 127u) & ~127u;
+  const uint32_t recv_base = (base + STAGES * STAGE_BYTES + (2 * STAGES + 2) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 127u) & ~127u;
+  const uint32_t recv_bar = bar_base + (2 * STAGES + 1) * 8;
+  constexpr uint32_t XCHG_BYTES = OWN_CHUNKS * 16384;   // fp32 partials one peer sends me: [OWN_CHUNKS][128 rows][32 columns]
   const uint32_t rank = SPLIT > 1 ? cluster_ctarank() : 0u;
 
   const int warp = threadIdx.x >> 5;
@@ -158,8 +161,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       mbar_init(bar_base + (STAGES + s) * 8, 1);
     }
     mbar_init(bar_base + 2 * STAGES * 8, 1);
+    if (SPLIT > 1) {
+      mbar_init(recv_bar, 1);
+      fence_mbar_init();
+      mbar_expect_tx(recv_bar, (SPLIT - 1) * XCHG_BYTES);   // the one arrival; the phase completes when every peer's slice landed
+    }
     fence_mbar_init();
     tma_prefetch_desc(&p.bmap);
+    tma_prefetch_desc(&p.amap[0]);
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(tmem_slot), MT * BLOCK_N);
@@ -169,6 +178,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (SPLIT > 1) cluster_arrive();   // #1: my barriers exist (peers wait for it before they copy into this CTA)
+  // everything above is independent of the predecessor kernel; from here on its outputs (activations, scale / shift) are read
+  pdl_wait();
+  pdl_launch_dependents();
   if (threadIdx.x == 0) dbg_mark(p, 1);
 
   if (warp == 0) {
@@ -203,6 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       dbg_mark(p, 9);
     }
     __syncwarp();
+    if (SPLIT > 1) { cluster_wait(); cluster_arrive(); }   // keep this warp in step with the cluster barrier phases (#1, #2)
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
@@ -234,8 +248,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       dbg_mark(p, 4);
     }
     __syncwarp();
+    if (SPLIT > 1) { cluster_wait(); cluster_arrive(); }
   } else if (SPLIT > 1) {
     // ================= split-K phase A: ship the chunks owned by peer CTAs =================
+    // The fp32 partials are staged in THIS CTA's shared memory (the operand ring is free once the accumulator is complete)
+    // in the exact layout of the receiver's buffer, then moved by one DSMEM bulk copy per peer that signals the peer's
+    // mbarrier -- r01 shipped them with st.shared::cluster from registers, which cost ~3.9 us per launch (phase probe).
     const int q = warp & 3;
     const int row = q * 32 + lane;
     if (nkb > 0) {
@@ -255,18 +273,31 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; ++j) rr[j] = 0u;
       }
-      const uint32_t slot = rank < owner ? rank : rank - 1;                       // my index among the owner's peers
-      const uint32_t local = recv_base + ((slot * OWN_CHUNKS + (SPLIT == 4 ? 0 : (c & 1))) * 128 + row) * 128;
-      const uint32_t remote = mapa_shared(local, owner);
+      // send area = start of the operand ring: one XCHG_BYTES block per peer, indexed like the peer's receive slots
+      const uint32_t pidx = owner < rank ? owner : owner - 1;                       // the peer's index among my peers
+      float* dst = reinterpret_cast<float*>(smem) + ((pidx * OWN_CHUNKS + (SPLIT == 4 ? 0 : (c & 1))) * 128 + row) * 32;
 #pragma unroll
-      for (int g = 0; g < 8; ++g)   // 16-byte groups swizzled by the row: conflict-free at the destination
-        st_cluster_v4(remote + (static_cast<uint32_t>(g ^ (row & 7)) << 4), __uint_as_float(rr[g * 4]), __uint_as_float(rr[g * 4 + 1]),
-                      __uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3]));
+      for (int g = 0; g < 8; ++g)   // 16-byte groups swizzled by the row: conflict-free here and at the receiver
+        *reinterpret_cast<float4*>(dst + ((g ^ (row & 7)) << 2)) =
+            make_float4(__uint_as_float(rr[g * 4]), __uint_as_float(rr[g * 4 + 1]), __uint_as_float(rr[g * 4 + 2]), __uint_as_float(rr[g * 4 + 3]));
     }
     tc_fence_before();
+    fence_proxy_async();                                  // my generic-proxy writes -> visible to the bulk-copy (async) proxy
+    asm volatile("bar.sync 1, 128;" ::: "memory");        // all four epilogue warps have staged their rows
+    cluster_wait();                                       // #1: every peer's receive barrier is initialised
+    if (threadIdx.x == 64) {
+#pragma unroll
+      for (int pj = 0; pj < SPLIT - 1; ++pj) {
+        const uint32_t pi = (uint32_t)pj;
+        const uint32_t peer = pi < rank ? pi : pi + 1;
+        const uint32_t slot = rank < peer ? rank : rank - 1;                        // my index among that peer's peers
+        bulk_copy_to_peer(mapa_shared(recv_base + slot * XCHG_BYTES, peer), base + pi * XCHG_BYTES, XCHG_BYTES, mapa_shared(recv_bar, peer));
+      }
+    }
+    mbar_wait(recv_bar, 0);                               // the peers' partials of MY columns have landed
+    cluster_arrive();                                     // #2: nothing more will be copied into / out of ... (see the end)
+    if (threadIdx.x == 64) dbg_mark(p, 6);
   }
-  if (SPLIT > 1) cluster_sync_all();
-  if (threadIdx.x == 64) dbg_mark(p, 6);
   if (warp >= 2) {
     // ================= epilogue (warps 2..5) =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -283,7 +314,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    if (SPLIT > 1) tc_fence_after();
     if (SPLIT == 1 && nkb > 0) {
       mbar_wait(bar_base + 2 * STAGES * 8, 0);
       tc_fence_after();
@@ -422,6 +452,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, MT * BLOCK_N);
   }
+  // #2: every CTA of the cluster has received all its slices, i.e. every bulk copy that READS this CTA's shared memory has
+  // completed -- only now may the CTA exit and its shared memory be handed to another block
+  if (SPLIT > 1) cluster_wait();
   if (threadIdx.x == 0) dbg_mark(p, 8);
 }
 
@@ -494,6 +527,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // set-up above overlaps the predecessor's tail; its outputs are read from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================= TMA producer: one continuous ring over all units =================
@@ -782,6 +817,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_mc_kernel(const __
   cluster_sync_all();      // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================= TMA producer: one continuous ring over all units =================
@@ -1155,7 +1192,7 @@ int tc_plan_tiles(const TcProblem& pb) {
 
 template <int BLOCK_N, int STAGES, int MT>
 static int launch_t(const TcConvParams& prm, int grid, cudaStream_t stream, char* err, size_t errlen) {
-  constexpr int SMEM = STAGES * (MT * 128 * 128 + BLOCK_N * 128) + (2 * STAGES + 1) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
+  constexpr int SMEM = STAGES * (MT * 128 * 128 + BLOCK_N * 128) + (2 * STAGES + 2) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -1165,8 +1202,7 @@ static int launch_t(const TcConvParams& prm, int grid, cudaStream_t stream, char
     }
     attr_done = true;
   }
-  conv_tc_kernel<BLOCK_N, STAGES, MT><<<grid, TC_THREADS, SMEM, stream>>>(prm);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(conv_tc_kernel<BLOCK_N, STAGES, MT>, dim3((unsigned)grid), dim3(TC_THREADS), SMEM, stream, 1, prm);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "conv_tc launch failed: %s", cudaGetErrorString(e));
     return 1;
@@ -1176,7 +1212,7 @@ static int launch_t(const TcConvParams& prm, int grid, cudaStream_t stream, char
 
 template <int SPLIT>
 static int launch_split(const TcConvParams& prm, int grid, cudaStream_t stream, char* err, size_t errlen) {
-  constexpr int SMEM = 4 * (128 * 128 + 128 * 128) + (2 * 4 + 1) * 8 + 16 + (4 * 2 + 3) * 128 * 4 + (SPLIT - 1) * (4 / SPLIT) * 16384 + 128 + 1024;
+  constexpr int SMEM = 4 * (128 * 128 + 128 * 128) + (2 * 4 + 2) * 8 + 16 + (4 * 2 + 3) * 128 * 4 + (SPLIT - 1) * (4 / SPLIT) * 16384 + 128 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128, 4, 1, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -1186,19 +1222,7 @@ static int launch_split(const TcConvParams& prm, int grid, cudaStream_t stream, 
     }
     attr_done = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid * SPLIT);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = SMEM;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = SPLIT;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, 4, 1, SPLIT>, prm);
+  cudaError_t e = launch_k(conv_tc_kernel<128, 4, 1, SPLIT>, dim3((unsigned)grid * SPLIT), dim3(TC_THREADS), SMEM, stream, SPLIT, prm);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "conv_tc split-K cluster launch failed: %s", cudaGetErrorString(e));
     return 1;
@@ -1223,8 +1247,8 @@ static int launch_persist(const TcConvParams& prm, int units, cudaStream_t strea
     if (sms < 1) sms = 148;
     attr_done = true;
   }
-  conv_tc_persist_kernel<BLOCK_N, STAGES, MT><<<units < sms ? units : sms, TC_THREADS, SMEM, stream>>>(prm, units);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(conv_tc_persist_kernel<BLOCK_N, STAGES, MT>, dim3((unsigned)(units < sms ? units : sms)), dim3(TC_THREADS), SMEM, stream,
+                           1, prm, units);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "conv_tc_persist launch failed: %s", cudaGetErrorString(e));
     return 1;

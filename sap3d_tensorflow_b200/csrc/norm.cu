@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                             float* moving_mean, float* moving_var, int training,
                                                             float momentum, float eps, float* scale, float* shift,
                                                             float* save_mean, float* save_rstd) {
+  pdl_wait();   // (programmatic dependent launch: the predecessor kernel has completed from here on)
+  pdl_launch_dependents();
   constexpr int LANES = 1024 / CPB;
   const int cx = threadIdx.x, ry = threadIdx.y;
   const int c = blockIdx.x * CPB + cx;
@@ -143,6 +145,8 @@ struct ApplyArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) apply_kernel(const ApplyArgs p) {
+  pdl_wait();   // (programmatic dependent launch: the predecessor kernel has completed from here on)
+  pdl_launch_dependents();
   const long long nvec = p.P * p.C / 8;
   const T* a = reinterpret_cast<const T*>(p.a);
   const T* b = reinterpret_cast<const T*>(p.b);
@@ -219,6 +223,8 @@ struct FusedApplyArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_fused_kernel(const FusedApplyArgs p) {
+  pdl_wait();   // (programmatic dependent launch: the predecessor kernel has completed from here on)
+  pdl_launch_dependents();
   __shared__ double red[4][2][64];
   __shared__ float s_scale[2][64], s_shift[2][64];
   const int C = p.ap.C;
@@ -397,6 +403,8 @@ SAP3D_DEVINL void bwd_common(const ApplyBwdArgs& p, long long e, long long sidx,
 // 256 threads = 8 channel-vector lanes (64 channels, one 128-byte line per position) x 32 position lanes.
 template <typename T>
 __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArgs p) {
+  pdl_wait();   // (programmatic dependent launch: the predecessor kernel has completed from here on)
+  pdl_launch_dependents();
   __shared__ float red[8][4][64];  // [warp][sum][channel]
   const int cv = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int c = blockIdx.y * 64 + cv * 8;
@@ -453,6 +461,8 @@ __global__ void __launch_bounds__(256) apply_bwd_reduce_kernel(const ApplyBwdArg
 __global__ void __launch_bounds__(1024) apply_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double M,
                                                                    float* coef, float* dgamma1, float* dbeta1, float* dgamma2,
                                                                    float* dbeta2) {
+  pdl_wait();   // (programmatic dependent launch: the predecessor kernel has completed from here on)
+  pdl_launch_dependents();
   __shared__ double sh[4][32][33];
   const int cx = threadIdx.x, ry = threadIdx.y;
   const int c = blockIdx.x * 32 + cx;
@@ -475,6 +485,8 @@ __global__ void __launch_bounds__(1024) apply_bwd_finalize_kernel(const float* _
 
 template <typename T>
 __global__ void __launch_bounds__(256) apply_bwd_kernel(const ApplyBwdArgs p) {
+  pdl_wait();   // (programmatic dependent launch: the predecessor kernel has completed from here on)
+  pdl_launch_dependents();
   const long long nvec = p.P * p.C / 8;
   T* da = reinterpret_cast<T*>(p.da);
   T* db = reinterpret_cast<T*>(p.db);
@@ -567,6 +579,8 @@ constexpr int NOB_PLANES = 16;     // position lanes per block
 
 template <typename T>
 __global__ void __launch_bounds__(256, 3) apply_bwd_reduce_nob_kernel(const ApplyBwdArgs p) {
+  pdl_wait();   // (programmatic dependent launch: the predecessor kernel has completed from here on)
+  pdl_launch_dependents();
   __shared__ float red[8][2][2][64];   // [warp][position lane pair within the warp][sum][channel]
   const int cv = threadIdx.x & 15, pl = threadIdx.x >> 4;
   const int c = blockIdx.y * 64 + cv * 4;
@@ -646,6 +660,8 @@ __global__ void __launch_bounds__(256, 3) apply_bwd_reduce_nob_kernel(const Appl
 // grid = (slabs, C/64); the slab count is independent of the reduce pass
 template <typename T, bool ACC>
 __global__ void __launch_bounds__(256, 3) apply_bwd_nob_kernel(const ApplyBwdArgs p) {
+  pdl_wait();   // (programmatic dependent launch: the predecessor kernel has completed from here on)
+  pdl_launch_dependents();
   const int cv = threadIdx.x & 15, pl = threadIdx.x >> 4;
   const int c = blockIdx.y * 64 + cv * 4;
   if (c >= p.C) return;
@@ -893,11 +909,11 @@ int sap3d_bn_finalize(const float* stats, int32_t rows, int32_t C, double count,
   if (!training && (!moving_mean || !moving_var)) return set_error("bn_finalize: inference mode needs moving statistics");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (training && rows >= 256)
-    bn_finalize_kernel<8><<<(C + 7) / 8, dim3(8, 128), 0, st>>>(stats, rows, C, count, gamma, beta, moving_mean, moving_var, training,
-                                                               momentum, eps, scale, shift, save_mean, save_rstd);
+    launch_k(bn_finalize_kernel<8>, dim3((C + 7) / 8), dim3(8, 128), 0, st, 1, stats, rows, C, count, gamma, beta, moving_mean, moving_var, training,
+             momentum, eps, scale, shift, save_mean, save_rstd);
   else
-    bn_finalize_kernel<32><<<(C + 31) / 32, dim3(32, 32), 0, st>>>(stats, rows, C, count, gamma, beta, moving_mean, moving_var, training,
-                                                                  momentum, eps, scale, shift, save_mean, save_rstd);
+    launch_k(bn_finalize_kernel<32>, dim3((C + 31) / 32), dim3(32, 32), 0, st, 1, stats, rows, C, count, gamma, beta, moving_mean, moving_var, training,
+             momentum, eps, scale, shift, save_mean, save_rstd);
   return check_launch("bn_finalize");
 }
 
@@ -924,8 +940,8 @@ int sap3d_affine_act(int32_t dtype, const void* a, const float* s1, const float*
   p.relu1 = relu1; p.relu2 = relu2; p.relu_out = relu_out;
   const long long nvec = P * C / 8;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == SAP3D_BF16) apply_kernel<bf16><<<ew_grid(nvec), 256, 0, st>>>(p);
-  else apply_kernel<float><<<ew_grid(nvec), 256, 0, st>>>(p);
+  if (dtype == SAP3D_BF16) launch_k(apply_kernel<bf16>, dim3(ew_grid(nvec)), dim3(256), 0, st, 1, p);
+  else launch_k(apply_kernel<float>, dim3(ew_grid(nvec)), dim3(256), 0, st, 1, p);
   return check_launch("affine_act");
 }
 
@@ -956,8 +972,8 @@ int sap3d_bn_apply_fused(int32_t dtype, const void* a, const float* stats1, int3
   p.prows = (int)prows;
   dim3 grid((unsigned)prows, (unsigned)chunks);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == SAP3D_BF16) bn_apply_fused_kernel<bf16><<<grid, 256, 0, st>>>(p);
-  else bn_apply_fused_kernel<float><<<grid, 256, 0, st>>>(p);
+  if (dtype == SAP3D_BF16) launch_k(bn_apply_fused_kernel<bf16>, grid, dim3(256), 0, st, 1, p);
+  else launch_k(bn_apply_fused_kernel<float>, grid, dim3(256), 0, st, 1, p);
   return check_launch("bn_apply_fused");
 }
 
@@ -1029,12 +1045,12 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
       rows = r3;
       p.rows = (int)rows;
       dim3 g3((unsigned)rows, (unsigned)chunks);
-      if (dtype == SAP3D_BF16) apply_bwd_reduce_nob_kernel<bf16><<<g3, 256, 0, st>>>(p);
-      else apply_bwd_reduce_nob_kernel<float><<<g3, 256, 0, st>>>(p);
-    } else if (dtype == SAP3D_BF16) apply_bwd_reduce_kernel<bf16><<<rgrid, 256, 0, st>>>(p);
-    else apply_bwd_reduce_kernel<float><<<rgrid, 256, 0, st>>>(p);
+      if (dtype == SAP3D_BF16) launch_k(apply_bwd_reduce_nob_kernel<bf16>, g3, dim3(256), 0, st, 1, p);
+      else launch_k(apply_bwd_reduce_nob_kernel<float>, g3, dim3(256), 0, st, 1, p);
+    } else if (dtype == SAP3D_BF16) launch_k(apply_bwd_reduce_kernel<bf16>, rgrid, dim3(256), 0, st, 1, p);
+    else launch_k(apply_bwd_reduce_kernel<float>, rgrid, dim3(256), 0, st, 1, p);
     if (check_launch("affine_act_bwd reduce")) return 1;
-    apply_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, st>>>(p.partial, (int)rows, C, count, ws, dgamma1, dbeta1, dgamma2, dbeta2);
+    launch_k(apply_bwd_finalize_kernel, dim3((C + 31) / 32), dim3(32, 32), 0, st, 1, p.partial, (int)rows, C, count, ws, dgamma1, dbeta1, dgamma2, dbeta2);
     if (check_launch("affine_act_bwd finalize")) return 1;
     p.coef = ws;
   }
@@ -1048,14 +1064,14 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
       if (slabs < 1) slabs = 1;
       dim3 ag((unsigned)slabs, (unsigned)chunks);
       if (dtype == SAP3D_BF16) {
-        if (acc_a) apply_bwd_nob_kernel<bf16, true><<<ag, 256, 0, st>>>(p);
-        else apply_bwd_nob_kernel<bf16, false><<<ag, 256, 0, st>>>(p);
+        if (acc_a) launch_k(apply_bwd_nob_kernel<bf16, true>, ag, dim3(256), 0, st, 1, p);
+        else launch_k(apply_bwd_nob_kernel<bf16, false>, ag, dim3(256), 0, st, 1, p);
       } else {
-        if (acc_a) apply_bwd_nob_kernel<float, true><<<ag, 256, 0, st>>>(p);
-        else apply_bwd_nob_kernel<float, false><<<ag, 256, 0, st>>>(p);
+        if (acc_a) launch_k(apply_bwd_nob_kernel<float, true>, ag, dim3(256), 0, st, 1, p);
+        else launch_k(apply_bwd_nob_kernel<float, false>, ag, dim3(256), 0, st, 1, p);
       }
-    } else if (dtype == SAP3D_BF16) apply_bwd_kernel<bf16><<<ew_grid(nvec), 256, 0, st>>>(p);
-    else apply_bwd_kernel<float><<<ew_grid(nvec), 256, 0, st>>>(p);
+    } else if (dtype == SAP3D_BF16) launch_k(apply_bwd_kernel<bf16>, dim3(ew_grid(nvec)), dim3(256), 0, st, 1, p);
+    else launch_k(apply_bwd_kernel<float>, dim3(ew_grid(nvec)), dim3(256), 0, st, 1, p);
     if (check_launch("affine_act_bwd apply")) return 1;
   }
   return 0;
