@@ -7,6 +7,8 @@
 // one read per operand and one write.
 #include <cooperative_groups.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/sap3d.h"
 #include "abi_util.cuh"
@@ -887,7 +889,125 @@ __global__ void __launch_bounds__(256) bn_bwd_coop_kernel(const ApplyBwdArgs p, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Few-row tensors (stage 3 of the backbone: 784 positions at batch 8): ONE block owns 16 channels for ALL positions, so the two
+// per-channel sums, the coefficients and the apply pass stay inside the block -- no grid barrier, no cooperative launch (which
+// waits until the whole grid can be co-resident: ~6 us of stall per launch behind the side stream's filter gradients, r02 trace),
+// deterministic.  The second pass re-reads the block's 16-channel slab (<= 100 KB) from L1 / L2.
+// 256 threads = 2 channel vectors (one 32-byte sector per position) x 128 position lanes.
+// ------------------------------------------------------------------------------------------------
+constexpr long long SLAB_MAX_P = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, const double M, float* dgamma1, float* dbeta1,
+                                                          float* dgamma2, float* dbeta2) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float red[8][4][16];   // [warp][sum][channel]
+  __shared__ float coef[4][16];
+  const int half = threadIdx.x & 1, rl = threadIdx.x >> 1;
+  const int c = blockIdx.x * 16 + half * 8;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  if (c < p.C) {
+    for (long long pos = rl; pos < p.P; pos += 128) {
+      float g1[8], g2[8], xh1[8], xh2[8];
+      bwd_common<T>(p, pos * p.C + c, c, c, g1, g2, xh1, xh2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += g1[j];
+        acc[1][j] += g1[j] * xh1[j];
+        acc[2][j] += g2[j];
+        acc[3][j] += g2[j] * xh2[j];
+      }
+    }
+  }
+  // lanes with equal (lane & 1) hold the same channels: fold the 16 positions of a warp
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[i][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      acc[i][j] = v;
+    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][i][lane * 8 + j] = acc[i][j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int i = threadIdx.x >> 4, ch = threadIdx.x & 15;
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += (double)red[w][i][ch];   // fixed order: deterministic
+    coef[i][ch] = (float)(t / M);
+    const int cc = blockIdx.x * 16 + ch;
+    if (cc < p.C) {
+      float* dst = i == 0 ? dbeta1 : (i == 1 ? dgamma1 : (i == 2 ? dbeta2 : dgamma2));
+      if (dst) dst[cc] += (float)t;
+    }
+  }
+  __syncthreads();
+  if (c >= p.C || (!p.da && !p.db)) return;
+  T* da = reinterpret_cast<T*>(p.da);
+  T* db = reinterpret_cast<T*>(p.db);
+  for (long long pos = rl; pos < p.P; pos += 128) {
+    const long long e = pos * p.C + c;
+    float g1[8], g2[8], xh1[8], xh2[8];
+    bwd_common<T>(p, e, c, c, g1, g2, xh1, xh2);
+    if (da) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sc = p.s1 ? p.s1[c + j] : 1.f;
+        o[j] = p.batch_stats1 ? sc * (g1[j] - coef[0][half * 8 + j] - xh1[j] * coef[1][half * 8 + j]) : sc * g1[j];
+      }
+      if (p.acc_a) {
+        float old[8];
+        Vec8<T>::load(da + e, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += old[j];
+      }
+      Vec8<T>::store(da + e, o);
+    }
+    if (db) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sc = p.s2 ? p.s2[c + j] : 1.f;
+        o[j] = p.batch_stats2 ? sc * (g2[j] - coef[2][half * 8 + j] - xh2[j] * coef[3][half * 8 + j]) : sc * g2[j];
+      }
+      if (p.acc_b) {
+        float old[8];
+        Vec8<T>::load(db + e, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += old[j];
+      }
+      Vec8<T>::store(db + e, o);
+    }
+  }
+}
+
 constexpr long long COOP_MAX_ELEMS = 4ll << 20;   // above this the three-launch form streams better (more blocks per SM)
+
+bool slab_enabled() {   // SAP3D_BN_BWD_SLAB=0: the cooperative form for every backbone tensor (r01 behaviour, for A/B runs)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAP3D_BN_BWD_SLAB");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int ew_grid(long long nvec) {
   long long b = (nvec + 255) / 256;
@@ -1015,6 +1135,15 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
     p.partial = ws + 4 * C;
     p.totals = reinterpret_cast<double*>(ws + (size_t)(296 * 4 + 4) * C + (((size_t)(296 * 4 + 4) * C) & 1));   // 8-byte aligned tail
     dim3 rgrid((unsigned)rows, (unsigned)chunks);
+    // few-row tensors (stage 3): one ordinary launch, every block owns 16 channels for all positions
+    if (phase == 0 && P <= SLAB_MAX_P && slab_enabled()) {
+      double M = count;
+      cudaError_t e = dtype == SAP3D_BF16
+                          ? launch_k(bn_bwd_slab_kernel<bf16>, dim3((unsigned)((C + 15) / 16)), dim3(256), 0, st, 1, p, M, dgamma1, dbeta1, dgamma2, dbeta2)
+                          : launch_k(bn_bwd_slab_kernel<float>, dim3((unsigned)((C + 15) / 16)), dim3(256), 0, st, 1, p, M, dgamma1, dbeta1, dgamma2, dbeta2);
+      if (e != cudaSuccess) return set_error("affine_act_bwd slab launch: %s", cudaGetErrorString(e));
+      return 0;
+    }
     // backbone-sized tensors: ONE cooperative launch (reduce -> grid.sync -> finalize -> apply) instead of three
     if (phase == 0 && (long long)P * C <= COOP_MAX_ELEMS) {
       static int max_blocks[2] = {0, 0};

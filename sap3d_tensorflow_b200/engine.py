@@ -111,7 +111,7 @@ class NormState:
 
 class Engine:
     def __init__(self, dtype: str = "bf16", training_graph: bool = False, device: str = "cuda:0", conv_impl: int = A.IMPL_AUTO,
-                 dropout_seed: int = 1234):
+                 dropout_seed: int = 1234, per_sample_statistics: bool = False):
         if not torch.cuda.is_available():
             raise A.Sap3dError("sap3d_tensorflow_b200 needs a CUDA device (B200); there is no CPU fallback")
         self.device = torch.device(device)
@@ -128,6 +128,16 @@ class Engine:
         self.taps: Dict[str, T] = {}
         self.finalized = False
         self.dropout_seed = dropout_seed
+        self._dropout_ops = 0    # per-engine salt of the dropout masks (two engines with one seed draw the same masks)
+        # inference graphs only: every batch-statistics BatchNorm takes its statistics PER CLIP, so a batch of B windows gives
+        # what B single-window runs give (the reference's gen_pred.py feeds one window per sess.run while the backbone's
+        # BatchNorm always uses batch statistics, p3d.py:140,350)
+        if per_sample_statistics and training_graph:
+            raise A.Sap3dError("per_sample_statistics is an inference-graph option")
+        self.per_sample_bn = per_sample_statistics
+        # BN moving averages follow the batch statistics only inside a training step (TF attaches UPDATE_OPS to train_op,
+        # train.py:170-172; sess.run(pred) leaves them alone).  Forward-only execution passes momentum = 1: moving * 1 + batch * 0
+        self.update_moving = False
         self.step = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.loss_buf = torch.zeros(1, device=self.device, dtype=torch.float64)
         self.bwd_ws: Optional[torch.Tensor] = None
@@ -523,8 +533,8 @@ class _NormActOp:
             e.sync_bn.all_reduce(co.stats)
             cnt *= e.sync_bn.world
         A.check(A.lib.sap3d_bn_finalize(A.ptr(co.stats), co.rows, co.raw.C, cnt, A.ptr(ns.gamma.w), A.ptr(ns.beta.w),
-                                        A.ptr(ns.mm.w), A.ptr(ns.mv.w), int(training), BN_MOMENTUM, BN_EPS, A.ptr(ns.scale),
-                                        A.ptr(ns.shift), A.ptr(ns.mean), A.ptr(ns.rstd), e.stream), "bn_finalize " + self.name)
+                                        A.ptr(ns.mm.w), A.ptr(ns.mv.w), int(training), BN_MOMENTUM if e.update_moving else 1.0, BN_EPS,
+                                        A.ptr(ns.scale), A.ptr(ns.shift), A.ptr(ns.mean), A.ptr(ns.rstd), e.stream), "bn_finalize " + self.name)
         e._count()
 
     FUSE_MAX_ROWS = 128   # statistics rows up to which finalize is folded into the apply launch (whole backbone)
@@ -546,9 +556,52 @@ class _NormActOp:
             A.ptr(n2.beta.w) if n2 else None, A.ptr(n2.mm.w) if n2 else None, A.ptr(n2.mv.w) if n2 else None, int(self.train2),
             A.ptr(n2.scale) if n2 else None, A.ptr(n2.shift) if n2 else None, A.ptr(n2.mean) if n2 else None,
             A.ptr(n2.rstd) if n2 else None, int(self.relu2), int(self.relu_out), A.ptr(self.y.buf), self.y.positions, self.y.C,
-            float(a.raw.positions), BN_MOMENTUM, BN_EPS, e.stream), "bn_apply_fused " + self.name)
+            float(a.raw.positions), BN_MOMENTUM if e.update_moving else 1.0, BN_EPS, e.stream), "bn_apply_fused " + self.name)
         e._count()
         return True
+
+    def _per_sample_affine(self, t: T, ns: NormState, slot: int):
+        """per-clip batch statistics: scale / shift [N][C] from the stored raw tensor -- GroupNorm's kernels with one channel per
+        group and BatchNorm's epsilon (moving averages are not touched: this is an inference-only mode)"""
+        e = self.eng
+        N, S, Cc = t.shape[0], t.positions // t.shape[0], t.C
+        if not hasattr(self, "_ps"):
+            self._ps = {}
+        if slot not in self._ps:
+            rows = A.lib.sap3d_sample_stats_rows(S, Cc, N)
+            f = lambda *shape: torch.empty(*shape, device=e.device, dtype=torch.float32)  # noqa: E731
+            self._ps[slot] = (rows, f(N, rows, 3, Cc), f(N, Cc), f(N, Cc), f(N, Cc), f(N, Cc))
+        rows, part, scale, shift, mean, rstd = self._ps[slot]
+        A.check(A.lib.sap3d_sample_channel_partials(e.dt, A.ptr(t.buf), None, N, S, Cc, rows, A.ptr(part), e.stream), "bn per-sample partials")
+        A.check(A.lib.sap3d_gn_finalize(A.ptr(part), rows, N, S, Cc, Cc, A.ptr(ns.gamma.w), A.ptr(ns.beta.w), BN_EPS, A.ptr(scale), A.ptr(shift),
+                                        A.ptr(mean), A.ptr(rstd), e.stream), "bn per-sample finalize")
+        e._count(2)
+        return scale, shift
+
+    def _fwd_per_sample(self):
+        e, n1, n2 = self.eng, self.n1, self.n2
+        s1 = t1 = s2 = t2 = None
+        if n1 is not None:
+            if self.train1:
+                s1, t1 = self._per_sample_affine(self.a.raw, n1, 0)
+            else:   # moving statistics: the same [C] vector for every clip, broadcast to [N][C]
+                self._finalize(self.a, n1, False)
+                N = self.a.raw.shape[0]
+                s1, t1 = n1.scale.repeat(N).contiguous(), n1.shift.repeat(N).contiguous()
+        if n2 is not None:
+            if self.train2:
+                s2, t2 = self._per_sample_affine(self.b_t, n2, 1)
+            else:
+                self._finalize(self.b, n2, False)
+                N = self.b_t.shape[0]
+                s2, t2 = n2.scale.repeat(N).contiguous(), n2.shift.repeat(N).contiguous()
+        y = self.y
+        A.check(A.lib.sap3d_affine_act(e.dt, A.ptr(self.a.raw.buf), A.ptr(s1), A.ptr(t1), int(self.relu1),
+                                       A.ptr(self.b_t.buf) if self.b_t is not None else None, A.ptr(s2), A.ptr(t2), int(self.relu2),
+                                       int(self.relu_out), A.ptr(y.buf), y.positions, y.C, y.positions // y.shape[0], e.stream),
+                "affine_act (per-sample statistics) " + self.name)
+        e._count()
+        self._keep = (s1, t1, s2, t2)
 
     def fwd(self):
         e = self.eng
@@ -556,6 +609,8 @@ class _NormActOp:
             return
         if isinstance(self.b, ConvOut) and self.b.op is not None and self.b.op.aux and e.use_side_stream:
             torch.cuda.current_stream(e.device).wait_stream(e.aux_stream)   # join the sibling branch
+        if e.per_sample_bn and ((self.n1 is not None and self.train1) or (self.n2 is not None and self.train2)):
+            return self._fwd_per_sample()
         if self._fwd_fused():
             return
         if self.n1 is not None:
@@ -639,13 +694,17 @@ class _PoolOp:
 
 
 class _DropoutOp:
-    _next_salt = 0
-
     def __init__(self, eng, x: T, rate, name):
         self.eng, self.x, self.rate, self.name = eng, x, float(rate), name
         self.y = eng.tensor(x.shape, name)
-        self.seed = eng.dropout_seed * 1000003 + _DropoutOp._next_salt
-        _DropoutOp._next_salt += 1
+        self.index = eng._dropout_ops          # position of this op among the engine's dropout ops
+        eng._dropout_ops += 1
+
+    @property
+    def seed(self):
+        """(engine seed, op index): read at launch / capture time, so attach_data_parallel can fold the rank into
+        eng.dropout_seed before the graphs are captured (replicas must not draw the same masks)"""
+        return (self.eng.dropout_seed * 1000003 + self.index) & 0x7FFFFFFFFFFFFFFF
 
     def fwd(self):
         e = self.eng

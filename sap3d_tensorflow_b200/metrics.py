@@ -85,7 +85,9 @@ def saliency_auc(saliency, fixation, jitter: bool = False, n_rep: int = 100, ste
     return out
 
 
-def AUC_Judd(saliency_map, fixation_map, jitter=False, seed=0) -> float:
+def AUC_Judd(saliency_map, fixation_map, jitter=True, seed=0) -> float:
+    """utils/metrics.py:25 (jitter defaults to True there too; train.py:259 and test.py:174 rely on the default).  The
+    reference draws the jitter from numpy's global RNG (irreproducible); here it is a counter hash of `seed`."""
     return float(saliency_auc(saliency_map, fixation_map, jitter=jitter, seed=seed)[0, 0])
 
 

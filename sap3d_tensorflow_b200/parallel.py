@@ -146,6 +146,11 @@ def attach_data_parallel(sess, bucket_mb: int = 32, sync_bn: bool = False, exact
     eng = sess.eng
     dist.broadcast(eng.flat_w, src=0)
     eng.pack_weights()
+    # every replica draws its own dropout masks: fold the rank into the seed before the step is captured (the mask hash
+    # depends only on (seed, op index, step, element index), so equal seeds would correlate the noise across the global batch)
+    eng.dropout_seed = eng.dropout_seed * 8191 + dist.get_rank() + 1
+    sess.graph_train = None
+    sess.graph_fwd = None
     ex = ExactGradientExchange() if exact else GradientExchange(eng, bucket_mb)
     sess.grad_hook = ex
     if sync_bn:

@@ -20,9 +20,11 @@ from .engine import Engine, T
 
 
 def placeholder(shape, dtype: str = "bf16", training_graph: bool = False, conv_impl: int = A.IMPL_AUTO, device="cuda:0",
-                dropout_seed: int = 1234) -> T:
-    """tf.placeholder(tf.float32, [B, 16, H, W, 3]) (train.py:143): creates the engine and its input tensor."""
-    eng = Engine(dtype, training_graph, device, conv_impl, dropout_seed)
+                dropout_seed: int = 1234, per_sample_statistics: bool = False) -> T:
+    """tf.placeholder(tf.float32, [B, 16, H, W, 3]) (train.py:143): creates the engine and its input tensor.
+    per_sample_statistics (inference graphs): batch-statistics BatchNorm layers normalise every clip on its own, so that
+    a batch of B windows reproduces B single-window sess.run calls (gen_pred.py:45,151 feeds one window at a time)."""
+    eng = Engine(dtype, training_graph, device, conv_impl, dropout_seed, per_sample_statistics)
     x = eng.tensor(shape, "input", needs_grad=False)
     eng.input = x
     eng.input_f32 = torch.zeros(tuple(shape), device=eng.device, dtype=torch.float32)
@@ -67,7 +69,11 @@ class Session:
         e = self.eng
         self._stage_input()
         e.begin_step()
-        e.forward()
+        e.update_moving = True      # UPDATE_OPS run with train_op only (train.py:170-172)
+        try:
+            e.forward()
+        finally:
+            e.update_moving = False
         e.backward(0 if split else None)
 
     def _overlap(self) -> bool:
@@ -131,8 +137,15 @@ class Session:
 
     # ---- public API ------------------------------------------------------------------------------
     def run(self, x: torch.Tensor, graph: bool = False) -> torch.Tensor:
-        """forward pass; returns the [B,16,H,W,1] fp32 saliency tensor (device)."""
-        self._feed(x)
+        """forward pass; returns the [B,16,H,W,1] fp32 saliency tensor (device).  x=None consumes the batch staged by prefetch().
+        The returned tensor is the head's output BUFFER: the next run / train_step overwrites it (clone it to keep it)."""
+        if x is None:
+            if not hasattr(self, "_staged"):
+                raise A.Sap3dError("run(None): no batch has been staged with prefetch()")
+            self._take_prefetched(False)
+            self._stage_input()
+        else:
+            self._feed(x)
         if graph:
             if self.eng.sync_bn is not None:
                 raise A.Sap3dError("synchronised BatchNorm runs in eager mode only (run(graph=False))")
@@ -144,9 +157,12 @@ class Session:
         return self.head.output
 
     def train_step(self, x: torch.Tensor, y: torch.Tensor, graph: bool = False) -> torch.Tensor:
-        """one iteration of train.py:217: returns the (device, fp64) loss scalar tensor."""
+        """one iteration of train.py:217: returns the (device, fp64) loss scalar tensor -- the engine's loss BUFFER, which the
+        next step overwrites (read it with .item() or clone it)."""
         e = self.eng
         if x is None:
+            if not hasattr(self, "_staged"):
+                raise A.Sap3dError("train_step(None, None): no batch has been staged with prefetch()")
             self._take_prefetched(True)      # batch staged by prefetch()
         else:
             if x.device.type != "cuda":

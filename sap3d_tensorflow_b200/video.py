@@ -39,6 +39,11 @@ def predict_video(sess, frames: torch.Tensor, graph: bool = True) -> Iterator[Tu
     """frames [T, H, W, 3] preprocessed (device, fp32).  Yields (frame index, saliency map [H, W]) in the order and with
     the selection rule of gen_pred.py: frames 0..15 from the first window, then the last frame of every later window."""
     B = sess.eng.input.shape[0]
+    if B > 1 and not sess.eng.per_sample_bn:
+        # the backbone's BatchNorm always uses batch statistics (p3d.py:140,350) and gen_pred.py feeds ONE window per
+        # sess.run: stacking windows would normalise every layer over B clips (and over the padding copies of the last batch)
+        raise A.Sap3dError("predict_video with a batch of windows needs placeholder(..., per_sample_statistics=True); "
+                           "without it use a batch-1 session (the reference's gen_pred.py placeholder is [1,16,112,112,3])")
     starts = list(window_starts(frames.shape[0]))
     for lo in range(0, len(starts), B):
         chunk = starts[lo:lo + B]

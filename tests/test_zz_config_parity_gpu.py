@@ -142,7 +142,7 @@ def _run_config(graph, builder, batch, size, out_kind, conditioning):
     print(f"  d(bf16-storage oracle, fp32 oracle): saliency rel {d_pred:.3e}, loss rel {d_loss:.3e}, gradient cosine global {cos:.5f} "
           f"worst {worst:.4f} ({wn}), update-direction agreement {agree:.4f}   <- bf16 storage noise of ANY implementation", flush=True)
     got32 = _engine_step(builder, "f32", batch, size, init, x, y)
-    _compare("fp32 CUDA vs fp32 oracle", got32, ref32, 1e-4, 1e-5, 1e-4, 0.999, out_kind)
+    _compare("fp32 CUDA vs fp32 oracle", got32, ref32, 1e-4, 1e-5, 1e-4, 0.999 if strict else 0.99, out_kind)
     del got32
     gotbf = _engine_step(builder, "bf16", batch, size, init, x, y)
     # strict: 1e-2 (north_star); otherwise the yardstick is the storage noise the oracle itself shows.  Gradients of the bf16
