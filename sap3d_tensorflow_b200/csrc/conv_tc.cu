@@ -256,6 +256,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     // mbarrier -- r01 shipped them with st.shared::cluster from registers, which cost ~3.9 us per launch (phase probe).
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    {   // per-column epilogue vectors -> shared memory, under the K loop (their global-load latency is off the critical path)
+      const int et0 = threadIdx.x - 64;
+      for (int cc = et0; cc < BLOCK_N; cc += 128) {
+        const int col = nt * BLOCK_N + cc;
+        const bool in = col < p.cout;
+        s_ep[cc] = (in && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
+        s_ep[BLOCK_N + cc] = (in && p.scale != nullptr) ? __ldg(p.scale + col) : 1.f;
+        s_ep[2 * BLOCK_N + cc] = (in && p.scale != nullptr) ? __ldg(p.shift + col) : 0.f;
+      }
+    }
     if (nkb > 0) {
       mbar_wait(bar_base + 2 * STAGES * 8, 0);
       tc_fence_after();
@@ -283,8 +293,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     }
     tc_fence_before();
     fence_proxy_async();                                  // my generic-proxy writes -> visible to the bulk-copy (async) proxy
-    asm volatile("bar.sync 1, 128;" ::: "memory");        // all four epilogue warps have staged their rows
+    asm volatile("bar.sync 1, 128;" ::: "memory");        // all four epilogue warps have staged their rows (and s_ep)
+    if (threadIdx.x == 64) dbg_mark(p, 11);
     cluster_wait();                                       // #1: every peer's receive barrier is initialised
+    if (threadIdx.x == 64) dbg_mark(p, 12);
     if (threadIdx.x == 64) {
 #pragma unroll
       for (int pj = 0; pj < SPLIT - 1; ++pj) {
@@ -303,7 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const bool want_stats = p.stats != nullptr;
-    {   // per-column epilogue vectors -> shared memory once per CTA (overlaps the K loop; the chunk loop reads broadcasts)
+    if (SPLIT == 1) {   // per-column epilogue vectors -> shared memory once per CTA (overlaps the K loop; the chunk loop reads broadcasts)
       const int et0 = threadIdx.x - 64;
       for (int cc = et0; cc < BLOCK_N; cc += 128) {
         const int col = nt * BLOCK_N + cc;
