@@ -92,6 +92,10 @@ int sap3d_conv_fwd(const sap3d_conv_desc* d, const void* x0, const void* x1, con
  * epilogue (utils/network.py:100-110 with training=False, p3d.py:343-345).  Tensor-core paths only: query with
  * sap3d_conv_fwd_on_tensor_cores(). */
 int sap3d_conv_fwd_on_tensor_cores(const sap3d_conv_desc* d);
+/* 1 when the forward operand buffer is a workspace sap3d_conv_fwd fills itself (the Cin = 3 stem's im2col form: packed filter +
+ * scratch + im2col matrix, which sap3d_conv_wgrad reuses through `fwd_operand`), 0 when it is the pre-packed filter that
+ * conv_fwd only reads.  A binding that must not write its inputs (TF custom op) allocates that workspace as an output. */
+int sap3d_conv_fwd_operand_is_workspace(const sap3d_conv_desc* d);
 int sap3d_conv_fwd_affine(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf, const void* w_fwd_packed,
                           const float* bias, const float* scale, const float* shift, int32_t relu, void* y, void* stream);
 /* dx_seg = data gradient w.r.t. segment `seg`; accumulate != 0 adds into dx */

@@ -64,6 +64,7 @@ _sig("sap3d_conv_packed_elems", [_P(ConvDesc), _i32], C.c_size_t)
 _sig("sap3d_conv_pack_weights", [_P(ConvDesc), _vp, _vp, _vp, _vp])
 _sig("sap3d_conv_fwd", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_conv_fwd_on_tensor_cores", [_P(ConvDesc)])
+_sig("sap3d_conv_fwd_operand_is_workspace", [_P(ConvDesc)])
 _sig("sap3d_conv_fwd_affine", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp])
 _sig("sap3d_conv_dgrad", [_P(ConvDesc), _i32, _vp, _vp, _vp, _vp, _i32, _vp])
 _sig("sap3d_conv_dgrad2_supported", [_P(ConvDesc)])

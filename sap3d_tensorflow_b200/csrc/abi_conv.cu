@@ -389,6 +389,14 @@ int sap3d_conv_fwd(const sap3d_conv_desc* d, const void* x0, const void* x1, con
   return conv_fwd_impl(d, x0, x1, w_tf, w_fwd_packed, bias, y, stats, nullptr, nullptr, 0, stream);
 }
 
+/* 1 when the forward operand buffer (sap3d_conv_packed_elems(d, 0) elements) is a WORKSPACE that sap3d_conv_fwd fills itself
+ * (the small-Cin im2col form: packed filter + scratch + im2col matrix, reused by sap3d_conv_wgrad); 0 when it is the
+ * pre-packed filter from sap3d_conv_pack_weights that conv_fwd only reads */
+int sap3d_conv_fwd_operand_is_workspace(const sap3d_conv_desc* d) {
+  if (!d) return 0;
+  return im2col_eligible(d) ? 1 : 0;
+}
+
 /* 1 when conv_fwd runs on the tensor cores for this descriptor (implicit GEMM or the small-Cin im2col form) */
 int sap3d_conv_fwd_on_tensor_cores(const sap3d_conv_desc* d) {
   if (check_desc(d)) return 0;

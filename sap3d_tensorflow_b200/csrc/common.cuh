@@ -36,6 +36,12 @@ SAP3D_DEVINL float2 unpack_bf16x2(uint32_t v) {
 // 8 contiguous elements <-> 8 floats (128-bit access for bf16, 2x128-bit for f32)
 template <typename T> struct Vec8;
 template <> struct Vec8<bf16> {
+  typedef uint4 Raw;   // 8 elements as loaded (4 registers): unpack when used
+  static SAP3D_DEVINL Raw load_raw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static SAP3D_DEVINL void unpack(const Raw& u, float (&v)[8]) {
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
   static SAP3D_DEVINL void load(const bf16* p, float (&v)[8]) {
     uint4 u = *reinterpret_cast<const uint4*>(p);
     float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
@@ -49,6 +55,16 @@ template <> struct Vec8<bf16> {
   }
 };
 template <> struct Vec8<float> {
+  struct Raw { float4 a, b; };
+  static SAP3D_DEVINL Raw load_raw(const float* p) {
+    Raw r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
+  }
+  static SAP3D_DEVINL void unpack(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
   static SAP3D_DEVINL void load(const float* p, float (&v)[8]) {
     float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;

@@ -362,15 +362,10 @@ struct ApplyBwdArgs {
   int batch_stats1, batch_stats2, acc_a, acc_b;
 };
 
-template <typename T>
-SAP3D_DEVINL void bwd_common(const ApplyBwdArgs& p, long long e, long long sidx, long long midx, float (&g1)[8], float (&g2)[8],
-                             float (&xh1)[8], float (&xh2)[8]) {
-  const T* dy = reinterpret_cast<const T*>(p.dy);
-  const T* a = reinterpret_cast<const T*>(p.a);
-  const T* b = reinterpret_cast<const T*>(p.b);
-  float d[8], av[8], z1[8], z2[8];
-  Vec8<T>::load(dy + e, d);
-  Vec8<T>::load(a + e, av);
+// masks and normalised values of 8 consecutive channels of one position from the already-loaded operand values
+SAP3D_DEVINL void bwd_compute(const ApplyBwdArgs& p, const float (&d)[8], const float (&av)[8], const float (&bv)[8], long long sidx,
+                              long long midx, float (&g1)[8], float (&g2)[8], float (&xh1)[8], float (&xh2)[8]) {
+  float z1[8], z2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float s = p.s1 ? p.s1[sidx + j] : 1.f, t = p.t1 ? p.t1[sidx + j] : 0.f;
@@ -378,8 +373,6 @@ SAP3D_DEVINL void bwd_common(const ApplyBwdArgs& p, long long e, long long sidx,
     xh1[j] = p.mean1 ? (av[j] - p.mean1[midx + (p.G ? 0 : j)]) * p.rstd1[midx + (p.G ? 0 : j)] : 0.f;
   }
   if (p.b) {
-    float bv[8];
-    Vec8<T>::load(b + e, bv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float s = p.s2 ? p.s2[sidx + j] : 1.f, t = p.s2 ? p.t2[sidx + j] : 0.f;
@@ -399,6 +392,21 @@ SAP3D_DEVINL void bwd_common(const ApplyBwdArgs& p, long long e, long long sidx,
     g1[j] = (p.relu1 && !(z1[j] > 0.f)) ? 0.f : u;
     g2[j] = (p.relu2 && !(z2[j] > 0.f)) ? 0.f : u;
   }
+}
+
+template <typename T>
+SAP3D_DEVINL void bwd_common(const ApplyBwdArgs& p, long long e, long long sidx, long long midx, float (&g1)[8], float (&g2)[8],
+                             float (&xh1)[8], float (&xh2)[8]) {
+  float d[8], av[8], bv[8];
+  Vec8<T>::load(reinterpret_cast<const T*>(p.dy) + e, d);
+  Vec8<T>::load(reinterpret_cast<const T*>(p.a) + e, av);
+  if (p.b) {
+    Vec8<T>::load(reinterpret_cast<const T*>(p.b) + e, bv);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bv[j] = 0.f;
+  }
+  bwd_compute(p, d, av, bv, sidx, midx, g1, g2, xh1, xh2);
 }
 
 // grid = (rows, C/64): each block reduces a slab of positions for one 64-channel chunk.
@@ -905,17 +913,40 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
   pdl_launch_dependents();
   __shared__ float red[8][4][16];   // [warp][sum][channel]
   __shared__ float coef[4][16];
+  constexpr int MAXIT = (int)(SLAB_MAX_P / 128);
   const int half = threadIdx.x & 1, rl = threadIdx.x >> 1;
   const int c = blockIdx.x * 16 + half * 8;
+  const bool live = c < p.C;
+  const T* dyp = reinterpret_cast<const T*>(p.dy);
+  const T* ap = reinterpret_cast<const T*>(p.a);
+  const T* bp = reinterpret_cast<const T*>(p.b);
+  // every position this thread owns is loaded ONCE, all loads in flight together (one memory latency for the whole slab);
+  // both passes then run from registers
+  typename Vec8<T>::Raw dr[MAXIT], ar[MAXIT], br[MAXIT];
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const long long pos = rl + it * 128;
+    if (live && pos < p.P) {
+      const long long e = pos * p.C + c;
+      dr[it] = Vec8<T>::load_raw(dyp + e);
+      ar[it] = Vec8<T>::load_raw(ap + e);
+      br[it] = bp ? Vec8<T>::load_raw(bp + e) : ar[it];
+    }
+  }
   float acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  if (c < p.C) {
-    for (long long pos = rl; pos < p.P; pos += 128) {
-      float g1[8], g2[8], xh1[8], xh2[8];
-      bwd_common<T>(p, pos * p.C + c, c, c, g1, g2, xh1, xh2);
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const long long pos = rl + it * 128;
+    if (live && pos < p.P) {
+      float g1[8], g2[8], xh1[8], xh2[8], dv[8], av[8], bv[8];
+      Vec8<T>::unpack(dr[it], dv);
+      Vec8<T>::unpack(ar[it], av);
+      Vec8<T>::unpack(br[it], bv);
+      bwd_compute(p, dv, av, bv, c, c, g1, g2, xh1, xh2);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         acc[0][j] += g1[j];
@@ -958,20 +989,30 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
     }
   }
   __syncthreads();
-  if (c >= p.C || (!p.da && !p.db)) return;
+  if (!live || (!p.da && !p.db)) return;
   T* da = reinterpret_cast<T*>(p.da);
   T* db = reinterpret_cast<T*>(p.db);
-  for (long long pos = rl; pos < p.P; pos += 128) {
+  float sc1[8], sc2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc1[j] = p.s1 ? p.s1[c + j] : 1.f;
+    sc2[j] = p.s2 ? p.s2[c + j] : 1.f;
+  }
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const long long pos = rl + it * 128;
+    if (pos >= p.P) continue;
     const long long e = pos * p.C + c;
-    float g1[8], g2[8], xh1[8], xh2[8];
-    bwd_common<T>(p, e, c, c, g1, g2, xh1, xh2);
+    float g1[8], g2[8], xh1[8], xh2[8], dv[8], av[8], bv[8];
+    Vec8<T>::unpack(dr[it], dv);
+    Vec8<T>::unpack(ar[it], av);
+    Vec8<T>::unpack(br[it], bv);
+    bwd_compute(p, dv, av, bv, c, c, g1, g2, xh1, xh2);
     if (da) {
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float sc = p.s1 ? p.s1[c + j] : 1.f;
-        o[j] = p.batch_stats1 ? sc * (g1[j] - coef[0][half * 8 + j] - xh1[j] * coef[1][half * 8 + j]) : sc * g1[j];
-      }
+      for (int j = 0; j < 8; ++j)
+        o[j] = p.batch_stats1 ? sc1[j] * (g1[j] - coef[0][half * 8 + j] - xh1[j] * coef[1][half * 8 + j]) : sc1[j] * g1[j];
       if (p.acc_a) {
         float old[8];
         Vec8<T>::load(da + e, old);
@@ -983,10 +1024,8 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
     if (db) {
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float sc = p.s2 ? p.s2[c + j] : 1.f;
-        o[j] = p.batch_stats2 ? sc * (g2[j] - coef[2][half * 8 + j] - xh2[j] * coef[3][half * 8 + j]) : sc * g2[j];
-      }
+      for (int j = 0; j < 8; ++j)
+        o[j] = p.batch_stats2 ? sc2[j] * (g2[j] - coef[2][half * 8 + j] - xh2[j] * coef[3][half * 8 + j]) : sc2[j] * g2[j];
       if (p.acc_b) {
         float old[8];
         Vec8<T>::load(db + e, old);

@@ -165,12 +165,20 @@ def test_cuda_preprocess_and_video_windows(lib_built):
     ref = dict(sp.video.predict_video(one, frames, graph=False))
     assert sorted(ref) == sorted(got)
     worst = max(float((got[k] - ref[k]).abs().max()) for k in ref)
-    assert worst < 1e-4, worst                                     # batch of 4 windows (+ padding copies) == 4 single runs
-    # without the per-sample mode a batch of windows is refused (it would normalise over the batch and its padding copies)
+    # without the per-sample mode a batch of windows is refused (it would normalise over the batch and its padding copies) ...
     xb = sp.placeholder([B, 16, size, size, 3], dtype="f32", training_graph=False)
     plain = sp.Session(sp.p3d.p3d_unet(xb, 0.0, B, False))
+    plain.eng.load_params(params)
     with pytest.raises(sp._abi.Sap3dError):
         next(iter(sp.video.predict_video(plain, frames)))
+    # ... and it really would give other maps: windows 1..4 through plain batch statistics vs one window per run
+    mixed = plain.run(torch.stack([frames[s:s + 16] for s in range(1, 1 + B)]), graph=False)
+    plain_diff = max(float((mixed[j, 15, :, :, 0] - ref[1 + j + 15]).abs().max()) for j in range(B))
+    print(f"per-sample statistics: max |batch-of-{B} - single-window| = {worst:.2e}; plain batch statistics: {plain_diff:.2e}")
+    # (32 x 32 frames leave 8 positions per channel in stage 3: the fp32 statistics of the two code paths -- conv-epilogue sums vs
+    # sums over the stored tensor -- differ in the last bits and 47 such blocks amplify that; the bound is what separates
+    # "same statistics" from "statistics over the batch")
+    assert worst < 1e-2 and plain_diff > 5 * worst, (worst, plain_diff)
     # forward-only execution leaves the BatchNorm moving statistics alone (UPDATE_OPS run with train_op only, train.py:170-172)
     for n, v in one.variables().items():
         if n.endswith(("moving_mean", "moving_variance")):
