@@ -58,96 +58,81 @@ ops.NotDifferentiable("Sap3dConvGradInput")
 ops.NotDifferentiable("Sap3dConvGradFilter")
 
 
-# ---- BatchNorm / GroupNorm + ReLU + residual add -----------------------------------------------------------------------
-def batch_norm(y, stats, gamma, beta, moving_mean, moving_variance, training, relu=True, residual=None, relu_out=False):
-    """tf.layers.batch_normalization(y, training=training) [+ tf.nn.relu] [+ residual, relu] (p3d.py:56-81,133-134).
-    The moving-average updates are added to tf.GraphKeys.UPDATE_OPS like the stock layer's (train.py:170-172)."""
-    count = 1.0
-    for s in y.shape[:4]:
-        count *= int(s)
-    scale, shift, mean, rstd, new_mm, new_mv = _sap3d.sap3d_bn_finalize(stats, gamma, beta, moving_mean, moving_variance, count=count,
-                                                                         training=training)
+# ---- BatchNorm / GroupNorm + ReLU + residual add (one op per normalisation layer) ---------------------------------------
+def batch_norm_act(conv_out, gamma, beta, moving_mean, moving_variance, training, relu=True, other=None, other_norm=None,
+                   relu_other=False, relu_out=False):
+    """tf.layers.batch_normalization(y, training=training) [+ tf.nn.relu] [+ other, relu] (p3d.py:56-81,133-134).
+    conv_out = (y, stats) from conv3d().  other: a plain tensor (identity shortcut, ST_C) or a second (y, stats) pair with its
+    own variables other_norm = (gamma, beta, moving_mean, moving_variance) (ST_B, projection shortcut).  The moving-average
+    updates are added to tf.GraphKeys.UPDATE_OPS like the stock layer's (train.py:170-172)."""
+    y, stats = conv_out
+    has_b, norm_b = other is not None, other_norm is not None
+    if norm_b:
+        b, stats_b = other
+        g2, b2, mm2, mv2 = other_norm
+    else:
+        b, stats_b = (other if has_b else y), stats
+        g2, b2, mm2, mv2 = gamma, beta, moving_mean, moving_variance
+    outs = _sap3d.sap3d_batch_norm_act(y, stats, gamma, beta, moving_mean, moving_variance, b, stats_b, g2, b2, mm2, mv2, training=training,
+                                       relu1=relu, relu2=relu_other, relu_out=relu_out, has_b=has_b, norm_b=norm_b)
     if training:
-        tf.add_to_collection(tf.GraphKeys.UPDATE_OPS, tf.assign(moving_mean, new_mm))
-        tf.add_to_collection(tf.GraphKeys.UPDATE_OPS, tf.assign(moving_variance, new_mv))
-    b = residual if residual is not None else y
-    out = _sap3d.sap3d_norm_apply(y, scale, shift, b, scale, shift, relu1=relu, relu2=False, relu_out=relu_out,
-                                  has_b=residual is not None, norm_b=False)
-    # the gradient op needs mean / rstd and the affine parameters: keep them reachable from the forward op
-    out.op._sap3d_bn = (mean, rstd, gamma, beta, training)
-    return out
+        tf.add_to_collection(tf.GraphKeys.UPDATE_OPS, tf.assign(moving_mean, outs[5]))
+        tf.add_to_collection(tf.GraphKeys.UPDATE_OPS, tf.assign(moving_variance, outs[6]))
+        if norm_b:
+            tf.add_to_collection(tf.GraphKeys.UPDATE_OPS, tf.assign(mm2, outs[11]))
+            tf.add_to_collection(tf.GraphKeys.UPDATE_OPS, tf.assign(mv2, outs[12]))
+    return outs[0]
 
 
-@ops.RegisterGradient("Sap3dNormApply")
-def _norm_apply_grad(op, dy):
-    a, s1, t1, b, s2, t2 = op.inputs
-    mean, rstd, _gamma, _beta, training = op._sap3d_bn
-    da, db, dgamma1, dbeta1, _dg2, _db2 = _sap3d.sap3d_norm_apply_grad(
-        dy, a, s1, t1, mean, rstd, b, s2, t2, mean, rstd, relu1=op.get_attr("relu1"), relu2=op.get_attr("relu2"),
-        relu_out=op.get_attr("relu_out"), has_b=op.get_attr("has_b"), norm_b=op.get_attr("norm_b"), batch_stats1=training,
-        batch_stats2=training)
-    # scale = gamma * rstd and shift = beta - mean * scale are functions of (gamma, beta) through Sap3dBnFinalize: with the
-    # batch statistics already differentiated inside the fused backward, d scale = dgamma / rstd and d shift = dbeta
-    return da, dgamma1 / rstd, dbeta1, (db if op.get_attr("has_b") else None), None, None
+@ops.RegisterGradient("Sap3dBatchNormAct")
+def _batch_norm_act_grad(op, dy, *_unused):
+    a, _sa, _g1, _b1, _mm1, _mv1, b, _sb, _g2, _b2, _mm2, _mv2 = op.inputs
+    o = op.outputs
+    has_b, norm_b = op.get_attr("has_b"), op.get_attr("norm_b")
+    da, db, dgamma1, dbeta1, dgamma2, dbeta2 = _sap3d.sap3d_batch_norm_act_grad(
+        dy, a, o[1], o[2], o[3], o[4], b, o[7], o[8], o[9], o[10], training=op.get_attr("training"), relu1=op.get_attr("relu1"),
+        relu2=op.get_attr("relu2"), relu_out=op.get_attr("relu_out"), has_b=has_b, norm_b=norm_b)
+    two = has_b and norm_b
+    # the statistics inputs carry no gradient of their own: the fused backward already goes through the batch statistics
+    return (da, None, dgamma1, dbeta1, None, None, db if has_b else None, None, dgamma2 if two else None, dbeta2 if two else None, None, None)
 
 
-@ops.RegisterGradient("Sap3dBnFinalize")
-def _bn_finalize_grad(op, dscale, dshift, *_unused):
-    _stats, gamma, _beta, _mm, _mv = op.inputs
-    rstd = op.outputs[3]
-    mean = op.outputs[2]
-    # (statistics carry no gradient here: Sap3dNormApplyGrad already contains the full BatchNorm backward)
-    return None, dscale * rstd - dshift * mean * rstd, dshift, None, None
+def group_norm_act(x, gamma, beta, relu=False, other=None, other_norm=None, relu_other=False, relu_out=False):
+    """GroupNorm (utils/network.py:65-87) [+ ReLU] [+ other, relu]; other_norm = (gamma, beta) of a second GroupNorm"""
+    has_b, norm_b = other is not None, other_norm is not None
+    b = other if has_b else x
+    g2, b2 = other_norm if norm_b else (gamma, beta)
+    return _sap3d.sap3d_group_norm_act(x, gamma, beta, b, g2, b2, relu1=relu, relu2=relu_other, relu_out=relu_out, has_b=has_b, norm_b=norm_b)[0]
 
 
-def group_norm(x, gamma, beta, relu=False, residual=None, relu_out=False):
-    """GroupNorm (utils/network.py:65-87) [+ ReLU] [+ residual, relu]"""
-    scale, shift, mean, rstd = _sap3d.sap3d_group_norm_stats(x, gamma, beta)
-    pps = 1
-    for s in x.shape[1:4]:
-        pps *= int(s)
-    b = residual if residual is not None else x
-    out = _sap3d.sap3d_norm_apply(x, scale, shift, b, scale, shift, relu1=relu, relu2=False, relu_out=relu_out, has_b=residual is not None,
-                                  norm_b=False, positions_per_sample=pps)
-    out.op._sap3d_gn = (mean, rstd, gamma, beta)
-    return out
+@ops.RegisterGradient("Sap3dGroupNormAct")
+def _group_norm_act_grad(op, dy, *_unused):
+    a, gamma1, _beta1, b, gamma2, _beta2 = op.inputs
+    o = op.outputs
+    has_b, norm_b = op.get_attr("has_b"), op.get_attr("norm_b")
+    da, db, dgamma1, dbeta1, dgamma2, dbeta2 = _sap3d.sap3d_group_norm_act_grad(
+        dy, a, o[1], o[2], o[3], o[4], gamma1, b, o[5], o[6], o[7], o[8], gamma2, relu1=op.get_attr("relu1"), relu2=op.get_attr("relu2"),
+        relu_out=op.get_attr("relu_out"), has_b=has_b, norm_b=norm_b)
+    two = has_b and norm_b
+    return da, dgamma1, dbeta1, (db if has_b else None), (dgamma2 if two else None), (dbeta2 if two else None)
 
 
-def _group_norm_apply_grad(op, dy):
-    a, s1, t1, b, s2, t2 = op.inputs
-    mean, rstd, gamma, _beta = op._sap3d_gn
-    da, db, dgamma, dbeta, _g2, _b2 = _sap3d.sap3d_group_norm_grad(dy, a, s1, t1, mean, rstd, gamma, b, s2, t2, mean, rstd, gamma,
-                                                                   relu1=op.get_attr("relu1"), relu2=op.get_attr("relu2"),
-                                                                   relu_out=op.get_attr("relu_out"), has_b=op.get_attr("has_b"),
-                                                                   norm_b=op.get_attr("norm_b"))
-    return da, dgamma, dbeta, (db if op.get_attr("has_b") else None)
-
-
-ops.NotDifferentiable("Sap3dGroupNormStats")     # its gradient is inside Sap3dGroupNormGrad (dgamma / dbeta returned there)
-ops.NotDifferentiable("Sap3dNormApplyGrad")
-ops.NotDifferentiable("Sap3dGroupNormGrad")
+ops.NotDifferentiable("Sap3dBatchNormActGrad")
+ops.NotDifferentiable("Sap3dGroupNormActGrad")
 
 
 # ---- CBAM block tail (gn/p3d_gn.py:175-177) ----------------------------------------------------------------------------
 def cbam_block_tail(c3, gamma3, beta3, residual, w0, b0, w1, b1, w_sp):
     """relu(GroupNorm(c3) + cbam_block(residual))"""
-    scale3, shift3, mean3, rstd3 = _sap3d.sap3d_group_norm_stats(c3, gamma3, beta3)
-    y, cscale, sp, att, save = _sap3d.sap3d_cbam_tail(c3, scale3, shift3, residual, w0, b0, w1, b1, w_sp)
-    y.op._sap3d_cbam = (mean3, rstd3, gamma3)
-    return y
+    return _sap3d.sap3d_cbam_tail(c3, gamma3, beta3, residual, w0, b0, w1, b1, w_sp)[0]
 
 
 @ops.RegisterGradient("Sap3dCbamTail")
 def _cbam_tail_grad(op, dy, *_unused):
-    c3, scale3, _shift3, r, w0, _b0, w1, _b1, w_sp = op.inputs
-    y, cscale, sp, att, save = op.outputs
-    mean3, rstd3, gamma3 = op._sap3d_cbam
-    dc3, dr, dgamma3, dbeta3, dw0, db0, dw1, db1, dw_sp = _sap3d.sap3d_cbam_tail_grad(dy, y, c3, scale3, mean3, rstd3, gamma3, r, w0, w1, w_sp,
-                                                                                    cscale, sp, att, save)
-    # d scale3 / d shift3 route the GroupNorm affine gradient back to gamma3 / beta3 through Sap3dGroupNormStats' outputs
-    tf.add_to_collection("sap3d_param_grads", (gamma3, dgamma3))
-    tf.add_to_collection("sap3d_param_grads", (op.inputs[2], dbeta3))
-    return dc3, None, None, dr, dw0, db0, dw1, db1, dw_sp
+    c3, gamma3, _beta3, r, w0, _b0, w1, _b1, w_sp = op.inputs
+    y, scale3, mean3, rstd3, cscale, sp, att, save = op.outputs
+    # one gradient per input, in input order: c3, gamma3, beta3, r, w0, b0, w1, b1, w_sp
+    return _sap3d.sap3d_cbam_tail_grad(dy, y, c3, scale3, mean3, rstd3, gamma3, r, w0, w1, w_sp, cscale, sp, att, save)
 
 
 ops.NotDifferentiable("Sap3dCbamTailGrad")
@@ -243,11 +228,3 @@ ops.NotDifferentiable("Sap3dSaliencyMetrics")
 ops.NotDifferentiable("Sap3dResizeBilinear")
 ops.NotDifferentiable("Sap3dSaliencyAuc")
 ops.NotDifferentiable("Sap3dPreprocessFrames")
-
-
-# the NormApply gradient depends on which statistics produced its scale / shift
-_bn_grad = _norm_apply_grad
-
-
-def _dispatch_norm_apply_grad(op, dy):
-    return _group_norm_apply_grad(op, dy) + (None, None) if hasattr(op, "_sap3d_gn") else _bn_grad(op, dy)

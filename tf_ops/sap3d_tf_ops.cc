@@ -319,91 +319,79 @@ class Sap3dConvGradFilterOp : public tf::OpKernel {
 REGISTER_KERNEL_BUILDER(Name("Sap3dConvGradFilter").Device(tf::DEVICE_GPU), Sap3dConvGradFilterOp);
 
 // =====================================================================================================================
-// scale, shift, mean, rstd, new_moving_mean, new_moving_variance = Sap3dBnFinalize(stats, gamma, beta, moving_mean, moving_variance)
-//   the statistics half of tf.layers.batch_normalization (p3d.py:58-127,344; utils/network.py:91): eps 1e-3, momentum 0.99,
-//   biased batch variance; training = false uses the moving statistics.  The new moving averages are OUTPUTS: the Python side
-//   assigns them inside UPDATE_OPS exactly where tf.layers.batch_normalization registers its updates (train.py:170-172).
+// One op per normalisation LAYER, so that gamma / beta are direct inputs and tf.gradients needs no knowledge of the kernels'
+// split into statistics and apply passes:
+//
+// y, scale1, shift1, mean1, rstd1, new_mm1, new_mv1, scale2, shift2, mean2, rstd2, new_mm2, new_mv2 =
+//     Sap3dBatchNormAct(a, stats_a, gamma1, beta1, moving_mean1, moving_variance1, b, stats_b, gamma2, beta2, moving_mean2, moving_variance2)
+//   y = relu_out?( relu1?(BN1(a)) + relu2?(BN2(b) | b) ): tf.layers.batch_normalization (p3d.py:58-127,344; utils/network.py:91; eps 1e-3,
+//   momentum 0.99, biased batch variance) + tf.nn.relu + the residual / ST_B / ST_C adds (p3d.py:56-81,133-134) in one pass.
+//   stats_* are the [rows][2][C] outputs of Sap3dConv.  has_b: b is used; norm_b: b goes through its own BatchNorm.
+//   The new moving averages are OUTPUTS: the Python wrapper assigns them inside UPDATE_OPS, where the stock layer registers its
+//   updates (train.py:170-172).
 // =====================================================================================================================
-REGISTER_OP("Sap3dBnFinalize")
-    .Input("stats: float").Input("gamma: float").Input("beta: float").Input("moving_mean: float").Input("moving_variance: float")
-    .Output("scale: float").Output("shift: float").Output("mean: float").Output("rstd: float")
-    .Output("new_moving_mean: float").Output("new_moving_variance: float")
-    .Attr("count: float").Attr("training: bool").Attr("momentum: float = 0.99").Attr("epsilon: float = 0.001")
+REGISTER_OP("Sap3dBatchNormAct")
+    .Input("a: T").Input("stats_a: float").Input("gamma1: float").Input("beta1: float").Input("moving_mean1: float").Input("moving_variance1: float")
+    .Input("b: T").Input("stats_b: float").Input("gamma2: float").Input("beta2: float").Input("moving_mean2: float").Input("moving_variance2: float")
+    .Output("y: T").Output("scale1: float").Output("shift1: float").Output("mean1: float").Output("rstd1: float")
+    .Output("new_moving_mean1: float").Output("new_moving_variance1: float")
+    .Output("scale2: float").Output("shift2: float").Output("mean2: float").Output("rstd2: float")
+    .Output("new_moving_mean2: float").Output("new_moving_variance2: float")
+    .Attr("T: {bfloat16, float}").Attr("training: bool").Attr("momentum: float = 0.99").Attr("epsilon: float = 0.001")
+    .Attr("relu1: bool = true").Attr("relu2: bool = false").Attr("relu_out: bool = false").Attr("has_b: bool = false").Attr("norm_b: bool = false")
     .SetShapeFn([](InferenceContext* c) {
-      for (int i = 0; i < 6; ++i) c->set_output(i, c->input(1));
+      c->set_output(0, c->input(0));
+      for (int i = 1; i < 7; ++i) c->set_output(i, c->input(2));
+      for (int i = 7; i < 13; ++i) c->set_output(i, c->input(8));
       return tf::Status::OK();
     });
 
-class Sap3dBnFinalizeOp : public tf::OpKernel {
+class Sap3dBatchNormActOp : public tf::OpKernel {
  public:
-  explicit Sap3dBnFinalizeOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
-    OP_REQUIRES_OK(c, c->GetAttr("count", &count_));
-    OP_REQUIRES_OK(c, c->GetAttr("training", &training_));
-    OP_REQUIRES_OK(c, c->GetAttr("momentum", &momentum_));
+  explicit Sap3dBatchNormActOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("training", &training_)); OP_REQUIRES_OK(c, c->GetAttr("momentum", &momentum_));
     OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_));
-  }
-  void Compute(tf::OpKernelContext* ctx) override {
-    const tf::Tensor& stats = ctx->input(0);
-    const tf::Tensor& gamma = ctx->input(1);
-    const tf::int32 C = static_cast<tf::int32>(gamma.NumElements());
-    tf::Tensor* out[4];
-    for (int i = 0; i < 4; ++i) OP_REQUIRES_OK(ctx, ctx->allocate_output(i, gamma.shape(), &out[i]));
-    tf::Tensor *mm = nullptr, *mv = nullptr;
-    OP_REQUIRES_OK(ctx, CopyOutput(ctx, 4, ctx->input(3), &mm));
-    OP_REQUIRES_OK(ctx, CopyOutput(ctx, 5, ctx->input(4), &mv));
-    SAP3D_OK(ctx, sap3d_bn_finalize(training_ ? F(stats) : nullptr, training_ ? static_cast<tf::int32>(stats.dim_size(0)) : 0, C, count_, F(gamma),
-                                    F(ctx->input(2)), F(mm), F(mv), training_, momentum_, eps_, F(out[0]), F(out[1]), F(out[2]), F(out[3]),
-                                    StreamOf(ctx)));
-  }
-
- private:
-  float count_, momentum_, eps_;
-  bool training_;
-};
-REGISTER_KERNEL_BUILDER(Name("Sap3dBnFinalize").Device(tf::DEVICE_GPU), Sap3dBnFinalizeOp);
-
-// y = Sap3dNormApply(a, scale1, shift1, b, scale2, shift2): y = relu_out?( relu1?(a*s1+t1) + relu2?(b*s2+t2 | b) ) -- the apply
-// half of tf.layers.batch_normalization / GroupNorm + tf.nn.relu + the residual adds (p3d.py:56-81,133-134;
-// gn/p3d_gn.py:49-51,177).  positions_per_sample > 0: per-sample scale / shift [N][C] (GroupNorm).
-REGISTER_OP("Sap3dNormApply")
-    .Input("a: T").Input("scale1: float").Input("shift1: float").Input("b: T").Input("scale2: float").Input("shift2: float")
-    .Output("y: T").Attr("T: {bfloat16, float}")
-    .Attr("relu1: bool").Attr("relu2: bool = false").Attr("relu_out: bool = false").Attr("has_b: bool = false").Attr("norm_b: bool = false")
-    .Attr("positions_per_sample: int = 0")
-    .SetShapeFn(SameAsInput0);
-
-class Sap3dNormApplyOp : public tf::OpKernel {
- public:
-  explicit Sap3dNormApplyOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
     OP_REQUIRES_OK(c, c->GetAttr("relu1", &r1_)); OP_REQUIRES_OK(c, c->GetAttr("relu2", &r2_));
     OP_REQUIRES_OK(c, c->GetAttr("relu_out", &ro_)); OP_REQUIRES_OK(c, c->GetAttr("has_b", &hb_));
-    OP_REQUIRES_OK(c, c->GetAttr("norm_b", &nb_)); OP_REQUIRES_OK(c, c->GetAttr("positions_per_sample", &pps_));
+    OP_REQUIRES_OK(c, c->GetAttr("norm_b", &nb_));
   }
   void Compute(tf::OpKernelContext* ctx) override {
     const tf::Tensor& a = ctx->input(0);
+    const tf::int64 C = a.dim_size(a.dims() - 1), Pn = a.NumElements() / C;
     tf::Tensor* y = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, a.shape(), &y));
-    const tf::int64 C = a.dim_size(a.dims() - 1), Pn = a.NumElements() / C;
-    SAP3D_OK(ctx, sap3d_affine_act(DtypeOf(a), P(a), F(ctx->input(1)), F(ctx->input(2)), r1_, hb_ ? P(ctx->input(3)) : nullptr,
-                                   FOrNull(ctx->input(4), nb_), FOrNull(ctx->input(5), nb_), r2_, ro_, P(y), Pn, static_cast<int32_t>(C), pps_,
-                                   StreamOf(ctx)));
+    const bool n2 = hb_ && nb_;
+    tf::Tensor* o[2][6];
+    for (int k = 0; k < 2; ++k) {
+      const int in0 = k == 0 ? 2 : 8;   // gamma_k; moving statistics at in0 + 2, in0 + 3
+      const tf::TensorShape shp = (k == 0 || n2) ? ctx->input(in0).shape() : tf::TensorShape({0});
+      for (int i = 0; i < 4; ++i) OP_REQUIRES_OK(ctx, ctx->allocate_output(1 + 6 * k + i, shp, &o[k][i]));
+      OP_REQUIRES_OK(ctx, CopyOutput(ctx, 1 + 6 * k + 4, ctx->input(in0 + 2), &o[k][4]));
+      OP_REQUIRES_OK(ctx, CopyOutput(ctx, 1 + 6 * k + 5, ctx->input(in0 + 3), &o[k][5]));
+      if (k == 1 && !n2) continue;
+      const tf::Tensor& stats = ctx->input(in0 - 1);
+      SAP3D_OK(ctx, sap3d_bn_finalize(training_ ? F(stats) : nullptr, training_ ? static_cast<tf::int32>(stats.dim_size(0)) : 0, static_cast<int32_t>(C),
+                                      static_cast<double>(Pn), F(ctx->input(in0)), F(ctx->input(in0 + 1)), F(o[k][4]), F(o[k][5]), training_, momentum_,
+                                      eps_, F(o[k][0]), F(o[k][1]), F(o[k][2]), F(o[k][3]), StreamOf(ctx)));
+    }
+    SAP3D_OK(ctx, sap3d_affine_act(DtypeOf(a), P(a), F(o[0][0]), F(o[0][1]), r1_, hb_ ? P(ctx->input(6)) : nullptr, n2 ? F(o[1][0]) : nullptr,
+                                   n2 ? F(o[1][1]) : nullptr, r2_, ro_, P(y), Pn, static_cast<int32_t>(C), 0, StreamOf(ctx)));
   }
 
  private:
-  bool r1_, r2_, ro_, hb_, nb_;
-  tf::int32 pps_;
+  bool training_, r1_, r2_, ro_, hb_, nb_;
+  float momentum_, eps_;
 };
-REGISTER_KERNEL_BUILDER(Name("Sap3dNormApply").Device(tf::DEVICE_GPU), Sap3dNormApplyOp);
+REGISTER_KERNEL_BUILDER(Name("Sap3dBatchNormAct").Device(tf::DEVICE_GPU), Sap3dBatchNormActOp);
 
-// da, db, dgamma1, dbeta1, dgamma2, dbeta2 = Sap3dNormApplyGrad(dy, a, scale1, shift1, mean1, rstd1, b, scale2, shift2, mean2, rstd2)
-// full BatchNorm backward (batch_stats* = true) or frozen-scale backward of the op above
-REGISTER_OP("Sap3dNormApplyGrad")
+// da, db, dgamma1, dbeta1, dgamma2, dbeta2 = Sap3dBatchNormActGrad(dy, a, scale1, shift1, mean1, rstd1, b, scale2, shift2, mean2, rstd2):
+// the full BatchNorm backward (training: through the batch statistics) of the op above, masks recomputed from a / b
+REGISTER_OP("Sap3dBatchNormActGrad")
     .Input("dy: T").Input("a: T").Input("scale1: float").Input("shift1: float").Input("mean1: float").Input("rstd1: float")
     .Input("b: T").Input("scale2: float").Input("shift2: float").Input("mean2: float").Input("rstd2: float")
     .Output("da: T").Output("db: T").Output("dgamma1: float").Output("dbeta1: float").Output("dgamma2: float").Output("dbeta2: float")
-    .Attr("T: {bfloat16, float}")
-    .Attr("relu1: bool").Attr("relu2: bool = false").Attr("relu_out: bool = false").Attr("has_b: bool = false").Attr("norm_b: bool = false")
-    .Attr("batch_stats1: bool = true").Attr("batch_stats2: bool = true")
+    .Attr("T: {bfloat16, float}").Attr("training: bool")
+    .Attr("relu1: bool = true").Attr("relu2: bool = false").Attr("relu_out: bool = false").Attr("has_b: bool = false").Attr("norm_b: bool = false")
     .SetShapeFn([](InferenceContext* c) {
       c->set_output(0, c->input(1));
       c->set_output(1, c->input(1));
@@ -411,13 +399,13 @@ REGISTER_OP("Sap3dNormApplyGrad")
       return tf::Status::OK();
     });
 
-class Sap3dNormApplyGradOp : public tf::OpKernel {
+class Sap3dBatchNormActGradOp : public tf::OpKernel {
  public:
-  explicit Sap3dNormApplyGradOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+  explicit Sap3dBatchNormActGradOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("training", &training_));
     OP_REQUIRES_OK(c, c->GetAttr("relu1", &r1_)); OP_REQUIRES_OK(c, c->GetAttr("relu2", &r2_));
     OP_REQUIRES_OK(c, c->GetAttr("relu_out", &ro_)); OP_REQUIRES_OK(c, c->GetAttr("has_b", &hb_));
-    OP_REQUIRES_OK(c, c->GetAttr("norm_b", &nb_)); OP_REQUIRES_OK(c, c->GetAttr("batch_stats1", &bs1_));
-    OP_REQUIRES_OK(c, c->GetAttr("batch_stats2", &bs2_));
+    OP_REQUIRES_OK(c, c->GetAttr("norm_b", &nb_));
   }
   void Compute(tf::OpKernelContext* ctx) override {
     const tf::Tensor& a = ctx->input(1);
@@ -429,69 +417,79 @@ class Sap3dNormApplyGradOp : public tf::OpKernel {
     tf::Tensor ws;
     OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, tf::TensorShape({static_cast<tf::int64>(sap3d_affine_act_bwd_workspace(static_cast<int32_t>(C)) / 4 + 16)}), &ws));
     const bool n2 = hb_ && nb_;
-    SAP3D_OK(ctx, sap3d_affine_act_bwd(DtypeOf(a), P(ctx->input(0)), P(a), F(ctx->input(2)), F(ctx->input(3)), FOrNull(ctx->input(4), bs1_),
-                                       FOrNull(ctx->input(5), bs1_), r1_, hb_ ? P(ctx->input(6)) : nullptr, FOrNull(ctx->input(7), n2),
-                                       FOrNull(ctx->input(8), n2), FOrNull(ctx->input(9), n2 && bs2_), FOrNull(ctx->input(10), n2 && bs2_), r2_, ro_,
-                                       Pn, static_cast<int32_t>(C), P(da), 0, hb_ ? P(db) : nullptr, 0, F(g[0]), F(g[1]), n2 ? F(g[2]) : nullptr,
+    SAP3D_OK(ctx, sap3d_affine_act_bwd(DtypeOf(a), P(ctx->input(0)), P(a), F(ctx->input(2)), F(ctx->input(3)), FOrNull(ctx->input(4), training_),
+                                       FOrNull(ctx->input(5), training_), r1_, hb_ ? P(ctx->input(6)) : nullptr, FOrNull(ctx->input(7), n2),
+                                       FOrNull(ctx->input(8), n2), FOrNull(ctx->input(9), n2 && training_), FOrNull(ctx->input(10), n2 && training_), r2_,
+                                       ro_, Pn, static_cast<int32_t>(C), P(da), 0, hb_ ? P(db) : nullptr, 0, F(g[0]), F(g[1]), n2 ? F(g[2]) : nullptr,
                                        n2 ? F(g[3]) : nullptr, P(&ws), StreamOf(ctx)));
   }
 
  private:
-  bool r1_, r2_, ro_, hb_, nb_, bs1_, bs2_;
+  bool training_, r1_, r2_, ro_, hb_, nb_;
 };
-REGISTER_KERNEL_BUILDER(Name("Sap3dNormApplyGrad").Device(tf::DEVICE_GPU), Sap3dNormApplyGradOp);
+REGISTER_KERNEL_BUILDER(Name("Sap3dBatchNormActGrad").Device(tf::DEVICE_GPU), Sap3dBatchNormActGradOp);
 
 // =====================================================================================================================
-// GroupNorm (utils/network.py:65-87 == gn/p3d_gn.py:24-46): per-(sample, channel) scale / shift + per-(sample, group) mean / rstd;
-// the apply pass is Sap3dNormApply with positions_per_sample = D*H*W.
+// y, scale1, shift1, mean1, rstd1, scale2, shift2, mean2, rstd2 = Sap3dGroupNormAct(a, gamma1, beta1, b, gamma2, beta2)
+//   y = relu_out?( relu1?(GN1(a)) + relu2?(GN2(b) | b) ): GroupNorm of utils/network.py:65-87 == gn/p3d_gn.py:24-46 (G = min(32, C), eps 1e-5,
+//   biased variance over (C/G, D, H, W) per sample, per-channel gamma / beta) + ReLU + adds (gn/p3d_gn.py:49-51,130-177)
 // =====================================================================================================================
-REGISTER_OP("Sap3dGroupNormStats")
-    .Input("x: T").Input("gamma: float").Input("beta: float")
-    .Output("scale: float").Output("shift: float").Output("mean: float").Output("rstd: float")
+REGISTER_OP("Sap3dGroupNormAct")
+    .Input("a: T").Input("gamma1: float").Input("beta1: float").Input("b: T").Input("gamma2: float").Input("beta2: float")
+    .Output("y: T").Output("scale1: float").Output("shift1: float").Output("mean1: float").Output("rstd1: float")
+    .Output("scale2: float").Output("shift2: float").Output("mean2: float").Output("rstd2: float")
     .Attr("T: {bfloat16, float}").Attr("groups: int = 32").Attr("epsilon: float = 0.00001")
+    .Attr("relu1: bool = true").Attr("relu2: bool = false").Attr("relu_out: bool = false").Attr("has_b: bool = false").Attr("norm_b: bool = false")
     .SetShapeFn([](InferenceContext* c) {
-      tf::int32 groups;
-      TF_RETURN_IF_ERROR(c->GetAttr("groups", &groups));
-      ShapeHandle x;
-      TF_RETURN_IF_ERROR(c->WithRank(c->input(0), 5, &x));
-      c->set_output(0, c->MakeShape({c->Dim(x, 0), c->Dim(x, 4)}));
-      c->set_output(1, c->MakeShape({c->Dim(x, 0), c->Dim(x, 4)}));
-      c->set_output(2, c->MakeShape({c->Dim(x, 0), c->UnknownDim()}));
-      c->set_output(3, c->MakeShape({c->Dim(x, 0), c->UnknownDim()}));
+      c->set_output(0, c->input(0));
+      for (int i = 1; i < 9; ++i) c->set_output(i, c->UnknownShapeOfRank(2));
       return tf::Status::OK();
     });
 
-class Sap3dGroupNormStatsOp : public tf::OpKernel {
+class Sap3dGroupNormActOp : public tf::OpKernel {
  public:
-  explicit Sap3dGroupNormStatsOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
-    OP_REQUIRES_OK(c, c->GetAttr("groups", &groups_));
-    OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_));
+  explicit Sap3dGroupNormActOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("groups", &groups_)); OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_));
+    OP_REQUIRES_OK(c, c->GetAttr("relu1", &r1_)); OP_REQUIRES_OK(c, c->GetAttr("relu2", &r2_));
+    OP_REQUIRES_OK(c, c->GetAttr("relu_out", &ro_)); OP_REQUIRES_OK(c, c->GetAttr("has_b", &hb_));
+    OP_REQUIRES_OK(c, c->GetAttr("norm_b", &nb_));
   }
   void Compute(tf::OpKernelContext* ctx) override {
-    const tf::Tensor& x = ctx->input(0);
-    const tf::int64 N = x.dim_size(0), C = x.dim_size(4), S = x.NumElements() / (N * C);
+    const tf::Tensor& a = ctx->input(0);
+    const tf::int64 N = a.dim_size(0), C = a.dim_size(4), S = a.NumElements() / (N * C);
     const tf::int32 G = groups_ < C ? groups_ : static_cast<tf::int32>(C);   // G = min(32, C), utils/network.py:73
-    tf::Tensor *scale = nullptr, *shift = nullptr, *mean = nullptr, *rstd = nullptr;
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({N, C}), &scale));
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({N, C}), &shift));
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({N, G}), &mean));
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, tf::TensorShape({N, G}), &rstd));
-    SAP3D_OK(ctx, sap3d_gn_stats(DtypeOf(x), P(x), static_cast<int32_t>(N), S, static_cast<int32_t>(C), G, F(ctx->input(1)), F(ctx->input(2)), eps_,
-                                 F(scale), F(shift), F(mean), F(rstd), StreamOf(ctx)));
+    const bool n2 = hb_ && nb_;
+    tf::Tensor* y = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, a.shape(), &y));
+    tf::Tensor* o[2][4];
+    for (int k = 0; k < 2; ++k) {
+      const bool on = k == 0 || n2;
+      OP_REQUIRES_OK(ctx, ctx->allocate_output(1 + 4 * k, on ? tf::TensorShape({N, C}) : tf::TensorShape({0, 0}), &o[k][0]));
+      OP_REQUIRES_OK(ctx, ctx->allocate_output(2 + 4 * k, on ? tf::TensorShape({N, C}) : tf::TensorShape({0, 0}), &o[k][1]));
+      OP_REQUIRES_OK(ctx, ctx->allocate_output(3 + 4 * k, on ? tf::TensorShape({N, G}) : tf::TensorShape({0, 0}), &o[k][2]));
+      OP_REQUIRES_OK(ctx, ctx->allocate_output(4 + 4 * k, on ? tf::TensorShape({N, G}) : tf::TensorShape({0, 0}), &o[k][3]));
+      if (!on) continue;
+      const tf::Tensor& x = k == 0 ? a : ctx->input(3);
+      SAP3D_OK(ctx, sap3d_gn_stats(DtypeOf(x), P(x), static_cast<int32_t>(N), S, static_cast<int32_t>(C), G, F(ctx->input(k == 0 ? 1 : 4)),
+                                   F(ctx->input(k == 0 ? 2 : 5)), eps_, F(o[k][0]), F(o[k][1]), F(o[k][2]), F(o[k][3]), StreamOf(ctx)));
+    }
+    SAP3D_OK(ctx, sap3d_affine_act(DtypeOf(a), P(a), F(o[0][0]), F(o[0][1]), r1_, hb_ ? P(ctx->input(3)) : nullptr, n2 ? F(o[1][0]) : nullptr,
+                                   n2 ? F(o[1][1]) : nullptr, r2_, ro_, P(y), N * S, static_cast<int32_t>(C), S, StreamOf(ctx)));
   }
 
  private:
   tf::int32 groups_;
   float eps_;
+  bool r1_, r2_, ro_, hb_, nb_;
 };
-REGISTER_KERNEL_BUILDER(Name("Sap3dGroupNormStats").Device(tf::DEVICE_GPU), Sap3dGroupNormStatsOp);
+REGISTER_KERNEL_BUILDER(Name("Sap3dGroupNormAct").Device(tf::DEVICE_GPU), Sap3dGroupNormActOp);
 
-// da, db, dgamma1, dbeta1, dgamma2, dbeta2 = Sap3dGroupNormGrad(...): backward of y = relu_out?( relu1?(GN1(a)) + relu2?(GN2(b) | b) )
-REGISTER_OP("Sap3dGroupNormGrad")
+// da, db, dgamma1, dbeta1, dgamma2, dbeta2 = Sap3dGroupNormActGrad(...)
+REGISTER_OP("Sap3dGroupNormActGrad")
     .Input("dy: T").Input("a: T").Input("scale1: float").Input("shift1: float").Input("mean1: float").Input("rstd1: float").Input("gamma1: float")
     .Input("b: T").Input("scale2: float").Input("shift2: float").Input("mean2: float").Input("rstd2: float").Input("gamma2: float")
     .Output("da: T").Output("db: T").Output("dgamma1: float").Output("dbeta1: float").Output("dgamma2: float").Output("dbeta2: float")
-    .Attr("T: {bfloat16, float}").Attr("relu1: bool").Attr("relu2: bool = false").Attr("relu_out: bool = false")
+    .Attr("T: {bfloat16, float}").Attr("relu1: bool = true").Attr("relu2: bool = false").Attr("relu_out: bool = false")
     .Attr("has_b: bool = false").Attr("norm_b: bool = false")
     .SetShapeFn([](InferenceContext* c) {
       c->set_output(0, c->input(1));
@@ -500,9 +498,9 @@ REGISTER_OP("Sap3dGroupNormGrad")
       return tf::Status::OK();
     });
 
-class Sap3dGroupNormGradOp : public tf::OpKernel {
+class Sap3dGroupNormActGradOp : public tf::OpKernel {
  public:
-  explicit Sap3dGroupNormGradOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+  explicit Sap3dGroupNormActGradOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
     OP_REQUIRES_OK(c, c->GetAttr("relu1", &r1_)); OP_REQUIRES_OK(c, c->GetAttr("relu2", &r2_));
     OP_REQUIRES_OK(c, c->GetAttr("relu_out", &ro_)); OP_REQUIRES_OK(c, c->GetAttr("has_b", &hb_));
     OP_REQUIRES_OK(c, c->GetAttr("norm_b", &nb_));
@@ -529,61 +527,76 @@ class Sap3dGroupNormGradOp : public tf::OpKernel {
  private:
   bool r1_, r2_, ro_, hb_, nb_;
 };
-REGISTER_KERNEL_BUILDER(Name("Sap3dGroupNormGrad").Device(tf::DEVICE_GPU), Sap3dGroupNormGradOp);
+REGISTER_KERNEL_BUILDER(Name("Sap3dGroupNormActGrad").Device(tf::DEVICE_GPU), Sap3dGroupNormActGradOp);
 
 // =====================================================================================================================
 // CBAM block tail of the GN backbone: y = relu(GN(c3) + cbam_block(r))   (gn/p3d_gn.py:175-177; utils/network.py:198-274)
-// scale3 / shift3 come from Sap3dGroupNormStats(c3).  cscale / sp / att / save are kept for the gradient op.
+// cscale / sp / att / save and the GroupNorm statistics are kept for the gradient op.
 // =====================================================================================================================
 REGISTER_OP("Sap3dCbamTail")
-    .Input("c3: T").Input("scale3: float").Input("shift3: float").Input("r: T")
+    .Input("c3: T").Input("gamma3: float").Input("beta3: float").Input("r: T")
     .Input("w0: float").Input("b0: float").Input("w1: float").Input("b1: float").Input("w_sp: float")
-    .Output("y: T").Output("cscale: float").Output("sp: float").Output("att: float").Output("save: float")
-    .Attr("T: {bfloat16, float}")
+    .Output("y: T").Output("scale3: float").Output("mean3: float").Output("rstd3: float")
+    .Output("cscale: float").Output("sp: float").Output("att: float").Output("save: float")
+    .Attr("T: {bfloat16, float}").Attr("groups: int = 32").Attr("epsilon: float = 0.00001")
     .SetShapeFn([](InferenceContext* c) {
       c->set_output(0, c->input(3));
-      for (int i = 1; i < 5; ++i) c->set_output(i, c->UnknownShape());
+      for (int i = 1; i < 8; ++i) c->set_output(i, c->UnknownShape());
       return tf::Status::OK();
     });
 
 class Sap3dCbamTailOp : public tf::OpKernel {
  public:
-  using tf::OpKernel::OpKernel;
+  explicit Sap3dCbamTailOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("groups", &groups_));
+    OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_));
+  }
   void Compute(tf::OpKernelContext* ctx) override {
     const tf::Tensor& r = ctx->input(3);
     const tf::int32 N = static_cast<tf::int32>(r.dim_size(0)), D = static_cast<tf::int32>(r.dim_size(1)), H = static_cast<tf::int32>(r.dim_size(2)),
                     W = static_cast<tf::int32>(r.dim_size(3)), C = static_cast<tf::int32>(r.dim_size(4));
     const tf::int64 S = static_cast<tf::int64>(D) * H * W;
-    const tf::int32 hidden = static_cast<tf::int32>(ctx->input(4).dim_size(1));
+    const tf::int32 hidden = static_cast<tf::int32>(ctx->input(4).dim_size(1)), G = groups_ < C ? groups_ : C;
     const tf::int32 rows = sap3d_sample_stats_rows(S, C, N);
-    tf::Tensor *y = nullptr, *cscale = nullptr, *sp = nullptr, *att = nullptr, *save = nullptr;
+    tf::Tensor *y = nullptr, *scale3 = nullptr, *mean3 = nullptr, *rstd3 = nullptr, *cscale = nullptr, *sp = nullptr, *att = nullptr, *save = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, r.shape(), &y));
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({N, C}), &cscale));
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({N, S, 2}), &sp));
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, tf::TensorShape({N, S}), &att));
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(4, tf::TensorShape({N, 2 * C + 2 * hidden}), &save));
-    tf::Tensor part;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({N, C}), &scale3));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({N, G}), &mean3));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, tf::TensorShape({N, G}), &rstd3));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(4, tf::TensorShape({N, C}), &cscale));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(5, tf::TensorShape({N, S, 2}), &sp));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(6, tf::TensorShape({N, S}), &att));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(7, tf::TensorShape({N, 2 * C + 2 * hidden}), &save));
+    tf::Tensor part, shift3;
     OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, tf::TensorShape({N, rows, 3, C}), &part));
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, tf::TensorShape({N, C}), &shift3));
+    const tf::Tensor& c3 = ctx->input(0);
+    SAP3D_OK(ctx, sap3d_gn_stats(DtypeOf(c3), P(c3), N, S, C, G, F(ctx->input(1)), F(ctx->input(2)), eps_, F(scale3), F(&shift3), F(mean3), F(rstd3),
+                                 StreamOf(ctx)));
     SAP3D_OK(ctx, sap3d_cbam_fwd(DtypeOf(r), P(r), N, D, H, W, C, hidden, F(ctx->input(4)), F(ctx->input(5)), F(ctx->input(6)), F(ctx->input(7)),
                                  F(ctx->input(8)), F(&part), rows, F(cscale), F(sp), F(att), F(save), StreamOf(ctx)));
-    SAP3D_OK(ctx, sap3d_cbam_merge(DtypeOf(r), P(ctx->input(0)), F(ctx->input(1)), F(ctx->input(2)), P(r), F(cscale), F(att), P(y), N, S, C,
-                                   StreamOf(ctx)));
+    SAP3D_OK(ctx, sap3d_cbam_merge(DtypeOf(r), P(c3), F(scale3), F(&shift3), P(r), F(cscale), F(att), P(y), N, S, C, StreamOf(ctx)));
   }
+
+ private:
+  tf::int32 groups_;
+  float eps_;
 };
 REGISTER_KERNEL_BUILDER(Name("Sap3dCbamTail").Device(tf::DEVICE_GPU), Sap3dCbamTailOp);
 
+// dc3, dgamma3, dbeta3, dr, dw0, db0, dw1, db1, dw_sp = Sap3dCbamTailGrad(...): one gradient per input of Sap3dCbamTail, in its order
 REGISTER_OP("Sap3dCbamTailGrad")
     .Input("dy: T").Input("y: T").Input("c3: T").Input("scale3: float").Input("mean3: float").Input("rstd3: float").Input("gamma3: float")
     .Input("r: T").Input("w0: float").Input("w1: float").Input("w_sp: float")
     .Input("cscale: float").Input("sp: float").Input("att: float").Input("save: float")
-    .Output("dc3: T").Output("dr: T").Output("dgamma3: float").Output("dbeta3: float")
+    .Output("dc3: T").Output("dgamma3: float").Output("dbeta3: float").Output("dr: T")
     .Output("dw0: float").Output("db0: float").Output("dw1: float").Output("db1: float").Output("dw_sp: float")
     .Attr("T: {bfloat16, float}")
     .SetShapeFn([](InferenceContext* c) {
       c->set_output(0, c->input(2));
-      c->set_output(1, c->input(7));
+      c->set_output(1, c->input(6));
       c->set_output(2, c->input(6));
-      c->set_output(3, c->input(6));
+      c->set_output(3, c->input(7));
       c->set_output(4, c->input(8));
       c->set_output(5, c->UnknownShapeOfRank(1));
       c->set_output(6, c->input(9));
@@ -601,23 +614,23 @@ class Sap3dCbamTailGradOp : public tf::OpKernel {
                     W = static_cast<tf::int32>(r.dim_size(3)), C = static_cast<tf::int32>(r.dim_size(4));
     const tf::int64 S = static_cast<tf::int64>(D) * H * W;
     const tf::int32 hidden = static_cast<tf::int32>(ctx->input(8).dim_size(1)), G = static_cast<tf::int32>(ctx->input(4).dim_size(1));
-    tf::Tensor *dc3 = nullptr, *dr = nullptr, *g[7];
+    tf::Tensor *dc3 = nullptr, *dr = nullptr, *dg3 = nullptr, *db3 = nullptr, *g[5];
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, r.shape(), &dc3));
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, r.shape(), &dr));
-    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 2, tf::TensorShape({C}), &g[0]));
-    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 3, tf::TensorShape({C}), &g[1]));
-    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 4, tf::TensorShape({C, hidden}), &g[2]));
-    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 5, tf::TensorShape({hidden}), &g[3]));
-    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 6, tf::TensorShape({hidden, C}), &g[4]));
-    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 7, tf::TensorShape({C}), &g[5]));
-    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 8, tf::TensorShape({7, 7, 7, 2, 1}), &g[6]));
+    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 1, tf::TensorShape({C}), &dg3));
+    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 2, tf::TensorShape({C}), &db3));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, r.shape(), &dr));
+    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 4, tf::TensorShape({C, hidden}), &g[0]));
+    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 5, tf::TensorShape({hidden}), &g[1]));
+    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 6, tf::TensorShape({hidden, C}), &g[2]));
+    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 7, tf::TensorShape({C}), &g[3]));
+    OP_REQUIRES_OK(ctx, ZeroOutput(ctx, 8, tf::TensorShape({7, 7, 7, 2, 1}), &g[4]));
     tf::Tensor ws;
     OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, tf::TensorShape({static_cast<tf::int64>(sap3d_gn_bwd_workspace(N, S, C) / 4 + 16)}), &ws));
     SAP3D_CUDA_OK(ctx, cudaMemsetAsync(P(&ws), 0, Bytes(ws), CudaStreamOf(ctx)));
     SAP3D_OK(ctx, sap3d_cbam_tail_bwd(DtypeOf(r), P(ctx->input(0)), P(ctx->input(1)), P(ctx->input(2)), F(ctx->input(3)), F(ctx->input(4)),
                                       F(ctx->input(5)), F(ctx->input(6)), P(r), N, D, H, W, C, G, hidden, F(ctx->input(8)), F(ctx->input(9)),
                                       F(ctx->input(10)), F(ctx->input(11)), F(ctx->input(12)), F(ctx->input(13)), F(ctx->input(14)), P(dc3), 0,
-                                      P(dr), 0, F(g[0]), F(g[1]), F(g[2]), F(g[3]), F(g[4]), F(g[5]), F(g[6]), P(&ws), StreamOf(ctx)));
+                                      P(dr), 0, F(dg3), F(db3), F(g[0]), F(g[1]), F(g[2]), F(g[3]), F(g[4]), P(&ws), StreamOf(ctx)));
   }
 };
 REGISTER_KERNEL_BUILDER(Name("Sap3dCbamTailGrad").Device(tf::DEVICE_GPU), Sap3dCbamTailGradOp);
