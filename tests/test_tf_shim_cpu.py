@@ -103,7 +103,7 @@ def test_integration_doc_uses_only_registered_ops():
     for fn in set(re.findall(r"_sap3d\.(\w+)", doc)):
         assert fn in by_func, f"INTEGRATION.md uses _sap3d.{fn}, which is not a registered op"
     helpers = {n.name for n in ast.parse(open(GRADS).read()).body if isinstance(n, ast.FunctionDef)}
-    for fn in set(re.findall(r"sap3d_grads\.(\w+)", doc)):
+    for fn in set(re.findall(r"sap3d_grads\.(\w+)\(", doc)):
         assert fn in helpers, f"INTEGRATION.md uses sap3d_grads.{fn}, which does not exist"
 
 
