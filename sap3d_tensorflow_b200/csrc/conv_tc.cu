@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += s_ep[c * 32 + j];
       }
+      if (threadIdx.x == 64) dbg_mark(p, 13);
       if (want_stats) {
         float s1[32], s2[32];
 #pragma unroll
@@ -389,6 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         s_stats[(q * 2 + 0) * BLOCK_N + c * 32 + lane] = c1;
         s_stats[(q * 2 + 1) * BLOCK_N + c * 32 + lane] = c2;
       }
+      if (threadIdx.x == 64) dbg_mark(p, 14);
       if (p.scale != nullptr) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_ep[BLOCK_N + c * 32 + j], s_ep[2 * BLOCK_N + c * 32 + j]);
@@ -435,6 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         }
       }
     }
+    if (threadIdx.x == 64) dbg_mark(p, 15);
     if (want_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int et = threadIdx.x - 64;  // 0..127

@@ -906,6 +906,28 @@ __global__ void __launch_bounds__(256) bn_bwd_coop_kernel(const ApplyBwdArgs p, 
 // ------------------------------------------------------------------------------------------------
 constexpr long long SLAB_MAX_P = 1024;
 
+// per-channel constants of the 8 channels a thread owns (registers: they are the same for every position)
+struct SlabConsts {
+  float s1[8], t1[8], m1[8], r1[8], s2[8], t2[8], m2[8], r2[8];
+};
+
+SAP3D_DEVINL void slab_masks(const ApplyBwdArgs& p, const SlabConsts& k, const float (&d)[8], const float (&av)[8], const float (&bv)[8],
+                             float (&g1)[8], float (&g2)[8], float (&xh1)[8], float (&xh2)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float z1 = fmaf(av[j], k.s1[j], k.t1[j]);
+    const float z2 = p.b ? fmaf(bv[j], k.s2[j], k.t2[j]) : 0.f;
+    xh1[j] = (av[j] - k.m1[j]) * k.r1[j];
+    xh2[j] = (bv[j] - k.m2[j]) * k.r2[j];
+    const float r1 = p.relu1 ? fmaxf(z1, 0.f) : z1;
+    const float r2 = p.relu2 ? fmaxf(z2, 0.f) : z2;
+    float u = d[j];
+    if (p.relu_out && !(r1 + r2 > 0.f)) u = 0.f;
+    g1[j] = (p.relu1 && !(z1 > 0.f)) ? 0.f : u;
+    g2[j] = (p.relu2 && !(z2 > 0.f)) ? 0.f : u;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, const double M, float* dgamma1, float* dbeta1,
                                                           float* dgamma2, float* dbeta2) {
@@ -933,6 +955,19 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
       br[it] = bp ? Vec8<T>::load_raw(bp + e) : ar[it];
     }
   }
+  SlabConsts k;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int cj = live ? c + j : 0;
+    k.s1[j] = p.s1 ? p.s1[cj] : 1.f;
+    k.t1[j] = p.t1 ? p.t1[cj] : 0.f;
+    k.m1[j] = p.mean1 ? p.mean1[cj] : 0.f;
+    k.r1[j] = p.mean1 ? p.rstd1[cj] : 0.f;     // frozen statistics: x-hat is not formed (0), as in bwd_compute
+    k.s2[j] = p.s2 ? p.s2[cj] : 1.f;
+    k.t2[j] = p.s2 ? p.t2[cj] : 0.f;
+    k.m2[j] = p.mean2 ? p.mean2[cj] : 0.f;
+    k.r2[j] = p.mean2 ? p.rstd2[cj] : 0.f;
+  }
   float acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -946,7 +981,7 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
       Vec8<T>::unpack(dr[it], dv);
       Vec8<T>::unpack(ar[it], av);
       Vec8<T>::unpack(br[it], bv);
-      bwd_compute(p, dv, av, bv, c, c, g1, g2, xh1, xh2);
+      slab_masks(p, k, dv, av, bv, g1, g2, xh1, xh2);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         acc[0][j] += g1[j];
@@ -992,11 +1027,11 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
   if (!live || (!p.da && !p.db)) return;
   T* da = reinterpret_cast<T*>(p.da);
   T* db = reinterpret_cast<T*>(p.db);
-  float sc1[8], sc2[8];
+  float c0[8], c1[8], c2[8], c3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    sc1[j] = p.s1 ? p.s1[c + j] : 1.f;
-    sc2[j] = p.s2 ? p.s2[c + j] : 1.f;
+    c0[j] = coef[0][half * 8 + j]; c1[j] = coef[1][half * 8 + j];
+    c2[j] = coef[2][half * 8 + j]; c3[j] = coef[3][half * 8 + j];
   }
 #pragma unroll
   for (int it = 0; it < MAXIT; ++it) {
@@ -1007,12 +1042,11 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
     Vec8<T>::unpack(dr[it], dv);
     Vec8<T>::unpack(ar[it], av);
     Vec8<T>::unpack(br[it], bv);
-    bwd_compute(p, dv, av, bv, c, c, g1, g2, xh1, xh2);
+    slab_masks(p, k, dv, av, bv, g1, g2, xh1, xh2);
     if (da) {
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = p.batch_stats1 ? sc1[j] * (g1[j] - coef[0][half * 8 + j] - xh1[j] * coef[1][half * 8 + j]) : sc1[j] * g1[j];
+      for (int j = 0; j < 8; ++j) o[j] = p.batch_stats1 ? k.s1[j] * (g1[j] - c0[j] - xh1[j] * c1[j]) : k.s1[j] * g1[j];
       if (p.acc_a) {
         float old[8];
         Vec8<T>::load(da + e, old);
@@ -1024,8 +1058,7 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
     if (db) {
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = p.batch_stats2 ? sc2[j] * (g2[j] - coef[2][half * 8 + j] - xh2[j] * coef[3][half * 8 + j]) : sc2[j] * g2[j];
+      for (int j = 0; j < 8; ++j) o[j] = p.batch_stats2 ? k.s2[j] * (g2[j] - c2[j] - xh2[j] * c3[j]) : k.s2[j] * g2[j];
       if (p.acc_b) {
         float old[8];
         Vec8<T>::load(db + e, old);

@@ -16,7 +16,7 @@ from sap3d_tensorflow_b200 import _abi as A  # noqa: E402
 dev = torch.device("cuda")
 PH = ["entry", "setup done", "first TMA issued", "first stage full (MMA starts)", "last MMA issued", "acc ready (split: ship)",
       "partials received", "epilogue done", "exit", "last TMA issued", "acc ready (no split)", "partials staged (split)",
-      "peers ready (split)"]
+      "peers ready (split)", "epilogue: last chunk loaded + partials added", "epilogue: last chunk statistics done", "epilogue: stores issued"]
 
 CASES = [
     # name, N, D, H, W, cin, cout, kernel
@@ -89,7 +89,7 @@ def main():
         ghz = float((dt_clk / dt_glb.clamp(min=1)).median())
         print(f"\n== {name}: M={N * D * H * W} K={k[0] * k[1] * k[2] * cin} N={cout}; {ncta} CTAs; chain of 50 in a graph: {chain_us:.2f} us per launch; "
               f"probe launch: first entry -> last exit {span:.2f} us, entry skew {skew:.2f} us, SM clock ~{ghz:.2f} GHz")
-        order = [0, 1, 2, 3, 9, 4, 5, 10, 11, 12, 6, 7, 8]
+        order = [0, 1, 2, 3, 9, 4, 5, 10, 11, 12, 6, 13, 14, 15, 7, 8]
         for i in order:
             v = clk[:, i] - clk[:, 0]
             ok = clk[:, i] != 0
