@@ -119,9 +119,39 @@ def _stem(_X: T, training: bool) -> T:
     return eng.tap("stem", nw.bn_relu(c, training, tap="stem"))
 
 
+class _ActivationOutput:
+    """network output that is an activation tensor (what Session.run returns for the stem-only graph)"""
+
+    def __init__(self, t: T):
+        self.eng, self.t = t.eng, t
+
+    @property
+    def output(self):
+        return self.t.buf
+
+
+def p3d_stem(_X, _dropout=0.0, batch_size=2, training=False):
+    """the frame-local head of every p3d.py graph on its own: conv 1x7x7 s(1,2,2) -> BN(training) -> ReLU (p3d.py:343-345).
+    With training=False (moving statistics) its output for one frame does not depend on the other frames of the clip, which is
+    what lets the sliding-window inference of gen_pred.py:88-135 compute it ONCE per frame (video.predict_video_cached).
+    _X: [F, D, H, W, 3] frames (D = 1 for single frames); returns a handle whose Session.run gives [F, D, H/2, W/2, 64]."""
+    if training:
+        raise NotImplementedError("p3d_stem is the inference-time frame cache (batch statistics would couple the frames)")
+    return _ActivationOutput(_stem(_X, False))
+
+
 def _backbone(_X: T, training: bool, skip_1_0: bool = True):
     eng = _X.eng
-    stem = _stem(_X, training)
+    if _X.C == 64:
+        # the input already IS the stem activation (frame cache of the sliding-window inference): keep TF's variable numbering
+        # by burning the names the stem's layers would have taken (firstconv1 is named explicitly; its BN is the first
+        # auto-numbered batch_normalization)
+        if training:
+            raise NotImplementedError("stem activations as graph input are an inference-only path")
+        eng.names.unique("", "batch_normalization")
+        stem = eng.tap("stem", _X)
+    else:
+        stem = _stem(_X, training)
     t = {}
     if skip_1_0:
         t["x_1_0"] = eng.tap("x_1_0", eng.maxpool(stem, *TEMPORAL_POOL, name="x_1_0"))

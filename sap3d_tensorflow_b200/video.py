@@ -55,3 +55,47 @@ def predict_video(sess, frames: torch.Tensor, graph: bool = True) -> Iterator[Tu
                     yield k, sal[j, k, :, :, 0].clone()
             else:
                 yield s + WINDOW - 1, sal[j, WINDOW - 1, :, :, 0].clone()
+
+
+def stem_activations(stem_sess, frames: torch.Tensor) -> torch.Tensor:
+    """frames [T, H, W, 3] (preprocessed) -> the per-frame stem output [T, H/2, W/2, 64] (p3d.p3d_stem: conv 1x7x7 + moving-statistics
+    BatchNorm + ReLU), computed once per frame in chunks of the stem session's batch size"""
+    F = stem_sess.eng.input.shape[0]
+    assert stem_sess.eng.input.shape[1] == 1, "the stem session takes single frames: placeholder([F, 1, H, W, 3])"
+    T = frames.shape[0]
+    out = None
+    for lo in range(0, T, F):
+        chunk = frames[lo:lo + F]
+        if chunk.shape[0] < F:
+            chunk = torch.cat([chunk, chunk[-1:].expand(F - chunk.shape[0], *chunk.shape[1:])])
+        act = stem_sess.run(chunk.float().unsqueeze(1), graph=True)          # [F, 1, h, w, 64]
+        if out is None:
+            out = torch.empty(T, *act.shape[2:], device=act.device, dtype=act.dtype)
+        n = min(F, T - lo)
+        out[lo:lo + n] = act[:n, 0]
+    return out
+
+
+def predict_video_cached(stem_sess, sess, frames: torch.Tensor, graph: bool = True) -> Iterator[Tuple[int, torch.Tensor]]:
+    """predict_video with the per-frame stem cache: consecutive windows of gen_pred.py:88-135 share 15 of their 16 frames, and the
+    stem (conv 1x7x7 s(1,2,2) + BatchNorm on moving statistics + ReLU, p3d.py:343-345 with training=False) is frame-local, so its
+    [H/2, W/2, 64] output is computed once per frame (stem_sess = Session(p3d.p3d_stem(placeholder([F,1,H,W,3])))) and the window
+    graph (sess, built on a placeholder of stem activations [B,16,H/2,W/2,64]) starts at the temporal pools.  Same maps as
+    predict_video; 1/16 of the stem work per window."""
+    B = sess.eng.input.shape[0]
+    if sess.eng.input.shape[-1] != 64:
+        raise A.Sap3dError("predict_video_cached: the window session must be built on a placeholder of stem activations [B,16,H/2,W/2,64]")
+    if B > 1 and not sess.eng.per_sample_bn:
+        raise A.Sap3dError("predict_video_cached with a batch of windows needs placeholder(..., per_sample_statistics=True)")
+    acts = stem_activations(stem_sess, frames)
+    starts = list(window_starts(frames.shape[0]))
+    for lo in range(0, len(starts), B):
+        chunk = starts[lo:lo + B]
+        batch = torch.stack([acts[s:s + WINDOW] for s in chunk] + [acts[chunk[-1]:chunk[-1] + WINDOW]] * (B - len(chunk)))
+        sal = sess.run(batch.float(), graph=graph)
+        for j, s in enumerate(chunk):
+            if s == 0:
+                for k in range(WINDOW):
+                    yield k, sal[j, k, :, :, 0].clone()
+            else:
+                yield s + WINDOW - 1, sal[j, WINDOW - 1, :, :, 0].clone()

@@ -183,3 +183,41 @@ def test_cuda_preprocess_and_video_windows(lib_built):
     for n, v in one.variables().items():
         if n.endswith(("moving_mean", "moving_variance")):
             assert torch.equal(v, params[n].to(v.device)), n
+
+
+@pytest.mark.gpu
+def test_sliding_window_stem_cache_gives_the_same_maps(lib_built):
+    """gen_pred.py:88-135: consecutive windows share 15 of 16 frames; the stem (conv 1x7x7 + moving-statistics BN + ReLU, p3d.py:343-345
+    with training=False) is frame-local, so video.predict_video_cached computes it once per frame.  Same maps as predict_video."""
+    import torch
+
+    import sap3d_tensorflow_b200 as sp
+
+    size, T, B = 64, 24, 4
+    rng = np.random.RandomState(1)
+    frames = sp.video.preprocess_frames(rng.randint(0, 256, (T, 72, 96, 3)).astype(np.uint8), size=size)
+    xin = sp.placeholder([B, 16, size, size, 3], dtype="bf16", training_graph=False, per_sample_statistics=True)
+    full = sp.Session(sp.p3d.p3d_unetplusplus_ds(xin, 0.0, B, False))
+    g0 = torch.Generator().manual_seed(5)
+    params = {}
+    for n, v in full.variables().items():      # non-trivial moving statistics / affines, attention gates switched on
+        if n.endswith("moving_variance"):
+            params[n] = 0.5 + torch.rand(v.shape, generator=g0)
+        elif n.endswith(("moving_mean", "beta")):
+            params[n] = 0.1 * torch.randn(v.shape, generator=g0)
+        elif n.startswith("gamma"):
+            params[n] = torch.full(v.shape, 0.5)
+        else:
+            params[n] = v.detach().cpu().clone()
+    full.eng.load_params(params)
+    want = dict(sp.video.predict_video(full, frames, graph=True))
+    stem = sp.Session(sp.p3d.p3d_stem(sp.placeholder([8, 1, size, size, 3], dtype="bf16", training_graph=False)))
+    stem.eng.load_params(params, strict=False)
+    win = sp.Session(sp.p3d.p3d_unetplusplus_ds(sp.placeholder([B, 16, size // 2, size // 2, 64], dtype="bf16", training_graph=False,
+                                                               per_sample_statistics=True), 0.0, B, False))
+    assert set(win.eng.params) | set(stem.eng.params) == set(full.eng.params)          # TF's variable numbering is preserved
+    win.eng.load_params(params, strict=False)
+    got = dict(sp.video.predict_video_cached(stem, win, frames, graph=True))
+    assert sorted(got) == sorted(want) == list(range(T))
+    worst = max(float((got[k] - want[k]).abs().max()) for k in want)
+    assert worst < 1e-6, worst          # same kernels on the same values: the cache changes where the stem runs, not what it computes
