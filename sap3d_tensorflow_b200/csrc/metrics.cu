@@ -39,15 +39,23 @@ __global__ void __launch_bounds__(MT) metrics_kernel(const float* __restrict__ p
   const float* p = pred + blockIdx.x * sp;
   const float* d = dens + blockIdx.x * sd;
   const float* f = fix ? fix + blockIdx.x * sf : nullptr;
+  // 128-bit loads when the map is 16-byte aligned (every 112 x 112 / 1080 x 960 map is); passes 2 and 3 re-read L1 / L2
+  const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(d) | (f ? reinterpret_cast<uintptr_t>(f) : 0)) % 16 == 0);
+  const long long nv = vec ? n / 4 : 0;
   // ---- pass 1: moments, extrema, fixation sums
   double s_p = 0, s_pp = 0, s_d = 0, s_dd = 0, s_pd = 0, s_fp = 0, s_f = 0;
   float mn_p = INFINITY, mx_p = -INFINITY, mn_d = INFINITY, mx_d = -INFINITY;
-  for (long long i = threadIdx.x; i < n; i += MT) {
-    const float a = p[i], b = d[i];
+  auto acc1 = [&](float a, float b, float fx) {
     s_p += a; s_pp += (double)a * a; s_d += b; s_dd += (double)b * b; s_pd += (double)a * b;
     mn_p = fminf(mn_p, a); mx_p = fmaxf(mx_p, a); mn_d = fminf(mn_d, b); mx_d = fmaxf(mx_d, b);
-    if (f && f[i] > 0.5f) { s_fp += a; s_f += 1.0; }
+    if (fx > 0.5f) { s_fp += a; s_f += 1.0; }
+  };
+  for (long long i = threadIdx.x; i < nv; i += MT) {
+    const float4 a = reinterpret_cast<const float4*>(p)[i], b = reinterpret_cast<const float4*>(d)[i];
+    const float4 fx = f ? reinterpret_cast<const float4*>(f)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc1(a.x, b.x, fx.x); acc1(a.y, b.y, fx.y); acc1(a.z, b.z, fx.z); acc1(a.w, b.w, fx.w);
   }
+  for (long long i = nv * 4 + threadIdx.x; i < n; i += MT) acc1(p[i], d[i], f ? f[i] : 0.f);
   s_p = block_sum(s_p, shd); s_pp = block_sum(s_pp, shd); s_d = block_sum(s_d, shd); s_dd = block_sum(s_dd, shd);
   s_pd = block_sum(s_pd, shd); s_fp = block_sum(s_fp, shd); s_f = block_sum(s_f, shd);
   mn_p = block_minmax(mn_p, false, shf); mx_p = block_minmax(mx_p, true, shf);
@@ -57,33 +65,41 @@ __global__ void __launch_bounds__(MT) metrics_kernel(const float* __restrict__ p
   const double sg_p = sqrt(fmax(s_pp / N - mu_p * mu_p, 0.0)), sg_d = sqrt(fmax(s_dd / N - mu_d * mu_d, 0.0));
   const double cc = (s_pd / N - mu_p * mu_d) / (sg_p * sg_d);
   const double nss = (s_fp / s_f - mu_p) / sg_p;
-  // ---- pass 2: SIM and the sum of the byte-scaled prediction
+  // ---- pass 2: SIM and the sum of the byte-scaled prediction.  The per-element work is fp64 (the reference is NumPy float64):
+  // the two normalising divisions per map are folded into ONE reciprocal each, computed once per block -- the r01 kernel did 7
+  // fp64 divisions per element and was fp64-issue bound at 0.8 TB/s (profiles/r01_k_ncu_bandwidth_summary.txt)
   const double rp = (double)mx_p - (double)mn_p, rd = (double)mx_d - (double)mn_d;
   const double sum_rp = (s_p - N * mn_p) / rp, sum_rd = (s_d - N * mn_d) / rd;
+  const double inv_p = 1.0 / (rp * sum_rp), inv_d = 1.0 / (rd * sum_rd);
   const float cscale = (mx_p - mn_p) == 0.f ? 1.f : (mx_p - mn_p);
   const float bscale = 255.0f / cscale;
-  double sim = 0, s_q = 0;
-  for (long long i = threadIdx.x; i < n; i += MT) {
-    const float a = p[i], b = d[i];
-    const double na = ((double)a - mn_p) / rp / sum_rp, nb = ((double)b - mn_d) / rd / sum_rd;
-    sim += fmin(na, nb);
-    const float bd = fminf(fmaxf((a - mn_p) * bscale, 0.f), 255.f) + 0.5f;
-    s_q += (double)(unsigned char)bd;
+  double sim = 0;
+  unsigned long long s_qi = 0;     // the byte-scaled values are integers: exact integer sum
+  auto acc2 = [&](float a, float b) {
+    sim += fmin(((double)a - mn_p) * inv_p, ((double)b - mn_d) * inv_d);
+    s_qi += (unsigned char)(fminf(fmaxf((a - mn_p) * bscale, 0.f), 255.f) + 0.5f);
+  };
+  for (long long i = threadIdx.x; i < nv; i += MT) {
+    const float4 a = reinterpret_cast<const float4*>(p)[i], b = reinterpret_cast<const float4*>(d)[i];
+    acc2(a.x, b.x); acc2(a.y, b.y); acc2(a.z, b.z); acc2(a.w, b.w);
   }
+  for (long long i = nv * 4 + threadIdx.x; i < n; i += MT) acc2(p[i], d[i]);
   sim = block_sum(sim, shd);
-  s_q = block_sum(s_q, shd);
-  // ---- pass 3: KL divergence
+  const double s_q = block_sum((double)s_qi, shd);
+  // ---- pass 3: KL divergence (one fp64 division and one fp64 log per element remain)
   const double eps = 2.2204e-16;
+  const double inv_q = s_q != 0.0 ? 1.0 / s_q : 1.0, inv_sd = s_d != 0.0 ? 1.0 / s_d : 1.0;
   double kl = 0;
-  for (long long i = threadIdx.x; i < n; i += MT) {
-    const float a = p[i], b = d[i];
-    const float bd = fminf(fmaxf((a - mn_p) * bscale, 0.f), 255.f) + 0.5f;
-    double m1 = (double)(unsigned char)bd;
-    if (s_q != 0.0) m1 /= s_q;
-    double m2 = (double)b;
-    if (s_d != 0.0) m2 /= s_d;
+  auto acc3 = [&](float a, float b) {
+    const double m1 = (double)(unsigned char)(fminf(fmaxf((a - mn_p) * bscale, 0.f), 255.f) + 0.5f) * inv_q;
+    const double m2 = (double)b * inv_sd;
     kl += m2 * log(eps + m2 / (m1 + eps));
+  };
+  for (long long i = threadIdx.x; i < nv; i += MT) {
+    const float4 a = reinterpret_cast<const float4*>(p)[i], b = reinterpret_cast<const float4*>(d)[i];
+    acc3(a.x, b.x); acc3(a.y, b.y); acc3(a.z, b.z); acc3(a.w, b.w);
   }
+  for (long long i = nv * 4 + threadIdx.x; i < n; i += MT) acc3(p[i], d[i]);
   kl = block_sum(kl, shd);
   if (threadIdx.x == 0) {
     out[blockIdx.x * 4 + 0] = cc;

@@ -898,7 +898,7 @@ __global__ void __launch_bounds__(256) bn_bwd_coop_kernel(const ApplyBwdArgs p, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Few-row tensors (stage 3 of the backbone: 784 positions at batch 8): ONE block owns 16 channels for ALL positions, so the two
+// Few-row tensors (stage 3 of the backbone: 784 positions at batch 8): ONE block owns 8 channels for ALL positions, so the two
 // per-channel sums, the coefficients and the apply pass stay inside the block -- no grid barrier, no cooperative launch (which
 // waits until the whole grid can be co-resident: ~6 us of stall per launch behind the side stream's filter gradients, r02 trace),
 // deterministic.  The second pass re-reads the block's 16-channel slab (<= 100 KB) from L1 / L2.
@@ -933,7 +933,7 @@ SAP3D_DEVINL void cp_async16(uint32_t smem_dst, const void* gsrc) {
 }
 SAP3D_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// The block's whole slab (dy, a, b: <= 1024 positions x 16 channels each) is fetched ONCE with cp.async -- every load of the
+// The block's whole slab (dy, a, b: <= 1024 positions x 8 channels each) is fetched ONCE with cp.async -- every load of the
 // block in flight together, one memory latency -- into shared memory laid out [tensor][iteration][thread], so both passes are
 // short rolled loops over conflict-free 16-byte shared-memory reads.  (A register-resident variant with both passes fully
 // unrolled ran 2x SLOWER than the cooperative kernel: 300 KB of straight-line code executed once per block is instruction-fetch
@@ -942,14 +942,14 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, const double M, float* dgamma1, float* dbeta1,
                                                           float* dgamma2, float* dbeta2) {
   extern __shared__ uint4 slab_sm[];
-  __shared__ float red[8][4][16];   // [warp][sum][channel]
-  __shared__ float coef[4][16];
+  __shared__ float red[8][4][8];   // [warp][sum][channel]
+  __shared__ float coef[4][8];
   constexpr int VB = 8 * (int)sizeof(T);           // bytes of one 8-channel vector
   constexpr int Q = VB / 16;                       // 16-byte pieces per vector
-  const int half = threadIdx.x & 1, rl = threadIdx.x >> 1;
-  const int c = blockIdx.x * 16 + half * 8;
+  const int rl = threadIdx.x;                      // 256 position lanes, one 8-channel vector each
+  const int c = blockIdx.x * 8;
   const bool live = c < p.C;
-  const int nit = (int)((p.P + 127) / 128);
+  const int nit = (int)((p.P + 255) / 256);
   const bool has_b = p.b != nullptr;
   const uint32_t sm0 = smem_u32(slab_sm);
   auto slot = [&](int t, int it) -> uint32_t { return sm0 + (uint32_t)(((t * nit + it) * 256 + (int)threadIdx.x) * VB); };
@@ -958,7 +958,7 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
   if (live) {
 #pragma unroll 1
     for (int it = 0; it < nit; ++it) {
-      const long long pos = rl + it * 128;
+      const long long pos = rl + it * 256;
       if (pos >= p.P) break;
       const long long e = pos * p.C + c;
 #pragma unroll
@@ -1003,7 +1003,7 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
   if (live) {
 #pragma unroll 1
     for (int it = 0; it < nit; ++it) {
-      if (rl + it * 128 >= p.P) break;
+      if (rl + it * 256 >= p.P) break;
       float g1[8], g2[8], xh1[8], xh2[8], dv[8], av[8], bv[8];
       fetch(it, dv, av, bv);
       slab_masks(p, k, dv, av, bv, g1, g2, xh1, xh2);
@@ -1016,12 +1016,13 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
       }
     }
   }
-  // lanes with equal (lane & 1) hold the same channels: fold the 16 positions of a warp
+  // every lane of a warp holds the same 8 channels: fold the 32 positions of the warp
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = acc[i][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -1029,20 +1030,20 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
       acc[i][j] = v;
     }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane < 2) {
+  if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp][i][lane * 8 + j] = acc[i][j];
+      for (int j = 0; j < 8; ++j) red[warp][i][j] = acc[i][j];
   }
   __syncthreads();
-  if (threadIdx.x < 64) {
-    const int i = threadIdx.x >> 4, ch = threadIdx.x & 15;
+  if (threadIdx.x < 32) {
+    const int i = threadIdx.x >> 3, ch = threadIdx.x & 7;
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += (double)red[w][i][ch];   // fixed order: deterministic
     coef[i][ch] = (float)(t / M);
-    const int cc = blockIdx.x * 16 + ch;
+    const int cc = blockIdx.x * 8 + ch;
     if (cc < p.C) {
       float* dst = i == 0 ? dbeta1 : (i == 1 ? dgamma1 : (i == 2 ? dbeta2 : dgamma2));
       if (dst) dst[cc] += (float)t;
@@ -1055,12 +1056,12 @@ __global__ void __launch_bounds__(256) bn_bwd_slab_kernel(const ApplyBwdArgs p, 
   float c0[8], c1[8], c2[8], c3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    c0[j] = coef[0][half * 8 + j]; c1[j] = coef[1][half * 8 + j];
-    c2[j] = coef[2][half * 8 + j]; c3[j] = coef[3][half * 8 + j];
+    c0[j] = coef[0][j]; c1[j] = coef[1][j];
+    c2[j] = coef[2][j]; c3[j] = coef[3][j];
   }
 #pragma unroll 1
   for (int it = 0; it < nit; ++it) {
-    const long long pos = rl + it * 128;
+    const long long pos = rl + it * 256;
     if (pos >= p.P) break;
     const long long e = pos * p.C + c;
     float g1[8], g2[8], xh1[8], xh2[8], dv[8], av[8], bv[8];
@@ -1230,22 +1231,22 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
     p.partial = ws + 4 * C;
     p.totals = reinterpret_cast<double*>(ws + (size_t)(296 * 4 + 4) * C + (((size_t)(296 * 4 + 4) * C) & 1));   // 8-byte aligned tail
     dim3 rgrid((unsigned)rows, (unsigned)chunks);
-    // few-row tensors (stage 3): one ordinary launch, every block owns 16 channels for all positions
+    // few-row tensors (stage 3): one ordinary launch, every block owns 8 channels for all positions
     if (phase == 0 && P <= SLAB_MAX_P && slab_enabled()) {
       double M = count;
       const size_t esz = dtype == SAP3D_BF16 ? 2 : 4;
-      const size_t smem = (size_t)3 * ((P + 127) / 128) * 256 * 8 * esz;
+      const size_t smem = (size_t)3 * ((P + 255) / 256) * 256 * 8 * esz;
       static bool attr_done[2] = {false, false};
       bool& done = attr_done[dtype == SAP3D_BF16 ? 0 : 1];
       if (!done) {
         const void* fn = dtype == SAP3D_BF16 ? (const void*)bn_bwd_slab_kernel<bf16> : (const void*)bn_bwd_slab_kernel<float>;
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)3 * (SLAB_MAX_P / 128) * 256 * 8 * esz)) != cudaSuccess)
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)3 * (SLAB_MAX_P / 256) * 256 * 8 * esz)) != cudaSuccess)
           return set_error("affine_act_bwd slab: cudaFuncSetAttribute failed");
         done = true;
       }
       cudaError_t e = dtype == SAP3D_BF16
-                          ? launch_k(bn_bwd_slab_kernel<bf16>, dim3((unsigned)((C + 15) / 16)), dim3(256), smem, st, 1, p, M, dgamma1, dbeta1, dgamma2, dbeta2)
-                          : launch_k(bn_bwd_slab_kernel<float>, dim3((unsigned)((C + 15) / 16)), dim3(256), smem, st, 1, p, M, dgamma1, dbeta1, dgamma2, dbeta2);
+                          ? launch_k(bn_bwd_slab_kernel<bf16>, dim3((unsigned)((C + 7) / 8)), dim3(256), smem, st, 1, p, M, dgamma1, dbeta1, dgamma2, dbeta2)
+                          : launch_k(bn_bwd_slab_kernel<float>, dim3((unsigned)((C + 7) / 8)), dim3(256), smem, st, 1, p, M, dgamma1, dbeta1, dgamma2, dbeta2);
       if (e != cudaSuccess) return set_error("affine_act_bwd slab launch: %s", cudaGetErrorString(e));
       return 0;
     }

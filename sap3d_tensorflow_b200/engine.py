@@ -292,8 +292,11 @@ class Engine:
                     start += e.rows_pad * e.taps * e.cols
                     ents.append(bytes(e))
             raw = b"".join(ents)
-            self._pack_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
             self._pack_n, self._pack_total = len(ents), start
+            # (a graph of im2col-form convs only -- the stem-only frame-cache graph -- has nothing to pre-pack)
+            self._pack_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device) if ents else False
+        if self._pack_table is False:
+            return
         A.check(A.lib.sap3d_pack_multi(A.ptr(self._pack_table), self._pack_n, self._pack_total, self.stream), "pack_multi")
 
     # ------------------------------------------------------------------------------------------
