@@ -73,10 +73,14 @@ __global__ void __launch_bounds__(MT) metrics_kernel(const float* __restrict__ p
   const double inv_p = 1.0 / (rp * sum_rp), inv_d = 1.0 / (rd * sum_rd);
   const float cscale = (mx_p - mn_p) == 0.f ? 1.f : (mx_p - mn_p);
   const float bscale = 255.0f / cscale;
+  // per-element arithmetic of passes 2 and 3 in fp32 (terms are ~1e-4 with 1e-7 relative rounding, far inside the 1e-3 metric
+  // tolerance; golden vectors agree to 1e-6), accumulated in fp64: what is left per element on the fp64 pipe is one conversion
+  // and one add.  With fp64 divisions / fp64 log per element the kernel was fp64-issue bound at 1.05 TB/s (r02 ncu).
+  const float mnp = mn_p, mnd = mn_d, inv_pf = (float)inv_p, inv_df = (float)inv_d;
   double sim = 0;
   unsigned long long s_qi = 0;     // the byte-scaled values are integers: exact integer sum
   auto acc2 = [&](float a, float b) {
-    sim += fmin(((double)a - mn_p) * inv_p, ((double)b - mn_d) * inv_d);
+    sim += (double)fminf((a - mnp) * inv_pf, (b - mnd) * inv_df);
     s_qi += (unsigned char)(fminf(fmaxf((a - mn_p) * bscale, 0.f), 255.f) + 0.5f);
   };
   for (long long i = threadIdx.x; i < nv; i += MT) {
@@ -86,14 +90,14 @@ __global__ void __launch_bounds__(MT) metrics_kernel(const float* __restrict__ p
   for (long long i = nv * 4 + threadIdx.x; i < n; i += MT) acc2(p[i], d[i]);
   sim = block_sum(sim, shd);
   const double s_q = block_sum((double)s_qi, shd);
-  // ---- pass 3: KL divergence (one fp64 division and one fp64 log per element remain)
-  const double eps = 2.2204e-16;
-  const double inv_q = s_q != 0.0 ? 1.0 / s_q : 1.0, inv_sd = s_d != 0.0 ? 1.0 / s_d : 1.0;
+  // ---- pass 3: KL divergence
+  const float eps = 2.2204e-16f;
+  const float inv_q = s_q != 0.0 ? (float)(1.0 / s_q) : 1.f, inv_sd = s_d != 0.0 ? (float)(1.0 / s_d) : 1.f;
   double kl = 0;
   auto acc3 = [&](float a, float b) {
-    const double m1 = (double)(unsigned char)(fminf(fmaxf((a - mn_p) * bscale, 0.f), 255.f) + 0.5f) * inv_q;
-    const double m2 = (double)b * inv_sd;
-    kl += m2 * log(eps + m2 / (m1 + eps));
+    const float m1 = (float)(unsigned char)(fminf(fmaxf((a - mn_p) * bscale, 0.f), 255.f) + 0.5f) * inv_q;
+    const float m2 = b * inv_sd;
+    kl += (double)(m2 * logf(eps + m2 / (m1 + eps)));
   };
   for (long long i = threadIdx.x; i < nv; i += MT) {
     const float4 a = reinterpret_cast<const float4*>(p)[i], b = reinterpret_cast<const float4*>(d)[i];
