@@ -21,21 +21,10 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   for (int i = 0; i < MT / 32; ++i) r += sh[i];
   return r;
 }
-__device__ __forceinline__ float block_minmax(float v, bool is_max, float* sh) {
-  v = is_max ? warp_max(v) : warp_min(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float r = sh[0];
-  for (int i = 1; i < MT / 32; ++i) r = is_max ? fmaxf(r, sh[i]) : fminf(r, sh[i]);
-  return r;
-}
-
 __global__ void __launch_bounds__(MT) metrics_kernel(const float* __restrict__ pred, const float* __restrict__ dens,
                                                       const float* __restrict__ fix, long long n, long long sp, long long sd,
                                                       long long sf, double* __restrict__ out) {
   __shared__ double shd[MT / 32];
-  __shared__ float shf[MT / 32];
   const float* p = pred + blockIdx.x * sp;
   const float* d = dens + blockIdx.x * sd;
   const float* f = fix ? fix + blockIdx.x * sf : nullptr;
@@ -56,10 +45,34 @@ __global__ void __launch_bounds__(MT) metrics_kernel(const float* __restrict__ p
     acc1(a.x, b.x, fx.x); acc1(a.y, b.y, fx.y); acc1(a.z, b.z, fx.z); acc1(a.w, b.w, fx.w);
   }
   for (long long i = nv * 4 + threadIdx.x; i < n; i += MT) acc1(p[i], d[i], f ? f[i] : 0.f);
-  s_p = block_sum(s_p, shd); s_pp = block_sum(s_pp, shd); s_d = block_sum(s_d, shd); s_dd = block_sum(s_dd, shd);
-  s_pd = block_sum(s_pd, shd); s_fp = block_sum(s_fp, shd); s_f = block_sum(s_f, shd);
-  mn_p = block_minmax(mn_p, false, shf); mx_p = block_minmax(mx_p, true, shf);
-  mn_d = block_minmax(mn_d, false, shf); mx_d = block_minmax(mx_d, true, shf);
+  // all eleven pass-1 reductions behind ONE block barrier (r01 / early r02: 11 block_sum calls = 22 barriers per map, which
+  // cost more than streaming the 150 KB of a 112 x 112 map triple)
+  __shared__ double sd1[7][MT / 32];
+  __shared__ float sf1[4][MT / 32];
+  {
+    double dv[7] = {s_p, s_pp, s_d, s_dd, s_pd, s_fp, s_f};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) dv[i] = warp_sum(dv[i]);
+    mn_p = warp_min(mn_p); mx_p = warp_max(mx_p); mn_d = warp_min(mn_d); mx_d = warp_max(mx_d);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) sd1[i][w] = dv[i];
+      sf1[0][w] = mn_p; sf1[1][w] = mx_p; sf1[2][w] = mn_d; sf1[3][w] = mx_d;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      double t = 0.0;
+      for (int k = 0; k < MT / 32; ++k) t += sd1[i][k];     // fixed order: deterministic, identical in every thread
+      dv[i] = t;
+    }
+    s_p = dv[0]; s_pp = dv[1]; s_d = dv[2]; s_dd = dv[3]; s_pd = dv[4]; s_fp = dv[5]; s_f = dv[6];
+    mn_p = sf1[0][0]; mx_p = sf1[1][0]; mn_d = sf1[2][0]; mx_d = sf1[3][0];
+    for (int k = 1; k < MT / 32; ++k) {
+      mn_p = fminf(mn_p, sf1[0][k]); mx_p = fmaxf(mx_p, sf1[1][k]); mn_d = fminf(mn_d, sf1[2][k]); mx_d = fmaxf(mx_d, sf1[3][k]);
+    }
+  }
   const double N = (double)n;
   const double mu_p = s_p / N, mu_d = s_d / N;
   const double sg_p = sqrt(fmax(s_pp / N - mu_p * mu_p, 0.0)), sg_d = sqrt(fmax(s_dd / N - mu_d * mu_d, 0.0));
@@ -88,8 +101,18 @@ __global__ void __launch_bounds__(MT) metrics_kernel(const float* __restrict__ p
     acc2(a.x, b.x); acc2(a.y, b.y); acc2(a.z, b.z); acc2(a.w, b.w);
   }
   for (long long i = nv * 4 + threadIdx.x; i < n; i += MT) acc2(p[i], d[i]);
-  sim = block_sum(sim, shd);
-  const double s_q = block_sum((double)s_qi, shd);
+  __shared__ double sd2[2][MT / 32];
+  double s_q;
+  {
+    sim = warp_sum(sim);
+    double q = warp_sum((double)s_qi);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sd2[0][w] = sim; sd2[1][w] = q; }
+    __syncthreads();
+    sim = 0.0; q = 0.0;
+    for (int k = 0; k < MT / 32; ++k) { sim += sd2[0][k]; q += sd2[1][k]; }
+    s_q = q;
+  }
   // ---- pass 3: KL divergence
   const float eps = 2.2204e-16f;
   const float inv_q = s_q != 0.0 ? (float)(1.0 / s_q) : 1.f, inv_sd = s_d != 0.0 ? (float)(1.0 / s_d) : 1.f;
