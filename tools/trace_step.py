@@ -47,7 +47,7 @@ agg = collections.defaultdict(lambda: [0.0, 0])
 busy = 0.0
 for e in last:
     d = e.time_range.end - e.time_range.start
-    nm = e.name.split("(")[0].replace("void ", "").replace("<unnamed>::", "").replace("sap3d::", "")
+    nm = e.name.replace("void ", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("sap3d::", "").split("(")[0]
     agg[nm][0] += d
     agg[nm][1] += 1
     busy += d
