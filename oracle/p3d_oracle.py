@@ -3,9 +3,16 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this; the product path never does.
 
-PARITY UNPINNED: the reference has no tests / golden vectors and TensorFlow cannot be installed in
-this image, so this restatement is anchored on the reference's own call-sites (cited per function)
-and on the TF-1.x op semantics restated in oracle/tf_semantics.py.
+PARITY PINNING.  The reference has no tests / golden vectors and TensorFlow cannot be installed in this image.
+  * PINNED to the reference's own code: the graph WIRING of every builder below (layer order, kernels, strides, scopes,
+    variable names, shapes and creation order, Python-2 integer division, `training` never reaching make_block) and the
+    composite ops the reference spells out in primitive tf ops (GroupNorm, CBAM, attention, smooth_l1_loss) --
+    tests/test_reference_wiring_cpu.py executes /root/reference/p3d.py, utils/network.py and gn/p3d_gn.py unmodified over a
+    TF-1.x API emulation (tests/golden/tf1_emulation.py) and compares outputs, variable sets and creation order with this
+    module, live in the build container and against tests/golden/reference_graphs_golden.npz everywhere.
+  * UNPINNED: what TensorFlow's own primitive kernels compute (tf.nn.conv3d, tf.layers.*, tf.nn.max_pool3d ... -- an
+    un-vendored dependency); that is oracle/tf_semantics.py, the published TF-1.x definitions, cross-checked only against
+    independent fp64 loops (oracle/np_direct.py).
 
 Graphs restated (reference file:line):
   p3d.p3d_unetplusplus_ds      p3d.py:340-399   (primary; what gen_pred.py:46 builds)
