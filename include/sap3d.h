@@ -41,6 +41,9 @@ int sap3d_device_ok(void);
 /* developer probe, not a reference call-site: per-CTA phase time stamps of the tcgen05 convolution kernel are written to
  * buf ([cta][16][2] uint64 device memory: clock64, globaltimer); NULL switches the probe off.  Process-global. */
 int sap3d_debug_conv_timing(void* buf);
+/* developer probe: how many convolution launches of this process took the halo-tile kernel (conv_tc.cu) so far; tests use it
+ * to prove that a case meant for that kernel did not silently take another one. */
+long long sap3d_debug_conv_halo_launches(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolution family.  Replaces tf.nn.conv3d (p3d.py:19,24,86,112,125,343), tf.nn.bias_add
@@ -342,6 +345,10 @@ int sap3d_pack_multi(const sap3d_pack_entry* entries_dev, int32_t n, int64_t tot
 /* tf.train.AdamOptimizer (train.py:168) over flat fp32 arrays; *step (device) is the 1-based iteration. */
 int sap3d_adam_step(float* w, const float* g, float* m, float* v, int64_t n, const int32_t* step, float lr, float b1, float b2,
                     float eps, float grad_scale, void* stream);
+/* the same update with the gradient given as fp32 (g_dtype SAP3D_F32) or bf16 (SAP3D_BF16: the all-reduced buckets of the
+ * data-parallel exchange, consumed without widening them back into the fp32 gradient buffer; new work, BASELINE configs[3]) */
+int sap3d_adam_step_g(float* w, const void* g, int32_t g_dtype, float* m, float* v, int64_t n, const int32_t* step, float lr, float b1,
+                      float b2, float eps, float grad_scale, void* stream);
 int sap3d_step_increment(int32_t* step, void* stream);
 /* f32 -> bf16 (src_dtype == SAP3D_F32) or bf16 -> f32 */
 int sap3d_cast(int32_t src_dtype, const void* src, void* dst, int64_t n, void* stream);

@@ -58,6 +58,7 @@ def _sig(name, argtypes, restype=C.c_int):
 
 _P = C.POINTER
 _sig("sap3d_debug_conv_timing", [_vp])
+_sig("sap3d_debug_conv_halo_launches", [], C.c_longlong)
 _sig("sap3d_conv_out_dims", [_P(ConvDesc), _P(C.c_int32)])
 _sig("sap3d_conv_stats_rows", [_P(ConvDesc)])
 _sig("sap3d_conv_packed_elems", [_P(ConvDesc), _i32], C.c_size_t)
@@ -134,6 +135,7 @@ _sig("sap3d_dropout", [_i32, _vp, _vp, _i64, _f32, _u64, _vp, _i32, _vp])
 _sig("sap3d_gate_fwd", [_i32, _vp, _vp, _vp, _vp, _i64, _vp])
 _sig("sap3d_gate_bwd", [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp])
 _sig("sap3d_adam_step", [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp])
+_sig("sap3d_adam_step_g", [_vp, _vp, _i32, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp])
 _sig("sap3d_step_increment", [_vp, _vp])
 _sig("sap3d_cast", [_i32, _vp, _vp, _i64, _vp])
 _i32x = _i32

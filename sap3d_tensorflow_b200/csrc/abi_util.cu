@@ -93,5 +93,6 @@ int sap3d_debug_conv_timing(void* buf) {
   sap3d::tc_set_debug_buffer(buf);
   return 0;
 }
+long long sap3d_debug_conv_halo_launches(void) { return sap3d::tc_halo_launches(); }
 int sap3d_device_ok(void) { return sap3d::require_device() == 0 ? 1 : 0; }
 }

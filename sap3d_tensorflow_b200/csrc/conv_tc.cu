@@ -31,6 +31,7 @@ constexpr int TC_MAX_MAPS = 28;   // 27 parity views of dy (transposed conv k3 s
 constexpr int TC_MAX_TAPS = 128;
 constexpr int TC_MAX_CLS = 64;
 constexpr int TC_THREADS = 192;
+constexpr int TC_HALO_MAX_ROWS = 160;   // halo-tile kernels: 128 + 2 * halo_inner rows per activation box, halo_inner <= 16
 
 struct TcTap {
   int8_t map, dw, dh, dd;
@@ -65,6 +66,9 @@ struct alignas(64) TcConvParams {
   const float* shift;
   int relu, accumulate, out_f32;
   int b_batched;       // the weight-side operand is per sample: third TMA coordinate = the tile's batch index
+  int balanced;        // persistent kernels: contiguous, equally long m-tile ranges per CTA (one class, one column tile)
+  int halo_rows;       // halo-tile kernels: rows of one activation box (128 + 2 * halo_inner); taps are sorted in triples
+  int halo_inner;      // ... rows per step along the halo axis (product of the inner box extents; multiple of 8)
   unsigned long long* dbg;   // phase-timing probe (tools/conv_phase_probe.py): [cta][16][2] = (clock64, globaltimer); normally NULL
 };
 
@@ -481,51 +485,89 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 // unit i+1, the TMA ring never drains between units, and the wave-quantisation tail of a 5.3-wave launch disappears
 // (every SM gets floor or ceil of units/SMs).
 // =================================================================================================
-template <int BLOCK_N, int STAGES, int MT>
+// HALO = 0: every k-block (tap, 64-channel chunk) is one ring stage holding MT activation boxes and one weight tile.
+// HALO = NB > 0 ("halo tile"): filter taps come in triples that differ only by -1/0/+1 along the OUTERMOST axis of the
+// output box (p.halo_inner rows per step, a multiple of 8).  One TMA box with two extra steps along that axis
+// (p.halo_rows = 128 + 2 * halo_inner rows) then contains the activation tile of all three taps as contiguous, swizzle-atom
+// aligned 128-row windows: the A operand of tap j is the SAME shared-memory buffer at +j * halo_inner * 128 bytes.  The
+// activation bytes pulled over the L2->SM fabric drop from 3 x 16 KB to halo_rows x 128 B (20 KB at halo_inner = 16) per
+// sub-tile and tap triple -- the fabric is what bounds the non-halo kernel (ncu: 4.17 GB per launch of the dominant decoder
+// conv at ~14 TB/s).  Activations and weights then have separate rings: STAGES halo buffers, HALO weight tiles.
+// Units: p.balanced (one class, one column tile) gives every CTA a CONTIGUOUS range of m-tiles of near-equal length
+// (floor or ceil of m_tiles / gridDim.x), walked in groups of MT with a last group of fewer sub-tiles; otherwise units are
+// (class, MT-group, column tile) triples taken round-robin.  Sub-tiles that are not live are neither loaded nor multiplied.
+template <int BLOCK_N, int STAGES, int MT, int HALO = 0>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __grid_constant__ TcConvParams p, const int total_units) {
   constexpr int A_BYTES = 128 * 128;
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+  constexpr int HALO_BUF_BYTES = TC_HALO_MAX_ROWS * 128;          // one sub-tile's halo box
+  constexpr int A_RING_BYTES = MT * HALO_BUF_BYTES;
+  constexpr int RING_BYTES = HALO ? STAGES * A_RING_BYTES + HALO * B_BYTES : STAGES * STAGE_BYTES;
   constexpr int NBUF = 2 * MT * BLOCK_N <= 512 ? 2 : 1;
   constexpr int TCOLS = NBUF * MT * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tfull[2], tempty[2]
-  constexpr int NBAR = 2 * STAGES + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + NBAR * 8);
-  float* s_stats = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + NBAR * 8 + 16);  // [4][2][BLOCK_N]
-  float* s_ep = s_stats + 4 * 2 * BLOCK_N;                                                  // [3][BLOCK_N]
-  const uint32_t tfull = bar_base + 2 * STAGES * 8, tempty = tfull + 16;
+  const uint32_t bar_base = base + RING_BYTES;
+  // HALO = 0: full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  // HALO > 0: afull[STAGES], aempty[STAGES], bfull[HALO], bempty[HALO], tfull[2], tempty[2]
+  constexpr int NRING_BAR = HALO ? 2 * STAGES + 2 * HALO : 2 * STAGES;
+  constexpr int NBAR = NRING_BAR + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RING_BYTES + NBAR * 8);
+  float* s_stats = reinterpret_cast<float*>(smem + RING_BYTES + NBAR * 8 + 16);  // [4][2][BLOCK_N]
+  float* s_ep = s_stats + 4 * 2 * BLOCK_N;                                        // [3][BLOCK_N]
+  const uint32_t tfull = bar_base + NRING_BAR * 8, tempty = tfull + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_groups = (p.m_tiles + MT - 1) / MT;
+  // balanced mode: this CTA's contiguous range of m-tiles
+  const int range_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.m_tiles / gridDim.x);
+  const int range_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.m_tiles / gridDim.x);
 
-  struct Unit { int nt, cls_id; int mts[MT], w0s[MT], h0s[MT], d0s[MT], n0s[MT]; bool live[MT]; };
-  auto decode = [&](int u, Unit& t) {
-    t.nt = u % p.n_tiles;
-    u /= p.n_tiles;
-    t.cls_id = u / m_groups;
-    const int mg = u - t.cls_id * m_groups;
+  struct Unit { int nt, cls_id, nsub; int mts[MT], w0s[MT], h0s[MT], d0s[MT], n0s[MT]; };
+  // cursor: balanced = next m-tile of the range, else the unit index; returns false when this CTA is done
+  auto next_unit = [&](int& cur, Unit& t) -> bool {
+    int mt0;
+    if (p.balanced) {
+      if (cur >= range_end) return false;
+      t.nt = 0;
+      t.cls_id = 0;
+      mt0 = cur;
+      t.nsub = min(MT, range_end - cur);
+      cur += t.nsub;
+    } else {
+      if (cur >= total_units) return false;
+      int u = cur;
+      cur += gridDim.x;
+      t.nt = u % p.n_tiles;
+      u /= p.n_tiles;
+      t.cls_id = u / m_groups;
+      mt0 = (u - t.cls_id * m_groups) * MT;
+      t.nsub = min(MT, p.m_tiles - mt0);
+    }
 #pragma unroll
     for (int sub = 0; sub < MT; ++sub) {
-      int mt = mg * MT + sub;
-      t.live[sub] = mt < p.m_tiles;
-      if (!t.live[sub]) mt = p.m_tiles - 1;
-      t.mts[sub] = mt;
-      int r = mt;
+      int r = min(mt0 + sub, p.m_tiles - 1);
+      t.mts[sub] = r;
       const int tw = r % p.tiles[0]; r /= p.tiles[0];
       const int th = r % p.tiles[1]; r /= p.tiles[1];
       const int td = r % p.tiles[2];
       const int tn = r / p.tiles[2];
       t.w0s[sub] = tw * p.box[0]; t.h0s[sub] = th * p.box[1]; t.d0s[sub] = td * p.box[2]; t.n0s[sub] = tn * p.box[3];
     }
+    return true;
   };
+  const int cur0 = p.balanced ? range_begin : static_cast<int>(blockIdx.x);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_base + s * 8, 1);
-      mbar_init(bar_base + (STAGES + s) * 8, 1);
+    if (HALO) {
+      for (int s = 0; s < 2 * STAGES + 2 * HALO; ++s) mbar_init(bar_base + s * 8, 1);
+    } else {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(bar_base + s * 8, 1);
+        mbar_init(bar_base + (STAGES + s) * 8, 1);
+      }
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull + b * 8, 1);
@@ -548,27 +590,62 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
   if (warp == 0) {
     // ================= TMA producer: one continuous ring over all units =================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = MT * p.box_rows * 128 + B_BYTES;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        Unit t;
-        decode(u, t);
-        const TcClass cls = p.cls[t.cls_id];
-        for (int ti = 0; ti < cls.tap_count; ++ti) {
-          const TcTap tap = p.taps[cls.tap_begin + ti];
-          const void* amap = &p.amap[tap.map];
-          for (int ch = 0; ch < tap.nchunk; ++ch) {
-            mbar_wait(bar_base + (STAGES + stage) * 8, phase ^ 1u);
-            const uint32_t full = bar_base + stage * 8;
-            const uint32_t sa = base + stage * STAGE_BYTES;
-            mbar_expect_tx(full, tx_bytes);
+      int cur = cur0;
+      Unit t;
+      if (HALO) {
+        const uint32_t afull = bar_base, aempty = bar_base + STAGES * 8, bfull = bar_base + 2 * STAGES * 8, bempty = bfull + HALO * 8;
+        const uint32_t b_ring = base + STAGES * A_RING_BYTES;
+        const uint32_t halo_bytes = p.halo_rows * 128;
+        int sa_i = 0, sb_i = 0;
+        uint32_t pa = 0, pb = 0;
+        while (next_unit(cur, t)) {
+          const TcClass cls = p.cls[t.cls_id];
+          for (int g = 0; g < cls.tap_count; g += 3) {
+            const TcTap tap = p.taps[cls.tap_begin + g];       // lowest offset along the halo axis: the box origin
+            const int k1 = p.taps[cls.tap_begin + g + 1].kofs, k2 = p.taps[cls.tap_begin + g + 2].kofs;
+            const void* amap = &p.amap[tap.map];
+            for (int ch = 0; ch < tap.nchunk; ++ch) {
+              mbar_wait(aempty + sa_i * 8, pa ^ 1u);
+              mbar_expect_tx(afull + sa_i * 8, t.nsub * halo_bytes);
 #pragma unroll
-            for (int sub = 0; sub < MT; ++sub)
-              tma_load_5d(sa + sub * A_BYTES, amap, full, (tap.c0 + ch) * 64, t.w0s[sub] + tap.dw, t.h0s[sub] + tap.dh, t.d0s[sub] + tap.dd,
-                          t.n0s[sub]);
-            tma_load_3d(sa + MT * A_BYTES, &p.bmap, full, tap.kofs + ch * 64, t.nt * BLOCK_N, p.b_batched ? t.n0s[0] : 0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+              for (int sub = 0; sub < MT; ++sub)
+                if (sub < t.nsub)
+                  tma_load_5d(base + sa_i * A_RING_BYTES + sub * HALO_BUF_BYTES, amap, afull + sa_i * 8, (tap.c0 + ch) * 64, t.w0s[sub] + tap.dw,
+                              t.h0s[sub] + tap.dh, t.d0s[sub] + tap.dd, t.n0s[sub]);
+              if (++sa_i == STAGES) { sa_i = 0; pa ^= 1u; }
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const int kofs = j == 0 ? tap.kofs : (j == 1 ? k1 : k2);
+                mbar_wait(bempty + sb_i * 8, pb ^ 1u);
+                mbar_expect_tx(bfull + sb_i * 8, B_BYTES);
+                tma_load_3d(b_ring + sb_i * B_BYTES, &p.bmap, bfull + sb_i * 8, kofs + ch * 64, t.nt * BLOCK_N, 0);
+                if (++sb_i == HALO) { sb_i = 0; pb ^= 1u; }
+              }
+            }
+          }
+        }
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        while (next_unit(cur, t)) {
+          const uint32_t tx_bytes = t.nsub * p.box_rows * 128 + B_BYTES;
+          const TcClass cls = p.cls[t.cls_id];
+          for (int ti = 0; ti < cls.tap_count; ++ti) {
+            const TcTap tap = p.taps[cls.tap_begin + ti];
+            const void* amap = &p.amap[tap.map];
+            for (int ch = 0; ch < tap.nchunk; ++ch) {
+              mbar_wait(bar_base + (STAGES + stage) * 8, phase ^ 1u);
+              const uint32_t full = bar_base + stage * 8;
+              const uint32_t sa = base + stage * STAGE_BYTES;
+              mbar_expect_tx(full, tx_bytes);
+#pragma unroll
+              for (int sub = 0; sub < MT; ++sub)
+                if (sub < t.nsub)
+                  tma_load_5d(sa + sub * A_BYTES, amap, full, (tap.c0 + ch) * 64, t.w0s[sub] + tap.dw, t.h0s[sub] + tap.dh, t.d0s[sub] + tap.dd,
+                              t.n0s[sub]);
+              tma_load_3d(sa + MT * A_BYTES, &p.bmap, full, tap.kofs + ch * 64, t.nt * BLOCK_N, p.b_batched ? t.n0s[0] : 0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       }
@@ -578,29 +655,60 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
-      int stage = 0, it = 0;
-      uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+      int cur = cur0, it = 0;
+      Unit t;
+      int stage = 0, sb_i = 0;
+      uint32_t phase = 0, pb = 0;
+      for (; next_unit(cur, t); ++it) {
         const int buf = it % NBUF;
         const uint32_t use = static_cast<uint32_t>(it / NBUF);
-        const int cls_id = (u / p.n_tiles) / m_groups;
-        const int nkb = p.cls[cls_id].nkb;
+        const int nkb = p.cls[t.cls_id].nkb;
         mbar_wait(tempty + buf * 8, (use & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * MT * BLOCK_N;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(bar_base + stage * 8, phase);
-          tc_fence_after();
-          const uint32_t sa = base + stage * STAGE_BYTES;
-          const uint64_t bdesc = umma_desc_sw128(sa + MT * A_BYTES, 16, 1024);
+        if (HALO) {
+          const uint32_t afull = bar_base, aempty = bar_base + STAGES * 8, bfull = bar_base + 2 * STAGES * 8, bempty = bfull + HALO * 8;
+          const uint32_t b_ring = base + STAGES * A_RING_BYTES;
+          const uint32_t tap_step = p.halo_inner * 128;          // bytes between the windows of consecutive taps (multiple of 1024)
+          for (int kg = 0; kg < nkb; kg += 3) {                  // one halo buffer = three k-blocks
+            mbar_wait(afull + stage * 8, phase);
+            const uint32_t sa = base + stage * A_RING_BYTES;
 #pragma unroll
-          for (int sub = 0; sub < MT; ++sub) {
-            const uint64_t adesc = umma_desc_sw128(sa + sub * A_BYTES, 16, 1024);
+            for (int j = 0; j < 3; ++j) {
+              mbar_wait(bfull + sb_i * 8, pb);
+              tc_fence_after();
+              const uint64_t bdesc = umma_desc_sw128(b_ring + sb_i * B_BYTES, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_bf16(tacc + sub * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int sub = 0; sub < MT; ++sub) {
+                if (sub < t.nsub) {
+                  const uint64_t adesc = umma_desc_sw128(sa + sub * HALO_BUF_BYTES + j * tap_step, 16, 1024);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) tc_mma_bf16(tacc + sub * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kg | j | k) != 0 ? 1u : 0u);
+                }
+              }
+              tc_commit(bempty + sb_i * 8);
+              if (++sb_i == HALO) { sb_i = 0; pb ^= 1u; }
+            }
+            tc_commit(aempty + stage * 8);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(bar_base + (STAGES + stage) * 8);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        } else {
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(bar_base + stage * 8, phase);
+            tc_fence_after();
+            const uint32_t sa = base + stage * STAGE_BYTES;
+            const uint64_t bdesc = umma_desc_sw128(sa + MT * A_BYTES, 16, 1024);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub) {
+              if (sub < t.nsub) {
+                const uint64_t adesc = umma_desc_sw128(sa + sub * A_BYTES, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tc_mma_bf16(tacc + sub * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            tc_commit(bar_base + (STAGES + stage) * 8);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
         if (nkb > 0) tc_commit(tfull + buf * 8);
         else mbar_arrive(tfull + buf * 8);               // bias-only class: nothing to wait for
@@ -613,10 +721,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
     const int row = q * 32 + lane;
     const bool want_stats = p.stats != nullptr;
     const int et = threadIdx.x - 64;
-    int it = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
-      Unit t;
-      decode(u, t);
+    int cur = cur0, it = 0;
+    Unit t;
+    for (; next_unit(cur, t); ++it) {
       const TcClass cls = p.cls[t.cls_id];
       const int nkb = cls.nkb;
       const int buf = it % NBUF;
@@ -633,8 +740,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * MT * BLOCK_N;
 #pragma unroll 1
-      for (int sub = 0; sub < MT; ++sub) {
-        if (!t.live[sub]) break;
+      for (int sub = 0; sub < t.nsub; ++sub) {
         int r = row;
         const int iw = r % p.box[0]; r /= p.box[0];
         const int ih = r % p.box[1]; r /= p.box[1];
@@ -721,7 +827,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
             }
           }
         }
-        if (sub + 1 == MT || !t.live[sub + 1 < MT ? sub + 1 : sub]) {
+        if (sub + 1 == t.nsub) {
           // last sub-tile of the unit has been read out of TMEM: hand the buffer back before the statistics tail
           tc_fence_before();
           mbar_arrive(tempty + buf * 8);
@@ -1245,13 +1351,16 @@ static int launch_split(const TcConvParams& prm, int grid, cudaStream_t stream, 
   return 0;
 }
 
-template <int BLOCK_N, int STAGES, int MT>
+template <int BLOCK_N, int STAGES, int MT, int HALO = 0>
 static int launch_persist(const TcConvParams& prm, int units, cudaStream_t stream, char* err, size_t errlen) {
-  constexpr int SMEM = STAGES * (MT * 128 * 128 + BLOCK_N * 128) + (2 * STAGES + 4) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
+  constexpr int RING = HALO ? STAGES * MT * TC_HALO_MAX_ROWS * 128 + HALO * BLOCK_N * 128 : STAGES * (MT * 128 * 128 + BLOCK_N * 128);
+  constexpr int NBAR = (HALO ? 2 * STAGES + 2 * HALO : 2 * STAGES) + 4;
+  constexpr int SMEM = RING + NBAR * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
+  static_assert(SMEM <= 232448, "persistent conv kernel exceeds the 227 KB of shared memory a CTA can opt in to");
   static bool attr_done = false;
   static int sms = 0;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BLOCK_N, STAGES, MT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
       snprintf(err, errlen, "cudaFuncSetAttribute(conv_tc_persist) failed: %s", cudaGetErrorString(e));
       return 1;
@@ -1262,8 +1371,10 @@ static int launch_persist(const TcConvParams& prm, int units, cudaStream_t strea
     if (sms < 1) sms = 148;
     attr_done = true;
   }
-  cudaError_t e = launch_k(conv_tc_persist_kernel<BLOCK_N, STAGES, MT>, dim3((unsigned)(units < sms ? units : sms)), dim3(TC_THREADS), SMEM, stream,
-                           1, prm, units);
+  // balanced mode hands out m-tiles (>= units), otherwise one CTA per unit up to the SM count
+  const int work = prm.balanced ? prm.m_tiles : units;
+  cudaError_t e = launch_k(conv_tc_persist_kernel<BLOCK_N, STAGES, MT, HALO>, dim3((unsigned)(work < sms ? work : sms)), dim3(TC_THREADS), SMEM,
+                           stream, 1, prm, units);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "conv_tc_persist launch failed: %s", cudaGetErrorString(e));
     return 1;
@@ -1313,6 +1424,8 @@ static int launch_persist_mc(const TcConvParams& prm, int m_groups, cudaStream_t
 
 static unsigned long long* g_conv_dbg = nullptr;
 void tc_set_debug_buffer(void* buf) { g_conv_dbg = reinterpret_cast<unsigned long long*>(buf); }
+static long long g_halo_launches = 0;
+long long tc_halo_launches() { return g_halo_launches; }
 
 // opt-in while it is being measured: SAP3D_CONV_MULTICAST=2 or 4 (cluster size); unset / 0 = off
 static int multicast_cluster() {
@@ -1322,6 +1435,92 @@ static int multicast_cluster() {
     v = (e != nullptr && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
   }
   return v;
+}
+
+// SAP3D_CONV_HALO: 0 = never use the halo-tile kernels, 1 (default) = two-sub-tile units only, 2 = also single-sub-tile units
+static int halo_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAP3D_CONV_HALO");
+    v = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
+  return v;
+}
+// SAP3D_CONV_BALANCED=0: persistent kernels take units round-robin even where contiguous equal ranges are possible
+static bool balanced_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAP3D_CONV_BALANCED");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// Halo-tile plan (see conv_tc_persist_kernel): the taps of a one-class problem grouped into triples that differ only by
+// consecutive offsets along axis X (1 = H, 2 = D), and an output box of exactly 128 rows whose outermost non-unit axis is X
+// with `inner` = rows per X step in {8, 16}.  Accepted only if the box needs exactly as many tiles as the default one.
+struct HaloPlan {
+  int axis = 0, inner = 0;
+  int box[4] = {1, 1, 1, 1};
+  long long tiles = 0;
+  std::vector<TcTapH> taps;   // reordered: triples, ascending along the axis
+};
+static bool plan_halo(const Merged& m, long long default_tiles, HaloPlan& best) {
+  if (m.classes.size() != 1) return false;
+  const std::vector<TcTapH>& taps = m.classes[0].taps;
+  if (taps.empty() || taps.size() % 3 != 0) return false;
+  bool found = false;
+  for (int X = 1; X <= 2; ++X) {
+    // group the taps
+    std::vector<TcTapH> ordered;
+    std::vector<char> used(taps.size(), 0);
+    bool ok = true;
+    for (size_t i = 0; i < taps.size() && ok; ++i) {
+      if (used[i]) continue;
+      std::vector<size_t> grp;
+      for (size_t j = i; j < taps.size(); ++j) {
+        if (used[j]) continue;
+        const TcTapH &a = taps[i], &b = taps[j];
+        bool same = a.view == b.view && a.c_begin == b.c_begin && a.nch == b.nch;
+        for (int d = 0; d < 4; ++d)
+          if (d != X) same = same && a.off[d] == b.off[d];
+        if (same) grp.push_back(j);
+      }
+      if (grp.size() != 3) { ok = false; break; }
+      std::sort(grp.begin(), grp.end(), [&](size_t a, size_t b) { return taps[a].off[X] < taps[b].off[X]; });
+      if (taps[grp[1]].off[X] != taps[grp[0]].off[X] + 1 || taps[grp[2]].off[X] != taps[grp[0]].off[X] + 2) { ok = false; break; }
+      for (size_t g : grp) {
+        used[g] = 1;
+        ordered.push_back(taps[g]);
+      }
+    }
+    if (!ok) continue;
+    // boxes of exactly 128 rows, unit extent above X
+    for (int bw = 1; bw <= std::min(m.ext[0], 128); ++bw) {
+      for (int bh = 1; bh <= std::min(m.ext[1], 128 / bw); ++bh) {
+        if (X == 1) {
+          if (bw * bh != 128) continue;
+        }
+        const int bd = X == 2 ? 128 / (bw * bh) : 1;
+        if (bw * bh * bd != 128 || bd > m.ext[2]) continue;
+        const int bx = X == 2 ? bd : bh;
+        const int inner = X == 2 ? bw * bh : bw;
+        if (bx < 2 || inner % 8 != 0 || 128 + 2 * inner > TC_HALO_MAX_ROWS) continue;
+        const long long tiles = (long long)((m.ext[0] + bw - 1) / bw) * ((m.ext[1] + bh - 1) / bh) * ((m.ext[2] + bd - 1) / bd) * m.ext[3];
+        if (tiles != default_tiles) continue;   // sap3d_conv_stats_rows() is planned with the default box: keep the tile count
+        const bool better = !found || tiles < best.tiles || (tiles == best.tiles && (inner < best.inner || (inner == best.inner && bw > best.box[0])));
+        if (better) {
+          found = true;
+          best.axis = X;
+          best.inner = inner;
+          best.box[0] = bw; best.box[1] = bh; best.box[2] = bd; best.box[3] = 1;
+          best.tiles = tiles;
+          best.taps = ordered;
+        }
+      }
+    }
+  }
+  return found;
 }
 
 int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen) {
@@ -1354,9 +1553,38 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
     else block_n = 128;
   }
   if (block_n > 64 && pb.rowsB % block_n != 0 && pb.rowsB < block_n) block_n = 64;
-  for (size_t v = 0; v < m.views.size(); ++v)
-    if (encode_view(&prm.amap[v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, box, err, errlen))
-      return 1;
+  // halo-tile kernel: persistent one-class problems with one column tile whose taps form triples along H or D
+  bool use_halo = false;
+  {
+    const long long n_tiles0 = (pb.cout + block_n - 1) / block_n;
+    const long long ctas0 = (long long)m.classes.size() * m_tiles * n_tiles0;
+    const int mt0 = pb.b_batch > 1 ? 1 : (pb.force_mt ? pb.force_mt : (ctas0 >= 4 * 148 ? 2 : 1));
+    const long long units0 = (long long)m.classes.size() * ((m_tiles + mt0 - 1) / mt0) * n_tiles0;
+    const int hm = halo_mode();
+    if (hm > 0 && units0 > 148 && pb.force_split >= 0 && multicast_cluster() == 0 && pb.b_batch <= 1 && n_tiles0 == 1 &&
+        (block_n == 128 || block_n == 256) && (mt0 == 2 || hm == 2)) {
+      HaloPlan hp;
+      if (plan_halo(m, m_tiles, hp)) {
+        int hbox[4] = {hp.box[0], hp.box[1], hp.box[2], hp.box[3]};
+        hbox[hp.axis] += 2;
+        bool enc_ok = true;
+        for (size_t v = 0; v < m.views.size() && enc_ok; ++v)
+          enc_ok = encode_view(&prm.amap[v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, hbox, err, errlen) == 0;
+        if (enc_ok) {
+          use_halo = true;
+          for (int i = 0; i < 4; ++i) box[i] = hp.box[i];
+          m_tiles = hp.tiles;
+          m.classes[0].taps = hp.taps;
+          prm.halo_inner = hp.inner;
+          prm.halo_rows = 128 + 2 * hp.inner;
+        }
+      }
+    }
+  }
+  if (!use_halo)
+    for (size_t v = 0; v < m.views.size(); ++v)
+      if (encode_view(&prm.amap[v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, box, err, errlen))
+        return 1;
   if (encode_b(&prm.bmap, pb.B, pb.Ktot, pb.rowsB, block_n, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
   prm.b_batched = pb.b_batch > 1 ? 1 : 0;
   if (encode_b(&prm.bmap_half, pb.B, pb.Ktot, pb.rowsB, block_n / 2, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
@@ -1447,6 +1675,16 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
     }
     if (block_n == 128) return mt == 2 ? launch_persist_mc<128, 4, 2, 4>(prm, mg, stream, err, errlen) : launch_persist_mc<128, 4, 1, 4>(prm, mg, stream, err, errlen);
     return mt == 2 ? launch_persist_mc<256, 3, 2, 4>(prm, mg, stream, err, errlen) : launch_persist_mc<256, 4, 1, 4>(prm, mg, stream, err, errlen);
+  }
+  prm.balanced = (prm.ncls == 1 && prm.n_tiles == 1 && pb.b_batch <= 1 && balanced_enabled()) ? 1 : 0;
+  if (use_halo) {
+    if (grid <= 148 || prm.box_rows != 128) {
+      snprintf(err, errlen, "tc_launch: halo plan inconsistent (grid %lld, box rows %d)", grid, prm.box_rows);
+      return 1;
+    }
+    ++g_halo_launches;
+    if (block_n == 128) return mt == 2 ? launch_persist<128, 3, 2, 6>(prm, (int)grid, stream, err, errlen) : launch_persist<128, 3, 1, 6>(prm, (int)grid, stream, err, errlen);
+    return mt == 2 ? launch_persist<256, 2, 2, 3>(prm, (int)grid, stream, err, errlen) : launch_persist<256, 3, 1, 4>(prm, (int)grid, stream, err, errlen);
   }
   if (grid > 148 && pb.force_split >= 0) {
     switch (block_n) {

@@ -58,6 +58,8 @@ int tc_plan_tiles(const TcProblem& pb);
 int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen);
 // phase-timing probe of conv_tc_kernel (developer tool): [cta][16][2] uint64 device buffer, or NULL to switch it off
 void tc_set_debug_buffer(void* buf);
+// launches that took the halo-tile persistent kernel so far (process-wide)
+long long tc_halo_launches();
 
 // wgrad: D[m][n] (+)= sum_pos P(pos + off)[m] * Q(pos)[n], fp32 atomics into dw
 struct TcWgradTap {

@@ -501,7 +501,23 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const T* __restrict__ dy,
 // ------------------------------------------------------------------------------------------------
 // Adam (TF-1.x formula): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); w -= lr_t * m / (sqrt(v) + eps)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+template <typename G>
+SAP3D_DEVINL void load_grad4(const G* g, long long i, float (&out)[4]);
+template <>
+SAP3D_DEVINL void load_grad4<float>(const float* g, long long i, float (&out)[4]) {
+  const float4 t = reinterpret_cast<const float4*>(g)[i];
+  out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+}
+template <>
+SAP3D_DEVINL void load_grad4<bf16>(const bf16* g, long long i, float (&out)[4]) {
+  const uint2 t = reinterpret_cast<const uint2*>(g)[i];
+  out[0] = __uint_as_float(t.x << 16); out[1] = __uint_as_float(t.x & 0xffff0000u);
+  out[2] = __uint_as_float(t.y << 16); out[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+// G = float: the gradient buffer of the engine; G = bf16: the all-reduced buckets of the data-parallel exchange, consumed
+// directly (no pass that widens them back into the fp32 buffer)
+template <typename G>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const G* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long long n, const int* __restrict__ step, float lr,
                                                     float b1, float b2, float eps, float gscale) {
   const float t = (float)step[0];
@@ -509,10 +525,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const 
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 wv = reinterpret_cast<float4*>(w)[i];
-    float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float gp[4];
+    load_grad4<G>(g, i, gp);
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
-    float* wp = &wv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+    float* wp = &wv.x; float* mp = &mv.x; float* vp = &vv.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float gg = gp[j] * gscale;
@@ -526,7 +543,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const 
   }
   // tail
   for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gg = g[i] * gscale;
+    const float gg = to_f32<G>(g[i]) * gscale;
     const float mm = b1 * m[i] + (1.f - b1) * gg;
     const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
     m[i] = mm;
@@ -538,7 +555,15 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const 
 __global__ void step_inc_kernel(int* step) { step[0] += 1; }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  // 8 elements per thread (two 16-byte loads, one 16-byte store) where both pointers allow it
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
+  const long long n8 = vec ? n / 8 : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    Vec8<float>::load(x + i * 8, v);
+    Vec8<bf16>::store(y + i * 8, v);
+  }
+  for (long long i = n8 * 8 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16_rn(x[i]);
 }
 __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n) {
@@ -723,8 +748,25 @@ int sap3d_adam_step(float* w, const float* g, float* m, float* v, int64_t n, con
                     float eps, float grad_scale, void* stream) {
   if (require_device()) return 1;
   if (!w || !g || !m || !v || !step) return set_error("adam_step: NULL pointer");
-  adam_kernel<<<egrid(n / 4 + 1), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, g, m, v, n, step, lr, b1, b2, eps, grad_scale);
+  adam_kernel<float><<<egrid(n / 4 + 1), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, g, m, v, n, step, lr, b1, b2, eps, grad_scale);
   return check_launch("adam_step");
+}
+
+int sap3d_adam_step_g(float* w, const void* g, int32_t g_dtype, float* m, float* v, int64_t n, const int32_t* step, float lr, float b1, float b2,
+                      float eps, float grad_scale, void* stream) {
+  if (require_device()) return 1;
+  if (!w || !g || !m || !v || !step) return set_error("adam_step_g: NULL pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (g_dtype == SAP3D_F32) {
+    if (reinterpret_cast<uintptr_t>(g) & 15u) return set_error("adam_step_g: fp32 gradient pointer must be 16-byte aligned");
+    adam_kernel<float><<<egrid(n / 4 + 1), 256, 0, st>>>(w, reinterpret_cast<const float*>(g), m, v, n, step, lr, b1, b2, eps, grad_scale);
+  } else if (g_dtype == SAP3D_BF16) {
+    if (reinterpret_cast<uintptr_t>(g) & 7u) return set_error("adam_step_g: bf16 gradient pointer must be 8-byte aligned");
+    adam_kernel<bf16><<<egrid(n / 4 + 1), 256, 0, st>>>(w, reinterpret_cast<const bf16*>(g), m, v, n, step, lr, b1, b2, eps, grad_scale);
+  } else {
+    return set_error("adam_step_g: gradient dtype must be SAP3D_F32 or SAP3D_BF16");
+  }
+  return check_launch("adam_step_g");
 }
 
 int sap3d_step_increment(int32_t* step, void* stream) {

@@ -60,14 +60,18 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- work decode: ((tap, mblock, nblock), split) -----------------------------------------------
+  // ---- work decode: (split, (mblock, nblock, tap)), tap fastest ----------------------------------
+  // CTAs that are resident together (consecutive blockIdx) then cover ALL taps of the SAME position slice: the dy tile is
+  // shared by every tap and the shifted x tiles overlap, so each wave streams its slice of x and dy from DRAM once and the
+  // other taps hit L2.  (With the split index fastest every wave walked the whole of x and dy -- 3 waves = 3.0x the
+  // algorithmic DRAM bytes in the r01/r02 ncu captures.)
   int w = blockIdx.x;
-  const int split = w % p.splits;
-  w /= p.splits;
+  const int tap_id = w % p.ntaps;
+  w /= p.ntaps;
   const int nb = w % p.nblocks;
   w /= p.nblocks;
   const int mb = w % p.mblocks;
-  const int tap_id = w / p.mblocks;
+  const int split = w / p.mblocks;
   const WgTap tap = p.taps[tap_id];
   const int per = (p.m_tiles + p.splits - 1) / p.splits;
   const int t_begin = split * per;

@@ -149,9 +149,12 @@ class Engine:
         self._pack_table = None
         self.pre_pack_ops: List = []
         self.var_prefix = ""   # tf.variable_scope wrapped around a whole builder (gn/p3d_gn.py:490 'P3D')
-        self._split_ops: Optional[int] = None      # data-parallel overlap: backward is cut here (see mark_dp_split)
-        self._split_param: Optional[str] = None
-        self.dp_split_offset: Optional[int] = None
+        # data-parallel overlap: backward is cut at these marks (see mark_dp_split): (ops recorded so far, last parameter so far)
+        self._split_marks: List[tuple] = []
+        self.dp_segments: List[tuple] = []          # after finalize(): (ops_lo, ops_hi, grad_lo, grad_hi) in BACKWARD order
+        self._split_ops: Optional[int] = None      # the LAST mark (the first cut backward meets); None = backward is not cut
+        self.dp_split_offset: Optional[int] = None  # ... and the offset of the first gradient element behind it
+        self.grad_source: Optional[torch.Tensor] = None   # bf16 copy of the gradients Adam should read instead of flat_g (DP exchange)
         self.side_stream = torch.cuda.Stream(device=self.device)   # filter gradients run here, off the critical path
         self.aux_stream = torch.cuda.Stream(device=self.device, priority=-1)   # forward: the second of two independent convs
         self.use_side_stream = True
@@ -182,11 +185,16 @@ class Engine:
         return p
 
     def mark_dp_split(self):
-        """called by the builders right before stage 3 of the backbone: everything created AFTER this point (stage 3, decoder,
-        head = ~88 % of the parameters, laid out at the END of the flat gradient buffer) finishes its backward FIRST, so the
-        data-parallel exchange of that tail can run while the gradients of stages 1-2 and the stem are still being computed."""
-        self._split_ops = len(self.bwd_ops)
-        self._split_param = next(reversed(self.params)) if self.params else None
+        """called by the builders between the stages of the backbone (and before the decoder): everything created AFTER a mark
+        finishes its backward BEFORE everything created ahead of it and lies behind it in the flat gradient buffer, so the
+        data-parallel exchange of a finished tail segment runs while the gradients of the earlier layers are still being
+        computed.  SAP3D_DP_MARKS (digits, default all) selects which of the builder's marks are kept: "2" = only the third."""
+        idx = getattr(self, "_mark_calls", 0)
+        self._mark_calls = idx + 1
+        keep = os.environ.get("SAP3D_DP_MARKS")
+        if keep is not None and str(idx) not in keep:
+            return
+        self._split_marks.append((len(self.bwd_ops), next(reversed(self.params)) if self.params else None))
 
     def _count(self, n=1):
         if self._counting == "fwd":
@@ -208,16 +216,21 @@ class Engine:
             if p.trainable:
                 n_train = off
         self.n_train = n_train
-        if self._split_ops is not None:
-            trainable = [p for p in ordered if p.trainable]
-            names = [p.name for p in trainable]
-            # first trainable parameter created after the mark
+        if self._split_marks:
             created = list(self.params)
-            k = created.index(self._split_param) + 1 if self._split_param in created else 0
-            later = [n for n in created[k:] if self.params[n].trainable]
-            self.dp_split_offset = self.params[later[0]].offset if later else None
-            if self.dp_split_offset is None or names.index(later[0]) == 0:
-                self._split_ops = None
+            cuts = []   # (ops index, gradient offset), ascending; marks with no trainable parameter on one side are dropped
+            for n_ops, last in self._split_marks:
+                k = created.index(last) + 1 if last in created else 0
+                later = [n for n in created[k:] if self.params[n].trainable]
+                o = self.params[later[0]].offset if later else None
+                if o is None or o == 0 or n_ops == 0 or (cuts and (o <= cuts[-1][1] or n_ops <= cuts[-1][0])):
+                    continue
+                cuts.append((n_ops, o))
+            if cuts:
+                ops_b = [0] + [c[0] for c in cuts] + [None]
+                g_b = [0] + [c[1] for c in cuts] + [n_train]
+                self.dp_segments = [(ops_b[i], ops_b[i + 1], g_b[i], g_b[i + 1]) for i in reversed(range(len(cuts) + 1))]
+                self._split_ops, self.dp_split_offset = cuts[-1]
         self.flat_w = torch.zeros(off, device=self.device, dtype=torch.float32)
         self.flat_g = torch.zeros(max(n_train, 1), device=self.device, dtype=torch.float32) if self.training_graph else None
         self.flat_m = torch.zeros(max(n_train, 1), device=self.device, dtype=torch.float32) if self.training_graph else None
@@ -381,18 +394,24 @@ class Engine:
         self._counting = None
 
     def backward(self, part: Optional[int] = None):
-        """part None: the whole backward pass; 0: the ops created after mark_dp_split (head, decoder, stage 3); 1: the rest.
-        Each part ends by joining the filter-gradient side stream, so its share of the flat gradient buffer is complete."""
+        """part None: the whole backward pass; k: segment k of dp_segments (0 = the ops created after the last mark_dp_split --
+        head, decoder, last stage --, ..., the last one = stem + first stage).  Each part ends by joining the filter-gradient side
+        stream, so its share of the flat gradient buffer is complete."""
         assert self.training_graph
         self._counting = "bwd"
-        split = self._split_ops if (part is not None and self._split_ops is not None) else 0
+        if part is not None and not self.dp_segments:
+            part = None
         if part in (None, 0):
             self.launches_bwd = 0
             for t in self.tensors:
                 t.gflag = False
             self.flat_g.zero_()
             self._count()
-        ops = self.bwd_ops if part is None else (self.bwd_ops[split:] if part == 0 else self.bwd_ops[:split])
+        if part is None:
+            ops = self.bwd_ops
+        else:
+            lo, hi = self.dp_segments[part][:2]
+            ops = self.bwd_ops[lo:hi]
         for f in reversed(ops):
             f()
         if self.use_side_stream:
@@ -400,8 +419,12 @@ class Engine:
         self._counting = None
 
     def adam(self, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
-        A.check(A.lib.sap3d_adam_step(A.ptr(self.flat_w), A.ptr(self.flat_g), A.ptr(self.flat_m), A.ptr(self.flat_v),
-                                      self.n_train, A.ptr(self.step), lr, b1, b2, eps, grad_scale, self.stream), "adam")
+        if self.grad_source is not None:     # all-reduced bf16 buckets of the data-parallel exchange, read in place
+            A.check(A.lib.sap3d_adam_step_g(A.ptr(self.flat_w), A.ptr(self.grad_source), A.BF16, A.ptr(self.flat_m), A.ptr(self.flat_v),
+                                            self.n_train, A.ptr(self.step), lr, b1, b2, eps, grad_scale, self.stream), "adam")
+        else:
+            A.check(A.lib.sap3d_adam_step(A.ptr(self.flat_w), A.ptr(self.flat_g), A.ptr(self.flat_m), A.ptr(self.flat_v),
+                                          self.n_train, A.ptr(self.step), lr, b1, b2, eps, grad_scale, self.stream), "adam")
         self.pack_weights()
 
     def begin_step(self):

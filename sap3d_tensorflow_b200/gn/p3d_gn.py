@@ -108,7 +108,7 @@ def _inference(_X: T, _dropout, training, pool4_filters):
     x = eng.maxpool(GroupNorm(c, relu=True, name="stem"), (2, 3, 3), (2, 2, 2), name="pool1")
     pools, cnt, dp3 = [], 0, None
     for si, (planes, num, inplanes, stride) in enumerate(STAGES):
-        if si == 2:
+        if si >= 1:                # data-parallel overlap: backward is cut before every stage but the first
             eng.mark_dp_split()
         blk = make_block(x, planes, num, inplanes, cnt, stride=stride)
         res = blk.infer()
@@ -151,7 +151,7 @@ def inference_p3d_decoder_block(_X, _dropout, batch_size=2, training=True):
     side = (((3, 3, 3), (1, 1, 1), 128), ((2, 3, 3), (2, 2, 2), 256), ((1, 3, 3), (4, 4, 4), 512))
     ups, cnt = [], 0
     for si, (planes, num, inplanes, stride) in enumerate(STAGES):
-        if si == 2:
+        if si >= 1:                # data-parallel overlap: backward is cut before every stage but the first
             eng.mark_dp_split()
         blk = make_block(x, planes, num, inplanes, cnt, stride=stride)
         res = blk.infer()

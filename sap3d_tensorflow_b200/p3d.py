@@ -158,7 +158,7 @@ def _backbone(_X: T, training: bool, skip_1_0: bool = True):
     x = eng.tap("pool1", eng.maxpool(stem, (2, 3, 3), (2, 2, 2), name="pool1"))
     cnt = 0
     for si, (planes, num, inplanes, stride) in enumerate(STAGES):
-        if si == 2:
+        if si >= 1:                # data-parallel overlap: backward is cut before every stage but the first
             eng.mark_dp_split()
         blk = make_block(x, planes, num, inplanes, cnt, stride=stride)
         res = blk.infer()
@@ -236,7 +236,7 @@ def p3d_concat(_X, _dropout, batch_size=2, training=True):
     side = ((1, 128), (2, 256), (4, 512))   # (stride, filters) of deconv_pool{2,3,4}
     ups, cnt = [], 0
     for si, (planes, num, inplanes, stride) in enumerate(STAGES):
-        if si == 2:
+        if si >= 1:                # data-parallel overlap: backward is cut before every stage but the first
             eng.mark_dp_split()
         blk = make_block(x, planes, num, inplanes, cnt, stride=stride)
         res = blk.infer()

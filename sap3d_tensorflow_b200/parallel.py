@@ -45,14 +45,24 @@ def reduce_metric_sums(sums: torch.Tensor, counts: torch.Tensor):
     return sums / counts
 
 
+def segment_buckets(segments, per: int):
+    """per gradient segment [lo, hi) (in the order backward completes them): its buckets, tail first"""
+    return [[(a + lo, b + lo) for a, b in make_buckets(hi - lo, per)] for lo, hi in segments]
+
+
 def split_buckets(n: int, per: int, split: int):
     """buckets of the tail [split, n) (exchanged while backward is still running) and of the head [0, split)"""
-    tail = [(lo + split, hi + split) for lo, hi in make_buckets(n - split, per)]
-    head = make_buckets(split, per)
+    tail, head = segment_buckets([(split, n), (0, split)], per)
     return tail, head
 
 
 class GradientExchange:
+    """sum-all-reduce of the flat gradient buffer as bf16 buckets on a communication stream.  The reduced buckets stay in
+    `buf` and Adam reads them there (Engine.grad_source): no pass widens them back into the fp32 buffer.
+    Overlapped form (the builders' mark_dp_split cuts backward into segments, one CUDA graph each): start(eng, k) after segment k
+    of the backward has finished -- its share of the gradient buffer is cast and its buckets are queued while the next segment
+    runs --, finish(eng) after the last one."""
+
     def __init__(self, eng, bucket_mb: int = 32):
         self.eng = eng
         n = eng.n_train
@@ -60,33 +70,32 @@ class GradientExchange:
         self.buf = torch.zeros(n, device=eng.device, dtype=torch.bfloat16)
         per = bucket_mb * 1024 * 1024 // 2
         self.buckets = make_buckets(n, per)
-        self.split = eng.dp_split_offset if eng._split_ops is not None else None
-        if self.split is not None:
-            self.tail, self.head = split_buckets(n, per, self.split)
+        self.segments = [(g_lo, g_hi) for (_, _, g_lo, g_hi) in eng.dp_segments] if len(eng.dp_segments) > 1 else []
+        self.seg_buckets = segment_buckets(self.segments, per)
         self.comm_stream = torch.cuda.Stream(device=eng.device)
         self._works = []
+        eng.grad_source = self.buf
 
-    # -- overlapped form: start() after the backward of stage 3 + decoder, finish() after the rest -------------------
-    def _reduce(self, eng, lo, hi, buckets):
+    def _reduce(self, eng, k):
+        lo, hi = self.segments[k]
         cur = torch.cuda.current_stream(eng.device)
         A.check(A.lib.sap3d_cast(A.F32, A.ptr(eng.flat_g[lo:hi]), A.ptr(self.buf[lo:hi]), hi - lo, cur.cuda_stream), "grad cast")
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
-            self._works += [dist.all_reduce(self.buf[a:b], op=dist.ReduceOp.SUM, async_op=True) for a, b in buckets]
+            self._works += [dist.all_reduce(self.buf[a:b], op=dist.ReduceOp.SUM, async_op=True) for a, b in self.seg_buckets[k]]
 
-    def start(self, eng):
-        self._works = []
-        self._reduce(eng, self.split, self.n, self.tail)
+    def start(self, eng, k: int = 0):
+        if k == 0:
+            self._works = []
+        self._reduce(eng, k)
 
     def finish(self, eng):
         cur = torch.cuda.current_stream(eng.device)
-        if self.split > 0:
-            self._reduce(eng, 0, self.split, self.head)
+        self._reduce(eng, len(self.segments) - 1)
         with torch.cuda.stream(self.comm_stream):
             for w in self._works:
                 w.wait()
         cur.wait_stream(self.comm_stream)
-        A.check(A.lib.sap3d_cast(A.BF16, A.ptr(self.buf), A.ptr(eng.flat_g), self.n, cur.cuda_stream), "grad uncast")
 
     def __call__(self, eng):
         cur = torch.cuda.current_stream(eng.device)
@@ -98,7 +107,10 @@ class GradientExchange:
             for w in works:
                 w.wait()
         cur.wait_stream(self.comm_stream)
-        A.check(A.lib.sap3d_cast(A.BF16, A.ptr(self.buf), A.ptr(eng.flat_g), self.n, st), "grad uncast")
+
+    def gradient(self) -> torch.Tensor:
+        """the exchanged gradient (fp32 copy of the bf16 buckets), for inspection"""
+        return self.buf.float()
 
 
 class SyncBatchNorm:
@@ -151,6 +163,7 @@ def attach_data_parallel(sess, bucket_mb: int = 32, sync_bn: bool = False, exact
     eng.dropout_seed = eng.dropout_seed * 8191 + dist.get_rank() + 1
     sess.graph_train = None
     sess.graph_fwd = None
+    eng.grad_source = None
     ex = ExactGradientExchange() if exact else GradientExchange(eng, bucket_mb)
     sess.grad_hook = ex
     if sync_bn:

@@ -79,7 +79,7 @@ class Session:
     def _overlap(self) -> bool:
         """data-parallel exchange overlapped with the tail of backward: needs the builder's split mark and a hook that can
         start on a partial gradient buffer"""
-        return self.eng._split_ops is not None and self.grad_hook is not None and hasattr(self.grad_hook, "start")
+        return len(self.eng.dp_segments) > 1 and self.grad_hook is not None and hasattr(self.grad_hook, "start")
 
     def _train_back(self):
         self.eng.adam(self.lr, grad_scale=self.grad_scale)
@@ -120,14 +120,16 @@ class Session:
             split = self._overlap()
             with torch.cuda.graph(ga, stream=cap):
                 self._train_front(split)
-            gm = None
-            if split:   # backward of stages 1-2 + stem: replayed while the tail of the gradient buffer is being all-reduced
-                gm = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gm, pool=ga.pool(), stream=cap):
-                    e.backward(1)
+            gms = []
+            if split:   # backward of the earlier segments, one graph each: replayed while the finished tail segments of the
+                for k in range(1, len(e.dp_segments)):   # gradient buffer are being all-reduced
+                    gm = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gm, pool=ga.pool(), stream=cap):
+                        e.backward(k)
+                    gms.append(gm)
             with torch.cuda.graph(gb, pool=ga.pool(), stream=cap):
                 self._train_back()
-            self.graph_train = (ga, gb, gm)
+            self.graph_train = (ga, gb, gms)
         else:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=cap):
@@ -175,12 +177,13 @@ class Session:
                 raise A.Sap3dError("synchronised BatchNorm runs in eager mode only (train_step(graph=False))")
             if self.graph_train is None:
                 self.capture(train=True)
-            ga, gb, gm = self.graph_train
+            ga, gb, gms = self.graph_train
             ga.replay()
-            if gm is not None:
-                self.grad_hook.start(e)      # all-reduce of the finished tail (stage 3 + decoder) starts on the comm stream
-                gm.replay()                  # ... while stages 1-2 and the stem run their backward
-                self.grad_hook.finish(e)
+            if gms:
+                for k, gm in enumerate(gms):
+                    self.grad_hook.start(e, k)   # all-reduce of the finished segment k starts on the comm stream ...
+                    gm.replay()                  # ... while the layers ahead of it run their backward
+                self.grad_hook.finish(e)         # last segment (stem + first stage), then wait for all of them
             elif self.grad_hook is not None:
                 self.grad_hook(e)
             gb.replay()

@@ -123,6 +123,26 @@ PERSIST_CASES = [
 ]
 
 
+# halo-tile form of the persistent kernel (taps in triples along the outermost box axis share one activation box); every case
+# must really take it (sap3d_debug_conv_halo_launches counts)
+HALO_CASES = [
+    ("halo along D, 784 tiles, two sub-tiles", 4, 8, 56, 56, [64], 128, (3, 3, 3), (1, 1, 1), False),
+    ("halo along D, two segments, 625 tiles (odd: CTAs end on a single sub-tile)", 25, 8, 20, 20, [64, 64], 128, (3, 3, 3), (1, 1, 1), False),
+    ("halo along D, 256 columns", 4, 8, 56, 56, [64], 256, (3, 3, 3), (1, 1, 1), False),
+    ("halo along H (1x3x3)", 10, 8, 32, 32, [64], 128, (1, 3, 3), (1, 1, 1), False),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=[c[0] for c in HALO_CASES])
+def test_halo_tile_conv(A, case):
+    import os
+    if os.environ.get("SAP3D_CONV_HALO", "1") == "0" or os.environ.get("SAP3D_CONV_MULTICAST", "0") in ("2", "4"):
+        pytest.skip("halo-tile kernels switched off by the environment")
+    before = A.lib.sap3d_debug_conv_halo_launches()
+    run_case(A, *case[1:], dtype=A.BF16, impl=A.IMPL_TC)
+    assert A.lib.sap3d_debug_conv_halo_launches() > before, "the case did not take the halo-tile kernel"
+
+
 @pytest.mark.parametrize("case", PERSIST_CASES, ids=[c[0] for c in PERSIST_CASES])
 def test_persistent_tensor_core_conv(A, case):
     run_case(A, *case[1:], dtype=A.BF16, impl=A.IMPL_TC)
@@ -168,7 +188,7 @@ def test_linearity_at_full_decoder_size(A):
     (bias off) and per-channel statistics consistent with the stored output."""
     dev = "cuda"
     st = torch.cuda.current_stream().cuda_stream
-    N, D, H, W = 2, 8, 56, 56
+    N, D, H, W = 4, 8, 56, 56   # 784 tiles: units of two sub-tiles, the halo-tile kernel of the benchmark's dominant launch
     torch.manual_seed(0)
     xs = [torch.randn(N, D, H, W, 128, device=dev).to(torch.bfloat16) for _ in range(2)]
     w = torch.randn(3, 3, 3, 256, 128, device=dev) * 0.02

@@ -194,7 +194,7 @@ def test_gradcheck_engine_self_consistency(lib_built):
 
 
 def test_split_backward_graphs_match_single_graph(lib_built):
-    """data-parallel overlap path (Session captures fwd + backward[stage 3, decoder] | backward[stages 1-2, stem] | Adam):
+    """data-parallel overlap path (Session captures fwd + backward[last segment] | backward[earlier segments], one graph each | Adam):
     with a no-op exchange hook the gradients and the updated weights are bit-identical to the unsplit graphs"""
     graph, batch, size = "p3d_unetplusplus_ds", 2, 64
     x = O.synthetic_clip(batch, 16, size, seed=0).cuda()
@@ -202,10 +202,13 @@ def test_split_backward_graphs_match_single_graph(lib_built):
 
     class Hook:
         calls = 0
+        segs = []
 
-        def start(self, eng):
+        def start(self, eng, k):
             Hook.calls += 1
-            assert float(eng.flat_g[eng.dp_split_offset:].abs().sum()) > 0      # the tail is complete ...
+            lo, hi = eng.dp_segments[k][2:]
+            Hook.segs.append(k)
+            assert float(eng.flat_g[lo:hi].abs().sum()) > 0      # segment k of the gradient buffer is complete ...
 
         def finish(self, eng):
             Hook.calls += 1
@@ -217,9 +220,10 @@ def test_split_backward_graphs_match_single_graph(lib_built):
         sess.grad_hook = hook
         sess.train_step(x, y, graph=True)      # (capture runs one eager step on a snapshot and restores it)
         torch.cuda.synchronize()
-        res.append((sess.eng.flat_g.clone(), sess.eng.flat_w.clone(), len([g for g in sess.graph_train if g is not None])))
+        nseg = len(sess.eng.dp_segments)
+        res.append((sess.eng.flat_g.clone(), sess.eng.flat_w.clone(), 2 + len(sess.graph_train[2])))
         del sess
-    assert res[0][2] == 2 and res[1][2] == 3 and Hook.calls == 2
+    assert nseg >= 2 and res[0][2] == 2 and res[1][2] == 1 + nseg and Hook.calls == nseg and Hook.segs == list(range(nseg - 1))
     # filter gradients use fp32 atomics (order-dependent in the last bits): compared to 1e-4 relative, not bitwise; the first
     # Adam step moves every weight by ~lr*sign(g), so last-bit differences at g ~ 0 show up as 2*lr on a few weights
     print("split vs single graph: grad rel", rel(res[1][0], res[0][0]), "weights rel", rel(res[1][1], res[0][1]))

@@ -29,7 +29,7 @@ def test_two_nccl_replicas_stay_identical_and_exchange_the_gradient_sum(lib_buil
     for d in res:
         assert d["checksums"][0] == d["checksums"][1], d["checksums"]                   # replicas bit-identical after 3 steps
         assert d["exchanged_vs_fp32_sum_rel"] < 1e-2, d["exchanged_vs_fp32_sum_rel"]     # bf16 buckets: 2^-9 per element
-        assert d["overlap_graphs"] == 3                                                  # the overlapped (split-backward) form ran
+        assert d["overlap_graphs"] == 1 + d["segments"] and d["segments"] >= 2            # the overlapped (split-backward) form ran
         assert d["dropout_seeds"][0] != d["dropout_seeds"][1]
         assert all(l == l for l in d["losses"])
     assert res[0]["losses"] != res[1]["losses"]                                          # different shards

@@ -86,7 +86,7 @@ torch.cuda.synchronize()
 def time_graphs(label):
     sess.graph_train = None
     sess.capture(train=True)
-    graphs = [g for g in (sess.graph_train[0], sess.graph_train[2], sess.graph_train[1]) if g is not None]
+    graphs = [sess.graph_train[0], *sess.graph_train[2], sess.graph_train[1]]
     for _ in range(2):
         for g in graphs:
             g.replay()
