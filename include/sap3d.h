@@ -44,6 +44,8 @@ int sap3d_debug_conv_timing(void* buf);
 /* developer probe: how many convolution launches of this process took the halo-tile kernel (conv_tc.cu) so far; tests use it
  * to prove that a case meant for that kernel did not silently take another one. */
 long long sap3d_debug_conv_halo_launches(void);
+/* ... and how many of those took its swapped-operand form (output channels on the M side, 256 positions per instruction) */
+long long sap3d_debug_conv_swap_launches(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolution family.  Replaces tf.nn.conv3d (p3d.py:19,24,86,112,125,343), tf.nn.bias_add

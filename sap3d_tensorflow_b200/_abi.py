@@ -59,6 +59,7 @@ def _sig(name, argtypes, restype=C.c_int):
 _P = C.POINTER
 _sig("sap3d_debug_conv_timing", [_vp])
 _sig("sap3d_debug_conv_halo_launches", [], C.c_longlong)
+_sig("sap3d_debug_conv_swap_launches", [], C.c_longlong)
 _sig("sap3d_conv_out_dims", [_P(ConvDesc), _P(C.c_int32)])
 _sig("sap3d_conv_stats_rows", [_P(ConvDesc)])
 _sig("sap3d_conv_packed_elems", [_P(ConvDesc), _i32], C.c_size_t)

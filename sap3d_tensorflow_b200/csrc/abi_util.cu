@@ -94,5 +94,6 @@ int sap3d_debug_conv_timing(void* buf) {
   return 0;
 }
 long long sap3d_debug_conv_halo_launches(void) { return sap3d::tc_halo_launches(); }
+long long sap3d_debug_conv_swap_launches(void) { return sap3d::tc_swap_launches(); }
 int sap3d_device_ok(void) { return sap3d::require_device() == 0 ? 1 : 0; }
 }

@@ -863,6 +863,254 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
 }
 
 // -------------------------------------------------------------------------------------------------------------------
+// Persistent halo-tile kernel with SWAPPED operands, for plain convolutions with 64 < cout <= 128:
+//     D[cout (128 TMEM lanes)][256 positions (columns)] = W[128 x K] * X[256 x K]^T
+// With the positions as the M side every tcgen05.mma is 128 x 128 x 16 and reads 4 KB of activations plus 4 KB of weights
+// from shared memory; with the positions as the N side one instruction covers TWO 128-position tiles (128 x 256 x 16: 4 KB of
+// weights + 8 KB of activations for twice the math), which is the form the 256-column data-gradient launches of the same
+// layers already run at (~1.45 vs ~1.23 PFLOP/s stand-alone).  A unit is a PAIR of 128-position tiles that are neighbours
+// along H (tile order is H-fastest here), fetched as ONE box of twice the H extent plus the two halo steps along the outermost
+// axis (<= 320 rows = 40 KB), so the window of tap j is 256 contiguous, swizzle-atom aligned rows.  A CTA's contiguous tile range
+// may start / end on an odd tile: those run as single-tile units (N = 128) through a second set of tensor maps
+// (amap[TC_SWAP_SINGLE_MAP + view]).
+// The accumulator is the TRANSPOSE of the output tile: epilogue thread = channel, so bias / affine / ReLU constants and the
+// BatchNorm sums are per-thread scalars (no warp transposes); 32 positions at a time go through a [32][128] bf16 staging tile
+// in shared memory and leave as 256-byte rows (16-byte stores).
+// -------------------------------------------------------------------------------------------------------------------
+constexpr int TC_SWAP_SINGLE_MAP = 4;     // amap[v] = pair box of view v, amap[4 + v] = single-tile box
+constexpr int TC_SWAP_MAX_ROWS = 320;     // rows of a pair box incl. halo (256 + 2 * 32)
+
+template <int NA, int NW>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_swap_kernel(const __grid_constant__ TcConvParams p) {
+  constexpr int ACT_BYTES = TC_SWAP_MAX_ROWS * 128;     // one activation ring slot (pair box with halo)
+  constexpr int W_BYTES = 128 * 128;                    // one weight tile: 128 couts x 64 channels
+  constexpr int RING_BYTES = NA * ACT_BYTES + NW * W_BYTES;
+  constexpr int STAGE_TILE = 32 * 128 * 2;              // [32 positions][128 channels] bf16
+  constexpr int NBAR = 2 * NA + 2 * NW + 4;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  uint8_t* s_stage = smem + RING_BYTES;                                            // [2][32][128] bf16
+  long long* s_off = reinterpret_cast<long long*>(smem + RING_BYTES + 2 * STAGE_TILE);   // [2][256] output element offset, -1 = outside
+  const uint32_t bar_base = base + RING_BYTES + 2 * STAGE_TILE + 2 * 256 * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RING_BYTES + 2 * STAGE_TILE + 2 * 256 * 8 + NBAR * 8);
+  const uint32_t afull = bar_base, aempty = afull + NA * 8, wfull = aempty + NA * 8, wempty = wfull + NW * 8;
+  const uint32_t tfull = wempty + NW * 8, tempty = tfull + 16;
+  const uint32_t w_ring = base + NA * ACT_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int range_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.m_tiles / gridDim.x);
+  const int range_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.m_tiles / gridDim.x);
+
+  struct Unit { int nsub, mt0, w0, h0, d0, n0; };
+  // tiles are numbered H-fastest; an even tile and its successor are H-neighbours (tiles[1] is even)
+  auto next_unit = [&](int& cur, Unit& t) -> bool {
+    if (cur >= range_end) return false;
+    t.mt0 = cur;
+    t.nsub = ((cur & 1) == 0 && cur + 1 < range_end) ? 2 : 1;
+    cur += t.nsub;
+    int r = t.mt0;
+    const int th = r % p.tiles[1]; r /= p.tiles[1];
+    const int tw = r % p.tiles[0]; r /= p.tiles[0];
+    const int td = r % p.tiles[2];
+    const int tn = r / p.tiles[2];
+    t.w0 = tw * p.box[0]; t.h0 = th * p.box[1]; t.d0 = td * p.box[2]; t.n0 = tn * p.box[3];
+    return true;
+  };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2 * NA + 2 * NW; ++s) mbar_init(bar_base + s * 8, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b * 8, 1);
+      mbar_init(tempty + b * 8, 128);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&p.bmap);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const TcClass cls = p.cls[0];
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int cur = range_begin, sa_i = 0, sw_i = 0;
+      uint32_t pa = 0, pw = 0;
+      Unit t;
+      while (next_unit(cur, t)) {
+        const uint32_t act_bytes = (128 + 2 * p.halo_inner) * t.nsub * 128;
+        const int map_ofs = t.nsub == 2 ? 0 : TC_SWAP_SINGLE_MAP;
+        for (int g = 0; g < cls.tap_count; g += 3) {
+          const TcTap tap = p.taps[cls.tap_begin + g];
+          const int k1 = p.taps[cls.tap_begin + g + 1].kofs, k2 = p.taps[cls.tap_begin + g + 2].kofs;
+          const void* amap = &p.amap[map_ofs + tap.map];
+          for (int ch = 0; ch < tap.nchunk; ++ch) {
+            mbar_wait(aempty + sa_i * 8, pa ^ 1u);
+            mbar_expect_tx(afull + sa_i * 8, act_bytes);
+            tma_load_5d(base + sa_i * ACT_BYTES, amap, afull + sa_i * 8, (tap.c0 + ch) * 64, t.w0 + tap.dw, t.h0 + tap.dh, t.d0 + tap.dd, t.n0);
+            if (++sa_i == NA) { sa_i = 0; pa ^= 1u; }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const int kofs = j == 0 ? tap.kofs : (j == 1 ? k1 : k2);
+              mbar_wait(wempty + sw_i * 8, pw ^ 1u);
+              mbar_expect_tx(wfull + sw_i * 8, W_BYTES);
+              tma_load_3d(w_ring + sw_i * W_BYTES, &p.bmap, wfull + sw_i * 8, kofs + ch * 64, 0, 0);
+              if (++sw_i == NW) { sw_i = 0; pw ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, 256, 0, 0), idesc1 = umma_idesc_bf16(128, 128, 0, 0);
+      int cur = range_begin, it = 0, sa_i = 0, sw_i = 0;
+      uint32_t pa = 0, pw = 0;
+      Unit t;
+      for (; next_unit(cur, t); ++it) {
+        const int buf = it & 1;
+        const uint32_t use = static_cast<uint32_t>(it >> 1);
+        const uint32_t idesc = t.nsub == 2 ? idesc2 : idesc1;
+        const uint32_t tap_step = p.halo_inner * t.nsub * 128;   // bytes between the windows of consecutive taps
+        mbar_wait(tempty + buf * 8, (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * 256;
+        for (int kg = 0; kg < cls.nkb; kg += 3) {
+          mbar_wait(afull + sa_i * 8, pa);
+          const uint32_t sx = base + sa_i * ACT_BYTES;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            mbar_wait(wfull + sw_i * 8, pw);
+            tc_fence_after();
+            const uint64_t wdesc = umma_desc_sw128(w_ring + sw_i * W_BYTES, 16, 1024);
+            const uint64_t xdesc = umma_desc_sw128(sx + j * tap_step, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_bf16(tacc, wdesc + 2 * k, xdesc + 2 * k, idesc, (kg | j | k) != 0 ? 1u : 0u);
+            tc_commit(wempty + sw_i * 8);
+            if (++sw_i == NW) { sw_i = 0; pw ^= 1u; }
+          }
+          tc_commit(aempty + sa_i * 8);
+          if (++sa_i == NA) { sa_i = 0; pa ^= 1u; }
+        }
+        tc_commit(tfull + buf * 8);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5): thread = output channel =================
+    const int q = warp & 3;
+    const int c = q * 32 + lane;          // TMEM lane = output channel
+    const int et = threadIdx.x - 64;      // 0..127
+    const bool cvalid = c < p.cout;
+    const bool want_stats = p.stats != nullptr;
+    const float bias_c = (cvalid && p.bias != nullptr) ? __ldg(p.bias + c) : 0.f;
+    const float scale_c = (cvalid && p.scale != nullptr) ? __ldg(p.scale + c) : 1.f;
+    const float shift_c = (cvalid && p.scale != nullptr) ? __ldg(p.shift + c) : 0.f;
+    const bool affine = p.scale != nullptr;
+    bf16* const out = reinterpret_cast<bf16*>(p.out);
+    int cur = range_begin, it = 0, sb = 0;   // sb: staging tile in use
+    Unit t;
+    for (; next_unit(cur, t); ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      const int npos = 128 * t.nsub;
+      long long* const offs = s_off + (it & 1) * 256;
+      // output offsets of the unit's positions (box order: w fastest, then h over nsub * box[1] rows, then d)
+      for (int i = et; i < npos; i += 128) {
+        int r = i;
+        const int iw = r % p.box[0]; r /= p.box[0];
+        const int bh = p.box[1] * t.nsub;
+        const int ih = r % bh; r /= bh;
+        const int id = r;
+        const int ow = t.w0 + iw, oh = t.h0 + ih, od = t.d0 + id;
+        const bool valid = ow < p.ext[0] && oh < p.ext[1] && od < p.ext[2] && id < p.box[2];
+        offs[i] = valid ? cls.out_ofs + ow * p.so[0] + oh * p.so[1] + od * p.so[2] + t.n0 * p.so[3] : -1ll;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull + buf * 8, use & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * 256 + (static_cast<uint32_t>(q * 32) << 16);
+      float s1 = 0.f, s2 = 0.f;
+      const int nchunk = npos / 32;
+#pragma unroll 1
+      for (int ck = 0; ck < nchunk; ++ck) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tacc + ck * 32, rr);
+        tmem_ld_wait();
+        if (ck + 1 == nchunk) {             // the accumulator has been read out: hand the buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty + buf * 8);
+        }
+        bf16* const st = reinterpret_cast<bf16*>(s_stage + sb * STAGE_TILE);
+        const uint32_t vmask = __ballot_sync(0xffffffffu, offs[ck * 32 + lane] >= 0);   // bit j: position j of the chunk is inside
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = __uint_as_float(rr[j]) + bias_c;
+          if (want_stats) {
+            const float m = ((vmask >> j) & 1u) ? v : 0.f;
+            s1 += m;
+            s2 = fmaf(m, m, s2);
+          }
+          if (affine) v = fmaf(v, scale_c, shift_c);
+          if (p.relu) v = fmaxf(v, 0.f);
+          st[j * 128 + c] = __float2bfloat16_rn(v);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // 32 positions x 256 B: thread -> (row et / 16 of each group of 8 positions, 16-byte segment et % 16)
+        const int seg = et & 15;
+        if (seg * 8 < p.cout) {
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int pl = ps * 8 + (et >> 4);
+            const long long o = offs[ck * 32 + pl];
+            if (o >= 0) {
+              uint4 val = *reinterpret_cast<const uint4*>(st + pl * 128 + seg * 8);
+              bf16* dst = out + o + seg * 8;
+              if (p.accumulate) {
+                float e[8], w8[8];
+                Vec8<bf16>::load(dst, e);
+                Vec8<bf16>::unpack(val, w8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w8[j] += e[j];
+                Vec8<bf16>::store(dst, w8);
+              } else {
+                *reinterpret_cast<uint4*>(dst) = val;
+              }
+            }
+          }
+        }
+        sb ^= 1;   // the other staging tile is free: its readers passed the bar.sync of the previous chunk
+        if (want_stats && (ck & 3) == 3) {   // 128 positions done: one statistics row per 128-position tile
+          if (cvalid) {
+            const long long srow = t.mt0 + (ck >> 2);
+            p.stats[(srow * 2 + 0) * p.cout + c] = s1;
+            p.stats[(srow * 2 + 1) * p.cout + c] = s2;
+          }
+          s1 = 0.f;
+          s2 = 0.f;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
 // Persistent kernel, 2-CTA cluster with MULTICAST weight tiles (single-class problems = plain convolutions).
 // The persistent kernel above is bound by the L2->SM crossbar (ncu: 4.17 GB per launch of the dominant decoder conv, 14.4
 // TB/s): per 64-channel k-block a CTA pulls MT x 16 KB of activations and BLOCK_N x 128 B of weights, and every CTA pulls
@@ -1382,6 +1630,33 @@ static int launch_persist(const TcConvParams& prm, int units, cudaStream_t strea
   return 0;
 }
 
+template <int NA, int NW>
+static int launch_swap(const TcConvParams& prm, cudaStream_t stream, char* err, size_t errlen) {
+  constexpr int SMEM = NA * TC_SWAP_MAX_ROWS * 128 + NW * 128 * 128 + 2 * 32 * 128 * 2 + 2 * 256 * 8 + (2 * NA + 2 * NW + 4) * 8 + 16 + 1024;
+  static_assert(SMEM <= 232448, "swapped-operand conv kernel exceeds the 227 KB of shared memory a CTA can opt in to");
+  static bool attr_done = false;
+  static int sms = 0;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_swap_kernel<NA, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "cudaFuncSetAttribute(conv_tc_swap) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) sms = 148;
+    attr_done = true;
+  }
+  const int ctas = prm.m_tiles / 2 < sms ? prm.m_tiles / 2 : sms;
+  cudaError_t e = launch_k(conv_tc_swap_kernel<NA, NW>, dim3((unsigned)ctas), dim3(TC_THREADS), SMEM, stream, 1, prm);
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "conv_tc_swap launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
 template <int BLOCK_N, int STAGES, int MT, int CL>
 static int launch_persist_mc(const TcConvParams& prm, int m_groups, cudaStream_t stream, char* err, size_t errlen) {
   constexpr int SMEM = STAGES * (MT * 128 * 128 + BLOCK_N * 128) + (2 * STAGES + 4) * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
@@ -1424,8 +1699,9 @@ static int launch_persist_mc(const TcConvParams& prm, int m_groups, cudaStream_t
 
 static unsigned long long* g_conv_dbg = nullptr;
 void tc_set_debug_buffer(void* buf) { g_conv_dbg = reinterpret_cast<unsigned long long*>(buf); }
-static long long g_halo_launches = 0;
+static long long g_halo_launches = 0, g_swap_launches = 0;
 long long tc_halo_launches() { return g_halo_launches; }
+long long tc_swap_launches() { return g_swap_launches; }
 
 // opt-in while it is being measured: SAP3D_CONV_MULTICAST=2 or 4 (cluster size); unset / 0 = off
 static int multicast_cluster() {
@@ -1445,6 +1721,15 @@ static int halo_mode() {
     v = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
   }
   return v;
+}
+// SAP3D_CONV_SWAP=0: halo-tile launches with 64 < cout <= 128 keep the positions on the M side (no swapped-operand kernel)
+static bool swap_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAP3D_CONV_SWAP");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 // SAP3D_CONV_BALANCED=0: persistent kernels take units round-robin even where contiguous equal ranges are possible
 static bool balanced_enabled() {
@@ -1554,7 +1839,7 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
   }
   if (block_n > 64 && pb.rowsB % block_n != 0 && pb.rowsB < block_n) block_n = 64;
   // halo-tile kernel: persistent one-class problems with one column tile whose taps form triples along H or D
-  bool use_halo = false;
+  bool use_halo = false, use_swap = false;
   {
     const long long n_tiles0 = (pb.cout + block_n - 1) / block_n;
     const long long ctas0 = (long long)m.classes.size() * m_tiles * n_tiles0;
@@ -1567,9 +1852,22 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
       if (plan_halo(m, m_tiles, hp)) {
         int hbox[4] = {hp.box[0], hp.box[1], hp.box[2], hp.box[3]};
         hbox[hp.axis] += 2;
+        // swapped operands (positions on the N side, 256 per instruction): halo along D, tiles paired along H
+        use_swap = swap_enabled() && hp.axis == 2 && block_n == 128 && pb.cout > 64 && pb.cout <= 128 && !pb.out_f32 && pb.out2 == nullptr &&
+                   mt0 == 2 && (int)m.views.size() <= TC_SWAP_SINGLE_MAP && ((m.ext[1] + hp.box[1] - 1) / hp.box[1]) % 2 == 0 &&
+                   2 * (128 + 2 * hp.inner) <= TC_SWAP_MAX_ROWS && hp.tiles >= 2 * 148;
         bool enc_ok = true;
-        for (size_t v = 0; v < m.views.size() && enc_ok; ++v)
-          enc_ok = encode_view(&prm.amap[v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, hbox, err, errlen) == 0;
+        for (size_t v = 0; v < m.views.size() && enc_ok; ++v) {
+          if (use_swap) {
+            int pbox[4] = {hbox[0], 2 * hbox[1], hbox[2], hbox[3]};
+            enc_ok = encode_view(&prm.amap[v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, pbox, err, errlen) == 0 &&
+                     encode_view(&prm.amap[TC_SWAP_SINGLE_MAP + v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, hbox, err,
+                                 errlen) == 0;
+          } else {
+            enc_ok = encode_view(&prm.amap[v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, hbox, err, errlen) == 0;
+          }
+        }
+        if (!enc_ok) use_swap = false;
         if (enc_ok) {
           use_halo = true;
           for (int i = 0; i < 4; ++i) box[i] = hp.box[i];
@@ -1683,6 +1981,10 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
       return 1;
     }
     ++g_halo_launches;
+    if (use_swap) {
+      ++g_swap_launches;
+      return launch_swap<3, 5>(prm, stream, err, errlen);
+    }
     if (block_n == 128) return mt == 2 ? launch_persist<128, 3, 2, 6>(prm, (int)grid, stream, err, errlen) : launch_persist<128, 3, 1, 6>(prm, (int)grid, stream, err, errlen);
     return mt == 2 ? launch_persist<256, 2, 2, 3>(prm, (int)grid, stream, err, errlen) : launch_persist<256, 3, 1, 4>(prm, (int)grid, stream, err, errlen);
   }

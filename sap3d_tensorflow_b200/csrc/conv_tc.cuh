@@ -60,6 +60,8 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
 void tc_set_debug_buffer(void* buf);
 // launches that took the halo-tile persistent kernel so far (process-wide)
 long long tc_halo_launches();
+// ... and, of those, the swapped-operand kernel (positions on the N side)
+long long tc_swap_launches();
 
 // wgrad: D[m][n] (+)= sum_pos P(pos + off)[m] * Q(pos)[n], fp32 atomics into dw
 struct TcWgradTap {

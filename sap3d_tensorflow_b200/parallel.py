@@ -10,6 +10,9 @@ parity runs -- two small latency-bound collectives per norm layer, eager mode on
 """
 from __future__ import annotations
 
+import os
+from typing import Optional
+
 import torch
 import torch.distributed as dist
 
@@ -79,9 +82,11 @@ class GradientExchange:
     def _reduce(self, eng, k):
         lo, hi = self.segments[k]
         cur = torch.cuda.current_stream(eng.device)
-        A.check(A.lib.sap3d_cast(A.F32, A.ptr(eng.flat_g[lo:hi]), A.ptr(self.buf[lo:hi]), hi - lo, cur.cuda_stream), "grad cast")
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
+            # the narrowing pass runs on the communication stream too: the main stream goes straight on to the next backward
+            # segment, which writes a disjoint part of flat_g
+            A.check(A.lib.sap3d_cast(A.F32, A.ptr(eng.flat_g[lo:hi]), A.ptr(self.buf[lo:hi]), hi - lo, self.comm_stream.cuda_stream), "grad cast")
             self._works += [dist.all_reduce(self.buf[a:b], op=dist.ReduceOp.SUM, async_op=True) for a, b in self.seg_buckets[k]]
 
     def start(self, eng, k: int = 0):
@@ -150,12 +155,14 @@ class ExactGradientExchange:
         dist.all_reduce(eng.flat_g, op=dist.ReduceOp.SUM, group=self.group)
 
 
-def attach_data_parallel(sess, bucket_mb: int = 32, sync_bn: bool = False, exact: bool = False):
+def attach_data_parallel(sess, bucket_mb: Optional[int] = None, sync_bn: bool = False, exact: bool = False):
     """installs the gradient all-reduce between backward and Adam; broadcasts rank 0's variables.
     sync_bn: BatchNorm statistics over the global batch (parity option).  exact: fp32 un-bucketed exchange."""
     if not dist.is_initialized():
         raise A.Sap3dError("torch.distributed is not initialised")
     eng = sess.eng
+    if bucket_mb is None:
+        bucket_mb = int(os.environ.get("SAP3D_DP_BUCKET_MB", "32"))
     dist.broadcast(eng.flat_w, src=0)
     eng.pack_weights()
     # every replica draws its own dropout masks: fold the rank into the seed before the step is captured (the mask hash

@@ -143,6 +143,27 @@ def test_halo_tile_conv(A, case):
     assert A.lib.sap3d_debug_conv_halo_launches() > before, "the case did not take the halo-tile kernel"
 
 
+# swapped-operand form of the halo-tile kernel (64 < cout <= 128: channels on the M side, pairs of H-neighbour tiles = 256 positions
+# per instruction, single tiles where a CTA's range starts / ends on an odd tile); expected launches of it per case
+SWAP_CASES = [
+    ("swap: 784 tiles", 1, 4, 8, 56, 56, [64], 128, (3, 3, 3), (1, 1, 1), False),
+    ("swap: ragged W (54 / 8), 630 tiles, cout 96", 1, 3, 8, 60, 54, [64], 96, (3, 3, 3), (1, 1, 1), False),
+    ("swap: boxes (16,1,8), ragged W (30 / 16), 128 -> 128: the data gradient (plain and accumulating) takes it too", 3, 3, 24, 36, 30, [128], 128, (3, 3, 3),
+     (1, 1, 1), False),
+]
+
+
+@pytest.mark.parametrize("case", SWAP_CASES, ids=[c[0] for c in SWAP_CASES])
+def test_swapped_operand_halo_conv(A, case):
+    import os
+    if any(os.environ.get(k, "1") == "0" for k in ("SAP3D_CONV_HALO", "SAP3D_CONV_SWAP")) or os.environ.get("SAP3D_CONV_MULTICAST", "0") in ("2", "4"):
+        pytest.skip("swapped-operand kernel switched off by the environment")
+    before = A.lib.sap3d_debug_conv_swap_launches()
+    # cout % 64 != 0: the forward runs on the tensor cores, the data / filter gradients fall to the CUDA-core kernels (IMPL_AUTO)
+    run_case(A, *case[2:], dtype=A.BF16, impl=A.IMPL_TC if case[8] % 64 == 0 else A.IMPL_AUTO)
+    assert A.lib.sap3d_debug_conv_swap_launches() - before == case[1], "launches of the swapped-operand kernel"
+
+
 @pytest.mark.parametrize("case", PERSIST_CASES, ids=[c[0] for c in PERSIST_CASES])
 def test_persistent_tensor_core_conv(A, case):
     run_case(A, *case[1:], dtype=A.BF16, impl=A.IMPL_TC)
