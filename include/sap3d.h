@@ -338,7 +338,8 @@ typedef struct sap3d_pack_entry {
   void* dst;          /* bf16 [rows_pad][taps*cols] */
   int32_t taps, rows, rows_pad, cols;
   int64_t s_tap, s_r, s_c;
-  int64_t start;      /* first element of this entry in the concatenated index space (filled by the caller) */
+  int64_t start;      /* first element of this entry in the concatenated index space (filled by the caller; index space only,
+                         not memory: every start and the total passed to sap3d_pack_multi are multiples of 4096) */
 } sap3d_pack_entry;
 /* fills up to two entries (forward / data-gradient operand; NULL destination skips one); returns the count */
 int sap3d_conv_pack_entries(const sap3d_conv_desc* d, const float* w_tf, void* w_fwd, void* w_dgrad, sap3d_pack_entry* out2);

@@ -301,8 +301,8 @@ class Engine:
                 n = A.lib.sap3d_conv_pack_entries(C.byref(c.desc), A.ptr(c.w.w), A.ptr(c.wf), A.ptr(c.wd), two)
                 for i in range(n):
                     e = two[i]
-                    e.start = start
-                    start += e.rows_pad * e.taps * e.cols
+                    e.start = start      # index space only: starts (and the total) are multiples of the kernel's 4096-element span
+                    start += (e.rows_pad * e.taps * e.cols + 4095) // 4096 * 4096
                     ents.append(bytes(e))
             raw = b"".join(ents)
             self._pack_n, self._pack_total = len(ents), start

@@ -60,20 +60,25 @@ def split_buckets(n: int, per: int, split: int):
 
 
 class GradientExchange:
-    """sum-all-reduce of the flat gradient buffer as bf16 buckets on a communication stream.  The reduced buckets stay in
-    `buf` and Adam reads them there (Engine.grad_source): no pass widens them back into the fp32 buffer.
-    Overlapped form (the builders' mark_dp_split cuts backward into segments, one CUDA graph each): start(eng, k) after segment k
-    of the backward has finished -- its share of the gradient buffer is cast and its buckets are queued while the next segment
-    runs --, finish(eng) after the last one."""
+    """sum-all-reduce of the flat gradient buffer as bf16 on a communication stream.  The reduced values stay in `buf` and
+    Adam reads them there (Engine.grad_source): no pass widens them back into the fp32 buffer.
+    Default (measured best at 2 and 8 GPUs, profiles/r02_c14_dp_timeline_8gpu.txt): ONE all-reduce call over the whole
+    buffer after backward -- 0.59 ms for 170 MB on 8 GPUs; 32 MB buckets cost 1.01 ms for the same bytes.
+    Overlapped form (overlap=True / SAP3D_DP_OVERLAP=1; the builders' mark_dp_split cuts backward into segments, one CUDA graph
+    each): start(eng, k) after segment k of the backward has finished -- its share of the gradient buffer is cast and its
+    all-reduce is queued while the next segment runs --, finish(eng) after the last one.  On this hardware the backward segment
+    that runs beside the all-reduce slows down by the all-reduce's own duration, so the overlap buys nothing (18.70 vs 18.49 ms
+    per step at 8 GPUs) and it is not the default."""
 
-    def __init__(self, eng, bucket_mb: int = 32):
+    def __init__(self, eng, bucket_mb: int = 0, overlap: bool = False):
         self.eng = eng
         n = eng.n_train
         self.n = n
         self.buf = torch.zeros(n, device=eng.device, dtype=torch.bfloat16)
-        per = bucket_mb * 1024 * 1024 // 2
+        per = bucket_mb * 1024 * 1024 // 2 if bucket_mb > 0 else n      # 0 = one all-reduce call per segment / buffer
         self.buckets = make_buckets(n, per)
-        self.segments = [(g_lo, g_hi) for (_, _, g_lo, g_hi) in eng.dp_segments] if len(eng.dp_segments) > 1 else []
+        self.overlap = bool(overlap) and len(eng.dp_segments) > 1
+        self.segments = [(g_lo, g_hi) for (_, _, g_lo, g_hi) in eng.dp_segments] if self.overlap else []
         self.seg_buckets = segment_buckets(self.segments, per)
         self.comm_stream = torch.cuda.Stream(device=eng.device)
         self._works = []
@@ -155,14 +160,18 @@ class ExactGradientExchange:
         dist.all_reduce(eng.flat_g, op=dist.ReduceOp.SUM, group=self.group)
 
 
-def attach_data_parallel(sess, bucket_mb: Optional[int] = None, sync_bn: bool = False, exact: bool = False):
+def attach_data_parallel(sess, bucket_mb: Optional[int] = None, sync_bn: bool = False, exact: bool = False, overlap: Optional[bool] = None):
     """installs the gradient all-reduce between backward and Adam; broadcasts rank 0's variables.
-    sync_bn: BatchNorm statistics over the global batch (parity option).  exact: fp32 un-bucketed exchange."""
+    sync_bn: BatchNorm statistics over the global batch (parity option).  exact: fp32 un-bucketed exchange.
+    bucket_mb: 0 = one all-reduce call (default; SAP3D_DP_BUCKET_MB overrides); overlap: run the exchange of finished backward
+    segments beside the rest of backward (default off; SAP3D_DP_OVERLAP=1)."""
     if not dist.is_initialized():
         raise A.Sap3dError("torch.distributed is not initialised")
     eng = sess.eng
     if bucket_mb is None:
-        bucket_mb = int(os.environ.get("SAP3D_DP_BUCKET_MB", "32"))
+        bucket_mb = int(os.environ.get("SAP3D_DP_BUCKET_MB", "0"))
+    if overlap is None:
+        overlap = os.environ.get("SAP3D_DP_OVERLAP", "0") == "1"
     dist.broadcast(eng.flat_w, src=0)
     eng.pack_weights()
     # every replica draws its own dropout masks: fold the rank into the seed before the step is captured (the mask hash
@@ -171,7 +180,7 @@ def attach_data_parallel(sess, bucket_mb: Optional[int] = None, sync_bn: bool = 
     sess.graph_train = None
     sess.graph_fwd = None
     eng.grad_source = None
-    ex = ExactGradientExchange() if exact else GradientExchange(eng, bucket_mb)
+    ex = ExactGradientExchange() if exact else GradientExchange(eng, bucket_mb, overlap)
     sess.grad_hook = ex
     if sync_bn:
         enable_sync_batch_norm(sess)

@@ -79,7 +79,8 @@ class Session:
     def _overlap(self) -> bool:
         """data-parallel exchange overlapped with the tail of backward: needs the builder's split mark and a hook that can
         start on a partial gradient buffer"""
-        return len(self.eng.dp_segments) > 1 and self.grad_hook is not None and hasattr(self.grad_hook, "start")
+        return (len(self.eng.dp_segments) > 1 and self.grad_hook is not None and hasattr(self.grad_hook, "start")
+                and getattr(self.grad_hook, "overlap", True))
 
     def _train_back(self):
         self.eng.adam(self.lr, grad_scale=self.grad_scale)

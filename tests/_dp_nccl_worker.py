@@ -37,7 +37,7 @@ def main():
 
     # (1) local gradient of this replica, no exchange (same weights everywhere: rank 0's, broadcast below)
     sess = build(1234)
-    parallel.attach_data_parallel(sess)                   # broadcast + bf16 bucket exchange + per-rank dropout seed
+    parallel.attach_data_parallel(sess)                   # broadcast + bf16 exchange (SAP3D_DP_OVERLAP picks the form) + per-rank dropout seed
     w0 = sess.eng.flat_w.clone()
     seeds = [None] * world
     dist.all_gather_object(seeds, int(sess.eng.dropout_seed))
@@ -64,7 +64,7 @@ def main():
     all_cs = [None] * world
     dist.all_gather_object(all_cs, cs)
     out = {"rank": rank, "world": world, "exchanged_vs_fp32_sum_rel": rel, "checksums": all_cs, "losses": losses, "dropout_seeds": seeds,
-           "overlap_graphs": 2 + len(sess.graph_train[2]), "segments": len(sess.eng.dp_segments)}
+           "overlap_graphs": 2 + len(sess.graph_train[2]), "segments": len(sess.eng.dp_segments), "overlap": bool(hook.overlap)}
     json.dump(out, open(os.environ["SAP3D_OUT"] + f".{rank}", "w"))
     dist.destroy_process_group()
 

@@ -231,6 +231,43 @@ def test_split_backward_graphs_match_single_graph(lib_built):
     assert rel(res[1][1], res[0][1]) < 1e-4
 
 
+def test_one_launch_repack_matches_the_per_filter_packing(lib_built):
+    """Engine.pack_weights (sap3d_pack_multi: every filter of the graph in one launch, 64 x 64 transposing tiles) produces
+    bit-identical bf16 operands to sap3d_conv_pack_weights filter by filter -- forward and data-gradient operands, transposed
+    convolutions, the decoder's segment-concatenated filters and the stem included"""
+    import ctypes as C
+
+    from sap3d_tensorflow_b200 import _abi as A
+
+    for graph in ("p3d_unetplusplus_ds", "p3d_concat"):
+        sess = build(graph, "bf16", True, 1, 64, dropout=0.0)
+        eng = sess.eng
+        torch.manual_seed(3)
+        eng.flat_w[:eng.n_train].copy_(torch.randn(eng.n_train, device="cuda"))
+        eng.pack_weights()
+        torch.cuda.synchronize()
+        st = torch.cuda.current_stream().cuda_stream
+        checked = 0
+        for c in eng.convs:
+            if c.wf is None and c.wd is None:
+                continue
+            wf = torch.full_like(c.wf, float("nan")) if c.wf is not None else None
+            wd = torch.full_like(c.wd, float("nan")) if c.wd is not None else None
+            A.check(A.lib.sap3d_conv_pack_weights(C.byref(c.desc), A.ptr(c.w.w), A.ptr(wf), A.ptr(wd), st), "pack")
+            torch.cuda.synchronize()
+            two = (A.PackEntry * 2)()
+            n = A.lib.sap3d_conv_pack_entries(C.byref(c.desc), A.ptr(c.w.w), A.ptr(c.wf), A.ptr(c.wd), two)
+            for i in range(n):     # compare exactly the ranges the table covers
+                e = two[i]
+                cnt = e.rows_pad * e.taps * e.cols
+                for got, ref in ((c.wf, wf), (c.wd, wd)):
+                    if got is not None and got.data_ptr() == e.dst:
+                        assert torch.equal(got[:cnt].view(torch.int16), ref[:cnt].view(torch.int16)), (graph, c.name, i)
+                        checked += 1
+        assert checked > 50, checked
+        del sess
+
+
 def test_prefetched_inputs_give_the_same_step(lib_built):
     """Session.prefetch() (H2D of the next batch on a copy stream) + train_step(None, None) == train_step(x, y)"""
     graph, batch, size = "p3d_unet", 2, 64

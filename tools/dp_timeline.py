@@ -4,6 +4,7 @@ backward segment, the exchange tail (finish), the optimizer graph -- for three m
   none    : graphs split as in production, no collective at all (hook that does nothing)   -> cost of splitting the graph
   serial  : one exchange after the whole backward (no overlap)                              -> raw all-reduce time
   overlap : production
+  *_1bucket : the same with one all-reduce call per segment instead of 32 MB buckets
 Prints one line per mode.  usage: torchrun ... tools/dp_timeline.py [batch] [size] [steps]"""
 import os
 import sys
@@ -40,14 +41,15 @@ def main():
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     x = ((torch.randint(0, 256, (B, 16, size, size, 3), generator=g).float() - torch.tensor([90.0, 102.0, 98.0])) / 255.0).to(dev)
     y = (torch.randint(0, 256, (B, 16, size, size), generator=g).float() / 255.0).to(dev)
-    for mode in ("none", "serial", "overlap"):
+    for mode in ("none", "serial", "serial_1bucket", "overlap", "overlap_1bucket"):
         xin = sp.placeholder([B, 16, size, size, 3], dtype="bf16", training_graph=True, device=f"cuda:{local}")
         sess = sp.Session(sp.p3d.p3d_unetplusplus_ds(xin, 0.5, B, True))
         if world > 1:
-            ex = parallel.attach_data_parallel(sess)
+            parallel.attach_data_parallel(sess, bucket_mb=0 if mode.endswith("1bucket") else 32, overlap=True)
         if mode == "none" or world == 1:
             sess.grad_hook = NoComm()
-        elif mode == "serial":
+            sess.eng.grad_source = None
+        elif mode.startswith("serial"):
             hook = sess.grad_hook
 
             class Serial:            # no start/finish attributes -> Session captures the unsplit graphs
