@@ -31,6 +31,7 @@ constexpr int TC_MAX_MAPS = 28;   // 27 parity views of dy (transposed conv k3 s
 constexpr int TC_MAX_TAPS = 128;
 constexpr int TC_MAX_CLS = 64;
 constexpr int TC_THREADS = 192;
+constexpr int TC_QD = 4;          // persistent kernels: depth of the in-CTA unit queue (producer -> MMA / epilogue warps)
 constexpr int TC_HALO_MAX_ROWS = 160;   // halo-tile kernels: 128 + 2 * halo_inner rows per activation box, halo_inner <= 16
 
 struct TcTap {
@@ -66,7 +67,10 @@ struct alignas(64) TcConvParams {
   const float* shift;
   int relu, accumulate, out_f32;
   int b_batched;       // the weight-side operand is per sample: third TMA coordinate = the tile's batch index
-  int balanced;        // persistent kernels: contiguous, equally long m-tile ranges per CTA (one class, one column tile)
+  int balanced;        // persistent kernels, one class and one column tile: units are m-tile groups, singles at the end
+  int n_units;         // persistent kernels: work units handed out through the ticket counter
+  int n_pair_units;    // balanced: units [0, n_pair_units) are groups of MT consecutive m-tiles, the rest single m-tiles
+  unsigned int* sched; // persistent kernels: {next unit ticket, CTAs finished}; zero at launch, reset by the last CTA
   int halo_rows;       // halo-tile kernels: rows of one activation box (128 + 2 * halo_inner); taps are sorted in triples
   int halo_inner;      // ... rows per step along the halo axis (product of the inner box extents; multiple of 8)
   unsigned long long* dbg;   // phase-timing probe (tools/conv_phase_probe.py): [cta][16][2] = (clock64, globaltimer); normally NULL
@@ -485,6 +489,19 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 // unit i+1, the TMA ring never drains between units, and the wave-quantisation tail of a 5.3-wave launch disappears
 // (every SM gets floor or ceil of units/SMs).
 // =================================================================================================
+// ticket counter of the persistent kernels: every CTA's last act.  All of a CTA's draws precede its call, so when the last CTA
+// arrives no draw is outstanding and the pair can be zeroed for the slot's next user.
+SAP3D_DEVINL void sched_finish(unsigned int* sched) {
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(sched + 1, 1u);
+    if (prev == gridDim.x - 1) {
+      sched[0] = 0u;
+      sched[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
 // HALO = 0: every k-block (tap, 64-channel chunk) is one ring stage holding MT activation boxes and one weight tile.
 // HALO = NB > 0 ("halo tile"): filter taps come in triples that differ only by -1/0/+1 along the OUTERMOST axis of the
 // output box (p.halo_inner rows per step, a multiple of 8).  One TMA box with two extra steps along that axis
@@ -493,11 +510,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 // activation bytes pulled over the L2->SM fabric drop from 3 x 16 KB to halo_rows x 128 B (20 KB at halo_inner = 16) per
 // sub-tile and tap triple -- the fabric is what bounds the non-halo kernel (ncu: 4.17 GB per launch of the dominant decoder
 // conv at ~14 TB/s).  Activations and weights then have separate rings: STAGES halo buffers, HALO weight tiles.
-// Units: p.balanced (one class, one column tile) gives every CTA a CONTIGUOUS range of m-tiles of near-equal length
-// (floor or ceil of m_tiles / gridDim.x), walked in groups of MT with a last group of fewer sub-tiles; otherwise units are
-// (class, MT-group, column tile) triples taken round-robin.  Sub-tiles that are not live are neither loaded nor multiplied.
+// Units are handed out DYNAMICALLY: the producer thread of every CTA draws the next unit index from a ticket counter in global
+// memory (p.sched) and passes it to the MMA and epilogue warps through a small shared-memory queue.  A CTA that gets its SM late
+// (the SM was held by a filter-gradient CTA of the side stream, or by an NCCL kernel) simply draws fewer units instead of sitting
+// on a fixed share of the work while the others idle; the static form doubled the kernel's duration whenever a few of the 148
+// CTAs could not be resident at once.  p.balanced (one class, one column tile): units are groups of MT consecutive m-tiles
+// followed by about one single m-tile per SM, so the ragged end of the kernel is one sub-tile long; otherwise units are
+// (class, MT-group, column tile) triples.  Sub-tiles that are not live are neither loaded nor multiplied.
 template <int BLOCK_N, int STAGES, int MT, int HALO = 0>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __grid_constant__ TcConvParams p, const int total_units) {
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __grid_constant__ TcConvParams p) {
   constexpr int A_BYTES = 128 * 128;
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
@@ -514,32 +535,46 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
   // HALO = 0: full[STAGES], empty[STAGES], tfull[2], tempty[2]
   // HALO > 0: afull[STAGES], aempty[STAGES], bfull[HALO], bempty[HALO], tfull[2], tempty[2]
   constexpr int NRING_BAR = HALO ? 2 * STAGES + 2 * HALO : 2 * STAGES;
-  constexpr int NBAR = NRING_BAR + 4;
+  constexpr int NBAR = NRING_BAR + 4 + 2 * TC_QD;   // ..., tfull[2], tempty[2], qfull[TC_QD], qempty[TC_QD]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RING_BYTES + NBAR * 8);
-  float* s_stats = reinterpret_cast<float*>(smem + RING_BYTES + NBAR * 8 + 16);  // [4][2][BLOCK_N]
+  int* s_q = reinterpret_cast<int*>(smem + RING_BYTES + NBAR * 8 + 16);           // unit queue [TC_QD]
+  float* s_stats = reinterpret_cast<float*>(smem + RING_BYTES + NBAR * 8 + 32);  // [4][2][BLOCK_N]
   float* s_ep = s_stats + 4 * 2 * BLOCK_N;                                        // [3][BLOCK_N]
   const uint32_t tfull = bar_base + NRING_BAR * 8, tempty = tfull + 16;
+  const uint32_t qfull = tempty + 16, qempty = qfull + TC_QD * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_groups = (p.m_tiles + MT - 1) / MT;
-  // balanced mode: this CTA's contiguous range of m-tiles
-  const int range_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.m_tiles / gridDim.x);
-  const int range_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.m_tiles / gridDim.x);
 
   struct Unit { int nt, cls_id, nsub; int mts[MT], w0s[MT], h0s[MT], d0s[MT], n0s[MT]; };
-  // cursor: balanced = next m-tile of the range, else the unit index; returns false when this CTA is done
-  auto next_unit = [&](int& cur, Unit& t) -> bool {
+  struct Cursor { int qi; uint32_t qp; };
+  // producer = true: draws a ticket and publishes it; false: takes the next published unit.  Returns false when the work is gone.
+  auto next_unit = [&](Cursor& cq, Unit& t, const bool producer) -> bool {
+    int u;
+    if (producer) {
+      mbar_wait(qempty + cq.qi * 8, cq.qp ^ 1u);
+      u = static_cast<int>(atomicAdd(p.sched, 1u));
+      if (u >= p.n_units) u = -1;
+      s_q[cq.qi] = u;
+      mbar_arrive(qfull + cq.qi * 8);
+    } else {
+      mbar_wait(qfull + cq.qi * 8, cq.qp);
+      u = s_q[cq.qi];
+      mbar_arrive(qempty + cq.qi * 8);
+    }
+    if (++cq.qi == TC_QD) { cq.qi = 0; cq.qp ^= 1u; }
+    if (u < 0) return false;
     int mt0;
     if (p.balanced) {
-      if (cur >= range_end) return false;
       t.nt = 0;
       t.cls_id = 0;
-      mt0 = cur;
-      t.nsub = min(MT, range_end - cur);
-      cur += t.nsub;
+      if (u < p.n_pair_units) {
+        mt0 = u * MT;
+        t.nsub = MT;
+      } else {
+        mt0 = p.n_pair_units * MT + (u - p.n_pair_units);
+        t.nsub = 1;
+      }
     } else {
-      if (cur >= total_units) return false;
-      int u = cur;
-      cur += gridDim.x;
       t.nt = u % p.n_tiles;
       u /= p.n_tiles;
       t.cls_id = u / m_groups;
@@ -558,20 +593,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
     }
     return true;
   };
-  const int cur0 = p.balanced ? range_begin : static_cast<int>(blockIdx.x);
 
   if (warp == 0 && lane == 0) {
-    if (HALO) {
-      for (int s = 0; s < 2 * STAGES + 2 * HALO; ++s) mbar_init(bar_base + s * 8, 1);
-    } else {
-      for (int s = 0; s < STAGES; ++s) {
-        mbar_init(bar_base + s * 8, 1);
-        mbar_init(bar_base + (STAGES + s) * 8, 1);
-      }
-    }
+    for (int s = 0; s < NRING_BAR; ++s) mbar_init(bar_base + s * 8, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull + b * 8, 1);
       mbar_init(tempty + b * 8, 128);
+    }
+    for (int s = 0; s < TC_QD; ++s) {
+      mbar_init(qfull + s * 8, 1);
+      mbar_init(qempty + s * 8, 129);   // the MMA thread + 128 epilogue threads
     }
     fence_mbar_init();
     tma_prefetch_desc(&p.bmap);
@@ -590,7 +621,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
   if (warp == 0) {
     // ================= TMA producer: one continuous ring over all units =================
     if (lane == 0) {
-      int cur = cur0;
+      Cursor cur = {0, 0u};
       Unit t;
       if (HALO) {
         const uint32_t afull = bar_base, aempty = bar_base + STAGES * 8, bfull = bar_base + 2 * STAGES * 8, bempty = bfull + HALO * 8;
@@ -598,7 +629,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
         const uint32_t halo_bytes = p.halo_rows * 128;
         int sa_i = 0, sb_i = 0;
         uint32_t pa = 0, pb = 0;
-        while (next_unit(cur, t)) {
+        while (next_unit(cur, t, true)) {
           const TcClass cls = p.cls[t.cls_id];
           for (int g = 0; g < cls.tap_count; g += 3) {
             const TcTap tap = p.taps[cls.tap_begin + g];       // lowest offset along the halo axis: the box origin
@@ -627,7 +658,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
       } else {
         int stage = 0;
         uint32_t phase = 0;
-        while (next_unit(cur, t)) {
+        while (next_unit(cur, t, true)) {
           const uint32_t tx_bytes = t.nsub * p.box_rows * 128 + B_BYTES;
           const TcClass cls = p.cls[t.cls_id];
           for (int ti = 0; ti < cls.tap_count; ++ti) {
@@ -655,11 +686,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N, 0, 0);
-      int cur = cur0, it = 0;
+      Cursor cur = {0, 0u};
+      int it = 0;
       Unit t;
       int stage = 0, sb_i = 0;
       uint32_t phase = 0, pb = 0;
-      for (; next_unit(cur, t); ++it) {
+      for (; next_unit(cur, t, false); ++it) {
         const int buf = it % NBUF;
         const uint32_t use = static_cast<uint32_t>(it / NBUF);
         const int nkb = p.cls[t.cls_id].nkb;
@@ -721,9 +753,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
     const int row = q * 32 + lane;
     const bool want_stats = p.stats != nullptr;
     const int et = threadIdx.x - 64;
-    int cur = cur0, it = 0;
+    Cursor cur = {0, 0u};
+    int it = 0;
     Unit t;
-    for (; next_unit(cur, t); ++it) {
+    for (; next_unit(cur, t, false); ++it) {
       const TcClass cls = p.cls[t.cls_id];
       const int nkb = cls.nkb;
       const int buf = it % NBUF;
@@ -860,6 +893,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
     tc_fence_after();
     tmem_dealloc(tmem_base, TCOLS);
   }
+  sched_finish(p.sched);
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -870,9 +904,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_persist_kernel(const __gri
 // weights + 8 KB of activations for twice the math), which is the form the 256-column data-gradient launches of the same
 // layers already run at (~1.45 vs ~1.23 PFLOP/s stand-alone).  A unit is a PAIR of 128-position tiles that are neighbours
 // along H (tile order is H-fastest here), fetched as ONE box of twice the H extent plus the two halo steps along the outermost
-// axis (<= 320 rows = 40 KB), so the window of tap j is 256 contiguous, swizzle-atom aligned rows.  A CTA's contiguous tile range
-// may start / end on an odd tile: those run as single-tile units (N = 128) through a second set of tensor maps
-// (amap[TC_SWAP_SINGLE_MAP + view]).
+// axis (<= 320 rows = 40 KB), so the window of tap j is 256 contiguous, swizzle-atom aligned rows.  The last units of the ticket
+// sequence are single tiles (N = 128, second set of tensor maps: amap[TC_SWAP_SINGLE_MAP + view]) so that the ragged end of the
+// kernel is one tile long.
 // The accumulator is the TRANSPOSE of the output tile: epilogue thread = channel, so bias / affine / ReLU constants and the
 // BatchNorm sums are per-thread scalars (no warp transposes); 32 positions at a time go through a [32][128] bf16 staging tile
 // in shared memory and leave as 256-byte rows (16-byte stores).
@@ -886,7 +920,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_swap_kernel(const __grid_c
   constexpr int W_BYTES = 128 * 128;                    // one weight tile: 128 couts x 64 channels
   constexpr int RING_BYTES = NA * ACT_BYTES + NW * W_BYTES;
   constexpr int STAGE_TILE = 32 * 128 * 2;              // [32 positions][128 channels] bf16
-  constexpr int NBAR = 2 * NA + 2 * NW + 4;
+  constexpr int NBAR = 2 * NA + 2 * NW + 4 + 2 * TC_QD;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -895,20 +929,39 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_swap_kernel(const __grid_c
   long long* s_off = reinterpret_cast<long long*>(smem + RING_BYTES + 2 * STAGE_TILE);   // [2][256] output element offset, -1 = outside
   const uint32_t bar_base = base + RING_BYTES + 2 * STAGE_TILE + 2 * 256 * 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RING_BYTES + 2 * STAGE_TILE + 2 * 256 * 8 + NBAR * 8);
+  int* s_q = reinterpret_cast<int*>(smem + RING_BYTES + 2 * STAGE_TILE + 2 * 256 * 8 + NBAR * 8 + 16);   // unit queue [TC_QD]
   const uint32_t afull = bar_base, aempty = afull + NA * 8, wfull = aempty + NA * 8, wempty = wfull + NW * 8;
   const uint32_t tfull = wempty + NW * 8, tempty = tfull + 16;
+  const uint32_t qfull = tempty + 16, qempty = qfull + TC_QD * 8;
   const uint32_t w_ring = base + NA * ACT_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int range_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.m_tiles / gridDim.x);
-  const int range_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.m_tiles / gridDim.x);
 
   struct Unit { int nsub, mt0, w0, h0, d0, n0; };
-  // tiles are numbered H-fastest; an even tile and its successor are H-neighbours (tiles[1] is even)
-  auto next_unit = [&](int& cur, Unit& t) -> bool {
-    if (cur >= range_end) return false;
-    t.mt0 = cur;
-    t.nsub = ((cur & 1) == 0 && cur + 1 < range_end) ? 2 : 1;
-    cur += t.nsub;
+  struct Cursor { int qi; uint32_t qp; };
+  // units come from the ticket counter (see conv_tc_persist_kernel): [0, n_pair_units) are pairs of H-neighbour tiles (tiles are
+  // numbered H-fastest and tiles[1] is even, so tile 2u and 2u + 1 are neighbours), the rest single tiles
+  auto next_unit = [&](Cursor& cq, Unit& t, const bool producer) -> bool {
+    int u;
+    if (producer) {
+      mbar_wait(qempty + cq.qi * 8, cq.qp ^ 1u);
+      u = static_cast<int>(atomicAdd(p.sched, 1u));
+      if (u >= p.n_units) u = -1;
+      s_q[cq.qi] = u;
+      mbar_arrive(qfull + cq.qi * 8);
+    } else {
+      mbar_wait(qfull + cq.qi * 8, cq.qp);
+      u = s_q[cq.qi];
+      mbar_arrive(qempty + cq.qi * 8);
+    }
+    if (++cq.qi == TC_QD) { cq.qi = 0; cq.qp ^= 1u; }
+    if (u < 0) return false;
+    if (u < p.n_pair_units) {
+      t.mt0 = 2 * u;
+      t.nsub = 2;
+    } else {
+      t.mt0 = 2 * p.n_pair_units + (u - p.n_pair_units);
+      t.nsub = 1;
+    }
     int r = t.mt0;
     const int th = r % p.tiles[1]; r /= p.tiles[1];
     const int tw = r % p.tiles[0]; r /= p.tiles[0];
@@ -923,6 +976,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_swap_kernel(const __grid_c
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull + b * 8, 1);
       mbar_init(tempty + b * 8, 128);
+    }
+    for (int s = 0; s < TC_QD; ++s) {
+      mbar_init(qfull + s * 8, 1);
+      mbar_init(qempty + s * 8, 129);   // the MMA thread + 128 epilogue threads
     }
     fence_mbar_init();
     tma_prefetch_desc(&p.bmap);
@@ -942,10 +999,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_swap_kernel(const __grid_c
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      int cur = range_begin, sa_i = 0, sw_i = 0;
+      Cursor cur = {0, 0u};
+      int sa_i = 0, sw_i = 0;
       uint32_t pa = 0, pw = 0;
       Unit t;
-      while (next_unit(cur, t)) {
+      while (next_unit(cur, t, true)) {
         const uint32_t act_bytes = (128 + 2 * p.halo_inner) * t.nsub * 128;
         const int map_ofs = t.nsub == 2 ? 0 : TC_SWAP_SINGLE_MAP;
         for (int g = 0; g < cls.tap_count; g += 3) {
@@ -974,10 +1032,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_swap_kernel(const __grid_c
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, 256, 0, 0), idesc1 = umma_idesc_bf16(128, 128, 0, 0);
-      int cur = range_begin, it = 0, sa_i = 0, sw_i = 0;
+      Cursor cur = {0, 0u};
+      int it = 0, sa_i = 0, sw_i = 0;
       uint32_t pa = 0, pw = 0;
       Unit t;
-      for (; next_unit(cur, t); ++it) {
+      for (; next_unit(cur, t, false); ++it) {
         const int buf = it & 1;
         const uint32_t use = static_cast<uint32_t>(it >> 1);
         const uint32_t idesc = t.nsub == 2 ? idesc2 : idesc1;
@@ -1018,9 +1077,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_swap_kernel(const __grid_c
     const float shift_c = (cvalid && p.scale != nullptr) ? __ldg(p.shift + c) : 0.f;
     const bool affine = p.scale != nullptr;
     bf16* const out = reinterpret_cast<bf16*>(p.out);
-    int cur = range_begin, it = 0, sb = 0;   // sb: staging tile in use
+    Cursor cur = {0, 0u};
+    int it = 0, sb = 0;   // sb: staging tile in use
     Unit t;
-    for (; next_unit(cur, t); ++it) {
+    for (; next_unit(cur, t, false); ++it) {
       const int buf = it & 1;
       const uint32_t use = static_cast<uint32_t>(it >> 1);
       const int npos = 128 * t.nsub;
@@ -1108,6 +1168,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_swap_kernel(const __grid_c
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  sched_finish(p.sched);
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -1602,8 +1663,8 @@ static int launch_split(const TcConvParams& prm, int grid, cudaStream_t stream, 
 template <int BLOCK_N, int STAGES, int MT, int HALO = 0>
 static int launch_persist(const TcConvParams& prm, int units, cudaStream_t stream, char* err, size_t errlen) {
   constexpr int RING = HALO ? STAGES * MT * TC_HALO_MAX_ROWS * 128 + HALO * BLOCK_N * 128 : STAGES * (MT * 128 * 128 + BLOCK_N * 128);
-  constexpr int NBAR = (HALO ? 2 * STAGES + 2 * HALO : 2 * STAGES) + 4;
-  constexpr int SMEM = RING + NBAR * 8 + 16 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
+  constexpr int NBAR = (HALO ? 2 * STAGES + 2 * HALO : 2 * STAGES) + 4 + 2 * TC_QD;
+  constexpr int SMEM = RING + NBAR * 8 + 32 + (4 * 2 + 3) * BLOCK_N * 4 + 1024;
   static_assert(SMEM <= 232448, "persistent conv kernel exceeds the 227 KB of shared memory a CTA can opt in to");
   static bool attr_done = false;
   static int sms = 0;
@@ -1619,10 +1680,9 @@ static int launch_persist(const TcConvParams& prm, int units, cudaStream_t strea
     if (sms < 1) sms = 148;
     attr_done = true;
   }
-  // balanced mode hands out m-tiles (>= units), otherwise one CTA per unit up to the SM count
-  const int work = prm.balanced ? prm.m_tiles : units;
-  cudaError_t e = launch_k(conv_tc_persist_kernel<BLOCK_N, STAGES, MT, HALO>, dim3((unsigned)(work < sms ? work : sms)), dim3(TC_THREADS), SMEM,
-                           stream, 1, prm, units);
+  (void)units;
+  cudaError_t e = launch_k(conv_tc_persist_kernel<BLOCK_N, STAGES, MT, HALO>, dim3((unsigned)(prm.n_units < sms ? prm.n_units : sms)), dim3(TC_THREADS),
+                           SMEM, stream, 1, prm);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "conv_tc_persist launch failed: %s", cudaGetErrorString(e));
     return 1;
@@ -1632,7 +1692,7 @@ static int launch_persist(const TcConvParams& prm, int units, cudaStream_t strea
 
 template <int NA, int NW>
 static int launch_swap(const TcConvParams& prm, cudaStream_t stream, char* err, size_t errlen) {
-  constexpr int SMEM = NA * TC_SWAP_MAX_ROWS * 128 + NW * 128 * 128 + 2 * 32 * 128 * 2 + 2 * 256 * 8 + (2 * NA + 2 * NW + 4) * 8 + 16 + 1024;
+  constexpr int SMEM = NA * TC_SWAP_MAX_ROWS * 128 + NW * 128 * 128 + 2 * 32 * 128 * 2 + 2 * 256 * 8 + (2 * NA + 2 * NW + 4 + 2 * TC_QD) * 8 + 32 + 1024;
   static_assert(SMEM <= 232448, "swapped-operand conv kernel exceeds the 227 KB of shared memory a CTA can opt in to");
   static bool attr_done = false;
   static int sms = 0;
@@ -1648,7 +1708,7 @@ static int launch_swap(const TcConvParams& prm, cudaStream_t stream, char* err, 
     if (sms < 1) sms = 148;
     attr_done = true;
   }
-  const int ctas = prm.m_tiles / 2 < sms ? prm.m_tiles / 2 : sms;
+  const int ctas = prm.n_units < sms ? prm.n_units : sms;
   cudaError_t e = launch_k(conv_tc_swap_kernel<NA, NW>, dim3((unsigned)ctas), dim3(TC_THREADS), SMEM, stream, 1, prm);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "conv_tc_swap launch failed: %s", cudaGetErrorString(e));
@@ -1711,6 +1771,66 @@ static int multicast_cluster() {
     v = (e != nullptr && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
   }
   return v;
+}
+
+// ticket counters of the persistent kernels: a pool of {next, done} pairs, zero-initialised once; every launch takes the next
+// slot and its last CTA zeroes it again, so a slot is clean whenever it comes round (4096 persistent launches later)
+constexpr int TC_SCHED_SLOTS = 4096;
+static unsigned int* sched_slot(cudaStream_t stream, char* err, size_t errlen) {
+  static unsigned int* pool[64] = {nullptr};
+  static unsigned int seq = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) {
+    snprintf(err, errlen, "tc_launch: device ordinal %d out of range", dev);
+    return nullptr;
+  }
+  if (pool[dev] == nullptr) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      snprintf(err, errlen, "tc_launch: the first persistent convolution of a process cannot be launched inside a stream capture "
+                            "(its ticket counters are allocated then): run the step once eagerly first");
+      return nullptr;
+    }
+    unsigned int* ptr = nullptr;
+    if (cudaMalloc(&ptr, TC_SCHED_SLOTS * 2 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(ptr, 0, TC_SCHED_SLOTS * 2 * sizeof(unsigned int)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+      snprintf(err, errlen, "tc_launch: allocating the ticket counters failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return nullptr;
+    }
+    pool[dev] = ptr;
+  }
+  return pool[dev] + 2 * (seq++ % TC_SCHED_SLOTS);
+}
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) sms = 148;
+  }
+  return sms;
+}
+// work units of a persistent launch (see conv_tc_persist_kernel): balanced problems = groups of mt tiles, then ~one single tile
+// per SM; others = (class, group, column tile) triples
+static int plan_units(TcConvParams& prm, int mt, long long grid, cudaStream_t stream, char* err, size_t errlen) {
+  if (prm.balanced) {
+    const int T = prm.m_tiles;
+    int singles = 0;
+    if (mt > 1) {
+      singles = std::min(T, sm_count());
+      while ((T - singles) % mt != 0) ++singles;   // terminates: T - T = 0
+    }
+    prm.n_pair_units = (T - singles) / mt;
+    prm.n_units = prm.n_pair_units + singles;
+  } else {
+    prm.n_pair_units = 0;
+    prm.n_units = (int)grid;
+  }
+  prm.sched = sched_slot(stream, err, errlen);
+  return prm.sched == nullptr ? 1 : 0;
 }
 
 // SAP3D_CONV_HALO: 0 = never use the halo-tile kernels, 1 (default) = two-sub-tile units only, 2 = also single-sub-tile units
@@ -1980,6 +2100,7 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
       snprintf(err, errlen, "tc_launch: halo plan inconsistent (grid %lld, box rows %d)", grid, prm.box_rows);
       return 1;
     }
+    if (plan_units(prm, use_swap ? 2 : mt, grid, stream, err, errlen)) return 1;
     ++g_halo_launches;
     if (use_swap) {
       ++g_swap_launches;
@@ -1989,6 +2110,7 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
     return mt == 2 ? launch_persist<256, 2, 2, 3>(prm, (int)grid, stream, err, errlen) : launch_persist<256, 3, 1, 4>(prm, (int)grid, stream, err, errlen);
   }
   if (grid > 148 && pb.force_split >= 0) {
+    if (plan_units(prm, mt, grid, stream, err, errlen)) return 1;
     switch (block_n) {
       case 64: return mt == 2 ? launch_persist<64, 4, 2>(prm, (int)grid, stream, err, errlen) : launch_persist<64, 6, 1>(prm, (int)grid, stream, err, errlen);
       case 128: return mt == 2 ? launch_persist<128, 4, 2>(prm, (int)grid, stream, err, errlen) : launch_persist<128, 4, 1>(prm, (int)grid, stream, err, errlen);

@@ -160,7 +160,7 @@ def test_swapped_operand_halo_conv(A, case):
         pytest.skip("swapped-operand kernel switched off by the environment")
     before = A.lib.sap3d_debug_conv_swap_launches()
     # cout % 64 != 0: the forward runs on the tensor cores, the data / filter gradients fall to the CUDA-core kernels (IMPL_AUTO)
-    run_case(A, *case[2:], dtype=A.BF16, impl=A.IMPL_TC if case[8] % 64 == 0 else A.IMPL_AUTO)
+    run_case(A, *case[2:], dtype=A.BF16, impl=A.IMPL_TC if case[7] % 64 == 0 else A.IMPL_AUTO)
     assert A.lib.sap3d_debug_conv_swap_launches() - before == case[1], "launches of the swapped-operand kernel"
 
 
