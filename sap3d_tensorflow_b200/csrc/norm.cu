@@ -602,10 +602,9 @@ SAP3D_DEVINL void nob_mask(const float (&d)[4], const float (&av)[4], const floa
   }
 }
 
-constexpr int NOB_INFLIGHT = 4;    // positions per thread per iteration
 constexpr int NOB_PLANES = 16;     // position lanes per block
 
-template <typename T>
+template <typename T, int NOB_INFLIGHT>   // NOB_INFLIGHT = positions per thread per iteration (loads issued before any is consumed)
 __global__ void __launch_bounds__(256, 3) apply_bwd_reduce_nob_kernel(const ApplyBwdArgs p) {
   pdl_wait();   // (programmatic dependent launch: the predecessor kernel has completed from here on)
   pdl_launch_dependents();
@@ -686,7 +685,7 @@ __global__ void __launch_bounds__(256, 3) apply_bwd_reduce_nob_kernel(const Appl
 }
 
 // grid = (slabs, C/64); the slab count is independent of the reduce pass
-template <typename T, bool ACC>
+template <typename T, bool ACC, int NOB_INFLIGHT>
 __global__ void __launch_bounds__(256, 3) apply_bwd_nob_kernel(const ApplyBwdArgs p) {
   pdl_wait();   // (programmatic dependent launch: the predecessor kernel has completed from here on)
   pdl_launch_dependents();
@@ -1215,6 +1214,16 @@ size_t sap3d_affine_act_bwd_workspace(int32_t C) { return (size_t)(296 * 4 + 4 +
 
 // phase 0: the whole backward.  phase 1: reductions only (coef = LOCAL sums / count at workspace[0 .. 4C)); phase 2: apply
 // only, reading coef from the workspace (the caller has summed it over the replicas in between: synchronised BatchNorm).
+// SAP3D_NOB_INFLIGHT=4|8: positions per thread kept in flight by the big-tensor BatchNorm-backward kernels (bf16)
+static int nob_inflight() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("SAP3D_NOB_INFLIGHT");
+    v = (e != nullptr && e[0] == '4') ? 4 : 8;
+  }
+  return v;
+}
+
 static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, const float* s1, const float* t1, const float* mean1,
                                const float* rstd1, int32_t relu1, const void* b, const float* s2, const float* t2,
                                const float* mean2, const float* rstd2, int32_t relu2, int32_t relu_out, int64_t P, int32_t C,
@@ -1298,8 +1307,10 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
       rows = r3;
       p.rows = (int)rows;
       dim3 g3((unsigned)rows, (unsigned)chunks);
-      if (dtype == SAP3D_BF16) launch_k(apply_bwd_reduce_nob_kernel<bf16>, g3, dim3(256), 0, st, 1, p);
-      else launch_k(apply_bwd_reduce_nob_kernel<float>, g3, dim3(256), 0, st, 1, p);
+      if (dtype == SAP3D_BF16) {
+        if (nob_inflight() == 8) launch_k(apply_bwd_reduce_nob_kernel<bf16, 8>, g3, dim3(256), 0, st, 1, p);
+        else launch_k(apply_bwd_reduce_nob_kernel<bf16, 4>, g3, dim3(256), 0, st, 1, p);
+      } else launch_k(apply_bwd_reduce_nob_kernel<float, 4>, g3, dim3(256), 0, st, 1, p);
     } else if (dtype == SAP3D_BF16) launch_k(apply_bwd_reduce_kernel<bf16>, rgrid, dim3(256), 0, st, 1, p);
     else launch_k(apply_bwd_reduce_kernel<float>, rgrid, dim3(256), 0, st, 1, p);
     if (check_launch("affine_act_bwd reduce")) return 1;
@@ -1317,11 +1328,16 @@ static int affine_act_bwd_impl(int32_t dtype, const void* dy, const void* a, con
       if (slabs < 1) slabs = 1;
       dim3 ag((unsigned)slabs, (unsigned)chunks);
       if (dtype == SAP3D_BF16) {
-        if (acc_a) launch_k(apply_bwd_nob_kernel<bf16, true>, ag, dim3(256), 0, st, 1, p);
-        else launch_k(apply_bwd_nob_kernel<bf16, false>, ag, dim3(256), 0, st, 1, p);
+        if (nob_inflight() == 8) {
+          if (acc_a) launch_k(apply_bwd_nob_kernel<bf16, true, 8>, ag, dim3(256), 0, st, 1, p);
+          else launch_k(apply_bwd_nob_kernel<bf16, false, 8>, ag, dim3(256), 0, st, 1, p);
+        } else {
+          if (acc_a) launch_k(apply_bwd_nob_kernel<bf16, true, 4>, ag, dim3(256), 0, st, 1, p);
+          else launch_k(apply_bwd_nob_kernel<bf16, false, 4>, ag, dim3(256), 0, st, 1, p);
+        }
       } else {
-        if (acc_a) launch_k(apply_bwd_nob_kernel<float, true>, ag, dim3(256), 0, st, 1, p);
-        else launch_k(apply_bwd_nob_kernel<float, false>, ag, dim3(256), 0, st, 1, p);
+        if (acc_a) launch_k(apply_bwd_nob_kernel<float, true, 4>, ag, dim3(256), 0, st, 1, p);
+        else launch_k(apply_bwd_nob_kernel<float, false, 4>, ag, dim3(256), 0, st, 1, p);
       }
     } else if (dtype == SAP3D_BF16) launch_k(apply_bwd_kernel<bf16>, dim3(ew_grid(nvec)), dim3(256), 0, st, 1, p);
     else launch_k(apply_bwd_kernel<float>, dim3(ew_grid(nvec)), dim3(256), 0, st, 1, p);

@@ -11,6 +11,7 @@ using namespace sap3d;
 
 namespace {
 
+constexpr int PACK_MAX_CACHED = 1024;
 constexpr int PACK_SPAN = 4096;   // elements per block iteration; the caller aligns every entry's `start` to it
 
 // one 8-element chunk of an entry (chunk index q within the entry): the r01 form, still used for entries whose inner extent
@@ -54,14 +55,20 @@ __device__ __forceinline__ void pack_chunk(const sap3d_pack_entry& en, long long
 // whole 128-byte destination lines out (r01/r02a: 16-byte stores to 32 different rows per warp; ncu 1.02 GB moved for 0.68 GB).
 __global__ void __launch_bounds__(256) pack_multi_kernel(const sap3d_pack_entry* __restrict__ tab, int n, long long total) {
   __shared__ float tile[64][65];
+  __shared__ long long s_start[PACK_MAX_CACHED];   // the entries' starts: the per-span binary search then never leaves the SM
   const int tid = threadIdx.x;
+  const bool cached = n <= PACK_MAX_CACHED;
+  if (cached) {
+    for (int i = tid; i < n; i += 256) s_start[i] = tab[i].start;
+    __syncthreads();
+  }
   const long long nspan = total / PACK_SPAN;
   for (long long span = blockIdx.x; span < nspan; span += gridDim.x) {
     const long long e0 = span * PACK_SPAN;
     int lo = 0, hi = n - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (tab[mid].start <= e0) lo = mid;
+      if ((cached ? s_start[mid] : tab[mid].start) <= e0) lo = mid;
       else hi = mid - 1;
     }
     const sap3d_pack_entry en = tab[lo];
