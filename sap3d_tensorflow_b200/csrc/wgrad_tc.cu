@@ -13,6 +13,7 @@
 // tiles (split-K); partial results are reduced into the fp32 gradient with red.global.add.f32.
 // Replaces cuDNN's conv3d backward-filter kernels behind tf.gradients (train.py:168).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -194,6 +195,156 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------------
+// TWO TAPS PER CTA, swapped roles, for Q (output-gradient) blocks of exactly 128 channels -- the decoder's 128-channel layers.
+// A 128 x 128 x 16 tcgen05.mma reads 4 KB + 4 KB of operands from shared memory for 64 cycles of math, so the shared-memory port
+// is as busy as the tensor pipe (see conv_tc.cu, conv_tc_swap_kernel).  Here the Q tile is the M side (128 couts = TMEM lanes) and
+// the N side is [P(tap a) | P(tap b)], 2 x 128 input channels: one 128 x 256 x 16 instruction per 16 positions computes the
+// transposed blocks dW_a^T | dW_b^T, the dy tile is fetched once for both taps (96 KB instead of 128 KB per position tile and
+// tap pair), and the epilogue thread owns a cout column of dW: its 256 accumulator columns go out as scalar red.global.add.f32
+// that are contiguous across the warp.  An odd last tap runs alone with N = 128.
+// -------------------------------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_pair_kernel(const __grid_constant__ WgParams p) {
+  constexpr int Q_BYTES = 2 * 16384;                 // 128 channels of Q: two 64-channel boxes
+  constexpr int P_BYTES = 4 * 16384;                 // 2 taps x 128 channels of P
+  constexpr int STAGE_BYTES = Q_BYTES + P_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- work decode: (split, mblock, tap pair), pair fastest (CTAs resident together share the position slice) ----
+  const int npairs = (p.ntaps + 1) / 2;
+  int w = blockIdx.x;
+  const int pair_id = w % npairs;
+  w /= npairs;
+  const int mb = w % p.mblocks;
+  const int split = w / p.mblocks;
+  const WgTap tap_a = p.taps[2 * pair_id];
+  const bool has_b = 2 * pair_id + 1 < p.ntaps;
+  const WgTap tap_b = p.taps[has_b ? 2 * pair_id + 1 : 2 * pair_id];
+  const int per = (p.m_tiles + p.splits - 1) / p.splits;
+  const int t_begin = split * per;
+  const int t_end = min(p.m_tiles, t_begin + per);
+  const int ntiles = max(0, t_end - t_begin);
+  const int ksteps = (p.box_rows + 15) / 16;
+
+  if (p.box_rows < 128) {     // rows >= box_rows are never written by TMA: zero them once (K padding contributes nothing)
+    const int row_bytes0 = p.box_rows * 128;
+    for (int s = 0; s < STAGES; ++s)
+      for (int blk = 0; blk < 6; ++blk) {
+        uint8_t* b0 = smem + s * STAGE_BYTES + blk * 16384;
+        for (int i = row_bytes0 + threadIdx.x * 16; i < 16384; i += WG_THREADS * 16) *reinterpret_cast<uint4*>(b0 + i) = make_uint4(0, 0, 0, 0);
+      }
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_base + s * 8, 1);
+      mbar_init(bar_base + (STAGES + s) * 8, 1);
+    }
+    mbar_init(bar_base + 2 * STAGES * 8, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.qmap);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = p.box_rows * 128 * (has_b ? 6 : 4);
+      const void* pmap_a = &p.pmap[tap_a.map];
+      const void* pmap_b = &p.pmap[tap_b.map];
+      for (int t = t_begin; t < t_end; ++t) {
+        int r = t;
+        const int tw = r % p.tiles[0]; r /= p.tiles[0];
+        const int th = r % p.tiles[1]; r /= p.tiles[1];
+        const int td = r % p.tiles[2];
+        const int tn = r / p.tiles[2];
+        const int w0 = tw * p.box[0], h0 = th * p.box[1], d0 = td * p.box[2], n0 = tn * p.box[3];
+        mbar_wait(bar_base + (STAGES + stage) * 8, phase ^ 1u);
+        const uint32_t full = bar_base + stage * 8;
+        const uint32_t sa = base + stage * STAGE_BYTES;
+        mbar_expect_tx(full, tx_bytes);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) tma_load_5d(sa + j * 16384, &p.qmap, full, j * 64, w0, h0, d0, n0);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_5d(sa + Q_BYTES + j * 16384, pmap_a, full, p.p_c0 + (mb * 2 + j) * 64, w0 + tap_a.dw, h0 + tap_a.dh, d0 + tap_a.dd, n0);
+        if (has_b) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_5d(sa + Q_BYTES + (2 + j) * 16384, pmap_b, full, p.p_c0 + (mb * 2 + j) * 64, w0 + tap_b.dw, h0 + tap_b.dh, d0 + tap_b.dd, n0);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = has_b ? umma_idesc_bf16(128, 256, 1, 1) : umma_idesc_bf16(128, 128, 1, 1);  // A and B MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(bar_base + stage * 8, phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * STAGE_BYTES;
+        const uint64_t adesc = umma_desc_sw128(sa, 16384, 1024);             // Q: 128 couts = M
+        const uint64_t bdesc = umma_desc_sw128(sa + Q_BYTES, 16384, 1024);   // P(tap a) | P(tap b): 64-channel blocks 16 KB apart
+        for (int k = 0; k < ksteps; ++k) tc_mma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (t | k) != 0 ? 1u : 0u);
+        tc_commit(bar_base + (STAGES + stage) * 8);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (ntiles > 0) tc_commit(bar_base + 2 * STAGES * 8);
+    }
+    __syncwarp();
+  } else if (ntiles > 0) {
+    const int q = warp & 3;
+    const int n = q * 32 + lane;          // channel of Q = column of the dW blocks = TMEM lane
+    mbar_wait(bar_base + 2 * STAGES * 8, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < (has_b ? 8 : 4); ++c) {
+      uint32_t rr[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
+      tmem_ld_wait();
+      const WgTap& tap = c < 4 ? tap_a : tap_b;
+      const int m0 = mb * 128 + (c & 3) * 32;     // first P channel (row of dW) of this chunk
+      float* out = p.dw + tap.dw_ofs + (long long)m0 * p.ldw + n;
+      if (n < p.N) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (m0 + j < p.M) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(out + (long long)j * p.ldw), "f"(__uint_as_float(rr[j])) : "memory");
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 // ---- host ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -256,6 +407,36 @@ static int wg_launch_t(const WgParams& prm, int grid, cudaStream_t stream, char*
   return 0;
 }
 
+static int wg_launch_pair(const WgParams& prm, int grid, cudaStream_t stream, char* err, size_t errlen) {
+  constexpr int STAGES = 2;
+  constexpr int SMEM = STAGES * 6 * 16384 + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_pair_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "cudaFuncSetAttribute(wgrad_tc_pair) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    attr_done = true;
+  }
+  wgrad_tc_pair_kernel<STAGES><<<grid, WG_THREADS, SMEM, stream>>>(prm);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "wgrad_tc_pair launch failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+// SAP3D_WGRAD_PAIR=0: 128-channel output-gradient blocks keep one tap per CTA
+static bool wg_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAP3D_WGRAD_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static long long wg_choose_box(const int ext[4], int box[4]) {
   long long best = -1;
   int bb[4] = {1, 1, 1, 1};
@@ -303,7 +484,8 @@ int tc_wgrad_launch(const TcWgradProblem& pb, cudaStream_t stream, char* err, si
   prm.mblocks = (pb.M + 127) / 128;
   prm.nblocks = (pb.N + block_n - 1) / block_n;
   prm.m_tiles = (int)m_tiles;
-  const long long out_tiles = (long long)prm.ntaps * prm.mblocks * prm.nblocks;
+  const bool pair = pb.N == 128 && prm.ntaps >= 2 && wg_pair_enabled();   // two taps per CTA, Q on the M side (wgrad_tc_pair_kernel)
+  const long long out_tiles = pair ? (long long)((prm.ntaps + 1) / 2) * prm.mblocks : (long long)prm.ntaps * prm.mblocks * prm.nblocks;
   // split count: the CTAs are one per SM (197 KB of shared memory), so the grid should fill WHOLE waves of 148.  Among the
   // splits that give 2.5 .. 4 waves pick the one wasting the least of its last wave; ties go to fewer splits (less fp32
   // reduction traffic).  (ceil(4*148 / tiles) used to give e.g. 54 tiles x 11 = 594 CTAs = four waves plus two CTAs.)
@@ -336,6 +518,7 @@ int tc_wgrad_launch(const TcWgradProblem& pb, cudaStream_t stream, char* err, si
     snprintf(err, errlen, "tc_wgrad: bad grid %lld", grid);
     return 1;
   }
+  if (pair) return wg_launch_pair(prm, (int)grid, stream, err, errlen);
   switch (block_n) {
     case 64: return wg_launch_t<64, 4>(prm, (int)grid, stream, err, errlen);
     case 128: return wg_launch_t<128, 3>(prm, (int)grid, stream, err, errlen);
