@@ -204,11 +204,19 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const __grid_const
 // transposed blocks dW_a^T | dW_b^T, the dy tile is fetched once for both taps (96 KB instead of 128 KB per position tile and
 // tap pair), and the epilogue thread owns a cout column of dW: its 256 accumulator columns go out as scalar red.global.add.f32
 // that are contiguous across the warp.  An odd last tap runs alone with N = 128.
+// MEASURED NEGATIVE (r02, x_1_2 filter gradient, same box): 368 us for both segment launches against 334 us with one tap per
+// CTA; 437 us with four 64-position stages.  Halving the number of output blocks (14 tap pairs instead of 27 taps) needs 42
+// position splits instead of 16 to fill the SMs, i.e. 2.6x the fp32 reduction traffic, and in the transposed accumulator a thread's
+// consecutive columns are different dW rows, so the reductions are scalar instead of 16-byte: the L2 atomic unit, not the tensor
+// pipe, sets the time (ncu: tensor pipe 45 %).  Kept opt-in (SAP3D_WGRAD_PAIR=1) with its parity tests; not used by default.
 // -------------------------------------------------------------------------------------------------------------------
-template <int STAGES>
+// ROWS = positions per pipeline stage (the TMA box): 64 gives four 48 KB stages; two 96 KB stages (ROWS = 128) left the tensor pipe
+// waiting for TMA (ncu: 45 % active, slower than the one-tap kernel).
+template <int STAGES, int ROWS>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_pair_kernel(const __grid_constant__ WgParams p) {
-  constexpr int Q_BYTES = 2 * 16384;                 // 128 channels of Q: two 64-channel boxes
-  constexpr int P_BYTES = 4 * 16384;                 // 2 taps x 128 channels of P
+  constexpr int BLK = ROWS * 128;                    // one [ROWS positions][64 channels] box
+  constexpr int Q_BYTES = 2 * BLK;                   // 128 channels of Q: two 64-channel boxes
+  constexpr int P_BYTES = 4 * BLK;                   // 2 taps x 128 channels of P
   constexpr int STAGE_BYTES = Q_BYTES + P_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -234,12 +242,12 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_pair_kernel(const __grid_
   const int ntiles = max(0, t_end - t_begin);
   const int ksteps = (p.box_rows + 15) / 16;
 
-  if (p.box_rows < 128) {     // rows >= box_rows are never written by TMA: zero them once (K padding contributes nothing)
+  if (p.box_rows < ROWS) {    // rows >= box_rows are never written by TMA: zero them once (K padding contributes nothing)
     const int row_bytes0 = p.box_rows * 128;
     for (int s = 0; s < STAGES; ++s)
       for (int blk = 0; blk < 6; ++blk) {
-        uint8_t* b0 = smem + s * STAGE_BYTES + blk * 16384;
-        for (int i = row_bytes0 + threadIdx.x * 16; i < 16384; i += WG_THREADS * 16) *reinterpret_cast<uint4*>(b0 + i) = make_uint4(0, 0, 0, 0);
+        uint8_t* b0 = smem + s * STAGE_BYTES + blk * BLK;
+        for (int i = row_bytes0 + threadIdx.x * 16; i < BLK; i += WG_THREADS * 16) *reinterpret_cast<uint4*>(b0 + i) = make_uint4(0, 0, 0, 0);
       }
     fence_proxy_async();
   }
@@ -280,14 +288,14 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_pair_kernel(const __grid_
         const uint32_t sa = base + stage * STAGE_BYTES;
         mbar_expect_tx(full, tx_bytes);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) tma_load_5d(sa + j * 16384, &p.qmap, full, j * 64, w0, h0, d0, n0);
+        for (int j = 0; j < 2; ++j) tma_load_5d(sa + j * BLK, &p.qmap, full, j * 64, w0, h0, d0, n0);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-          tma_load_5d(sa + Q_BYTES + j * 16384, pmap_a, full, p.p_c0 + (mb * 2 + j) * 64, w0 + tap_a.dw, h0 + tap_a.dh, d0 + tap_a.dd, n0);
+          tma_load_5d(sa + Q_BYTES + j * BLK, pmap_a, full, p.p_c0 + (mb * 2 + j) * 64, w0 + tap_a.dw, h0 + tap_a.dh, d0 + tap_a.dd, n0);
         if (has_b) {
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            tma_load_5d(sa + Q_BYTES + (2 + j) * 16384, pmap_b, full, p.p_c0 + (mb * 2 + j) * 64, w0 + tap_b.dw, h0 + tap_b.dh, d0 + tap_b.dd, n0);
+            tma_load_5d(sa + Q_BYTES + (2 + j) * BLK, pmap_b, full, p.p_c0 + (mb * 2 + j) * 64, w0 + tap_b.dw, h0 + tap_b.dh, d0 + tap_b.dd, n0);
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -305,8 +313,8 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_pair_kernel(const __grid_
         mbar_wait(bar_base + stage * 8, phase);
         tc_fence_after();
         const uint32_t sa = base + stage * STAGE_BYTES;
-        const uint64_t adesc = umma_desc_sw128(sa, 16384, 1024);             // Q: 128 couts = M
-        const uint64_t bdesc = umma_desc_sw128(sa + Q_BYTES, 16384, 1024);   // P(tap a) | P(tap b): 64-channel blocks 16 KB apart
+        const uint64_t adesc = umma_desc_sw128(sa, BLK, 1024);               // Q: 128 couts = M
+        const uint64_t bdesc = umma_desc_sw128(sa + Q_BYTES, BLK, 1024);     // P(tap a) | P(tap b): 64-channel blocks one box apart
         for (int k = 0; k < ksteps; ++k) tc_mma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (t | k) != 0 ? 1u : 0u);
         tc_commit(bar_base + (STAGES + stage) * 8);
         if (++stage == STAGES) {
@@ -408,18 +416,18 @@ static int wg_launch_t(const WgParams& prm, int grid, cudaStream_t stream, char*
 }
 
 static int wg_launch_pair(const WgParams& prm, int grid, cudaStream_t stream, char* err, size_t errlen) {
-  constexpr int STAGES = 2;
-  constexpr int SMEM = STAGES * 6 * 16384 + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int STAGES = 2, ROWS = 128;   // (4 stages of 64 positions measured slower still: 437 us)
+  constexpr int SMEM = STAGES * 6 * ROWS * 128 + (2 * STAGES + 1) * 8 + 16 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_pair_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_pair_kernel<STAGES, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
       snprintf(err, errlen, "cudaFuncSetAttribute(wgrad_tc_pair) failed: %s", cudaGetErrorString(e));
       return 1;
     }
     attr_done = true;
   }
-  wgrad_tc_pair_kernel<STAGES><<<grid, WG_THREADS, SMEM, stream>>>(prm);
+  wgrad_tc_pair_kernel<STAGES, ROWS><<<grid, WG_THREADS, SMEM, stream>>>(prm);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     snprintf(err, errlen, "wgrad_tc_pair launch failed: %s", cudaGetErrorString(e));
@@ -427,12 +435,12 @@ static int wg_launch_pair(const WgParams& prm, int grid, cudaStream_t stream, ch
   }
   return 0;
 }
-// SAP3D_WGRAD_PAIR=0: 128-channel output-gradient blocks keep one tap per CTA
+// SAP3D_WGRAD_PAIR=1: 128-channel output-gradient blocks take two taps per CTA (off by default: measured slower)
 static bool wg_pair_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SAP3D_WGRAD_PAIR");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   return v != 0;
 }
@@ -469,6 +477,8 @@ int tc_wgrad_launch(const TcWgradProblem& pb, cudaStream_t stream, char* err, si
   memset(&prm, 0, sizeof(prm));
   int box[4];
   const long long m_tiles = wg_choose_box(pb.ext, box);
+  // two taps per CTA (wgrad_tc_pair_kernel; opt-in, see there)
+  const bool pair = pb.N == 128 && pb.taps.size() >= 2 && wg_pair_enabled();
   for (size_t v = 0; v < pb.pviews.size(); ++v)
     if (wg_encode_view(&prm.pmap[v], pb.pviews[v], box, err, errlen)) return 1;
   if (wg_encode_view(&prm.qmap, pb.q, box, err, errlen)) return 1;
@@ -484,7 +494,6 @@ int tc_wgrad_launch(const TcWgradProblem& pb, cudaStream_t stream, char* err, si
   prm.mblocks = (pb.M + 127) / 128;
   prm.nblocks = (pb.N + block_n - 1) / block_n;
   prm.m_tiles = (int)m_tiles;
-  const bool pair = pb.N == 128 && prm.ntaps >= 2 && wg_pair_enabled();   // two taps per CTA, Q on the M side (wgrad_tc_pair_kernel)
   const long long out_tiles = pair ? (long long)((prm.ntaps + 1) / 2) * prm.mblocks : (long long)prm.ntaps * prm.mblocks * prm.nblocks;
   // split count: the CTAs are one per SM (197 KB of shared memory), so the grid should fill WHOLE waves of 148.  Among the
   // splits that give 2.5 .. 4 waves pick the one wasting the least of its last wave; ties go to fewer splits (less fp32

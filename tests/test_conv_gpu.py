@@ -204,6 +204,29 @@ def test_cuda_core_conv(A, case, dtype):
     run_case(A, *case[1:], dtype=A.F32 if dtype == "f32" else A.BF16, impl=A.IMPL_SIMT)
 
 
+OPT_IN = [
+    ("SAP3D_WGRAD_PAIR", "1", "x_1_1 or x_2_x or halo_tile_conv"),     # two-tap filter-gradient kernel (measured slower; kept opt-in)
+    ("SAP3D_CONV_MULTICAST", "2", "persistent_tensor_core_conv"),        # weight-tile multicast clusters (measured slower; kept opt-in)
+    ("SAP3D_CONV_HALO", "0", "persistent_tensor_core_conv or linearity"),  # the r01-form persistent kernel stays the fallback
+]
+
+
+@pytest.mark.parametrize("var,val,expr", OPT_IN, ids=[f"{v}={x}" for v, x, _ in OPT_IN])
+def test_opt_in_and_fallback_kernels_keep_parity(A, var, val, expr):
+    """kernels that are NOT on the default path (environment switches read once per process) stay parity-green: the relevant cases
+    of this file are re-run in a child process with the switch set"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get(var) is not None:
+        pytest.skip("already running under the switch")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        f"({expr}) and not opt_in"], env=dict(os.environ, **{var: val}), cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
+
+
 def test_linearity_at_full_decoder_size(A):
     """size-independent property at the BASELINE size (8 x 56 x 56, 128+128 -> 128): conv(a*x) == a*conv(x)
     (bias off) and per-channel statistics consistent with the stored output."""
