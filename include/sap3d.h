@@ -103,6 +103,34 @@ int sap3d_conv_fwd_on_tensor_cores(const sap3d_conv_desc* d);
 int sap3d_conv_fwd_operand_is_workspace(const sap3d_conv_desc* d);
 int sap3d_conv_fwd_affine(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf, const void* w_fwd_packed,
                           const float* bias, const float* scale, const float* shift, int32_t relu, void* y, void* stream);
+
+/* Training graphs: tf.nn.conv3d followed by tf.layers.batch_normalization(training=True) (+ tf.nn.relu, + the bottleneck's residual
+ * add and its ReLU; p3d.py:83-136, make_block p3d.py:143-166) as ONE launch.  The convolution writes its raw output and the
+ * per-tile statistics rows as sap3d_conv_fwd does (the backward pass reads them); then every CTA of the launch waits at a grid
+ * barrier, finalises the batch statistics of its own columns exactly as sap3d_bn_finalize would (scale / shift / mean / rstd
+ * and the moving averages are written once per channel) and writes
+ *     y = relu_out?( relu1?(raw * scale + shift) + residual )
+ * from the accumulators it still holds.  Only for problems whose CTAs are all resident at once (the backbone's stage-2/3 layers):
+ * ask sap3d_conv_fwd_bn_supported() first (1 = yes; needs a device).  Measured on B200: one launch less per layer but ~1 us
+ * slower per layer than sap3d_conv_fwd + sap3d_bn_apply_fused, so this repo's engine uses it only on request. */
+typedef struct sap3d_bn_fuse {
+  const float* gamma;      /* [cout] */
+  const float* beta;
+  float* moving_mean;      /* nullable; updated with `momentum` (1.0 leaves them unchanged) */
+  float* moving_var;
+  float momentum, eps;
+  float* scale;            /* outputs, [cout] each */
+  float* shift;
+  float* mean;             /* nullable */
+  float* rstd;             /* nullable */
+  int32_t relu1;
+  const void* residual;    /* nullable, bf16, same shape as the output */
+  int32_t relu_out;
+  void* y;                 /* normalised output, bf16 */
+} sap3d_bn_fuse;
+int sap3d_conv_fwd_bn_supported(const sap3d_conv_desc* d);
+int sap3d_conv_fwd_bn(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf, const void* w_fwd_packed,
+                      const float* bias, void* raw, float* stats, const sap3d_bn_fuse* f, void* stream);
 /* dx_seg = data gradient w.r.t. segment `seg`; accumulate != 0 adds into dx */
 int sap3d_conv_dgrad(const sap3d_conv_desc* d, int32_t seg, const void* dy, const float* w_tf,
                      const void* w_dgrad_packed, void* dx, int32_t accumulate, void* stream);

@@ -67,6 +67,14 @@ _sig("sap3d_conv_pack_weights", [_P(ConvDesc), _vp, _vp, _vp, _vp])
 _sig("sap3d_conv_fwd", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_conv_fwd_on_tensor_cores", [_P(ConvDesc)])
 _sig("sap3d_conv_fwd_operand_is_workspace", [_P(ConvDesc)])
+class BnFuse(C.Structure):
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("moving_mean", C.c_void_p), ("moving_var", C.c_void_p),
+                ("momentum", C.c_float), ("eps", C.c_float), ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p),
+                ("rstd", C.c_void_p), ("relu1", C.c_int32), ("residual", C.c_void_p), ("relu_out", C.c_int32), ("y", C.c_void_p)]
+
+
+_sig("sap3d_conv_fwd_bn_supported", [_P(ConvDesc)])
+_sig("sap3d_conv_fwd_bn", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _P(BnFuse), _vp])
 _sig("sap3d_conv_fwd_affine", [_P(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp])
 _sig("sap3d_conv_dgrad", [_P(ConvDesc), _i32, _vp, _vp, _vp, _vp, _i32, _vp])
 _sig("sap3d_conv_dgrad2_supported", [_P(ConvDesc)])

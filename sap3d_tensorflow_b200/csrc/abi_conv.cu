@@ -504,6 +504,51 @@ static int conv_fwd_impl(const sap3d_conv_desc* d, const void* x0, const void* x
   return 0;
 }
 
+int sap3d_conv_fwd_bn_supported(const sap3d_conv_desc* d) {
+  if (check_desc(d)) return 0;
+  if (!tc_eligible(d) || d->out_f32 || d->dtype != SAP3D_BF16 || require_device()) return 0;
+  ConvGeom g;
+  make_geom(d, g);
+  TcProblem pb;
+  build_fwd_problem(d, g, nullptr, nullptr, pb);
+  pb.B = nullptr; pb.out = nullptr; pb.bias = nullptr; pb.stats = nullptr; pb.scale = nullptr; pb.shift = nullptr;
+  pb.relu = 0; pb.accumulate = 0; pb.out_f32 = 0; pb.force_block_n = 0;
+  pb.query_fuse_bn = 1;
+  char err[256];
+  return tc_launch(pb, nullptr, err, sizeof(err)) == 0 ? 1 : 0;
+}
+
+int sap3d_conv_fwd_bn(const sap3d_conv_desc* d, const void* x0, const void* x1, const float* w_tf, const void* w_fwd_packed,
+                      const float* bias, void* raw, float* stats, const sap3d_bn_fuse* f, void* stream) {
+  (void)w_tf;
+  if (check_desc(d)) return 1;
+  if (!x0 || !raw || !stats || !f || (d->nseg > 1 && !x1)) return set_error("conv_fwd_bn: NULL argument");
+  if (!f->y || !f->scale || !f->shift) return set_error("conv_fwd_bn: y / scale / shift must be given");
+  if (require_device()) return 1;
+  if (!tc_eligible(d) || d->out_f32 || d->dtype != SAP3D_BF16) return set_error("conv_fwd_bn: bf16 tensor-core descriptors only");
+  if (!w_fwd_packed) return set_error("conv_fwd_bn: needs the packed weights");
+  ConvGeom g;
+  make_geom(d, g);
+  TcProblem pb;
+  build_fwd_problem(d, g, x0, x1, pb);
+  pb.B = w_fwd_packed;
+  pb.out = raw;
+  pb.bias = d->has_bias ? bias : nullptr;
+  pb.stats = stats;
+  pb.scale = nullptr; pb.shift = nullptr;
+  pb.relu = 0; pb.accumulate = 0; pb.out_f32 = 0; pb.force_block_n = 0;
+  TcFuseBN fb;
+  fb.gamma = f->gamma; fb.beta = f->beta; fb.moving_mean = f->moving_mean; fb.moving_var = f->moving_var;
+  fb.momentum = f->momentum; fb.eps = f->eps;
+  fb.count = (double)d->N * g.d[0].O * g.d[1].O * g.d[2].O;
+  fb.scale = f->scale; fb.shift = f->shift; fb.mean = f->mean; fb.rstd = f->rstd;
+  fb.relu1 = f->relu1; fb.residual = f->residual; fb.relu_out = f->relu_out; fb.y = f->y;
+  pb.fuse_bn = &fb;
+  char err[512];
+  if (tc_launch(pb, reinterpret_cast<cudaStream_t>(stream), err, sizeof(err))) return set_error("%s", err);
+  return 0;
+}
+
 static int conv_dgrad_impl(const sap3d_conv_desc* d, int32_t seg, const void* dy, const float* w_tf, const void* w_dgrad_packed,
                            void* dx, int32_t accumulate, void* dx2, int32_t accumulate2, void* stream);
 

@@ -71,6 +71,8 @@ struct alignas(64) TcConvParams {
   int n_units;         // persistent kernels: work units handed out through the ticket counter
   int n_pair_units;    // balanced: units [0, n_pair_units) are groups of MT consecutive m-tiles, the rest single m-tiles
   unsigned int* sched; // persistent kernels: {next unit ticket, CTAs finished}; zero at launch, reset by the last CTA
+  TcFuseBN fuse;       // conv_tc_kernel: BatchNorm finished inside the launch when fuse.y != NULL (grid barrier on gbar)
+  unsigned int* gbar;  // {arrivals, CTAs past the barrier}: a slot of the same zero-initialised pool as sched
   int halo_rows;       // halo-tile kernels: rows of one activation box (128 + 2 * halo_inner); taps are sorted in triples
   int halo_inner;      // ... rows per step along the halo axis (product of the inner box extents; multiple of 8)
   unsigned long long* dbg;   // phase-timing probe (tools/conv_phase_probe.py): [cta][16][2] = (clock64, globaltimer); normally NULL
@@ -466,6 +468,147 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
       }
     }
     if (want_stats && sub + 1 < MT) asm volatile("bar.sync 1, 128;" ::: "memory");  // s_stats is reused by the next sub-tile
+    if (BLOCK_N == 128 && MT == 1 && p.fuse.y != nullptr) {
+      // ================= BatchNorm finished in place (TcFuseBN) =================
+      // (1) grid barrier: every CTA's statistics rows are in global memory.  All CTAs of the launch are resident (<= one per SM,
+      //     checked by the host), so spinning is safe.
+      const int et = threadIdx.x - 64;
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        atomicAdd(p.gbar, 1u);
+        unsigned int seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.gbar) : "memory");
+        } while (seen < gridDim.x);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // (2) finalise my columns: fp64 sums over the statistics rows in a fixed order, as sap3d_bn_finalize does
+      {
+        const int cc = et;
+        const int col = nt * BLOCK_N + cc;
+        const bool mine = SPLIT == 1 || (SPLIT == 4 ? (uint32_t)(cc >> 5) : (uint32_t)(cc >> 6)) == rank;
+        if (col < p.cout && mine) {
+          double ta = 0.0, tb = 0.0;
+          for (int r0 = 0; r0 < p.m_tiles; r0 += 8) {     // 16 loads in flight, then the sums in row order
+            float fa[8], fb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool in = r0 + i < p.m_tiles;
+              const long long r = in ? r0 + i : r0;
+              fa[i] = __ldcg(p.stats + (r * 2 + 0) * p.cout + col);
+              fb[i] = __ldcg(p.stats + (r * 2 + 1) * p.cout + col);
+              if (!in) { fa[i] = 0.f; fb[i] = 0.f; }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              ta += (double)fa[i];
+              tb += (double)fb[i];
+            }
+          }
+          const double m = ta / p.fuse.count;
+          double vv = tb / p.fuse.count - m * m;
+          if (vv < 0.0) vv = 0.0;
+          const float mean = (float)m, var = (float)vv;
+          const float rstd = rsqrtf(var + p.fuse.eps);
+          const float g = p.fuse.gamma ? __ldg(p.fuse.gamma + col) : 1.f;
+          const float bt = p.fuse.beta ? __ldg(p.fuse.beta + col) : 0.f;
+          const float sc = g * rstd, sh = bt - mean * g * rstd;
+          s_ep[BLOCK_N + cc] = sc;
+          s_ep[2 * BLOCK_N + cc] = sh;
+          if (mt == 0) {      // one CTA per column publishes the per-channel results
+            p.fuse.scale[col] = sc;
+            p.fuse.shift[col] = sh;
+            if (p.fuse.mean) p.fuse.mean[col] = mean;
+            if (p.fuse.rstd) p.fuse.rstd[col] = rstd;
+            if (p.fuse.moving_mean) {
+              p.fuse.moving_mean[col] = p.fuse.moving_mean[col] * p.fuse.momentum + mean * (1.f - p.fuse.momentum);
+              p.fuse.moving_var[col] = p.fuse.moving_var[col] * p.fuse.momentum + var * (1.f - p.fuse.momentum);
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // (3) second pass over the accumulator (still in TMEM; the peers' partials still in the receive buffer)
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = nt * BLOCK_N + c * 32;
+        if (col0 >= p.cout) break;
+        if (SPLIT > 1 && (SPLIT == 4 ? (uint32_t)c : (uint32_t)(c >> 1)) != rank) continue;
+        uint32_t rr[32];
+        if (nkb > 0) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rr[j] = 0u;
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+        if (SPLIT > 1) {
+#pragma unroll
+          for (int sl = 0; sl < SPLIT - 1; ++sl) {
+            const float* rb = reinterpret_cast<const float*>(smem + (recv_base - base)) + ((sl * OWN_CHUNKS + (SPLIT == 4 ? 0 : (c & 1))) * 128 + row) * 32;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 f = *reinterpret_cast<const float4*>(rb + ((g ^ (row & 7)) << 2));
+              v[g * 4] += f.x; v[g * 4 + 1] += f.y; v[g * 4 + 2] += f.z; v[g * 4 + 3] += f.w;
+            }
+          }
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += s_ep[c * 32 + j];
+        }
+        // the backward pass normalises the STORED (bf16) raw tensor: use the same rounded value here
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_ep[BLOCK_N + c * 32 + j], s_ep[2 * BLOCK_N + c * 32 + j]);
+        if (p.fuse.relu1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (valid) {
+          if (p.fuse.residual != nullptr) {
+            const bf16* rp = reinterpret_cast<const bf16*>(p.fuse.residual) + row_off + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (col0 + g * 8 < p.cout) {
+                float e[8];
+                Vec8<bf16>::load(rp + g * 8, e);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] += e[j];
+              }
+            }
+          }
+          if (p.fuse.relu_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          bf16* o = reinterpret_cast<bf16*>(p.fuse.y) + row_off + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (col0 + g * 8 < p.cout) {
+              float w8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w8[j] = v[g * 8 + j];
+              Vec8<bf16>::store(o + g * 8, w8);
+            }
+          }
+        }
+      }
+      // (4) hand the barrier slot back: the last CTA to get here zeroes it for its next user
+      if (et == 0) {
+        const unsigned int prev = atomicAdd(p.gbar + 1, 1u);
+        if (prev == gridDim.x - 1) {
+          p.gbar[0] = 0u;
+          p.gbar[1] = 0u;
+          __threadfence();
+        }
+      }
+    }
     }  // sub
     if (threadIdx.x == 64) dbg_mark(p, 7);
     tc_fence_before();
@@ -1660,6 +1803,35 @@ static int launch_split(const TcConvParams& prm, int grid, cudaStream_t stream, 
   return 0;
 }
 
+// how many SPLIT-CTA clusters of the split-K kernel can be resident at once (GPC granularity can leave it below SMs / SPLIT):
+// the in-launch BatchNorm needs EVERY CTA of the launch resident, its grid barrier would otherwise never complete
+template <int SPLIT>
+static int split_max_clusters() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  constexpr int SMEM = 4 * (128 * 128 + 128 * 128) + (2 * 4 + 2) * 8 + 16 + (4 * 2 + 3) * 128 * 4 + (SPLIT - 1) * (4 / SPLIT) * 16384 + 128 + 1024;
+  cudaFuncSetAttribute(conv_tc_kernel<128, 4, 1, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(SPLIT * 32);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = SPLIT;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<128, 4, 1, SPLIT>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  cached = n;
+  return cached;
+}
+
 template <int BLOCK_N, int STAGES, int MT, int HALO = 0>
 static int launch_persist(const TcConvParams& prm, int units, cudaStream_t stream, char* err, size_t errlen) {
   constexpr int RING = HALO ? STAGES * MT * TC_HALO_MAX_ROWS * 128 + HALO * BLOCK_N * 128 : STAGES * (MT * 128 * 128 + BLOCK_N * 128);
@@ -1977,7 +2149,7 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
                    mt0 == 2 && (int)m.views.size() <= TC_SWAP_SINGLE_MAP && ((m.ext[1] + hp.box[1] - 1) / hp.box[1]) % 2 == 0 &&
                    2 * (128 + 2 * hp.inner) <= TC_SWAP_MAX_ROWS && hp.tiles >= 2 * 148;
         bool enc_ok = true;
-        for (size_t v = 0; v < m.views.size() && enc_ok; ++v) {
+        for (size_t v = 0; v < m.views.size() && enc_ok && !pb.query_fuse_bn; ++v) {
           if (use_swap) {
             int pbox[4] = {hbox[0], 2 * hbox[1], hbox[2], hbox[3]};
             enc_ok = encode_view(&prm.amap[v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, pbox, err, errlen) == 0 &&
@@ -1999,14 +2171,16 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
       }
     }
   }
-  if (!use_halo)
+  if (!use_halo && !pb.query_fuse_bn)
     for (size_t v = 0; v < m.views.size(); ++v)
       if (encode_view(&prm.amap[v], m.views[v].base, m.views[v].C, m.views[v].dim, m.views[v].stride, box, err, errlen))
         return 1;
-  if (encode_b(&prm.bmap, pb.B, pb.Ktot, pb.rowsB, block_n, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
   prm.b_batched = pb.b_batch > 1 ? 1 : 0;
-  if (encode_b(&prm.bmap_half, pb.B, pb.Ktot, pb.rowsB, block_n / 2, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
-  if (encode_b(&prm.bmap_quarter, pb.B, pb.Ktot, pb.rowsB, block_n / 4, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
+  if (!pb.query_fuse_bn) {
+    if (encode_b(&prm.bmap, pb.B, pb.Ktot, pb.rowsB, block_n, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
+    if (encode_b(&prm.bmap_half, pb.B, pb.Ktot, pb.rowsB, block_n / 2, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
+    if (encode_b(&prm.bmap_quarter, pb.B, pb.Ktot, pb.rowsB, block_n / 4, pb.b_batch, pb.b_batch_stride, err, errlen)) return 1;
+  }
   int ntap = 0;
   for (size_t c = 0; c < m.classes.size(); ++c) {
     TcClass& dc = prm.cls[c];
@@ -2073,6 +2247,7 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
     return 1;
   }
   // few output tiles and a long K loop (stage-2/3 backbone layers): split K over a cluster of 2 or 4 CTAs
+  int split_sel = 1;
   if (block_n == 128 && mt == 1 && pb.force_split >= 0) {
     int min_nkb = 1 << 30;
     for (int c = 0; c < prm.ncls; ++c) min_nkb = std::min(min_nkb, prm.cls[c].nkb);
@@ -2081,9 +2256,26 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
       if (grid <= 37 && min_nkb >= 8) split = 4;
       else if (grid <= 74 && min_nkb >= 8) split = 2;
     }
-    if (split == 4 && min_nkb >= 4) return launch_split<4>(prm, (int)grid, stream, err, errlen);
-    if (split == 2 && min_nkb >= 2) return launch_split<2>(prm, (int)grid, stream, err, errlen);
+    if (split == 4 && min_nkb >= 4) split_sel = 4;
+    else if (split == 2 && min_nkb >= 2) split_sel = 2;
   }
+  // BatchNorm finished inside the launch (TcFuseBN): the non-persistent 128-column kernel with every CTA resident at once
+  if (pb.fuse_bn != nullptr || pb.query_fuse_bn) {
+    const bool fuse_ok = block_n == 128 && mt == 1 && prm.ncls == 1 && !pb.out_f32 && pb.out2 == nullptr && pb.b_batch <= 1 &&
+                         pb.scale == nullptr && !pb.relu && !pb.accumulate && grid <= 148 &&
+                         (split_sel == 1 ? grid <= sm_count() : grid <= (split_sel == 4 ? split_max_clusters<4>() : split_max_clusters<2>())) &&
+                         pb.force_split >= 0 && (pb.query_fuse_bn || pb.stats != nullptr);
+    if (pb.query_fuse_bn) return fuse_ok ? 0 : 2;
+    if (!fuse_ok) {
+      snprintf(err, errlen, "tc_launch: this problem cannot finish its BatchNorm inside the launch (ask sap3d_conv_fwd_bn_supported first)");
+      return 1;
+    }
+    prm.fuse = *pb.fuse_bn;
+    prm.gbar = sched_slot(stream, err, errlen);
+    if (prm.gbar == nullptr) return 1;
+  }
+  if (split_sel == 4) return launch_split<4>(prm, (int)grid, stream, err, errlen);
+  if (split_sel == 2) return launch_split<2>(prm, (int)grid, stream, err, errlen);
   // more work units than SMs (decoder layers): persistent CTAs with double-buffered accumulators
   if (grid > 148 && pb.force_split >= 0 && prm.ncls == 1 && block_n >= 128 && pb.b_batch <= 1 && multicast_cluster() != 0) {
     const int mg = (int)m_groups;

@@ -27,6 +27,32 @@ struct TcClassH {
   std::vector<TcTapH> taps;
   long long out_ofs;  // element offset of the class inside the output tensor
 };
+// batch-statistics BatchNorm (+ReLU, + residual) finished INSIDE the convolution kernel (conv_tc_kernel, training graphs):
+// the raw output and its statistics rows are still written (the backward pass reads them), then the CTAs of the launch meet at
+// a grid barrier, every CTA finalises the statistics of its own columns and writes the normalised tensor from the accumulators
+// it still holds in TMEM.  Can replace the sap3d_bn_apply_fused launch that follows every backbone convolution.
+// MEASURED NEGATIVE (r02): 140 launches per training step disappear, but the step gets SLOWER (18.2 vs 17.8 ms): the fused tail
+// is a chain of global round trips (statistics store + fence, barrier arrive, barrier observe, statistics loads, residual
+// load) of ~0.7 us each, ~6.5 us per layer, while the separate kernel -- launched programmatically, its set-up overlapping the
+// convolution's tail -- adds ~5.5 us.  The engine therefore uses it only on request (SAP3D_CONV_FUSE_BN=1); the entry point and
+// its parity tests stay.
+struct TcFuseBN {
+  const float* gamma;
+  const float* beta;
+  float* moving_mean;      // updated with `momentum` (1.0 = leave alone), like sap3d_bn_finalize
+  float* moving_var;
+  float momentum, eps;
+  double count;            // positions the statistics cover
+  float* scale;            // per-channel outputs, [cout] each (the backward pass and inference read them)
+  float* shift;
+  float* mean;
+  float* rstd;
+  int relu1;               // y = relu_out?( relu1?(raw * scale + shift) + residual )
+  const void* residual;    // nullable, bf16, same layout as the output
+  int relu_out;
+  void* y;                 // normalised output, bf16, same layout as the raw output
+};
+
 struct TcProblem {
   std::vector<TcView> views;
   std::vector<TcClassH> classes;
@@ -50,6 +76,8 @@ struct TcProblem {
   // span samples and dims are not merged.  1 = one shared B (every convolution).
   int b_batch = 1;
   long long b_batch_stride = 0;   // elements
+  const TcFuseBN* fuse_bn = nullptr;   // finish a batch-statistics BatchNorm inside the launch (see TcFuseBN); tc_launch fails if it cannot
+  int query_fuse_bn = 0;               // 1: tc_launch only answers whether fuse_bn is possible for this problem: 0 = yes, 2 = no
 };
 
 // number of M tiles (per class) the launcher will use for these extents (after dim merging)

@@ -449,6 +449,7 @@ class _ConvOp:
         stats = torch.zeros(rows, 2, cout, device=eng.device, dtype=torch.float32) if want_stats else None
         self.out = ConvOut(raw, stats, rows, self)
         self.fused_affine = None   # (NormState, relu): inference-mode BN (+ReLU) applied in the conv epilogue
+        self.fused_bn = None       # _NormActOp: training-mode BatchNorm finished inside this conv's launch (sap3d_conv_fwd_bn)
         self.aux = False           # forward launch on the aux stream (independent sibling branch, joined by its consumer)
         self.use_tc = eng.dt == A.BF16
         nf = A.lib.sap3d_conv_packed_elems(C.byref(self.desc), 0)
@@ -485,6 +486,17 @@ class _ConvOp:
                                                 A.ptr(self.b.w) if self.b is not None else None, A.ptr(ns.scale), A.ptr(ns.shift),
                                                 int(relu), A.ptr(self.out.raw.buf), e.stream), "conv_fwd_affine " + self.name)
             e._count(2)
+            return
+        nop = self.fused_bn
+        if nop is not None and nop.fuse_active():
+            ns = nop.n1
+            f = A.BnFuse(A.ptr(ns.gamma.w), A.ptr(ns.beta.w), A.ptr(ns.mm.w), A.ptr(ns.mv.w), BN_MOMENTUM if e.update_moving else 1.0, BN_EPS,
+                         A.ptr(ns.scale), A.ptr(ns.shift), A.ptr(ns.mean), A.ptr(ns.rstd), int(nop.relu1),
+                         A.ptr(nop.b_t.buf) if nop.b_t is not None else None, int(nop.relu_out), A.ptr(nop.y.buf))
+            A.check(A.lib.sap3d_conv_fwd_bn(C.byref(self.desc), A.ptr(self.xs[0].buf), A.ptr(x1), A.ptr(self.w.w), A.ptr(self.wf),
+                                            A.ptr(self.b.w) if self.b is not None else None, A.ptr(self.out.raw.buf),
+                                            A.ptr(self.out.stats), C.byref(f), e.stream), "conv_fwd_bn " + self.name)
+            e._count()
             return
         A.check(A.lib.sap3d_conv_fwd(C.byref(self.desc), A.ptr(self.xs[0].buf), A.ptr(x1), A.ptr(self.w.w), A.ptr(self.wf),
                                      A.ptr(self.b.w) if self.b is not None else None, A.ptr(self.out.raw.buf),
@@ -549,6 +561,23 @@ class _NormActOp:
         self.y = eng.tensor(a.raw.shape, name)
         if eng.training_graph:
             a.raw.ensure_grad()
+        # training graphs, on request (SAP3D_CONV_FUSE_BN=1; measured slower than the two launches, see conv_tc.cuh): a
+        # batch-statistics BatchNorm (+ReLU, + plain residual) whose convolution keeps every CTA resident (backbone stages 2-3) is
+        # finished inside that convolution's launch; nothing is launched here then
+        self.fused_conv = None
+        if (eng.training_graph and n1 is not None and train1 and n2 is None and not relu2 and not isinstance(b, ConvOut)
+                and a.op is not None and a.op.use_tc and not a.op.aux and a.op.fused_bn is None and a.op.fused_affine is None
+                and eng.dt == A.BF16 and a.stats is not None and os.environ.get("SAP3D_CONV_FUSE_BN", "0") == "1"
+                and (self.b_t is None or (self.b_t.shape == a.raw.shape and self.b_t is not a.raw))
+                and A.lib.sap3d_conv_fwd_bn_supported(C.byref(a.op.desc)) == 1):
+            a.op.fused_bn = self
+            self.fused_conv = a.op
+
+    def fuse_active(self) -> bool:
+        """the producing convolution finishes this norm (decided per run: synchronised / per-sample statistics need the
+        separate launches)"""
+        e = self.eng
+        return self.fused_conv is not None and e.sync_bn is None and not e.per_sample_bn
 
     def _finalize(self, co: ConvOut, ns: NormState, training: bool):
         e = self.eng
@@ -631,7 +660,7 @@ class _NormActOp:
 
     def fwd(self):
         e = self.eng
-        if self.folded:
+        if self.folded or self.fuse_active():
             return
         if isinstance(self.b, ConvOut) and self.b.op is not None and self.b.op.aux and e.use_side_stream:
             torch.cuda.current_stream(e.device).wait_stream(e.aux_stream)   # join the sibling branch

@@ -252,3 +252,63 @@ def test_linearity_at_full_decoder_size(A):
     y, stats = outs[0]
     assert rel(stats[:, 0].sum(0), y.sum(dim=(0, 1, 2, 3))) < 5e-3
     assert rel(stats[:, 1].sum(0), (y * y).sum(dim=(0, 1, 2, 3))) < 5e-3
+
+
+# BatchNorm finished inside the convolution launch (sap3d_conv_fwd_bn: grid barrier + second pass over the TMEM accumulators) against
+# the two-launch form it replaces (sap3d_conv_fwd + sap3d_bn_apply_fused) on the same inputs: backbone stage-2/3 geometries
+FUSE_BN_CASES = [
+    ("stage 3 conv1 1x1x1 1024->256 (split-K x4)", 8, 2, 7, 7, 1024, 256, (1, 1, 1), True, False, False),
+    ("stage 3 convS 1x3x3 256->256 (split-K x4)", 8, 2, 7, 7, 256, 256, (1, 3, 3), True, False, False),
+    ("stage 3 convT 3x1x1 256->256 + s (ST_C)", 8, 2, 7, 7, 256, 256, (3, 1, 1), True, True, False),
+    ("stage 3 conv3 1x1x1 256->1024 + x, ReLU after the add (56 CTAs, no split)", 8, 2, 7, 7, 256, 1024, (1, 1, 1), False, True, True),
+    ("stage 2 conv1 1x1x1 512->128 (49 tiles, split-K x2)", 8, 4, 14, 14, 512, 128, (1, 1, 1), True, False, False),
+    ("ragged: 5 x 3 x 7 x 7 positions, cout 192", 5, 3, 7, 7, 128, 192, (1, 3, 3), True, True, True),
+]
+
+
+@pytest.mark.parametrize("case", FUSE_BN_CASES, ids=[c[0] for c in FUSE_BN_CASES])
+def test_batchnorm_finished_inside_the_conv_launch(A, case):
+    _, N, D, H, W, cin, cout, k, relu1, with_res, relu_out = case
+    dev = "cuda"
+    st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(cin * 7 + cout)
+    x = torch.randn(N, D, H, W, cin, device=dev).to(torch.bfloat16)
+    w = (torch.randn(*k, cin, cout, device=dev) / (cin * k[0] * k[1] * k[2]) ** 0.5)
+    d = A.make_conv_desc(A.BF16, N, D, H, W, [cin], cout, k, (1, 1, 1), False, False, False, A.IMPL_TC)
+    assert A.lib.sap3d_conv_fwd_bn_supported(C.byref(d)) == 1
+    wf = torch.zeros(A.lib.sap3d_conv_packed_elems(C.byref(d), 0), device=dev, dtype=torch.bfloat16)
+    A.check(A.lib.sap3d_conv_pack_weights(C.byref(d), A.ptr(w), A.ptr(wf), None, st), "pack")
+    rows = A.lib.sap3d_conv_stats_rows(C.byref(d))
+    P = N * D * H * W
+    gamma, beta = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev) * 0.2
+    res = torch.randn(N, D, H, W, cout, device=dev).to(torch.bfloat16) if with_res else None
+    out = {}
+    for form in ("two launches", "one launch"):
+        raw = torch.full((N, D, H, W, cout), float("nan"), device=dev, dtype=torch.bfloat16)
+        y = torch.full_like(raw, float("nan"))
+        stats = torch.zeros(rows, 2, cout, device=dev)
+        mm, mv = torch.zeros(cout, device=dev), torch.ones(cout, device=dev)
+        sc, sh, mean, rstd = (torch.full((cout,), float("nan"), device=dev) for _ in range(4))
+        if form == "two launches":
+            A.check(A.lib.sap3d_conv_fwd(C.byref(d), A.ptr(x), None, A.ptr(w), A.ptr(wf), None, A.ptr(raw), A.ptr(stats), st), "fwd")
+            A.check(A.lib.sap3d_bn_apply_fused(A.BF16, A.ptr(raw), A.ptr(stats), rows, A.ptr(gamma), A.ptr(beta), A.ptr(mm), A.ptr(mv), 1, A.ptr(sc),
+                                               A.ptr(sh), A.ptr(mean), A.ptr(rstd), int(relu1), A.ptr(res), 0, None, 0, None, None, None, None, 0,
+                                               None, None, None, None, 0, int(relu_out), A.ptr(y), P, cout, float(P), 0.9, 1e-3, st), "apply")
+        else:
+            f = A.BnFuse(A.ptr(gamma), A.ptr(beta), A.ptr(mm), A.ptr(mv), 0.9, 1e-3, A.ptr(sc), A.ptr(sh), A.ptr(mean), A.ptr(rstd), int(relu1),
+                         A.ptr(res), int(relu_out), A.ptr(y))
+            for _ in range(3):     # repeated launches reuse the barrier slots: each must leave its slot clean
+                mm.zero_(); mv.fill_(1.0)
+                A.check(A.lib.sap3d_conv_fwd_bn(C.byref(d), A.ptr(x), None, A.ptr(w), A.ptr(wf), None, A.ptr(raw), A.ptr(stats), C.byref(f), st), "fwd_bn")
+        torch.cuda.synchronize()
+        out[form] = (raw.clone(), y.clone(), stats.clone(), sc.clone(), sh.clone(), mean.clone(), rstd.clone(), mm.clone(), mv.clone())
+    a, b = out["two launches"], out["one launch"]
+    assert torch.equal(a[0].view(torch.int16), b[0].view(torch.int16))          # raw output: the same first pass
+    assert torch.equal(a[2], b[2])                                              # statistics rows
+    for i in (3, 4, 5, 6, 7, 8):
+        assert not torch.isnan(b[i]).any()
+        assert rel(b[i], a[i]) < 1e-6, (i, rel(b[i], a[i]))
+    assert not torch.isnan(b[1].float()).any()
+    assert rel(b[1], a[1]) < 2e-3, rel(b[1], a[1])                             # bf16 last-bit differences at most
+    mism = (a[1].view(torch.int16) != b[1].view(torch.int16)).float().mean().item()
+    assert mism < 1e-2, mism
