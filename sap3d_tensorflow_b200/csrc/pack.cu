@@ -45,8 +45,17 @@ __device__ __forceinline__ void pack_chunk(const sap3d_pack_entry& en, long long
   }
   float v[8];
   const float* src = en.src + tap * en.s_tap + r * en.s_r + c * en.s_c;
+  if (en.s_c == 1 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {   // contiguous source: two 16-byte loads instead of eight scalar ones
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (r < en.rows) {
+      a = __ldg(reinterpret_cast<const float4*>(src));
+      b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    }
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = r < en.rows ? __ldg(src + j * en.s_c) : 0.f;
+    for (int j = 0; j < 8; ++j) v[j] = r < en.rows ? __ldg(src + j * en.s_c) : 0.f;
+  }
   Vec8<bf16>::store(reinterpret_cast<bf16*>(en.dst) + ((long long)r * en.taps + tap) * en.cols + c, v);
 }
 

@@ -15,7 +15,7 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control no
 python tools/run_dominant_kernel.py fwd > $O/ev_plain_dom.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:conv_tc_ -s 1 -c 1 -f -o $O/r02_full_conv_dominant python tools/run_dominant_kernel.py fwd > $O/ev_ncu_dom.log 2>&1
 python tools/run_dominant_kernel.py wgrad > $O/ev_plain_wg.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:wgrad_tc -s 1 -c 1 -f -o $O/r02_full_wgrad_dominant python tools/run_dominant_kernel.py wgrad > $O/ev_ncu_wg.log 2>&1
 # inside the training step
-timeout 300 $NCUF -k 'regex:conv_tc_kernel.*1, 4>' -s 60 -c 1 -o $O/r02_full_conv_splitk python tools/profile_step.py $G 8 112 train > $O/ev_ncu_splitk.log 2>&1
+timeout 300 $NCUF --kernel-name-base mangled -k regex:conv_tc_kernelILi128ELi4ELi1ELi4E -s 60 -c 1 -o $O/r02_full_conv_splitk python tools/profile_step.py $G 8 112 train > $O/ev_ncu_splitk.log 2>&1
 timeout 300 $NCUF -k 'regex:bn_bwd_slab' -s 40 -c 1 -o $O/r02_full_bn_slab python tools/profile_step.py $G 8 112 train > $O/ev_ncu_slab.log 2>&1
 timeout 300 $NCUF -k 'regex:apply_bwd_reduce_nob|apply_bwd_nob' -s 2 -c 2 -o $O/r02_full_bn_nob python tools/profile_step.py $G 8 112 train > $O/ev_ncu_nob.log 2>&1
 timeout 300 $NCUS -k 'regex:bn_apply_fused|bn_bwd_coop|bn_finalize|apply_kernel|maxpool|pack_multi|adam_kernel|flash_' -c 40 -o $O/r02_sol_step_kernels python tools/profile_step.py $G 8 112 train > $O/ev_ncu_sol.log 2>&1

@@ -39,6 +39,9 @@ FULL = [
                                "8 x 8 x 56 x 56 positions (M = 200704, K = 6912, N = 128; 355.1 GFLOP, 156 MB algorithmic)"),
     ("r02_full_wgrad_dominant", "filter gradient of the same layer, timed alone (tools/run_dominant_kernel.py wgrad): dW[27][256][128] += P^T Q over 200704 "
                                 "positions, per 128-channel input segment (2 launches; 355.1 GFLOP together; algorithmic DRAM per launch: x segment 51.4 MB + dy 51.4 MB)"),
+    ("r02_full_conv_halo", "the same launch on the un-swapped halo-tile kernel (SAP3D_CONV_SWAP=0 form, captured before the swap existed): "
+                           "positions on the M side, three taps per activation box"),
+    ("r02_full_wgrad_pair", "opt-in two-tap filter-gradient kernel on the same layer (SAP3D_WGRAD_PAIR=1; measured slower, DESIGN 3.3)"),
     ("r02_full_conv_splitk", "split-K cluster conv inside the training step (stage-3 backbone layer, 784 positions)"),
     ("r02_full_bn_slab", "BatchNorm backward of a stage-3 tensor (784 positions) inside the training step: one block per 8 channels, no grid barrier"),
     ("r02_full_bn_nob", "BatchNorm backward of a decoder tensor (8 x 8 x 56 x 56 x 128 = 25.7 M elements) inside the training step: reduce, then apply"),
@@ -49,6 +52,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__cluster_size", "launch__shared_mem_per_block_dynamic", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed.sum"]
+dom_kernel = ""
 lines, traffic, l2sm = [f"ncu --set full --clock-control none --import-source on (cold caches, serialised launches); measured peaks: {peaks['hbm_gbs']} GB/s HBM, "
                         f"{peaks['bf16_tflops']} / {peaks['bf16_tflops_sustained']} TFLOP/s bf16 burst / sustained (MEASURED_PEAKS.json)", ""], None, None
 for f, desc in FULL:
@@ -69,13 +73,14 @@ for f, desc in FULL:
         lines.append(f"     -> DRAM traffic {b / 1e6:.1f} MB in {t * 1e6:.1f} us = {b / t / 1e9:.0f} GB/s = {b / t / 1e9 / peaks['hbm_gbs']:.2f} of the measured HBM peak")
         if f == "r02_full_conv_dominant":
             traffic = b
+            dom_kernel = short(r[hdr.index("Kernel Name")])[:80]
             i2 = hdr.index("l1tex__m_xbar2l1tex_read_bytes.sum")
             l2sm = float(r[i2]) * scale[units[i2]]
             lines.append(f"     -> 355.14 GFLOP / {t * 1e6:.1f} us = {355.14e9 / t / 1e12:.0f} TFLOP/s under ncu (the bench's CUDA-event timing is the reported one)")
     lines.append("")
 open(os.path.join(P, f"{tag}_ncu_full_summary.txt"), "w").write("\n".join(lines) + "\n")
 if traffic is not None:
-    json.dump({"kernel": "conv_tc_persist_kernel<128,4,2> x_1_2 fwd B=8", "dram_bytes_per_launch": traffic,
+    json.dump({"kernel": dom_kernel + " x_1_2 fwd B=8", "dram_bytes_per_launch": traffic,
                "algorithmic_bytes_per_launch": 2 * 51380224 + 1769472 + 51380224, "l2_to_sm_bytes_per_launch": l2sm,
                "source": f"profiles/{tag}_ncu_full_summary.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
               open(os.path.join(P, "dominant_kernel_traffic.json"), "w"), indent=1)
