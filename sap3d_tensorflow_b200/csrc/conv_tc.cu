@@ -2023,6 +2023,15 @@ static bool swap_enabled() {
   }
   return v != 0;
 }
+// SAP3D_CONV_NARROW=0: never trade 256-column tiles for twice as many 128-column units
+static bool narrow_tiles_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAP3D_CONV_NARROW");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 // SAP3D_CONV_BALANCED=0: persistent kernels take units round-robin even where contiguous equal ranges are possible
 static bool balanced_enabled() {
   static int v = -1;
@@ -2126,8 +2135,13 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
   int block_n = pb.force_block_n;
   if (block_n == 0) {
     if (pb.cout <= 64) block_n = 64;
-    else if (pb.cout % 256 == 0 && m_tiles * (long long)m.classes.size() * (pb.cout / 256) >= 148) block_n = 256;
-    else block_n = 128;
+    else if (pb.cout % 256 == 0 && m_tiles * (long long)m.classes.size() * (pb.cout / 256) >= 148) {
+      // 256-column tiles unless they fill the persistent rounds so badly that twice as many 128-column units win despite their
+      // less efficient MMA shape (~0.85x): e.g. 196 units on 148 SMs = two rounds at 66 %, 392 half-size units = three at 88 %
+      const long long u256 = m_tiles * (long long)m.classes.size() * (pb.cout / 256), u128 = 2 * u256, sms = sm_count();
+      const double f256 = (double)u256 / (double)(((u256 + sms - 1) / sms) * sms), f128 = (double)u128 / (double)(((u128 + sms - 1) / sms) * sms);
+      block_n = (narrow_tiles_enabled() && f128 * 0.85 > f256) ? 128 : 256;
+    } else block_n = 128;
   }
   if (block_n > 64 && pb.rowsB % block_n != 0 && pb.rowsB < block_n) block_n = 64;
   // halo-tile kernel: persistent one-class problems with one column tile whose taps form triples along H or D
