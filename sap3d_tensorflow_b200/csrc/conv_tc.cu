@@ -2023,12 +2023,14 @@ static bool swap_enabled() {
   }
   return v != 0;
 }
-// SAP3D_CONV_NARROW=0: never trade 256-column tiles for twice as many 128-column units
+// SAP3D_CONV_NARROW=1: trade 256-column tiles for twice as many 128-column units where the 256-column units fill the persistent
+// rounds badly.  Off by default: measured on the level-2 decoder layers (196 units on 148 SMs) it LOSES -- 13 launches went from
+// ~62 to ~76 us; the 128-column MMA shape and the extra weight traffic cost more than the third, better filled round gains.
 static bool narrow_tiles_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SAP3D_CONV_NARROW");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   return v != 0;
 }
