@@ -313,12 +313,18 @@ def run_eval(args):
     def one_pass(host: bool):
         sums = torch.zeros(nmet, device=dev, dtype=torch.float64)
         cnts = torch.zeros(nmet, device=dev, dtype=torch.float64)
+        if host:
+            sess.prefetch(xs[0])     # as in the training arm: the NEXT batch's H2D copy runs on the copy stream under the current batch
         for i in range(nb):
             j = i % pool
-            x = xs[j] if host else xs_dev[j]
             d = dens[j].to(dev, non_blocking=True) if host else dens_dev[j]
             f = fixs[j].to(dev, non_blocking=True) if host else fixs_dev[j]
-            pred = sess.run(x, graph=True)
+            if host:
+                pred = sess.run(None, graph=True)            # consumes the staged batch
+                if i + 1 < nb:
+                    sess.prefetch(xs[(i + 1) % pool])
+            else:
+                pred = sess.run(xs_dev[j], graph=True)
             r = score(pred, d, f)
             sums += r["sum"]
             cnts += r["count"]

@@ -21,6 +21,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 
 #include "abi_util.cuh"
 #include "common.cuh"
@@ -1931,9 +1933,9 @@ static int launch_persist_mc(const TcConvParams& prm, int m_groups, cudaStream_t
 
 static unsigned long long* g_conv_dbg = nullptr;
 void tc_set_debug_buffer(void* buf) { g_conv_dbg = reinterpret_cast<unsigned long long*>(buf); }
-static long long g_halo_launches = 0, g_swap_launches = 0;
-long long tc_halo_launches() { return g_halo_launches; }
-long long tc_swap_launches() { return g_swap_launches; }
+static std::atomic<long long> g_halo_launches{0}, g_swap_launches{0};
+long long tc_halo_launches() { return g_halo_launches.load(); }
+long long tc_swap_launches() { return g_swap_launches.load(); }
 
 // opt-in while it is being measured: SAP3D_CONV_MULTICAST=2 or 4 (cluster size); unset / 0 = off
 static int multicast_cluster() {
@@ -1950,13 +1952,15 @@ static int multicast_cluster() {
 constexpr int TC_SCHED_SLOTS = 4096;
 static unsigned int* sched_slot(cudaStream_t stream, char* err, size_t errlen) {
   static unsigned int* pool[64] = {nullptr};
-  static unsigned int seq = 0;
+  static std::atomic<unsigned int> seq{0};   // (host threads may launch concurrently; the pool itself is set up under `mu`)
+  static std::mutex mu;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) {
     snprintf(err, errlen, "tc_launch: device ordinal %d out of range", dev);
     return nullptr;
   }
+  std::lock_guard<std::mutex> lock(mu);
   if (pool[dev] == nullptr) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
@@ -1973,7 +1977,7 @@ static unsigned int* sched_slot(cudaStream_t stream, char* err, size_t errlen) {
     }
     pool[dev] = ptr;
   }
-  return pool[dev] + 2 * (seq++ % TC_SCHED_SLOTS);
+  return pool[dev] + 2 * (seq.fetch_add(1u) % TC_SCHED_SLOTS);
 }
 static int sm_count() {
   static int sms = 0;
