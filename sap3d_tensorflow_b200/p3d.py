@@ -87,7 +87,8 @@ class Bottleneck:
             r = eng.conv([x], pl * BLOCK_EXPANSION, one, s,
                          get_conv_weight(eng, f"dw3d_{i}", [1, 1, 1, self.inplanes, pl * BLOCK_EXPANSION]), name=f"dw3d_{i}")
             nsr = nw._bn_state(eng, pl * BLOCK_EXPANSION)
-            r.op.aux = True         # the projection shortcut only needs the block input
+            # (not flagged aux: created after conv3 to keep TF's variable numbering, it would only hop to the aux stream behind c3
+            #  and be joined immediately -- three launches per step, no overlap to win)
             y = eng.norm_act(c3, ns3, tr, False, b=r, n2=nsr, train2=tr, relu2=False, relu_out=True, name=f"b{i}")
         else:
             y = eng.norm_act(c3, ns3, tr, False, b=x, relu_out=True, name=f"b{i}")
