@@ -2307,6 +2307,21 @@ int tc_launch(const TcProblem& pb, cudaStream_t stream, char* err, size_t errlen
     return mt == 2 ? launch_persist_mc<256, 3, 2, 4>(prm, mg, stream, err, errlen) : launch_persist_mc<256, 4, 1, 4>(prm, mg, stream, err, errlen);
   }
   prm.balanced = (prm.ncls == 1 && prm.n_tiles == 1 && pb.b_batch <= 1 && balanced_enabled()) ? 1 : 0;
+  {   // SAP3D_CONV_TRACE=1: one line per launch on stderr (developer aid: which kernel form every layer takes)
+    static int trace = -1;
+    if (trace < 0) {
+      const char* e = getenv("SAP3D_CONV_TRACE");
+      trace = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    if (trace) {
+      int ntaps = 0, nkb = 0;
+      for (int c = 0; c < prm.ncls; ++c) { ntaps += prm.cls[c].tap_count; nkb += prm.cls[c].nkb; }
+      fprintf(stderr, "[conv_trace] ext=%dx%dx%dx%d cout=%d ncls=%d taps=%d nkb=%d views=%d box=%d,%d,%d,%d m_tiles=%d block_n=%d mt=%d grid=%lld split=%d %s\n",
+              prm.ext[0], prm.ext[1], prm.ext[2], prm.ext[3], prm.cout, prm.ncls, ntaps, nkb, (int)m.views.size(), prm.box[0], prm.box[1],
+              prm.box[2], prm.box[3], prm.m_tiles, block_n, mt, grid, split_sel,
+              use_swap ? "swap" : (use_halo ? "halo" : (split_sel > 1 ? "splitk" : (grid > 148 && pb.force_split >= 0 ? "persist" : "plain"))));
+    }
+  }
   if (use_halo) {
     if (grid <= 148 || prm.box_rows != 128) {
       snprintf(err, errlen, "tc_launch: halo plan inconsistent (grid %lld, box rows %d)", grid, prm.box_rows);
