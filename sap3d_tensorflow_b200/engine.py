@@ -155,7 +155,12 @@ class Engine:
         self._split_ops: Optional[int] = None      # the LAST mark (the first cut backward meets); None = backward is not cut
         self.dp_split_offset: Optional[int] = None  # ... and the offset of the first gradient element behind it
         self.grad_source: Optional[torch.Tensor] = None   # bf16 copy of the gradients Adam should read instead of flat_g (DP exchange)
-        self.side_stream = torch.cuda.Stream(device=self.device)   # filter gradients run here, off the critical path
+        # filter gradients run on side streams, off the critical path.  Several, taken round-robin: the ~200 small filter-gradient
+        # launches of the backbone are independent of each other, and ONE stream serialised them into a 0.6 ms backlog that was still
+        # draining after the main chain had finished (in-graph trace, r02).  SAP3D_WGRAD_STREAMS=1 restores the single stream.
+        self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, int(os.environ.get("SAP3D_WGRAD_STREAMS", "3"))))]
+        self.side_stream = self.side_streams[0]   # also the home of the padded-filter folds (stream order = dependency)
+        self._wgrad_rr = 0
         self.aux_stream = torch.cuda.Stream(device=self.device, priority=-1)   # forward: the second of two independent convs
         self.use_side_stream = True
 
@@ -415,7 +420,8 @@ class Engine:
         for f in reversed(ops):
             f()
         if self.use_side_stream:
-            torch.cuda.current_stream(self.device).wait_stream(self.side_stream)   # join the filter-gradient branch
+            for ss in self.side_streams:
+                torch.cuda.current_stream(self.device).wait_stream(ss)   # join the filter-gradient branches
         self._counting = None
 
     def adam(self, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
@@ -527,9 +533,12 @@ class _ConvOp:
         x1 = self.xs[1].buf if len(self.xs) > 1 else None
         main = torch.cuda.current_stream(e.device)
         if e.use_side_stream:
-            # fork: the filter gradient only needs dy (ready on `main`) and the saved inputs; it is joined before Adam
-            e.side_stream.wait_stream(main)
-            st = e.side_stream.cuda_stream
+            # fork: the filter gradient only needs dy (ready on `main`) and the saved inputs; it is joined before Adam.  Filters that
+            # are folded afterwards (zero-padded attention projections, _PaddedFilter.bwd on side_streams[0]) stay on that stream.
+            ss = e.side_streams[0] if isinstance(self.w, _TempParam) else e.side_streams[e._wgrad_rr % len(e.side_streams)]
+            e._wgrad_rr += 1
+            ss.wait_stream(main)
+            st = ss.cuda_stream
         else:
             st = e.stream
         A.check(A.lib.sap3d_conv_wgrad(C.byref(self.desc), A.ptr(self.xs[0].buf), A.ptr(x1), A.ptr(dy), A.ptr(self.w.g),
