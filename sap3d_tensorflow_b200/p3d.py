@@ -141,8 +141,16 @@ def p3d_stem(_X, _dropout=0.0, batch_size=2, training=False):
     return _ActivationOutput(_stem(_X, False))
 
 
-def _backbone(_X: T, training: bool, skip_1_0: bool = True):
+def _backbone(_X: T, training: bool, skip_1_0: bool = True, forks=None):
+    """forks: {feature name: n} -> the returned dict holds a LIST of n cross-branch aliases (Engine.fork) for that feature instead
+    of the tensor, one per consumer branch; recorded right behind the feature's producer so that, in the backward pass, the main
+    chain waits for the consumer branches exactly where it is about to need the feature's gradient"""
     eng = _X.eng
+    forks = forks or {}
+
+    def out(name, x):
+        n = forks.get(name, 0)
+        return [eng.fork(x, f"{name}/fork{i}") for i in range(n)] if n else x
     if _X.C == 64:
         # the input already IS the stem activation (frame cache of the sliding-window inference): keep TF's variable numbering
         # by burning the names the stem's layers would have taken (firstconv1 is named explicitly; its BN is the first
@@ -155,7 +163,7 @@ def _backbone(_X: T, training: bool, skip_1_0: bool = True):
         stem = _stem(_X, training)
     t = {}
     if skip_1_0:
-        t["x_1_0"] = eng.tap("x_1_0", eng.maxpool(stem, *TEMPORAL_POOL, name="x_1_0"))
+        t["x_1_0"] = out("x_1_0", eng.tap("x_1_0", eng.maxpool(stem, *TEMPORAL_POOL, name="x_1_0")))
     x = eng.tap("pool1", eng.maxpool(stem, (2, 3, 3), (2, 2, 2), name="pool1"))
     cnt = 0
     for si, (planes, num, inplanes, stride) in enumerate(STAGES):
@@ -165,36 +173,57 @@ def _backbone(_X: T, training: bool, skip_1_0: bool = True):
         res = blk.infer()
         cnt = blk.cnt
         x = eng.tap(f"x_{si + 2}_0", eng.maxpool(res, *TEMPORAL_POOL, name=f"x_{si + 2}_0"))
-        t[f"x_{si + 2}_0"] = x
+        t[f"x_{si + 2}_0"] = out(f"x_{si + 2}_0", x)
     return t
 
 
 def _unetpp(_X: T, _dropout: float, training: bool, sa: bool):
+    """The decoder runs on two branches beside the backbone (Engine.branch; SAP3D_BRANCHES=0 = one stream, same ops, same order):
+      branch 2 (early): upx_3_0, x_2_1, upx_2_0, x_1_1 -- they need only x_1_0 .. x_3_0, so their forward runs beside the 36-block
+                        stage of the backbone and their backward beside the rest of the decoder's, off the critical path;
+      branch 1 (late):  everything that needs x_4_0 (x_4_0_sa ... x_1_3, head).
+    The creation order of the layers -- TF's variable numbering -- is the reference's."""
     eng = _X.eng
-    t = _backbone(_X, training)
-    x10, x20, x30, x40 = t["x_1_0"], t["x_2_0"], t["x_3_0"], t["x_4_0"]
+    br = eng.branches_enabled
+    t = _backbone(_X, training, forks={"x_1_0": 1, "x_2_0": 1, "x_3_0": 2, "x_4_0": 1} if br else None)
+    if br:
+        (x10,), (x20,), (x30, x30e), (x40,) = t["x_1_0"], t["x_2_0"], t["x_3_0"], t["x_4_0"]
+    else:
+        x10, x20, x30, x40 = t["x_1_0"], t["x_2_0"], t["x_3_0"], t["x_4_0"]
+        x30e = x30
     att = (lambda h, name, **kw: eng.tap(name, nw.attention(h, name, training=training, **kw))) if sa else (lambda h, name, **kw: h)
-    x40 = att(x40, "x_4_0_sa")
-    up40 = nw.transpose_conv3d(x40, 512, [1, 3, 3], [2, 2, 2], training, "upx_4_0")
-    x31 = nw.conv3d(nw.concat([x30, up40]), 512, [2, 3, 3], [1, 1, 1], training, "x_3_1")
-    x31 = att(x31, "x_3_1_sa")
-    up30 = nw.transpose_conv3d(x30, 256, [2, 3, 3], [2, 2, 2], training, "upx_3_0")
-    x21 = nw.conv3d(nw.concat([x20, up30]), 256, [3, 3, 3], [1, 1, 1], training, "x_2_1")
-    up31 = nw.transpose_conv3d(x31, 256, [2, 3, 3], [2, 2, 2], training, "upx_3_1")
-    x22 = nw.conv3d(nw.concat([x21, up31]), 256, [3, 3, 3], [1, 1, 1], training, "x_2_2")
-    x22 = att(x22, "x_2_2_sa")
-    up20 = nw.transpose_conv3d(x20, 128, [3, 3, 3], [2, 2, 2], training, "upx_2_0")
-    x11 = nw.conv3d(nw.concat([x10, up20]), 128, [3, 3, 3], [1, 1, 1], training, "x_1_1")
-    up21 = nw.transpose_conv3d(x21, 128, [3, 3, 3], [2, 2, 2], training, "upx_2_1")
-    x12 = nw.conv3d(nw.concat([x11, up21]), 128, [3, 3, 3], [1, 1, 1], training, "x_1_2")
-    up22 = nw.transpose_conv3d(x22, 128, [3, 3, 3], [2, 2, 2], training, "upx_2_2")
-    x13 = nw.conv3d(nw.concat([x12, up22]), 128, [3, 3, 3], [1, 1, 1], training, "x_1_3")
-    x13 = att(x13, "x_1_3_sa", subsample=True)
-    if training:
-        x13 = eng.dropout(x13, _dropout, name="x_1_3_drop")
-    w = eng.param("x_0_1/kernel", [3, 3, 3, 1, x13.C], "glorot_t")
-    b = eng.param("x_0_1/bias", [1], "zeros")
-    return eng.head(x13, w, b, (3, 3, 3), 2, sigmoid=True, name="x_0_1")
+    with eng.branch(1):
+        eng.consume_forked([x40, x30])
+        x40 = att(x40, "x_4_0_sa")
+        up40 = nw.transpose_conv3d(x40, 512, [1, 3, 3], [2, 2, 2], training, "upx_4_0")
+        x31 = nw.conv3d(nw.concat([x30, up40]), 512, [2, 3, 3], [1, 1, 1], training, "x_3_1")
+        x31 = att(x31, "x_3_1_sa")
+    with eng.branch(2):
+        eng.consume_forked([x30e, x20, x10])
+        up30 = nw.transpose_conv3d(x30e, 256, [2, 3, 3], [2, 2, 2], training, "upx_3_0")
+        x21 = nw.conv3d(nw.concat([x20, up30]), 256, [3, 3, 3], [1, 1, 1], training, "x_2_1")
+        x21l = eng.fork(x21, "x_2_1/fork")          # for the late branch (upx_2_1, x_2_2)
+    with eng.branch(1):
+        up31 = nw.transpose_conv3d(x31, 256, [2, 3, 3], [2, 2, 2], training, "upx_3_1")
+        eng.consume_forked([x21l])
+        x22 = nw.conv3d(nw.concat([x21l, up31]), 256, [3, 3, 3], [1, 1, 1], training, "x_2_2")
+        x22 = att(x22, "x_2_2_sa")
+    with eng.branch(2):
+        up20 = nw.transpose_conv3d(x20, 128, [3, 3, 3], [2, 2, 2], training, "upx_2_0")
+        x11 = nw.conv3d(nw.concat([x10, up20]), 128, [3, 3, 3], [1, 1, 1], training, "x_1_1")
+        x11l = eng.fork(x11, "x_1_1/fork")
+    with eng.branch(1):
+        up21 = nw.transpose_conv3d(x21l, 128, [3, 3, 3], [2, 2, 2], training, "upx_2_1")
+        eng.consume_forked([x11l])
+        x12 = nw.conv3d(nw.concat([x11l, up21]), 128, [3, 3, 3], [1, 1, 1], training, "x_1_2")
+        up22 = nw.transpose_conv3d(x22, 128, [3, 3, 3], [2, 2, 2], training, "upx_2_2")
+        x13 = nw.conv3d(nw.concat([x12, up22]), 128, [3, 3, 3], [1, 1, 1], training, "x_1_3")
+        x13 = att(x13, "x_1_3_sa", subsample=True)
+        if training:
+            x13 = eng.dropout(x13, _dropout, name="x_1_3_drop")
+        w = eng.param("x_0_1/kernel", [3, 3, 3, 1, x13.C], "glorot_t")
+        b = eng.param("x_0_1/bias", [1], "zeros")
+        return eng.head(x13, w, b, (3, 3, 3), 2, sigmoid=True, name="x_0_1")
 
 
 def p3d_unetplusplus_ds(_X, _dropout, batch_size=2, training=True, SA=False):

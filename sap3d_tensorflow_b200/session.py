@@ -119,6 +119,7 @@ class Session:
         if train:
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             split = self._overlap()
+            e.branches_suspended = bool(split)   # several backward graphs: no cross-graph events (Engine._branches_active)
             with torch.cuda.graph(ga, stream=cap):
                 self._train_front(split)
             gms = []

@@ -372,3 +372,21 @@ def test_full_size_properties_of_the_baseline_config(lib_built):
     # zero gradients by construction: conv biases in front of batch-statistics norms, and the four attention blocks' 3.1 M
     # parameters while their gate gamma is still at its initial 0 (utils/network.py:191-192) -- 5 % of the variables
     assert 0.9 < moved < 0.99, moved
+
+
+def test_decoder_branches_keep_parity(lib_built):
+    """SAP3D_BRANCHES=1 (the UNet++ decoder on two streams beside the backbone, cross-branch tensors through Engine.fork /
+    consume_forked) is an opt-in schedule of the SAME ops: the forward-parity, training-step and split-backward tests of this file
+    are re-run in a child process with it switched on"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("SAP3D_BRANCHES") is not None:
+        pytest.skip("already running under the switch")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "(forward_parity or training_step or training_reduces or split_backward or prefetched or full_size) and not branches"],
+                       env=dict(os.environ, SAP3D_BRANCHES="1"), cwd=root, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
+

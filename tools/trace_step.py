@@ -63,3 +63,21 @@ with open(args.out.replace(".txt", "_list.txt"), "w") as f:
     for e in last:
         f.write(f"{(e.time_range.start - t0):10.1f} gap={(e.time_range.start - prev):7.1f} dur={(e.time_range.end - e.time_range.start):8.1f}  {e.name[:110]}\n")
         prev = e.time_range.end
+# the same list with the CUDA stream of every activity (from the chrome-trace export): "<start us> <dur us> <stream> <name>"
+try:
+    import json
+    jpath = args.out.replace(".txt", "_chrome.json")
+    prof.export_chrome_trace(jpath)
+    tr = json.load(open(jpath))
+    ks = [ev for ev in tr["traceEvents"] if ev.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "ts" in ev]
+    ks.sort(key=lambda ev: ev["ts"])
+    n3 = len(ks) // 3
+    lastk = ks[2 * n3:]
+    k0 = lastk[0]["ts"]
+    with open(args.out.replace(".txt", "_streams.txt"), "w") as f:
+        for ev in lastk:
+            f.write(f"{ev['ts'] - k0:10.1f} {ev.get('dur', 0):8.1f} {ev.get('args', {}).get('stream', -1):4d} {ev['name'][:100]}\n")
+    os.remove(jpath)
+except Exception as ex:  # noqa: BLE001  (developer tool: the aggregate above is the product)
+    print("stream list not written:", ex)
+
