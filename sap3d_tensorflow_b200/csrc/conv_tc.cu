@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     }
     __syncwarp();
     if (SPLIT > 1) { cluster_wait(); cluster_arrive(); }
-  } else if (SPLIT > 1) {
+  } else if constexpr (SPLIT > 1) {
     // ================= split-K phase A: ship the chunks owned by peer CTAs =================
     // The fp32 partials are staged in THIS CTA's shared memory (the operand ring is free once the accumulator is complete)
     // in the exact layout of the receiver's buffer, then moved by one DSMEM bulk copy per peer that signals the peer's
@@ -628,11 +628,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 
 
 // =================================================================================================
-// Persistent form for layers with more work units than SMs (the decoder): one CTA per SM walks the units
-// u = blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulators are DOUBLE-BUFFERED in TMEM (2 x MT x BLOCK_N columns
-// when that fits in 512), so the epilogue of unit i (tcgen05.ld, bias, statistics, stores) runs under the MMAs of
-// unit i+1, the TMA ring never drains between units, and the wave-quantisation tail of a 5.3-wave launch disappears
-// (every SM gets floor or ceil of units/SMs).
+// Persistent form for layers with more work units than SMs (the decoder): one CTA per SM takes units from a ticket
+// counter (r01: u = blockIdx.x, blockIdx.x + gridDim.x, ...).  The accumulators are DOUBLE-BUFFERED in TMEM
+// (2 x MT x BLOCK_N columns when that fits in 512), so the epilogue of unit i (tcgen05.ld, bias, statistics, stores) runs
+// under the MMAs of unit i+1, the TMA ring never drains between units, and the wave-quantisation tail of a 5.3-wave
+// launch disappears.
 // =================================================================================================
 // ticket counter of the persistent kernels: every CTA's last act.  All of a CTA's draws precede its call, so when the last CTA
 // arrives no draw is outstanding and the pair can be zeroed for the slot's next user.
