@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--graph", default=None)
-    ap.add_argument("--batch", type=int, default=8, help="clips per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU and step (default: 8 for the training workloads, 32 for eval)")
     ap.add_argument("--size", type=int, default=112)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "gn160", "eval"],
@@ -43,7 +43,13 @@ def parse():
     ap.add_argument("--full-res", action="store_true",
                     help="--workload eval: test.py convention (upsample the last frame to 1080x960, CC/SIM/AUC_Judd/AUC_Borji/NSS)")
     ap.add_argument("--eager", action="store_true", help="no CUDA-graph replay (debug)")
-    return ap.parse_args()
+    ap.add_argument("--bn-statistics", default="clip", choices=["clip", "batch"],
+                    help="--workload eval: the backbone's batch-statistics BatchNorm normalises every clip on its own (what gen_pred.py's "
+                         "one-window-per-sess.run gives; default) or the whole batch of clips together")
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 32 if args.workload == "eval" else 8
+    return args
 
 
 DEFAULT_GRAPH = "p3d_unetplusplus_ds"     # p3d.py:340 (what gen_pred.py:46 builds); named literally: the reference arm must not
@@ -292,7 +298,8 @@ def run_eval(args):
     graph = args.graph or default_graph()
     B, size = args.batch, args.size
     dev = torch.device("cuda", local_rank)
-    xin = sp.placeholder([B, 16, size, size, 3], dtype="bf16", training_graph=False, device=f"cuda:{local_rank}")
+    xin = sp.placeholder([B, 16, size, size, 3], dtype="bf16", training_graph=False, device=f"cuda:{local_rank}",
+                         per_sample_statistics=(args.bn_statistics == "clip"))
     head = getattr(sp.p3d, graph)(xin, 0.0, B, False)
     sess = sp.Session(head)
     lo, hi = parallel.shard_clips(args.clips, rank, world)
@@ -373,7 +380,8 @@ def run_eval(args):
             "n_gpus": world, "steps": reps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{graph} inference (training=False) + saliency metrics over {args.clips} clips 16x{size}x{size}, "
-                                   f"batch {B} per iteration, clips sharded contiguously over {world} rank(s)",
+                                   f"batch {B} per iteration ({'per-clip' if args.bn_statistics == 'clip' else 'per-batch'} BatchNorm statistics), "
+                                   f"clips sharded contiguously over {world} rank(s)",
                        "parallelism": f"dp{world}", "cuda_graph": True, "metric_means": [float(v) for v in means_host.tolist()],
                        "metric_names": ["CC", "SIM", "AUC_Judd", "AUC_Borji", "NSS"] if args.full_res else ["CC", "SIM", "NSS", "KLdiv"],
                        "l2": "every batch's activations (> 1 GB) exceed the 126 MB L2"},
