@@ -321,6 +321,16 @@ int sap3d_sample_stats_rows(int64_t S, int32_t C, int32_t N);
  * x*scale[n][c]) */
 int sap3d_sample_channel_partials(int32_t dtype, const void* x, const float* scale, int32_t N, int64_t S, int32_t C, int32_t rows,
                                   float* part, void* stream);
+/* Per-clip batch-statistics BatchNorm (+ReLU, + second operand with or without its own per-clip norm) in ONE launch:
+ *     y = relu_out?( relu1?(bn_clip(a)) + relu2?(bn_clip(b) | b) ),   statistics over the S positions of each of the N clips.
+ * tf.layers.batch_normalization(training=True) as gen_pred.py sees it -- one 16-frame window per sess.run, so every window is
+ * normalised on its own (gen_pred.py:88-135) -- for a BATCH of windows; replaces the three launches
+ * sap3d_sample_channel_partials + sap3d_gn_finalize + sap3d_affine_act for tensors whose (clip, 64-channel) slab is at most
+ * 128 KB (sap3d_sample_norm_apply_supported).  gamma2 == NULL: b is added as it is.  Moving averages are not touched. */
+int sap3d_sample_norm_apply_supported(int32_t dtype, int64_t S, int32_t C);
+int sap3d_sample_norm_apply(int32_t dtype, const void* a, const float* gamma1, const float* beta1, int32_t relu1, const void* b,
+                            const float* gamma2, const float* beta2, int32_t relu2, int32_t relu_out, void* y, int32_t N, int64_t S,
+                            int32_t C, float eps, void* stream);
 /* GroupNorm: partials -> per-(sample,channel) scale/shift [N][C] (+ per-(sample,group) mean/rstd [N][G]) */
 int sap3d_gn_finalize(const float* part, int32_t rows, int32_t N, int64_t S, int32_t C, int32_t G, const float* gamma,
                       const float* beta, float eps, float* scale, float* shift, float* save_mean, float* save_rstd, void* stream);

@@ -121,6 +121,8 @@ _u64 = C.c_uint64
 _sig("sap3d_bn_finalize", [_vp, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_gn_stats", [_i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp])
 _sig("sap3d_affine_act", [_i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _i64, _vp])
+_sig("sap3d_sample_norm_apply_supported", [_i32, _i64, _i32])
+_sig("sap3d_sample_norm_apply", [_i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i64, _i32, _f32, _vp])
 _sig("sap3d_bn_apply_fused", [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32,
                               _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _f64, _f32,
                               _f32, _vp])

@@ -759,6 +759,142 @@ __global__ void __launch_bounds__(256, 3) apply_bwd_nob_kernel(const ApplyBwdArg
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-clip batch-statistics BatchNorm (+ReLU, + second operand) in ONE launch, for the inference path that normalises every clip
+// of a batch on its own (placeholder(per_sample_statistics=True): what gen_pred.py's one-window-per-sess.run gives).  The generic
+// path takes three launches per norm (per-sample partial sums, finalize, apply); for the backbone's small tensors that is pure
+// launch latency (165 norms per forward pass).  Here one block owns (clip n, 64 channels): pass 1 sums x and x^2 over the clip's
+// S positions (second operand too when it has its own norm), the block derives scale / shift in shared memory, pass 2 re-reads
+// the slab (L2-resident: S x 64 channels <= 128 KB, checked by the host) and writes
+//     y = relu_out?( relu1?(a * s1 + t1) + relu2?(b * s2 + t2 | b) ).
+// block = 16 channel lanes (4 channels each) x 16 position lanes; grid = (N, C / 64).
+// ------------------------------------------------------------------------------------------------
+struct SampleNormArgs {
+  const void* a; const float* g1; const float* b1;
+  const void* b; const float* g2; const float* b2;   // b nullable; g2 != NULL: b has its own per-clip norm
+  void* y;
+  long long S;
+  int C;
+  float eps;
+  int relu1, relu2, relu_out;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) sample_norm_apply_kernel(const SampleNormArgs p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ double red[4][16][64];     // [sum a, sumsq a, sum b, sumsq b][position lane][channel]
+  __shared__ float coef[4][64];         // scale1, shift1, scale2, shift2
+  const int cv = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  const int n = blockIdx.x;
+  const int c = blockIdx.y * 64 + cv * 4;
+  const bool live = c < p.C;
+  const bool norm2 = p.b != nullptr && p.g2 != nullptr;
+  const T* a = reinterpret_cast<const T*>(p.a) + (long long)n * p.S * p.C;
+  const T* b = p.b ? reinterpret_cast<const T*>(p.b) + (long long)n * p.S * p.C : nullptr;
+  T* y = reinterpret_cast<T*>(p.y) + (long long)n * p.S * p.C;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  if (live) {
+    for (long long pos0 = pl; pos0 < p.S; pos0 += 64) {     // four positions per thread in flight
+      typename Vec4<T>::Raw ra[4], rb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long pos = pos0 + 16 * u;
+        if (pos < p.S) {
+          ra[u] = Vec4<T>::load(a + pos * p.C + c);
+          if (norm2) rb[u] = Vec4<T>::load(b + pos * p.C + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (pos0 + 16 * u >= p.S) break;
+        float v[4];
+        Vec4<T>::unpack(ra[u], v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[0][j] += v[j]; acc[1][j] = fmaf(v[j], v[j], acc[1][j]); }
+        if (norm2) {
+          Vec4<T>::unpack(rb[u], v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { acc[2][j] += v[j]; acc[3][j] = fmaf(v[j], v[j], acc[3][j]); }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[i][pl][cv * 4 + j] = (double)acc[i][j];
+  __syncthreads();
+  if (threadIdx.x < 128) {     // (norm, channel): fixed-order sums over the 16 position lanes
+    const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+    const int cc = blockIdx.y * 64 + ch;
+    if (cc < p.C && (which == 0 || norm2)) {
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int l = 0; l < 16; ++l) { s1 += red[which * 2][l][ch]; s2 += red[which * 2 + 1][l][ch]; }
+      const double m = s1 / (double)p.S;
+      double var = s2 / (double)p.S - m * m;
+      if (var < 0.0) var = 0.0;
+      const float rstd = rsqrtf((float)var + p.eps);
+      const float* g = which == 0 ? p.g1 : p.g2;
+      const float* bt = which == 0 ? p.b1 : p.b2;
+      const float gg = g ? g[cc] : 1.f, bb = bt ? bt[cc] : 0.f;
+      coef[which * 2][ch] = gg * rstd;
+      coef[which * 2 + 1][ch] = bb - (float)m * gg * rstd;
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  float s1[4], t1[4], s2[4], t2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s1[j] = coef[0][cv * 4 + j]; t1[j] = coef[1][cv * 4 + j];
+    s2[j] = norm2 ? coef[2][cv * 4 + j] : 1.f; t2[j] = norm2 ? coef[3][cv * 4 + j] : 0.f;
+  }
+  for (long long pos0 = pl; pos0 < p.S; pos0 += 64) {
+    typename Vec4<T>::Raw ra[4], rb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long pos = pos0 + 16 * u;
+      if (pos < p.S) {
+        ra[u] = Vec4<T>::load(a + pos * p.C + c);
+        if (b) rb[u] = Vec4<T>::load(b + pos * p.C + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+    const long long pos = pos0 + 16 * u;
+    if (pos >= p.S) break;
+    float v[4], r[4];
+    Vec4<T>::unpack(ra[u], v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      r[j] = fmaf(v[j], s1[j], t1[j]);
+      if (p.relu1) r[j] = fmaxf(r[j], 0.f);
+    }
+    if (b) {
+      float w[4];
+      Vec4<T>::unpack(rb[u], w);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float q = norm2 ? fmaf(w[j], s2[j], t2[j]) : w[j];
+        if (p.relu2) q = fmaxf(q, 0.f);
+        r[j] += q;
+      }
+    }
+    if (p.relu_out) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = fmaxf(r[j], 0.f);
+    }
+    Vec4<T>::store(y + pos * p.C + c, r);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // single-launch backward (cooperative grid): reduce -> grid.sync -> per-chunk finalize in shared memory -> apply.
 // grid = (rows, C/64) co-resident blocks; every block owns one 64-channel chunk and one slab of positions in both
 // passes, so the second pass re-reads what the block itself just read (L1/L2 hits for backbone-sized tensors).
@@ -1176,6 +1312,30 @@ int sap3d_affine_act(int32_t dtype, const void* a, const float* s1, const float*
   if (dtype == SAP3D_BF16) launch_k(apply_kernel<bf16>, dim3(ew_grid(nvec)), dim3(256), 0, st, 1, p);
   else launch_k(apply_kernel<float>, dim3(ew_grid(nvec)), dim3(256), 0, st, 1, p);
   return check_launch("affine_act");
+}
+
+int sap3d_sample_norm_apply_supported(int32_t dtype, int64_t S, int32_t C) {
+  const int esz = dtype == SAP3D_BF16 ? 2 : 4;
+  // one block walks its (clip, 64-channel) slab twice: worth it while the slab is small (the backbone's stages 2-3; at S = 6272 the
+  // serial walk of one block per slab was slower than the three parallel launches, measured)
+  return (C % 4 == 0 && S > 0 && S * 64 * esz <= (128ll << 10)) ? 1 : 0;
+}
+
+int sap3d_sample_norm_apply(int32_t dtype, const void* a, const float* gamma1, const float* beta1, int32_t relu1, const void* b,
+                            const float* gamma2, const float* beta2, int32_t relu2, int32_t relu_out, void* y, int32_t N, int64_t S,
+                            int32_t C, float eps, void* stream) {
+  if (require_device()) return 1;
+  if (!a || !y) return set_error("sample_norm_apply: NULL tensor");
+  if (!sap3d_sample_norm_apply_supported(dtype, S, C)) return set_error("sample_norm_apply: shape not supported (S = %lld, C = %d)", (long long)S, C);
+  if ((gamma2 || beta2) && !b) return set_error("sample_norm_apply: a second norm needs a second operand");
+  SampleNormArgs p;
+  p.a = a; p.g1 = gamma1; p.b1 = beta1; p.b = b; p.g2 = gamma2; p.b2 = beta2; p.y = y;
+  p.S = S; p.C = C; p.eps = eps; p.relu1 = relu1; p.relu2 = relu2; p.relu_out = relu_out;
+  const dim3 grid((unsigned)N, (unsigned)((C + 63) / 64));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == SAP3D_BF16) launch_k(sample_norm_apply_kernel<bf16>, grid, dim3(256), 0, st, 1, p);
+  else launch_k(sample_norm_apply_kernel<float>, grid, dim3(256), 0, st, 1, p);
+  return check_launch("sample_norm_apply");
 }
 
 int sap3d_bn_apply_fused(int32_t dtype, const void* a, const float* stats1, int32_t rows1, const float* gamma1, const float* beta1,

@@ -787,6 +787,18 @@ class _NormActOp:
 
     def _fwd_per_sample(self):
         e, n1, n2 = self.eng, self.n1, self.n2
+        y = self.y
+        N, S = y.shape[0], y.positions // y.shape[0]
+        # one launch when every norm involved takes per-clip batch statistics and the (clip, 64-channel) slab is small -- the
+        # whole backbone; SAP3D_SAMPLE_NORM_FUSED=0 restores partials + finalize + apply
+        if (n1 is not None and self.train1 and (n2 is None or self.train2) and os.environ.get("SAP3D_SAMPLE_NORM_FUSED", "1") != "0"
+                and A.lib.sap3d_sample_norm_apply_supported(e.dt, S, y.C) == 1):
+            A.check(A.lib.sap3d_sample_norm_apply(
+                e.dt, A.ptr(self.a.raw.buf), A.ptr(n1.gamma.w), A.ptr(n1.beta.w), int(self.relu1),
+                A.ptr(self.b_t.buf) if self.b_t is not None else None, A.ptr(n2.gamma.w) if n2 else None, A.ptr(n2.beta.w) if n2 else None,
+                int(self.relu2), int(self.relu_out), A.ptr(y.buf), N, S, y.C, BN_EPS, e.stream), "sample_norm_apply " + self.name)
+            e._count()
+            return
         s1 = t1 = s2 = t2 = None
         if n1 is not None:
             if self.train1:

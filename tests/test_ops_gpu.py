@@ -436,3 +436,62 @@ def test_attention_core(A, dtn, tdt, tol, shape):
                                       B, Nq, Nk, dk, dv, dk, dk, dv, Nk, dv, stream()), "attnb")
     torch.cuda.synchronize()
     assert rel(dg, gr.grad) < 4 * tol and rel(df, fr.grad) < 4 * tol and rel(dh, hr.grad) < 4 * tol
+
+
+@pytest.mark.parametrize("dtn,tdt,tol", DT)
+@pytest.mark.parametrize("case", [("stage 3 tail: bn(a) + x, relu", 4, 98, 1024, False, True, False, False, True),
+                                  ("ST_B: relu(bn(t)) + relu(bn(s))", 3, 784, 128, True, True, True, True, False),
+                                  ("plain bn + relu, ragged C", 5, 37, 72, True, False, False, False, False),
+                                  ("ST_C: s + relu(bn(t))", 2, 1000, 64, True, True, False, False, False)],
+                         ids=lambda c: c[0] if isinstance(c, tuple) else None)
+def test_per_clip_batchnorm_in_one_launch(A, dtn, tdt, tol, case):
+    """sap3d_sample_norm_apply (one launch) == sap3d_sample_channel_partials + sap3d_gn_finalize(G = C) + sap3d_affine_act, and both
+    == the per-clip batch-statistics BatchNorm written out in torch"""
+    _, N, S, Cc, relu1, with_b, norm2, relu2, relu_out = case
+    dev = "cuda"
+    dt = A.BF16 if dtn == "bf16" else A.F32
+    torch.manual_seed(N * 1000 + S + Cc)
+    a = (torch.randn(N, S, Cc, device=dev) * 1.5 + 0.3).to(tdt)
+    b = (torch.randn(N, S, Cc, device=dev) * 0.7 - 0.2).to(tdt) if with_b else None
+    g1, b1 = torch.rand(Cc, device=dev) + 0.5, torch.randn(Cc, device=dev) * 0.3
+    g2, b2 = (torch.rand(Cc, device=dev) + 0.5, torch.randn(Cc, device=dev) * 0.3) if norm2 else (None, None)
+    eps = 1e-3
+    if A.lib.sap3d_sample_norm_apply_supported(dt, S, Cc) != 1:
+        assert S * 64 * (2 if dtn == "bf16" else 4) > (128 << 10)       # only slabs over the 128 KB limit are refused
+        pytest.skip("slab larger than the one-launch form takes")
+
+    def clip_bn(x, g, bt):
+        xf = x.float()
+        m = xf.mean(dim=1, keepdim=True)
+        v = xf.var(dim=1, unbiased=False, keepdim=True)
+        return (xf - m) * torch.rsqrt(v + eps) * g + bt
+
+    ref = clip_bn(a, g1, b1)
+    if relu1:
+        ref = torch.relu(ref)
+    if with_b:
+        q = clip_bn(b, g2, b2) if norm2 else b.float()
+        ref = ref + (torch.relu(q) if relu2 else q)
+    if relu_out:
+        ref = torch.relu(ref)
+    y = torch.full_like(a, float("nan"))
+    A.check(A.lib.sap3d_sample_norm_apply(dt, A.ptr(a), A.ptr(g1), A.ptr(b1), int(relu1), A.ptr(b), A.ptr(g2), A.ptr(b2), int(relu2), int(relu_out),
+                                          A.ptr(y), N, S, Cc, eps, stream()), "sample_norm_apply")
+    torch.cuda.synchronize()
+    assert not torch.isnan(y.float()).any()
+    assert rel(y, ref) < 3 * tol, rel(y, ref)
+    if Cc % 8 == 0:     # the three-launch path it replaces (needs C % 8 == 0)
+        rows = A.lib.sap3d_sample_stats_rows(S, Cc, N)
+        f = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)  # noqa: E731
+        coef = []
+        for x, g, bt in ((a, g1, b1),) + (((b, g2, b2),) if norm2 else ()):
+            part, sc, sh, mean, rstd = f(N, rows, 3, Cc), f(N, Cc), f(N, Cc), f(N, Cc), f(N, Cc)
+            A.check(A.lib.sap3d_sample_channel_partials(dt, A.ptr(x), None, N, S, Cc, rows, A.ptr(part), stream()), "partials")
+            A.check(A.lib.sap3d_gn_finalize(A.ptr(part), rows, N, S, Cc, Cc, A.ptr(g), A.ptr(bt), eps, A.ptr(sc), A.ptr(sh), A.ptr(mean), A.ptr(rstd),
+                                            stream()), "finalize")
+            coef += [sc, sh]
+        y3 = torch.full_like(a, float("nan"))
+        A.check(A.lib.sap3d_affine_act(dt, A.ptr(a), A.ptr(coef[0]), A.ptr(coef[1]), int(relu1), A.ptr(b), A.ptr(coef[2]) if norm2 else None,
+                                       A.ptr(coef[3]) if norm2 else None, int(relu2), int(relu_out), A.ptr(y3), N * S, Cc, S, stream()), "affine_act")
+        torch.cuda.synchronize()
+        assert rel(y, y3) < (2e-3 if dtn == "bf16" else 1e-5), rel(y, y3)
