@@ -52,7 +52,7 @@ def test_shim_compiles_against_the_header_stand_ins():
 def test_every_op_has_shape_function_and_gpu_kernel():
     text = open(CC).read()
     ops = registered_ops()
-    assert len(ops) >= 28, sorted(ops)
+    assert len(ops) >= 31, sorted(ops)
     for name in ops:
         assert re.search(r'REGISTER_KERNEL_BUILDER\(Name\("%s"\)\.Device\(tf::DEVICE_GPU\)' % name, text), name
         block = text[text.index('REGISTER_OP("%s")' % name):]
@@ -114,5 +114,5 @@ def test_reference_call_site_families_are_reachable_from_the_ops():
                   "sap3d_cbam_tail_bwd", "sap3d_maxpool3d_fwd", "sap3d_maxpool3d_bwd", "sap3d_flash_attn_fwd", "sap3d_flash_attn_bwd",
                   "sap3d_attention_fwd", "sap3d_attention_bwd", "sap3d_gate_fwd", "sap3d_gate_bwd", "sap3d_head_fwd", "sap3d_head_bwd",
                   "sap3d_loss_smooth_l1_ex", "sap3d_dropout", "sap3d_concat_channels", "sap3d_split_channels", "sap3d_adam_step",
-                  "sap3d_saliency_metrics", "sap3d_resize_bilinear", "sap3d_saliency_auc", "sap3d_preprocess_frames"):
+                  "sap3d_saliency_metrics", "sap3d_resize_bilinear", "sap3d_saliency_auc", "sap3d_preprocess_frames", "sap3d_sample_norm_apply"):
         assert re.search(r"\b%s\(" % entry, text), entry

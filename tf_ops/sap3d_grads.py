@@ -119,6 +119,7 @@ def _group_norm_act_grad(op, dy, *_unused):
 
 ops.NotDifferentiable("Sap3dBatchNormActGrad")
 ops.NotDifferentiable("Sap3dGroupNormActGrad")
+ops.NotDifferentiable("Sap3dClipBatchNormAct")  # per-clip statistics: the gen_pred.py inference path only
 
 
 # ---- CBAM block tail (gn/p3d_gn.py:175-177) ----------------------------------------------------------------------------

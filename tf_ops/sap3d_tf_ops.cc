@@ -484,6 +484,63 @@ class Sap3dGroupNormActOp : public tf::OpKernel {
 };
 REGISTER_KERNEL_BUILDER(Name("Sap3dGroupNormAct").Device(tf::DEVICE_GPU), Sap3dGroupNormActOp);
 
+// =====================================================================================================================
+// y = Sap3dClipBatchNormAct(a, gamma1, beta1, b, gamma2, beta2): the backbone's batch-statistics BatchNorm as gen_pred.py sees it
+// (one 16-frame window per sess.run, gen_pred.py:88-135 -- so every window is normalised on its own) for a BATCH of windows:
+// statistics over (D, H, W) per clip and channel, + ReLU + second operand, in one launch where the clip's slab is small
+// (sap3d_sample_norm_apply), else per-clip partial sums + finalize + apply.  Inference only: no gradient, moving averages untouched.
+// =====================================================================================================================
+REGISTER_OP("Sap3dClipBatchNormAct")
+    .Input("a: T").Input("gamma1: float").Input("beta1: float").Input("b: T").Input("gamma2: float").Input("beta2: float")
+    .Output("y: T")
+    .Attr("T: {bfloat16, float}").Attr("epsilon: float = 0.001")
+    .Attr("relu1: bool = true").Attr("relu2: bool = false").Attr("relu_out: bool = false").Attr("has_b: bool = false").Attr("norm_b: bool = false")
+    .SetShapeFn([](InferenceContext* c) {
+      c->set_output(0, c->input(0));
+      return tf::Status::OK();
+    });
+
+class Sap3dClipBatchNormActOp : public tf::OpKernel {
+ public:
+  explicit Sap3dClipBatchNormActOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_));
+    OP_REQUIRES_OK(c, c->GetAttr("relu1", &r1_)); OP_REQUIRES_OK(c, c->GetAttr("relu2", &r2_));
+    OP_REQUIRES_OK(c, c->GetAttr("relu_out", &ro_)); OP_REQUIRES_OK(c, c->GetAttr("has_b", &hb_));
+    OP_REQUIRES_OK(c, c->GetAttr("norm_b", &nb_));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& a = ctx->input(0);
+    const tf::int64 N = a.dim_size(0), C = a.dim_size(4), S = a.NumElements() / (N * C);
+    const bool n2 = hb_ && nb_;
+    tf::Tensor* y = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, a.shape(), &y));
+    if (sap3d_sample_norm_apply_supported(DtypeOf(a), S, static_cast<int32_t>(C)) == 1) {
+      SAP3D_OK(ctx, sap3d_sample_norm_apply(DtypeOf(a), P(a), F(ctx->input(1)), F(ctx->input(2)), r1_, hb_ ? P(ctx->input(3)) : nullptr,
+                                            n2 ? F(ctx->input(4)) : nullptr, n2 ? F(ctx->input(5)) : nullptr, r2_, ro_, P(y),
+                                            static_cast<int32_t>(N), S, static_cast<int32_t>(C), eps_, StreamOf(ctx)));
+      return;
+    }
+    // large slabs: GroupNorm's kernels with one channel per group
+    tf::Tensor coef[2][4];
+    for (int k = 0; k < 2; ++k) {
+      if (k == 1 && !n2) break;
+      const tf::Tensor& x = k == 0 ? a : ctx->input(3);
+      for (int i = 0; i < 4; ++i) OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_FLOAT, tf::TensorShape({N, C}), &coef[k][i]));
+      SAP3D_OK(ctx, sap3d_gn_stats(DtypeOf(x), P(x), static_cast<int32_t>(N), S, static_cast<int32_t>(C), static_cast<int32_t>(C),
+                                   F(ctx->input(k == 0 ? 1 : 4)), F(ctx->input(k == 0 ? 2 : 5)), eps_, F(&coef[k][0]), F(&coef[k][1]),
+                                   F(&coef[k][2]), F(&coef[k][3]), StreamOf(ctx)));
+    }
+    SAP3D_OK(ctx, sap3d_affine_act(DtypeOf(a), P(a), F(&coef[0][0]), F(&coef[0][1]), r1_, hb_ ? P(ctx->input(3)) : nullptr,
+                                   n2 ? F(&coef[1][0]) : nullptr, n2 ? F(&coef[1][1]) : nullptr, r2_, ro_, P(y), N * S, static_cast<int32_t>(C), S,
+                                   StreamOf(ctx)));
+  }
+
+ private:
+  float eps_;
+  bool r1_, r2_, ro_, hb_, nb_;
+};
+REGISTER_KERNEL_BUILDER(Name("Sap3dClipBatchNormAct").Device(tf::DEVICE_GPU), Sap3dClipBatchNormActOp);
+
 // da, db, dgamma1, dbeta1, dgamma2, dbeta2 = Sap3dGroupNormActGrad(...)
 REGISTER_OP("Sap3dGroupNormActGrad")
     .Input("dy: T").Input("a: T").Input("scale1: float").Input("shift1: float").Input("mean1: float").Input("rstd1: float").Input("gamma1: float")
