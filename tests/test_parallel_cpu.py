@@ -32,6 +32,43 @@ def test_split_buckets_cover_tail_then_head():
         assert all(lo >= split for lo, _ in tail) and all(hi <= split for _, hi in head)
 
 
+def test_segment_buckets_follow_the_backward_segments():
+    """multi-segment exchange (Engine.dp_segments: the gradient ranges in the order backward completes them, tail first): every
+    segment is bucketed on its own, tail bucket first, and together they cover the buffer exactly once"""
+    from sap3d_tensorflow_b200.parallel import segment_buckets
+
+    n = 84_922_240
+    segments = [(3_000_128, n), (262_976, 3_000_128), (0, 262_976)]       # the _ds graph's three segments (r02 trace)
+    for per in (16 * 1024 * 1024, n):                                      # 32 MB buckets; one call per segment
+        sb = segment_buckets(segments, per)
+        assert len(sb) == len(segments)
+        for (lo, hi), buckets in zip(segments, sb):
+            assert buckets[0][1] == hi and buckets[-1][0] == lo            # tail first, nothing outside the segment
+            assert all(buckets[i][0] == buckets[i + 1][1] for i in range(len(buckets) - 1))
+            assert all(0 < b - a <= per for a, b in buckets)
+        cover = sorted(b for bs in sb for b in bs)
+        assert cover[0][0] == 0 and cover[-1][1] == n and all(cover[i][1] == cover[i + 1][0] for i in range(len(cover) - 1))
+    assert [len(b) for b in segment_buckets(segments, n)] == [1, 1, 1]
+
+
+def test_bench_defaults_per_workload(monkeypatch):
+    """bench.py: 8 clips per GPU for the training workloads (configs[1]), 32 clips per iteration and per-clip BatchNorm statistics
+    for the evaluation workload (configs[4], gen_pred.py semantics); explicit flags win"""
+    import importlib.util
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for argv, want in [([], ("train", 8, "clip")), (["--workload", "eval"], ("eval", 32, "clip")),
+                       (["--workload", "eval", "--batch", "8", "--bn-statistics", "batch"], ("eval", 8, "batch")),
+                       (["--workload", "gn160"], ("gn160", 8, "clip")), (["--batch", "32"], ("train", 32, "clip"))]:
+        monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+        a = bench.parse()
+        assert (a.workload, a.batch, a.bn_statistics) == want, (argv, a)
+
+
 def test_clip_sharding_partitions_the_evaluation_set():
     from sap3d_tensorflow_b200.parallel import shard_clips
 
