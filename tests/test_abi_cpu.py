@@ -72,3 +72,32 @@ def test_dropout_hash_is_deterministic_and_unbiased():
     m1, m2 = keep_mask(7, 100000, 0.5), keep_mask(7, 100000, 0.5)
     assert (m1 == m2).all() and abs(m1.mean() - 0.5) < 0.01
     assert abs(keep_mask(8, 100000, 0.25).mean() - 0.75) < 0.01
+
+
+def _prototypes():
+    """{name: number of parameters} of every function declared in include/sap3d.h"""
+    text = open(os.path.join(ROOT, "include", "sap3d.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = {}
+    for m in re.finditer(r"\b(sap3d_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return protos
+
+
+def test_ctypes_bindings_match_the_header_prototypes(lib_built):
+    """every function the Python host binds (_abi.py: argtypes) takes exactly as many arguments as include/sap3d.h declares:
+    a binding that drifts from the header would otherwise only show up as a wrong value or a crash on the GPU"""
+    from sap3d_tensorflow_b200 import _abi as A
+
+    protos = _prototypes()
+    assert len(protos) >= 60
+    checked = 0
+    for name, n in protos.items():
+        fn = getattr(A.lib, name)
+        if fn.argtypes is None:      # not bound with a signature (restype-only helpers)
+            continue
+        assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
+        checked += 1
+    assert checked >= 55, checked
